@@ -1,0 +1,179 @@
+/* libphyloforge_b200.so — C ABI of the B200-native population-phylogeny hot path.
+ *
+ * The reference (wangyayaya/PhyloForge) has no FFI on this path: its boundary is two
+ * Python methods and a shell command line. Each entry point below
+ * replaces one step of that path and cites the reference lines it stands in for
+ * (paths relative to the reference root). INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *  - every function returns 0 (PF_OK) or a non-zero status; pf_last_error() gives the
+ *    message of the last failure on the calling thread. There is no CPU fallback.
+ *  - pointers named d_* are DEVICE pointers owned by the caller (PyTorch tensors on the
+ *    Python side); h_* are host pointers. No entry point allocates memory that outlives
+ *    the call unless documented. `stream` is a cudaStream_t passed as void* (NULL = the
+ *    default stream). Calls are asynchronous on `stream` unless documented.
+ *  - genotype codes: 0 hom-REF, 1 HET, 2 hom-ALT, 3 missing.
+ *  - packed layout ("planes"): uint32 words; sample tile T = i / PF_TILE (64), site word
+ *    w = s / 32, plane p (0 = low code bit L, 1 = high code bit H):
+ *        planes[((T * n_words + w) * 2 + p) * 64 + (i % 64)], bit (s % 32) = bit p of code(i, s)
+ *    padding samples and padding sites hold code 3 (L = H = 1).
+ */
+#ifndef PHYLOFORGE_B200_H
+#define PHYLOFORGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define PF_API extern "C" __attribute__((visibility("default")))
+#else
+#define PF_API extern
+#endif
+
+#define PF_TILE 64
+
+/* ------------------------------------------------------------------ status / info */
+PF_API const char* pf_last_error(void);
+PF_API const char* pf_version(void);
+PF_API int pf_tile(void);
+PF_API int pf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* total_mem,
+                          int* l2_bytes);
+
+/* Integer-pipe microbenchmark (roofline denominator of pf_pair_counts).
+ * kind: 0 POPC, 1 LOP3, 2 IADD, 3 IMAD, 4 POPC:LOP3 1:4, 5 POPC:IMAD 1:4, 6 LOP3:IMAD 1:1,
+ *       7 plain pair-word body with missing data, 8 plain pair-word body without.
+ * Synchronous. Outputs thread-level instructions per second and per clock per SM. */
+PF_API int pf_microbench_int_pipe(int kind, int iters, double* ops_per_s,
+                                  double* ops_per_clk_per_sm, void* stream);
+
+/* ------------------------------------------------------------------ layout helpers */
+/* number of uint32 words in a planes buffer for n_samples x n_words */
+PF_API int64_t pf_planes_len(int64_t n_samples, int64_t n_words);
+
+/* ------------------------------------------------------------------ synthetic genotypes
+ * Counter-based, integer-only generator (bit-identical to oracle/pf_oracle.c:pfo_synth_codes):
+ * code(i, s) depends only on (seed, global site s, sample i), so any sharding of the site
+ * axis yields the same global matrix (SURVEY.md §8(d) "Synthetic inputs").
+ * Writes site-major codes d_codes[(s - site0) * ld + i] for s in [site0, site0 + n_sites). */
+PF_API int pf_synth_codes(uint8_t* d_codes, int64_t n_samples, int64_t ld, int64_t site0,
+                          int64_t n_sites, uint64_t seed, int n_pops, uint32_t miss_ppm,
+                          void* stream);
+
+/* ------------------------------------------------------------------ genotype packer
+ * Replaces the per-genotype re-encoding loop of VcfTree.convert_vcf_to_seq
+ * (treetool/vcftree.py:96-134) and SvTree.convert_vcf_to_seq (treetool/svtree.py:37-120)
+ * once genotypes are byte codes: site-major u8 codes -> bit planes.
+ * d_codes[r * ld + i] is the code of sample i in row r. If d_rows != NULL the k-th packed
+ * site is row d_rows[k] (gather of surviving sites, vcftree.py:113-119), else row k.
+ * Packs n_sites sites into words [word0, word0 + ceil(n_sites/32)) of a planes buffer that
+ * has n_words words per tile; sites beyond n_sites in the last word get code 3.
+ * Codes > 3 are a caller error (masked to 2 bits). */
+PF_API int pf_pack_codes_u8(const uint8_t* d_codes, int64_t ld, const int64_t* d_rows,
+                            int64_t n_samples, int64_t n_sites, uint32_t* d_planes,
+                            int64_t n_words, int64_t word0, void* stream);
+
+/* planes -> sample-major u8 codes d_out[i * ld_out + s] for s in [0, n_sites) taken from
+ * words [word0, ...). Used to emit the reference's on-disk artefacts and by parity tests. */
+PF_API int pf_unpack_codes_u8(const uint32_t* d_planes, int64_t n_words, int64_t word0,
+                              int64_t n_samples, int64_t n_sites, uint8_t* d_out,
+                              int64_t ld_out, void* stream);
+
+/* u8 matrix transpose with row gather: d_out[i * ld_out + k] = d_in[d_rows[k] * ld_in + i]
+ * (d_rows NULL -> row k). Site-major characters -> the per-sample sequences the reference
+ * writes (vcftree.py:133-143, svtree.py:122-125). */
+PF_API int pf_transpose_u8(const uint8_t* d_in, int64_t ld_in, const int64_t* d_rows,
+                           int64_t n_rows, int64_t n_cols, uint8_t* d_out, int64_t ld_out,
+                           void* stream);
+
+/* ------------------------------------------------------------------ VCF text on the GPU
+ * Line index of a text buffer: d_line_start[k] = byte offset of line k (k < *n_lines),
+ * d_line_start[n_lines] = n_bytes sentinel is NOT written; line k ends at the '\n' before
+ * line k+1 or at n_bytes. Replaces read().splitlines() of VcfTree.cutFile
+ * (vcftree.py:75-76) / readlines() of svtree.py:35-36. Synchronous (returns the count).
+ * d_work must hold pf_line_index_work_bytes(n_bytes) bytes. capacity = max lines. */
+PF_API int64_t pf_line_index_work_bytes(int64_t n_bytes);
+PF_API int pf_line_index(const uint8_t* d_text, int64_t n_bytes, int64_t* d_line_start,
+                         int64_t capacity, int64_t* h_n_lines, void* d_work, void* stream);
+
+/* Per-line status written by the parsers (d_line_info[k]):
+ *  bits 0-1  number of matrix columns the line yields (SNP: 0/1; SV: 0/1/2)
+ *  bit  2    SNP: the kept site fits the 2-bit code (biallelic A/C/G/T, or ALT '.')
+ *  bits 8-15 error class, 0 = none (see PF_LINE_ERR_*). A line with an error is one on
+ *            which the unmodified reference raises (-> "Failed to Convert", exit 1) or
+ *            desynchronises its rows; the host raises on any error. */
+#define PF_LINE_COLS(x) ((x) & 3)
+#define PF_LINE_FITS2BIT(x) (((x) >> 2) & 1)
+#define PF_LINE_ERR(x) (((x) >> 8) & 0xff)
+#define PF_LINE_ERR_FIELDS 1      /* fewer than 10 fields or sample count != n_samples */
+#define PF_LINE_ERR_ALLELE_INDEX 2 /* allele index out of range (IndexError in the reference) */
+#define PF_LINE_ERR_ALLELE_CHAR 3  /* homozygous non-ACGT/./'*' allele (reference returns None) */
+#define PF_LINE_ERR_EMPTY_GT 4     /* empty first FORMAT subfield (reference desynchronises rows) */
+#define PF_LINE_ERR_TOO_MANY_ALLELES 5 /* more than 8 single-base alleles */
+#define PF_LINE_ERR_SV_INFO 6      /* INFO item without exactly one '=' before SVTYPE (ValueError) */
+#define PF_LINE_ERR_SV_HAPLOID 7   /* GT without '/' or '|' (reference re-uses stale alleles) */
+#define PF_LINE_ERR_NEG_INDEX 8    /* signed / exotic integer the reference would accept */
+
+/* SNP lines -> reference characters and 2-bit codes, site-major.
+ * For line k (rows of d_chars/d_codes, leading dimension ld >= n_samples):
+ *   d_chars[k*ld+i] = the character VcfTree.generate_ambiguous_code yields
+ *                     (vcftree.py:26-65 via 120-133), d_codes[k*ld+i] = its 2-bit code.
+ * Lines that start with '#', are blank, or have an allele longer than one base
+ * (vcftree.py:113-119) get 0 columns. One CTA per line. */
+PF_API int pf_vcf_snp_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t* d_line_start,
+                            int64_t n_lines, int64_t n_samples, uint8_t* d_chars,
+                            uint8_t* d_codes, int64_t ld, int32_t* d_line_info, void* stream);
+
+/* SV lines -> presence/absence characters ('0','1','.') and codes (0, 2, 3), two rows per
+ * line: row 2k is the first column of line k, row 2k+1 the second (only meaningful when
+ * the line yields 2 columns). svtree.py:37-120. */
+PF_API int pf_vcf_sv_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t* d_line_start,
+                           int64_t n_lines, int64_t n_samples, uint8_t* d_chars,
+                           uint8_t* d_codes, int64_t ld, int32_t* d_line_info, void* stream);
+
+/* Exclusive scan of PF_LINE_COLS over lines -> gather rows. d_rows[c] = source row of matrix
+ * column c (SNP: line index; SV: 2*line + which). If require_fit != 0 SNP lines whose
+ * FITS2BIT bit is clear are left out (and counted in h_summary[2]).
+ * Synchronous. h_summary[0] = total columns, [1] = number of lines with an error,
+ * [2] = kept lines that do not fit 2 bits, [3] = first line with an error (or -1),
+ * [4] = its error class. rows_per_line = 1 (SNP) or 2 (SV). */
+PF_API int pf_vcf_select_rows(const int32_t* d_line_info, int64_t n_lines, int rows_per_line,
+                              int require_fit, int64_t* d_rows, int64_t capacity,
+                              int64_t* h_summary, void* stream);
+
+/* ------------------------------------------------------------------ all-pairs counts
+ * The arithmetic the reference delegates to `treebest nj` (treetool/script.py:359-360):
+ * for every sample pair (i, j), over the sites of words [word_begin, word_end):
+ *   V  = #sites where both codes != 3
+ *   D1 = #valid sites where the codes differ
+ *   D2 = #valid sites where {code_i, code_j} = {0, 2}
+ * ACCUMULATES (+=, integer atomics, order-independent) into d_counts, three n x ld int32
+ * matrices laid out [3][n_samples][ld] in the order V, D1, D2; both triangles and the
+ * diagonal are written. The caller zeroes d_counts before the first call; multi-GPU
+ * callers sum the matrices of all site shards (NCCL allreduce).
+ * variant: 0 = auto, 1 = plain popcount kernel, 2 = carry-save kernel. */
+PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n_words,
+                          int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
+                          int variant, void* stream);
+
+/* counts -> fp64 distances, one IEEE divide of exactly converted integers per pair:
+ *   metric 0: p-distance D1 / V;  metric 1: IBS distance (D1 + D2) / (2 V).
+ * V == 0 -> 1.0 and the pair is counted in *d_n_zero_valid (int32, caller-zeroed).
+ * The diagonal is 0. d_dist is n x ld_dist. */
+PF_API int pf_normalise(const int32_t* d_counts, int64_t n_samples, int64_t ld, int metric,
+                        double* d_dist, int64_t ld_dist, int32_t* d_n_zero_valid, void* stream);
+
+/* ------------------------------------------------------------------ neighbor joining
+ * Saitou-Nei / Studier-Keppler NJ exactly as restated in oracle/pf_oracle.c:pfo_nj
+ * (the stand-in for the absent `treebest nj`, script.py:359-360): fp64, no FMA
+ * contraction, row sums in the fixed 32-lane strided + butterfly order, Q argmin ties ->
+ * lowest slot i then lowest slot j, merged node replaces slot i, last slot moves into j.
+ * d_dist (n x ld, symmetric, zero diagonal) is destroyed. Outputs (device):
+ *   d_merge[3*t+0..2] for t < n-3: node ids (a, b) joined at step t and 0;
+ *   d_merge[3*(n-3)+0..2]: the three node ids of the final trifurcation;
+ *   d_len likewise: branch lengths of those children.
+ * Node ids: leaves 0..n-1; the node created at step t is n + t. n >= 3.
+ * d_work must hold pf_nj_work_bytes(n) bytes. One cooperative persistent launch. */
+PF_API int64_t pf_nj_work_bytes(int64_t n);
+PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len,
+                 void* d_work, void* stream);
+
+#endif /* PHYLOFORGE_B200_H */
