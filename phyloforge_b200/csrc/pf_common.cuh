@@ -48,4 +48,4 @@ int pf_fail_code(int code, const char* fmt, ...);  // records message, returns c
     return pf_fail_code(PF_ERR_INTERNAL, "unknown exception");                  \
   }
 
-static inline int64_t pf_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline __host__ __device__ int64_t pf_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -1,0 +1,181 @@
+"""Host-side driver of the hot path: device buffers (PyTorch tensors, used only as
+memory + streams) and the calls into libphyloforge_b200.so.
+
+Stages (reference lines they replace):
+  pack       site-major genotype codes -> bit planes      vcftree.py:120-133, svtree.py:84-120
+  counts     all-pairs V / D1 / D2 integer matrices       `treebest nj` (script.py:359-360)
+  allreduce  sum of the site shards' count matrices       (new: sites sharded over GPUs)
+  normalise  counts -> fp64 p-distance / IBS distance     `treebest nj`
+  nj         neighbor-joining join order + branch lengths `treebest nj`
+
+There is no CPU path: every stage raises if the CUDA library or a GPU is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PhyloForgeError, check
+from .newick import merges_to_newick, two_leaf_newick
+
+TILE = 64
+METRICS = {"p": 0, "pdist": 0, "p-distance": 0, 0: 0, "ibs": 1, "IBS": 1, 1: 1}
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+@dataclass
+class TreeResult:
+    newick: str
+    merge: np.ndarray
+    length: np.ndarray
+    dist: torch.Tensor | None = None
+    counts: torch.Tensor | None = None
+    n_zero_valid: int = 0
+    timings_ms: dict = field(default_factory=dict)
+
+
+class Engine:
+    """One engine per process / per GPU (one process per GPU under torchrun)."""
+
+    def __init__(self, device: int | None = None):
+        if not torch.cuda.is_available():
+            raise PhyloForgeError("no CUDA device: phyloforge_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        torch.cuda.set_device(self.device)
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        mem, l2 = C.c_int64(), C.c_int()
+        check(self.lib.pf_device_info(C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem), C.byref(l2)))
+        self.sm_count, self.cc = sm.value, (maj.value, mnr.value)
+        self.total_mem, self.l2_bytes = mem.value, l2.value
+        if self.cc[0] != 10:
+            raise PhyloForgeError(f"compute capability {self.cc} is not sm_100: this library is B200-only")
+
+    # ------------------------------------------------------------------ buffers
+    @staticmethod
+    def n_words(n_sites: int) -> int:
+        return (n_sites + 31) // 32
+
+    def alloc_planes(self, n_samples: int, n_words: int) -> torch.Tensor:
+        n = int(self.lib.pf_planes_len(n_samples, n_words))
+        return torch.empty(n, dtype=torch.int32, device=self.device)
+
+    def alloc_counts(self, n_samples: int) -> torch.Tensor:
+        return torch.zeros((3, n_samples, n_samples), dtype=torch.int32, device=self.device)
+
+    # ------------------------------------------------------------------ stages
+    def synth_codes(self, n_samples: int, site0: int, n_sites: int, seed: int = 42,
+                    n_pops: int | None = None, miss_ppm: int = 0, out: torch.Tensor | None = None):
+        """Site-major u8 codes [n_sites, ld] generated on the device."""
+        if n_pops is None:
+            n_pops = max(2, n_samples // 25)
+        ld = (n_samples + 3) // 4 * 4
+        if out is None:
+            out = torch.empty((n_sites, ld), dtype=torch.uint8, device=self.device)
+        check(self.lib.pf_synth_codes(out.data_ptr(), n_samples, out.stride(0), site0, n_sites, seed, n_pops,
+                                      miss_ppm, _stream_ptr()))
+        return out
+
+    def pack_codes(self, codes: torch.Tensor, n_samples: int, planes: torch.Tensor, n_words: int,
+                   word0: int = 0, rows: torch.Tensor | None = None, n_sites: int | None = None):
+        """codes: site-major u8 [rows, ld]; packs n_sites sites starting at word0."""
+        assert codes.dtype == torch.uint8 and codes.is_cuda and codes.stride(1) == 1
+        if n_sites is None:
+            n_sites = int(rows.numel()) if rows is not None else codes.shape[0]
+        if rows is not None:
+            assert rows.dtype == torch.int64 and rows.is_cuda
+        check(self.lib.pf_pack_codes_u8(codes.data_ptr(), codes.stride(0), _lib.ptr(rows), n_samples, n_sites,
+                                        planes.data_ptr(), n_words, word0, _stream_ptr()))
+
+    def unpack_codes(self, planes: torch.Tensor, n_samples: int, n_words: int, n_sites: int,
+                     word0: int = 0) -> torch.Tensor:
+        """Sample-major u8 codes [n_samples, n_sites]."""
+        out = torch.empty((n_samples, max(n_sites, 1)), dtype=torch.uint8, device=self.device)
+        check(self.lib.pf_unpack_codes_u8(planes.data_ptr(), n_words, word0, n_samples, n_sites, out.data_ptr(),
+                                          out.stride(0), _stream_ptr()))
+        return out[:, :n_sites]
+
+    def transpose_u8(self, mat: torch.Tensor, n_cols: int, rows: torch.Tensor | None = None,
+                     n_rows: int | None = None) -> torch.Tensor:
+        """out[i, k] = mat[rows[k], i]: site-major characters -> per-sample sequences."""
+        if n_rows is None:
+            n_rows = int(rows.numel()) if rows is not None else mat.shape[0]
+        out = torch.empty((n_cols, max(n_rows, 1)), dtype=torch.uint8, device=self.device)
+        check(self.lib.pf_transpose_u8(mat.data_ptr(), mat.stride(0), _lib.ptr(rows), n_rows, n_cols,
+                                       out.data_ptr(), out.stride(0), _stream_ptr()))
+        return out[:, :n_rows]
+
+    def pair_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, counts: torch.Tensor,
+                    word_begin: int = 0, word_end: int | None = None, variant: int = 0):
+        """counts[3, n, n] int32 += V / D1 / D2 over words [word_begin, word_end)."""
+        if word_end is None:
+            word_end = n_words
+        assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
+        check(self.lib.pf_pair_counts(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
+                                      counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
+
+    def allreduce_counts(self, counts: torch.Tensor):
+        """Sum the site shards' count matrices over all ranks (NCCL over NVLink). Integer
+        addition is associative, so the totals are bit-identical for any number of GPUs."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+
+    def normalise(self, counts: torch.Tensor, metric="ibs"):
+        n = counts.shape[1]
+        dist_m = torch.empty((n, n), dtype=torch.float64, device=self.device)
+        nz = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(self.lib.pf_normalise(counts.data_ptr(), n, counts.stride(1), METRICS[metric], dist_m.data_ptr(),
+                                    dist_m.stride(0), nz.data_ptr(), _stream_ptr()))
+        return dist_m, nz
+
+    def nj(self, dist_m: torch.Tensor, destroy: bool = False):
+        """fp64 [n, n] -> (merge int32 [n-2, 3], length fp64 [n-2, 3]) device tensors."""
+        n = dist_m.shape[0]
+        if n < 3:
+            raise PhyloForgeError("pf_nj needs at least 3 samples")
+        work_d = dist_m if destroy else dist_m.clone()
+        merge = torch.zeros((n - 2, 3), dtype=torch.int32, device=self.device)
+        length = torch.zeros((n - 2, 3), dtype=torch.float64, device=self.device)
+        work = torch.empty(int(self.lib.pf_nj_work_bytes(n)), dtype=torch.uint8, device=self.device)
+        check(self.lib.pf_nj(work_d.data_ptr(), n, work_d.stride(0), merge.data_ptr(), length.data_ptr(),
+                             work.data_ptr(), _stream_ptr()))
+        return merge, length
+
+    # ------------------------------------------------------------------ composed path
+    def tree_from_planes(self, planes: torch.Tensor, n_samples: int, n_words: int, names,
+                         metric="ibs", variant: int = 0, keep: bool = True) -> TreeResult:
+        """counts -> (allreduce) -> distances -> NJ -> Newick, on the current stream."""
+        counts = self.alloc_counts(n_samples)
+        self.pair_counts(planes, n_samples, n_words, counts, variant=variant)
+        self.allreduce_counts(counts)
+        return self.tree_from_counts(counts, names, metric=metric, keep=keep)
+
+    def tree_from_counts(self, counts: torch.Tensor, names, metric="ibs", keep: bool = True) -> TreeResult:
+        n = counts.shape[1]
+        dist_m, nz = self.normalise(counts, metric)
+        if n == 1:
+            return TreeResult(f"{names[0]};", np.zeros((0, 3), np.int32), np.zeros((0, 3)), dist_m, counts)
+        if n == 2:
+            d = float(dist_m[0, 1].item())
+            return TreeResult(two_leaf_newick(names, d), np.zeros((0, 3), np.int32), np.zeros((0, 3)),
+                              dist_m, counts, int(nz.item()))
+        merge, length = self.nj(dist_m, destroy=not keep)
+        merge_h = merge.cpu().numpy()
+        length_h = length.cpu().numpy()
+        newick = merges_to_newick(merge_h, length_h, list(names))
+        return TreeResult(newick, merge_h, length_h, dist_m if keep else None, counts if keep else None,
+                          int(nz.item()))
+
+    # ------------------------------------------------------------------ microbenchmarks
+    def microbench_int_pipe(self, kind: int, iters: int = 2000):
+        a, b = C.c_double(), C.c_double()
+        check(self.lib.pf_microbench_int_pipe(kind, iters, C.byref(a), C.byref(b), _stream_ptr()))
+        return a.value, b.value

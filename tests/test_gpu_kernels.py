@@ -1,0 +1,192 @@
+"""Parity tests proper: every CUDA stage, called through the C ABI, against the CPU oracle
+on the same seeded inputs (bit-exact for packed matrices, integer counts, distances, NJ)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cpu as oracle, treecmp
+from phyloforge_b200.newick import merges_to_newick
+
+pytestmark = pytest.mark.gpu
+
+
+def _random_codes(rng, n, m, miss):
+    c = rng.integers(0, 3, size=(m, n), dtype=np.uint8)          # site-major
+    if miss > 0:
+        c[rng.random((m, n)) < miss] = 3
+    return c
+
+
+def _pack(engine, codes_sitemajor, ld=None):
+    m, n = codes_sitemajor.shape
+    ld = ld or n
+    buf = np.full((m, ld), 3, dtype=np.uint8)
+    buf[:, :n] = codes_sitemajor
+    d = torch.from_numpy(buf).to(engine.device)
+    nw = engine.n_words(m)
+    planes = engine.alloc_planes(n, nw)
+    planes.fill_(0x5A5A5A5A)                                     # poison: pack must write every word
+    engine.pack_codes(d, n, planes, nw)
+    return planes, nw
+
+
+@pytest.mark.parametrize("n,m,miss,ld", [
+    (2, 1, 0.0, None), (3, 31, 0.0, None), (3, 32, 0.5, None), (5, 33, 0.1, 8), (50, 1000, 0.0, 52),
+    (64, 64, 0.05, None), (65, 100, 0.05, 68), (67, 257, 1.0, None), (130, 4099, 0.02, 132),
+    (200, 3, 0.0, 201),
+])
+def test_pack_planes_bit_exact(engine, n, m, miss, ld):
+    rng = np.random.default_rng(n * 1000 + m)
+    codes = _random_codes(rng, n, m, miss)
+    planes, nw = _pack(engine, codes, ld)
+    want = oracle.pack_planes(np.ascontiguousarray(codes.T))
+    got = planes.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want)
+    back = engine.unpack_codes(planes, n, nw, m).cpu().numpy()
+    assert np.array_equal(back, codes.T)
+    # canonical 2-bit sample-major matrix of SURVEY §8(c).1 from the unpacked codes
+    assert np.array_equal(oracle.pack_canonical(back), oracle.pack_canonical(np.ascontiguousarray(codes.T)))
+
+
+def test_pack_with_row_gather_and_word_offset(engine):
+    rng = np.random.default_rng(5)
+    n, rows_total = 37, 500
+    codes = _random_codes(rng, n, rows_total, 0.1)
+    keep = np.sort(rng.choice(rows_total, size=173, replace=False)).astype(np.int64)
+    d = torch.from_numpy(codes).to(engine.device)
+    nw_total = 10
+    planes = engine.alloc_planes(n, nw_total)
+    planes.fill_(-1)
+    engine.pack_codes(d, n, planes, nw_total, word0=2, rows=torch.from_numpy(keep).to(engine.device))
+    sel = np.ascontiguousarray(codes[keep].T)
+    want = oracle.pack_planes(sel, n_words=6)
+    got = planes.cpu().numpy().view(np.uint32).reshape(-1, nw_total, 2, 64)
+    assert np.array_equal(got[:, 2:8].reshape(-1), want)
+    assert (got[:, :2] == 0xFFFFFFFF).all() and (got[:, 8:] == 0xFFFFFFFF).all()
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("n,m,miss", [
+    (2, 10, 0.0), (3, 100, 0.3), (50, 4000, 0.0), (64, 2048, 0.05), (65, 1025, 0.05), (129, 5000, 0.0),
+    (130, 3333, 0.5), (70, 40000, 0.001), (200, 70, 1.0),
+])
+def test_pair_counts_bit_exact(engine, n, m, miss, variant):
+    rng = np.random.default_rng(n * 7 + m)
+    codes = _random_codes(rng, n, m, miss)
+    if n >= 50:
+        codes[:, 3] = 3                                           # an all-missing sample
+        codes[:, 5] = codes[:, 4]                                 # a duplicate pair
+    planes, nw = _pack(engine, codes)
+    counts = engine.alloc_counts(n)
+    engine.pair_counts(planes, n, nw, counts, variant=variant)
+    want = oracle.pair_counts(np.ascontiguousarray(codes.T))
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+
+
+def test_pair_counts_word_ranges_accumulate(engine):
+    """Counting word ranges separately and accumulating == one pass (the multi-GPU identity)."""
+    rng = np.random.default_rng(11)
+    n, m = 90, 6400
+    codes = _random_codes(rng, n, m, 0.03)
+    planes, nw = _pack(engine, codes)
+    whole = engine.alloc_counts(n)
+    engine.pair_counts(planes, n, nw, whole)
+    parts = engine.alloc_counts(n)
+    for b, e in ((0, 7), (7, 64), (64, 65), (65, nw)):
+        engine.pair_counts(planes, n, nw, parts, word_begin=b, word_end=e)
+    assert torch.equal(whole, parts)
+
+
+@pytest.mark.parametrize("metric", ["ibs", "p"])
+def test_normalise_bit_exact(engine, metric):
+    rng = np.random.default_rng(3)
+    n, m = 40, 900
+    codes = _random_codes(rng, n, m, 0.4)
+    codes[:, 7] = 3
+    want_counts = oracle.pair_counts(np.ascontiguousarray(codes.T))
+    counts = torch.from_numpy(want_counts.astype(np.int32)).to(engine.device)
+    dist, nz = engine.normalise(counts, metric)
+    want, want_nz = oracle.normalise(want_counts, metric)
+    assert np.array_equal(dist.cpu().numpy(), want)              # within 1e-12 relative: in fact bit-exact
+    assert int(nz.item()) == want_nz and want_nz > 0
+
+
+def _check_nj(engine, dist):
+    n = dist.shape[0]
+    d = torch.from_numpy(dist).to(engine.device)
+    merge, length = engine.nj(d)
+    want_m, want_l = oracle.nj(dist)
+    names = [f"t{i}" for i in range(n)]
+    got_nw = merges_to_newick(merge.cpu().numpy(), length.cpu().numpy(), names)
+    want_nw = merges_to_newick(want_m, want_l, names)
+    rf, dl = treecmp.compare(got_nw, want_nw)
+    assert rf == 0                                               # Robinson-Foulds distance 0
+    assert dl <= 1e-9                                            # branch lengths within 1e-9
+    assert np.array_equal(merge.cpu().numpy(), want_m)           # in fact the same join order
+    assert np.array_equal(length.cpu().numpy(), want_l)          # and bit-identical lengths
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 33, 64, 257])
+def test_nj_random_distances(engine, n):
+    rng = np.random.default_rng(n)
+    a = rng.random((n, n))
+    dist = (a + a.T) / 2
+    np.fill_diagonal(dist, 0.0)
+    _check_nj(engine, dist)
+
+
+def test_nj_many_exact_ties(engine):
+    """Rational distances with a common denominator: Q ties are real and must break the same way."""
+    rng = np.random.default_rng(99)
+    n = 120
+    a = rng.integers(0, 6, size=(n, n)).astype(np.float64) / 8.0
+    dist = np.triu(a, 1)
+    dist = dist + dist.T
+    _check_nj(engine, dist)
+    _check_nj(engine, np.ones((50, 50)) - np.eye(50))            # star: everything ties
+
+
+def test_nj_from_genotypes(engine):
+    n, m = 300, 20000
+    codes = oracle.synth_codes(n, 0, m, seed=1, miss_ppm=50000)
+    counts = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
+    dist, _ = oracle.normalise(counts, "ibs")
+    _check_nj(engine, dist)
+
+
+def test_synth_generator_matches_oracle_and_is_shard_invariant(engine):
+    n = 123
+    a = engine.synth_codes(n, 1000, 700, seed=42, miss_ppm=100000)[:, :n].cpu().numpy()
+    assert np.array_equal(a, oracle.synth_codes(n, 1000, 700, seed=42, miss_ppm=100000))
+    b = engine.synth_codes(n, 1300, 400, seed=42, miss_ppm=100000)[:, :n].cpu().numpy()
+    assert np.array_equal(a[300:], b)
+    big = engine.synth_codes(n, (1 << 33) + 5, 64, seed=42)[:, :n].cpu().numpy()   # 64-bit site index
+    assert np.array_equal(big, oracle.synth_codes(n, (1 << 33) + 5, 64, seed=42))
+
+
+def test_transpose_u8(engine):
+    rng = np.random.default_rng(8)
+    a = rng.integers(0, 255, size=(301, 77), dtype=np.uint8)
+    rows = np.array([5, 0, 300, 17, 17, 250], dtype=np.int64)
+    d = torch.from_numpy(a).to(engine.device)
+    out = engine.transpose_u8(d, 77, rows=torch.from_numpy(rows).to(engine.device))
+    assert np.array_equal(out.cpu().numpy(), a[rows].T)
+    out2 = engine.transpose_u8(d, 77)
+    assert np.array_equal(out2.cpu().numpy(), a.T)
+
+
+def test_end_to_end_tree_matches_oracle(engine):
+    n, m = 150, 30000
+    names = [f"id{i}" for i in range(n)]
+    codes = engine.synth_codes(n, 0, m, seed=3, miss_ppm=20000)
+    nw = engine.n_words(m)
+    planes = engine.alloc_planes(n, nw)
+    engine.pack_codes(codes, n, planes, nw)
+    for metric in ("ibs", "p"):
+        res = engine.tree_from_planes(planes, n, nw, names, metric=metric)
+        sm = np.ascontiguousarray(oracle.synth_codes(n, 0, m, seed=3, miss_ppm=20000).T)
+        counts = oracle.pair_counts(sm, method="bits")
+        dist, _ = oracle.normalise(counts, metric)
+        merge, length = oracle.nj(dist)
+        rf, dl = treecmp.compare(res.newick, merges_to_newick(merge, length, names))
+        assert (rf, dl) == (0, 0.0)
