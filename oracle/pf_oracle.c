@@ -269,18 +269,30 @@ PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* 
     for (int64_t a = 0; a < na; ++a) r[a] = pfo_rowsum32(dist + a * ld, na);
     const double n2 = (double)(na - 2);
     double best = INFINITY;
-    int64_t ba = 0, bb = 1;
-    /* sequential scan in (a, b) lexicographic order with strict '<' == lowest a, then b */
-    for (int64_t a = 0; a < na; ++a) {
-      const double* row = dist + a * ld;
-      const double ra = r[a];
-      for (int64_t b = a + 1; b < na; ++b) {
-        double q = n2 * row[b];
-        q = q - ra;
-        q = q - r[b];
-        if (q < best) { best = q; ba = a; bb = b; }
+    int64_t ba = INT64_MAX, bb = INT64_MAX;
+    /* minimum of (q, a, b) in lexicographic order == first strict minimum of a sequential
+     * scan in (a, b) order; the order-independent form lets the rows be scanned in parallel */
+#pragma omp parallel
+    {
+      double tq = INFINITY;
+      int64_t ta = INT64_MAX, tb = INT64_MAX;
+#pragma omp for schedule(dynamic, 8) nowait
+      for (int64_t a = 0; a < na; ++a) {
+        const double* row = dist + a * ld;
+        const double ra = r[a];
+        for (int64_t b = a + 1; b < na; ++b) {
+          double q = n2 * row[b];
+          q = q - ra;
+          q = q - r[b];
+          if (q < tq || (q == tq && (a < ta || (a == ta && b < tb)))) { tq = q; ta = a; tb = b; }
+        }
+      }
+#pragma omp critical
+      {
+        if (tq < best || (tq == best && (ta < ba || (ta == ba && tb < bb)))) { best = tq; ba = ta; bb = tb; }
       }
     }
+    if (ba == INT64_MAX) { ba = 0; bb = 1; }  /* no finite candidate (NaN input) */
     const double dab = dist[ba * ld + bb];
     double tt = r[ba] - r[bb];
     tt = tt / (2.0 * n2);

@@ -39,6 +39,8 @@ class TreeResult:
     counts: torch.Tensor | None = None
     n_zero_valid: int = 0
     timings_ms: dict = field(default_factory=dict)
+    d2h_bytes: int = 0
+    dist_host: np.ndarray | None = None
 
 
 class Engine:
@@ -122,11 +124,9 @@ class Engine:
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
 
     def allreduce_counts(self, counts: torch.Tensor):
-        """Sum the site shards' count matrices over all ranks (NCCL over NVLink). Integer
-        addition is associative, so the totals are bit-identical for any number of GPUs."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        """Sum the site shards' count matrices over all ranks (NCCL over NVLink)."""
+        from .sharding import allreduce_counts
+        allreduce_counts(counts)
 
     def normalise(self, counts: torch.Tensor, metric="ibs"):
         n = counts.shape[1]
@@ -151,28 +151,86 @@ class Engine:
 
     # ------------------------------------------------------------------ composed path
     def tree_from_planes(self, planes: torch.Tensor, n_samples: int, n_words: int, names,
-                         metric="ibs", variant: int = 0, keep: bool = True) -> TreeResult:
-        """counts -> (allreduce) -> distances -> NJ -> Newick, on the current stream."""
+                         metric="ibs", variant: int = 0, keep: bool = True,
+                         n_sites: int | None = None) -> TreeResult:
+        """counts -> (allreduce) -> distances -> NJ -> Newick, on the current stream. `n_words` is
+        the planes buffer's words per tile; only the words that hold the `n_sites` packed sites are
+        counted (a buffer sized for an upper bound has unwritten words behind them)."""
+        word_end = n_words if n_sites is None else (n_sites + 31) // 32
         counts = self.alloc_counts(n_samples)
-        self.pair_counts(planes, n_samples, n_words, counts, variant=variant)
+        self.pair_counts(planes, n_samples, n_words, counts, word_end=word_end, variant=variant)
         self.allreduce_counts(counts)
         return self.tree_from_counts(counts, names, metric=metric, keep=keep)
 
-    def tree_from_counts(self, counts: torch.Tensor, names, metric="ibs", keep: bool = True) -> TreeResult:
+    def tree_from_counts(self, counts: torch.Tensor, names, metric="ibs", keep: bool = True,
+                         fetch_dist: bool = False) -> TreeResult:
         n = counts.shape[1]
         dist_m, nz = self.normalise(counts, metric)
+        dist_host = dist_m.cpu().numpy() if fetch_dist else None
         if n == 1:
-            return TreeResult(f"{names[0]};", np.zeros((0, 3), np.int32), np.zeros((0, 3)), dist_m, counts)
+            return TreeResult(f"{names[0]};", np.zeros((0, 3), np.int32), np.zeros((0, 3)), dist_m, counts,
+                              dist_host=dist_host)
         if n == 2:
             d = float(dist_m[0, 1].item())
             return TreeResult(two_leaf_newick(names, d), np.zeros((0, 3), np.int32), np.zeros((0, 3)),
-                              dist_m, counts, int(nz.item()))
+                              dist_m, counts, int(nz.item()), dist_host=dist_host)
         merge, length = self.nj(dist_m, destroy=not keep)
         merge_h = merge.cpu().numpy()
         length_h = length.cpu().numpy()
         newick = merges_to_newick(merge_h, length_h, list(names))
         return TreeResult(newick, merge_h, length_h, dist_m if keep else None, counts if keep else None,
-                          int(nz.item()))
+                          int(nz.item()), dist_host=dist_host)
+
+    def tree_from_host_codes(self, host_codes: torch.Tensor, n_samples: int, names, metric="ibs",
+                             chunk_sites: int = 1 << 19, variant: int = 0) -> TreeResult:
+        """End-to-end entry for genotypes that live in HOST memory: `host_codes` is a (pinned)
+        site-major u8 matrix [n_sites, ld] holding this rank's site shard. Chunks of sites are
+        copied host->device on a copy stream while the previous chunk is packed and counted; the
+        count matrices are then allreduced over the ranks, normalised and joined, and the result
+        (distance matrix, join list -> Newick) is read back to the host."""
+        assert host_codes.dtype == torch.uint8 and not host_codes.is_cuda and host_codes.stride(1) == 1
+        chunk_sites = max(32, chunk_sites // 32 * 32)
+        m, ld = host_codes.shape[0], host_codes.stride(0)
+        compute = torch.cuda.current_stream()
+        copy = self._copy_stream()
+        bufs = self._host_path_buffers(chunk_sites, ld, n_samples)
+        counts = self.alloc_counts(n_samples)
+        nw_chunk = chunk_sites // 32
+        done = [None, None]
+        for k, c0 in enumerate(range(0, m, chunk_sites)):
+            c1 = min(m, c0 + chunk_sites)
+            buf = bufs["codes"][k & 1]
+            with torch.cuda.stream(copy):
+                if done[k & 1] is not None:
+                    copy.wait_event(done[k & 1])          # the kernels that read this buffer are finished
+                buf[:c1 - c0].copy_(host_codes[c0:c1], non_blocking=True)
+                arrived = torch.cuda.Event()
+                arrived.record(copy)
+            compute.wait_event(arrived)
+            self.pack_codes(buf, n_samples, bufs["planes"], nw_chunk, n_sites=c1 - c0)
+            self.pair_counts(bufs["planes"], n_samples, nw_chunk, counts, word_end=(c1 - c0 + 31) // 32,
+                             variant=variant)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            done[k & 1] = ev
+        self.allreduce_counts(counts)
+        res = self.tree_from_counts(counts, names, metric=metric, keep=True, fetch_dist=True)
+        res.d2h_bytes = int(res.dist_host.nbytes + res.merge.nbytes + res.length.nbytes)
+        return res
+
+    def _copy_stream(self):
+        if getattr(self, "_copy", None) is None:
+            self._copy = torch.cuda.Stream(device=self.device)
+        return self._copy
+
+    def _host_path_buffers(self, chunk_sites: int, ld: int, n_samples: int):
+        key = (chunk_sites, ld, n_samples)
+        if getattr(self, "_hp_key", None) != key:
+            self._hp = {"codes": [torch.empty((chunk_sites, ld), dtype=torch.uint8, device=self.device)
+                                  for _ in range(2)],
+                        "planes": self.alloc_planes(n_samples, chunk_sites // 32)}
+            self._hp_key = key
+        return self._hp
 
     # ------------------------------------------------------------------ microbenchmarks
     def microbench_int_pipe(self, kind: int, iters: int = 2000):

@@ -128,7 +128,7 @@ class RunCmd:
             sys.exit(1)
         t0 = time.perf_counter()
         res = eng.tree_from_planes(packed.planes, packed.n_samples, packed.n_words, packed.names,
-                                   metric=self.distance)
+                                   metric=self.distance, n_sites=packed.n_sites)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         with open(out_file, "w") as f:

@@ -1,0 +1,32 @@
+"""Site sharding across GPUs: the site axis is cut into contiguous,
+word-aligned (32-site) ranges — the axis the reference chunks across worker processes
+(treetool/vcftree.py:77-93). Each rank counts its own sites for all sample pairs; the
+integer count matrices are summed with one allreduce."""
+from __future__ import annotations
+
+
+def shard_words(n_words: int, world: int, rank: int):
+    """Contiguous word range [begin, end) of `rank`; the first n_words % world ranks get one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank {rank} of {world}")
+    base, extra = divmod(n_words, world)
+    begin = rank * base + min(rank, extra)
+    end = begin + base + (1 if rank < extra else 0)
+    return begin, end
+
+
+def shard_sites(n_sites: int, world: int, rank: int):
+    """Site range [begin, end) of `rank`, cut at 32-site word boundaries."""
+    n_words = (n_sites + 31) // 32
+    wb, we = shard_words(n_words, world, rank)
+    return min(wb * 32, n_sites), min(we * 32, n_sites)
+
+
+def allreduce_counts(counts):
+    """Sum the site shards' count matrices over all ranks, in place (NCCL over NVLink on the
+    GPUs; gloo in the CPU tests). Integer addition is associative, so the totals are
+    bit-identical for any number of ranks. No-op without an initialised process group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    return counts

@@ -190,3 +190,19 @@ def test_end_to_end_tree_matches_oracle(engine):
         merge, length = oracle.nj(dist)
         rf, dl = treecmp.compare(res.newick, merges_to_newick(merge, length, names))
         assert (rf, dl) == (0, 0.0)
+
+
+def test_host_buffer_path_matches_resident_path(engine):
+    """Engine.tree_from_host_codes (chunked H2D overlapped with pack + counts) == resident path."""
+    n, m = 100, 10000
+    names = [f"h{i}" for i in range(n)]
+    codes = engine.synth_codes(n, 0, m, seed=5, miss_ppm=10000)
+    host = codes.cpu().pin_memory()
+    nw = engine.n_words(m)
+    planes = engine.alloc_planes(n, nw)
+    engine.pack_codes(codes, n, planes, nw)
+    want = engine.tree_from_planes(planes, n, nw, names)
+    for chunk in (1024, 4096, 1 << 20):
+        got = engine.tree_from_host_codes(host, n, names, chunk_sites=chunk)
+        assert torch.equal(got.counts, want.counts) and got.newick == want.newick
+        assert np.array_equal(got.dist_host, want.dist.cpu().numpy()) and got.d2h_bytes > 0
