@@ -50,7 +50,7 @@ UNIT = "pair-sites/s"
 SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
-NCU_TRAFFIC_BYTES = None
+NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
 def pair_sites(n, m):
@@ -311,20 +311,33 @@ def run_ours(args):
     popc_ops, _ = eng.microbench_int_pipe(0, 1500)
     lop3_ops, _ = eng.microbench_int_pipe(1, 1500)
     pair_words = n * (n - 1) // 2 * my_words       # algorithmic: unordered pairs x words of this rank
-    # algorithmic op count per unordered pair per 32-site word:
-    #   without missing data 2 POPC (+2 LOP3), with missing data 3 POPC (+4.5 LOP3)
-    popc_per_pw = 2.0 if miss == 0 else 3.0
-    peak_pw = popc_ops / popc_per_pw
+    # Instructions the kernel needs per unordered pair per 32-site word (DESIGN.md "Kernels";
+    # counted in the SASS of pair_counts_kernel):
+    #   plain popcount (variant 1): 2 LOP3 + 2 POPC without missing data, 4.5 LOP3 + 3 POPC with
+    #   carry-save (variant 0/2)  : 4 LOP3 + 1 POPC (+1 IMAD) without missing data; chunks that hold
+    #                               missing genotypes run the plain body
+    csa = args.variant != 1
+    if miss == 0:
+        lop_per_pw, popc_per_pw = (4.0, 1.0) if csa else (2.0, 2.0)
+    else:
+        lop_per_pw, popc_per_pw = 4.5, 3.0
+    peak_pw = min(lop3_ops / lop_per_pw, popc_ops / popc_per_pw)
+    binding = "LOP3" if lop3_ops / lop_per_pw < popc_ops / popc_per_pw else "POPC"
     achieved_pw = pair_words / (counts_ms * 1e-3)
-    roofline = {"bound": "int-pipe (POPC)", "achieved": achieved_pw * 32 / 1e12, "peak": peak_pw * 32 / 1e12,
-                "unit": "Tpair-sites/s", "frac": achieved_pw / peak_pw,
+    plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
+    roofline = {"bound": "int-pipe (%s binding)" % binding, "achieved": achieved_pw * 32 / 1e12,
+                "peak": peak_pw * 32 / 1e12, "unit": "Tpair-sites/s", "frac": achieved_pw / peak_pw,
                 "traffic": NCU_TRAFFIC_BYTES,
-                "kernel": "pair_counts", "kernel_ms": counts_ms,
+                "kernel": "pair_counts_kernel<%s>" % ("carry-save" if csa else "plain"), "kernel_ms": counts_ms,
+                "ops_per_pair_word": {"lop3": lop_per_pw, "popc": popc_per_pw},
+                "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
                 "peak_source": "pf_microbench_int_pipe measured in this run: POPC %.3g ops/s, LOP3 %.3g ops/s; "
-                               "peak = POPC rate / %g POPC per pair-word x 32 sites (MEASURED_PEAKS.json has no "
-                               "integer-pipe peak)" % (popc_ops, lop3_ops, popc_per_pw),
-                "note": "algorithmic pair-words = unordered sample pairs x 32-site words; the kernel also "
-                        "computes the redundant half of diagonal tiles"}
+                               "peak = min(LOP3 rate / %.1f, POPC rate / %.1f) pair-words/s x 32 sites "
+                               "(MEASURED_PEAKS.json has no integer-pipe peak)" % (popc_ops, lop3_ops, lop_per_pw,
+                                                                                  popc_per_pw),
+                "note": "algorithmic pair-words = unordered sample pairs x 32-site words of this rank; "
+                        "frac_of_plain_popcount_roofline is against SURVEY 8(d)'s POPC-only bound "
+                        "(POPC rate / 2 or 3 per pair-word), which the carry-save kernel may exceed"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -45,6 +45,10 @@ PF_API int pf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* 
 PF_API int pf_microbench_int_pipe(int kind, int iters, double* ops_per_s,
                                   double* ops_per_clk_per_sm, void* stream);
 
+/* Probe of the legacy warp-level tensor paths: kind 0 mma.sync b1
+ * and.popc (m16n8k256), 1 b1 xor.popc, 2 s8 (m16n8k32). Synchronous; multiply-accumulates/s. */
+PF_API int pf_microbench_mma(int kind, int iters, double* macs_per_s, void* stream);
+
 /* ------------------------------------------------------------------ layout helpers */
 /* number of uint32 words in a planes buffer for n_samples x n_words */
 PF_API int64_t pf_planes_len(int64_t n_samples, int64_t n_words);

@@ -168,15 +168,17 @@ def metric_id(metric) -> int:
 
 
 # ------------------------------------------------------------------ NJ
-def nj(dist: np.ndarray):
-    """fp64 [n, n] -> (merge int32 [n-2, 3], len fp64 [n-2, 3]); see pf_nj in the header."""
+def nj(dist: np.ndarray, from_scratch: bool = False):
+    """fp64 [n, n] -> (merge int32 [n-2, 3], len fp64 [n-2, 3]); see pf_nj in the header.
+    from_scratch=True recomputes all row sums every iteration (checker of the incremental sums)."""
     d = np.array(dist, dtype=np.float64, order="C", copy=True)
     n = d.shape[0]
     if n < 3:
         raise ValueError("NJ needs n >= 3")
     merge = np.zeros((n - 2, 3), dtype=np.int32)
     length = np.zeros((n - 2, 3), dtype=np.float64)
-    rc = lib().pfo_nj(_p(d), C.c_int64(n), C.c_int64(n), _p(merge), _p(length))
+    fn = lib().pfo_nj_from_scratch if from_scratch else lib().pfo_nj
+    rc = fn(_p(d), C.c_int64(n), C.c_int64(n), _p(merge), _p(length))
     if rc != 0:
         raise RuntimeError(f"pfo_nj failed: {rc}")
     return merge, length
@@ -184,8 +186,8 @@ def nj(dist: np.ndarray):
 
 def nj_numpy(dist: np.ndarray):
     """Independent restatement of the same NJ spec in plain Python/numpy (tiny n): row sums
-    in the 32-lane strided + butterfly order, Q argmin ties -> lowest (i, j), merged node in
-    slot i, last slot moved into slot j. Used to check pfo_nj."""
+    in the 32-lane strided + butterfly order once, then updated incrementally; Q argmin ties ->
+    lowest (i, j), merged node in slot i, last slot moved into slot j. Used to check pfo_nj."""
     d = np.array(dist, dtype=np.float64, copy=True)
     n = d.shape[0]
     node = list(range(n))
@@ -206,8 +208,8 @@ def nj_numpy(dist: np.ndarray):
             off >>= 1
         return p[0]
 
+    r = [rowsum(d[a, :na]) for a in range(na)]
     while na > 3:
-        r = [rowsum(d[a, :na]) for a in range(na)]
         n2 = np.float64(na - 2)
         best, ba, bb = np.inf, 0, 1
         for a in range(na):
@@ -218,7 +220,8 @@ def nj_numpy(dist: np.ndarray):
                 if q < best:
                     best, ba, bb = q, a, b
         dab = d[ba, bb]
-        tt = (r[ba] - r[bb]) / (np.float64(2.0) * n2)
+        ra, rb = r[ba], r[bb]
+        tt = (ra - rb) / (np.float64(2.0) * n2)
         la = np.float64(0.5) * dab + tt
         lb = dab - la
         merge[t] = (node[ba], node[bb], 0)
@@ -226,9 +229,12 @@ def nj_numpy(dist: np.ndarray):
         for k in range(na):
             if k in (ba, bb):
                 continue
-            v = np.float64(0.5) * ((d[ba, k] + d[bb, k]) - dab)
+            dak, dbk = d[ba, k], d[bb, k]
+            v = np.float64(0.5) * ((dak + dbk) - dab)
+            r[k] = ((r[k] - dak) - dbk) + v
             d[ba, k] = v
             d[k, ba] = v
+        r[ba] = np.float64(0.5) * ((ra + rb) - np.float64(na) * dab)
         d[ba, ba] = 0.0
         last = na - 1
         if bb != last:
@@ -236,6 +242,7 @@ def nj_numpy(dist: np.ndarray):
             d[:na, bb] = d[:na, last].copy()
             d[bb, bb] = 0.0
             node[bb] = node[last]
+            r[bb] = r[last]
         node[ba] = n + t
         na -= 1
         t += 1

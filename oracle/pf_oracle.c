@@ -255,18 +255,29 @@ static double pfo_rowsum32(const double* row, int64_t n) {
 }
 
 /* dist: n x ld symmetric, zero diagonal; destroyed. merge: 3*(n-2) ints, len: 3*(n-2)
- * doubles, laid out as documented for pf_nj in include/phyloforge_b200.h. n >= 3. */
-PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* len) {
+ * doubles, laid out as documented for pf_nj in include/phyloforge_b200.h. n >= 3.
+ *
+ * Row sums: r is summed once, in the fixed order of pfo_rowsum32, and then maintained
+ * incrementally (as most NJ implementations do), each update a fixed sequence of fp64
+ * operations so that the GPU kernel can reproduce it bit for bit:
+ *     r_k   <- ((r_k - d_ak) - d_bk) + d_uk            for the untouched nodes k
+ *     r_u   <- 0.5 * ((r_a + r_b) - n * d_ab)          for the merged node u (= sum_k d_uk)
+ * mode 1 (checker of the checker): recompute every row sum from scratch each iteration. */
+static int pfo_nj_impl(double* dist, int64_t n, int64_t ld, int32_t* merge, double* len, int from_scratch) {
   if (n < 3) return 1;
   int64_t na = n;
   int32_t* node = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
   double* r = (double*)malloc(sizeof(double) * (size_t)n);
   if (!node || !r) { free(node); free(r); return 2; }
   for (int64_t s = 0; s < n; ++s) node[s] = (int32_t)s;
+#pragma omp parallel for schedule(static)
+  for (int64_t a = 0; a < na; ++a) r[a] = pfo_rowsum32(dist + a * ld, na);
   int64_t t = 0;
   while (na > 3) {
+    if (from_scratch) {
 #pragma omp parallel for schedule(static)
-    for (int64_t a = 0; a < na; ++a) r[a] = pfo_rowsum32(dist + a * ld, na);
+      for (int64_t a = 0; a < na; ++a) r[a] = pfo_rowsum32(dist + a * ld, na);
+    }
     const double n2 = (double)(na - 2);
     double best = INFINITY;
     int64_t ba = INT64_MAX, bb = INT64_MAX;
@@ -294,7 +305,8 @@ PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* 
     }
     if (ba == INT64_MAX) { ba = 0; bb = 1; }  /* no finite candidate (NaN input) */
     const double dab = dist[ba * ld + bb];
-    double tt = r[ba] - r[bb];
+    const double ra = r[ba], rb = r[bb];
+    double tt = ra - rb;
     tt = tt / (2.0 * n2);
     double la = 0.5 * dab;
     la = la + tt;
@@ -303,11 +315,21 @@ PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* 
     len[3 * t + 0] = la; len[3 * t + 1] = lb; len[3 * t + 2] = 0.0;
     for (int64_t k = 0; k < na; ++k) {
       if (k == ba || k == bb) continue;
-      double d = dist[ba * ld + k] + dist[bb * ld + k];
+      const double dak = dist[ba * ld + k], dbk = dist[bb * ld + k];
+      double d = dak + dbk;
       d = d - dab;
       d = 0.5 * d;
+      double rk = r[k] - dak;
+      rk = rk - dbk;
+      rk = rk + d;
+      r[k] = rk;
       dist[ba * ld + k] = d;
       dist[k * ld + ba] = d;
+    }
+    {
+      double ru = ra + rb;
+      ru = ru - (double)na * dab;
+      r[ba] = 0.5 * ru;
     }
     dist[ba * ld + ba] = 0.0;
     const int64_t last = na - 1;
@@ -318,6 +340,7 @@ PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* 
       }
       dist[bb * ld + bb] = 0.0;
       node[bb] = node[last];
+      r[bb] = r[last];
     }
     node[ba] = (int32_t)(n + t);
     --na;
@@ -332,4 +355,14 @@ PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* 
   free(node);
   free(r);
   return 0;
+}
+
+PFO_API int pfo_nj(double* dist, int64_t n, int64_t ld, int32_t* merge, double* len) {
+  return pfo_nj_impl(dist, n, ld, merge, len, 0);
+}
+
+/* same algorithm with every row sum recomputed from scratch each iteration: used by the tests
+ * to show that the incremental sums do not change the tree on generic (tie-free) inputs */
+PFO_API int pfo_nj_from_scratch(double* dist, int64_t n, int64_t ld, int32_t* merge, double* len) {
+  return pfo_nj_impl(dist, n, ld, merge, len, 1);
 }

@@ -198,3 +198,91 @@ PF_API int pf_microbench_int_pipe(int kind, int iters, double* ops_per_s,
   return 0;
   PF_TRY_END
 }
+
+// ---------------------------------------------------------------------------------------
+// Probe of the legacy warp-level MMA paths on sm_100a ("whether legacy
+// mma.sync b1 (AND/XOR + POPC) is usefully fast on sm_100 — probe before investing").
+// kind 0: mma.sync m16n8k256 b1 and.popc    kind 1: b1 xor.popc    kind 2: m16n8k32 s8
+// Reports multiply-accumulate (bit-AND-popc) operations per second.
+namespace {
+
+template <int KIND>
+__global__ void __launch_bounds__(256, 4) mma_probe_kernel(int iters, uint32_t seed, int* sink) {
+  uint32_t a[4], b[2];
+  int c[4][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a[k] = seed * (k + 3) + threadIdx.x;
+  b[0] = seed ^ 0x9e3779b9u;
+  b[1] = seed + 77u * threadIdx.x;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) c[u][k] = 0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // 4 independent accumulator tiles
+      if (KIND == 0) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k256.row.col.s32.b1.b1.s32.and.popc {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+            "{%0,%1,%2,%3};"
+            : "+r"(c[u][0]), "+r"(c[u][1]), "+r"(c[u][2]), "+r"(c[u][3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      } else if (KIND == 1) {
+        asm volatile(
+            "mma.sync.aligned.m16n8k256.row.col.s32.b1.b1.s32.xor.popc {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+            "{%0,%1,%2,%3};"
+            : "+r"(c[u][0]), "+r"(c[u][1]), "+r"(c[u][2]), "+r"(c[u][3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      } else {
+        asm volatile(
+            "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+r"(c[u][0]), "+r"(c[u][1]), "+r"(c[u][2]), "+r"(c[u][3])
+            : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+      }
+    }
+  }
+  int acc = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc ^= c[u][k];
+  if (acc == 0x7fffffff) sink[0] = acc;
+}
+
+}  // namespace
+
+PF_API int pf_microbench_mma(int kind, int iters, double* macs_per_s, void* stream) {
+  PF_TRY_BEGIN
+  if (kind < 0 || kind > 2 || iters <= 0 || !macs_per_s) return pf_fail("pf_microbench_mma: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int grid = sms * 8;
+  int* sink = nullptr;
+  PF_CUDA(cudaMalloc(&sink, sizeof(int)));
+  cudaEvent_t e0, e1;
+  PF_CUDA(cudaEventCreate(&e0));
+  PF_CUDA(cudaEventCreate(&e1));
+  auto launch = [&](int it) {
+    if (kind == 0) mma_probe_kernel<0><<<grid, 256, 0, s>>>(it, 12345u, sink);
+    else if (kind == 1) mma_probe_kernel<1><<<grid, 256, 0, s>>>(it, 12345u, sink);
+    else mma_probe_kernel<2><<<grid, 256, 0, s>>>(it, 12345u, sink);
+  };
+  launch(iters / 4 + 1);
+  PF_CUDA(cudaEventRecord(e0, s));
+  launch(iters);
+  PF_CUDA(cudaEventRecord(e1, s));
+  PF_CUDA(cudaEventSynchronize(e1));
+  PF_CUDA(cudaGetLastError());
+  float ms = 0.f;
+  PF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  const double k = (kind == 2) ? 32.0 : 256.0;
+  const double macs = double(grid) * 8.0 /*warps*/ * iters * 4.0 * 16.0 * 8.0 * k;
+  *macs_per_s = macs / (double(ms) * 1e-3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(sink);
+  return PF_OK;
+  PF_TRY_END
+}

@@ -69,10 +69,65 @@ struct PairParams {
   int n_pairs;         // n_tiles * (n_tiles + 1) / 2
   int chunks_per_split;
   int n_chunks;
+  int two;             // the constant 2, kept in a register on purpose (see csa())
 };
 
+// operand words of one 32-site word for this thread's 4 i-samples and 4 j-samples
+struct Operands {
+  uint32_t li[4], hi[4], lj[4], hj[4];
+};
+__device__ __forceinline__ Operands load_operands(const uint32_t* si, const uint32_t* sj, int w, int ty, int tx) {
+  const uint4 a = *reinterpret_cast<const uint4*>(si + w * 128 + 4 * ty);
+  const uint4 b = *reinterpret_cast<const uint4*>(si + w * 128 + 64 + 4 * ty);
+  const uint4 c = *reinterpret_cast<const uint4*>(sj + w * 128 + 4 * tx);
+  const uint4 d = *reinterpret_cast<const uint4*>(sj + w * 128 + 64 + 4 * tx);
+  Operands o;
+  o.li[0] = a.x; o.li[1] = a.y; o.li[2] = a.z; o.li[3] = a.w;
+  o.hi[0] = b.x; o.hi[1] = b.y; o.hi[2] = b.z; o.hi[3] = b.w;
+  o.lj[0] = c.x; o.lj[1] = c.y; o.lj[2] = c.z; o.lj[3] = c.w;
+  o.hj[0] = d.x; o.hj[1] = d.y; o.hj[2] = d.z; o.hj[3] = d.w;
+  return o;
+}
+
+// LOP3 with a fixed truth table; written as PTX so that ptxas keeps exactly these eight
+// logic instructions per pair per word pair instead of re-associating them into more
+__device__ __forceinline__ uint32_t lop3_xor2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, 0, 0x3c;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t lop3_xor_andn(uint32_t a, uint32_t b, uint32_t c) {  // (a ^ b) & ~c
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x14;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t lop3_maj(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+__device__ __forceinline__ uint32_t lop3_xor3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+
+// carry-save step: (ones, carry) <- ones + x0 + x1 per bit; the carries weigh 2.
+// `two` is the constant 2 held in a register (a kernel parameter), so the accumulate is an
+// IMAD on the fma pipe and the logic pipe is left to the LOP3s.
+__device__ __forceinline__ void csa(uint32_t& ones, uint32_t x0, uint32_t x1, int& acc, int two) {
+  const uint32_t carry = lop3_maj(ones, x0, x1);
+  ones = lop3_xor3(ones, x0, x1);
+  asm("mad.lo.s32 %0, %1, %2, %0;" : "+r"(acc) : "r"(__popc(carry)), "r"(two));
+}
+
+// CSA = false: one POPC per stream per word (variant 1).
+// CSA = true : words are taken two at a time through a carry-save adder, halving the POPCs
+//              at the price of two LOP3 per stream per word pair (variant 2): the quarter-rate
+//              POPC pipe and the full-rate logic pipe then carry equal load.
+template <bool CSA>
 __global__ void __launch_bounds__(THREADS, 2)
-pair_counts_plain(const PairParams P) {
+pair_counts_kernel(const PairParams P) {
   extern __shared__ __align__(128) uint32_t smem[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
 
@@ -126,11 +181,17 @@ pair_counts_plain(const PairParams P) {
   const int real_i = static_cast<int>(min(static_cast<long long>(PF_TILE), static_cast<long long>(P.n_samples) - static_cast<long long>(ti) * PF_TILE));
   const int real_j = static_cast<int>(min(static_cast<long long>(PF_TILE), static_cast<long long>(P.n_samples) - static_cast<long long>(tj) * PF_TILE));
 
+  // cH counts valid sites whose low code bits differ (het vs hom), cD the {0,2} sites;
+  // D1 = cH + cD, D2 = cD. oH/oD are the carry-save "ones" words (CSA only).
   int cV[4][4], cH[4][4], cD[4][4];
+  uint32_t oH[4][4], oD[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) cV[a][b] = cH[a][b] = cD[a][b] = 0;
+    for (int b = 0; b < 4; ++b) {
+      cV[a][b] = cH[a][b] = cD[a][b] = 0;
+      oH[a][b] = oD[a][b] = 0u;
+    }
   int full_valid_sites = 0;  // sites of chunks that had no missing data
 
   for (int c = c_begin; c < c_end; ++c) {
@@ -155,49 +216,70 @@ pair_counts_plain(const PairParams P) {
     if (any_missing) {
 #pragma unroll 2
       for (int w = 0; w < kw; ++w) {
-        const uint4 li4 = *reinterpret_cast<const uint4*>(si + w * 128 + 4 * ty);
-        const uint4 hi4 = *reinterpret_cast<const uint4*>(si + w * 128 + 64 + 4 * ty);
-        const uint4 lj4 = *reinterpret_cast<const uint4*>(sj + w * 128 + 4 * tx);
-        const uint4 hj4 = *reinterpret_cast<const uint4*>(sj + w * 128 + 64 + 4 * tx);
-        const uint32_t li[4] = {li4.x, li4.y, li4.z, li4.w}, hi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-        const uint32_t lj[4] = {lj4.x, lj4.y, lj4.z, lj4.w}, hj[4] = {hj4.x, hj4.y, hj4.z, hj4.w};
+        const Operands o = load_operands(si, sj, w, ty, tx);
         uint32_t vi[4], vj[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          vi[a] = ~(li[a] & hi[a]);
-          vj[a] = ~(lj[a] & hj[a]);
+          vi[a] = ~(o.li[a] & o.hi[a]);
+          vj[a] = ~(o.lj[a] & o.hj[a]);
         }
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const uint32_t W = vi[a] & vj[b];
-            const uint32_t hd = (li[a] ^ lj[b]) & W;   // het vs hom among valid
-            const uint32_t u = (hi[a] ^ hj[b]) & W;
-            const uint32_t d2 = u & ~hd;               // {0,2} pairs
+            const uint32_t hd = (o.li[a] ^ o.lj[b]) & W;   // het vs hom among valid
+            const uint32_t u = (o.hi[a] ^ o.hj[b]) & W;
+            const uint32_t d2 = u & ~hd;                   // {0,2} pairs
             cV[a][b] += __popc(W);
             cH[a][b] += __popc(hd);
             cD[a][b] += __popc(d2);
           }
       }
     } else {
+      if (CSA) {
+        int w = 0;
+        for (; w + 2 <= kw; w += 2) {
+          const Operands p = load_operands(si, sj, w, ty, tx);
+          const Operands q = load_operands(si, sj, w + 1, ty, tx);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t h0 = lop3_xor2(p.li[a], p.lj[b]);
+              const uint32_t h1 = lop3_xor2(q.li[a], q.lj[b]);
+              const uint32_t e0 = lop3_xor_andn(p.hi[a], p.hj[b], h0);
+              const uint32_t e1 = lop3_xor_andn(q.hi[a], q.hj[b], h1);
+              csa(oH[a][b], h0, h1, cH[a][b], P.two);
+              csa(oD[a][b], e0, e1, cD[a][b], P.two);
+            }
+        }
+        if (w < kw) {  // odd tail word of a short chunk
+          const Operands p = load_operands(si, sj, w, ty, tx);
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t h0 = p.li[a] ^ p.lj[b];
+              const uint32_t e0 = (p.hi[a] ^ p.hj[b]) & ~h0;
+              cH[a][b] += __popc(h0);
+              cD[a][b] += __popc(e0);
+            }
+        }
+      } else {
 #pragma unroll 2
-      for (int w = 0; w < kw; ++w) {
-        const uint4 li4 = *reinterpret_cast<const uint4*>(si + w * 128 + 4 * ty);
-        const uint4 hi4 = *reinterpret_cast<const uint4*>(si + w * 128 + 64 + 4 * ty);
-        const uint4 lj4 = *reinterpret_cast<const uint4*>(sj + w * 128 + 4 * tx);
-        const uint4 hj4 = *reinterpret_cast<const uint4*>(sj + w * 128 + 64 + 4 * tx);
-        const uint32_t li[4] = {li4.x, li4.y, li4.z, li4.w}, hi[4] = {hi4.x, hi4.y, hi4.z, hi4.w};
-        const uint32_t lj[4] = {lj4.x, lj4.y, lj4.z, lj4.w}, hj[4] = {hj4.x, hj4.y, hj4.z, hj4.w};
+        for (int w = 0; w < kw; ++w) {
+          const Operands o = load_operands(si, sj, w, ty, tx);
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const uint32_t hd = li[a] ^ lj[b];
-            const uint32_t d2 = (hi[a] ^ hj[b]) & ~hd;
-            cH[a][b] += __popc(hd);
-            cD[a][b] += __popc(d2);
-          }
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t hd = o.li[a] ^ o.lj[b];
+              const uint32_t d2 = (o.hi[a] ^ o.hj[b]) & ~hd;
+              cH[a][b] += __popc(hd);
+              cD[a][b] += __popc(d2);
+            }
+        }
       }
       full_valid_sites += kw * 32;
     }
@@ -218,9 +300,11 @@ pair_counts_plain(const PairParams P) {
     for (int b = 0; b < 4; ++b) {
       const int64_t j = static_cast<int64_t>(tj) * PF_TILE + 4 * tx + b;
       if (j >= P.n_samples) continue;
+      const int ch = cH[a][b] + (CSA ? __popc(oH[a][b]) : 0);
+      const int cd = cD[a][b] + (CSA ? __popc(oD[a][b]) : 0);
       const int v = cV[a][b] + full_valid_sites;
-      const int d1 = cH[a][b] + cD[a][b];
-      const int d2 = cD[a][b];
+      const int d1 = ch + cd;
+      const int d2 = cd;
       atomicAdd(V + i * P.ld + j, v);
       atomicAdd(D1 + i * P.ld + j, d1);
       atomicAdd(D2 + i * P.ld + j, d2);
@@ -266,6 +350,7 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
   P.n_tiles = static_cast<int>(pf_ceil_div(n_samples, PF_TILE));
   P.n_pairs = P.n_tiles * (P.n_tiles + 1) / 2;
   P.n_chunks = static_cast<int>(pf_ceil_div(word_end - word_begin, KC));
+  P.two = 2;
   // split-K so that the grid is >= ~24 waves of 2 CTAs/SM, but keep >= 4 chunks per CTA
   const int64_t target_ctas = static_cast<int64_t>(sms) * 2 * 24;
   int64_t splits = pf_ceil_div(target_ctas, P.n_pairs);
@@ -278,9 +363,9 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
   if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts: grid too large");
 
   const size_t smem_bytes = static_cast<size_t>(STAGES) * 2 * SIDE_WORDS * sizeof(uint32_t);
-  PF_CUDA(cudaFuncSetAttribute(pair_counts_plain, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem_bytes)));
-  pair_counts_plain<<<static_cast<unsigned>(grid), THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);
+  auto kernel = (variant == 1) ? pair_counts_kernel<false> : pair_counts_kernel<true>;
+  PF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  kernel<<<static_cast<unsigned>(grid), THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);
   PF_CUDA(cudaGetLastError());
   return PF_OK;
   PF_TRY_END

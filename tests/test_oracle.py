@@ -153,3 +153,19 @@ def test_treecmp_detects_differences():
     assert treecmp.compare(a, "((a:1,b:1.5):1,c:1,(d:1,e:1):1);") == (0, 0.5)
     assert treecmp.compare(a, "(c:1,(e:1,d:1):1,(b:1,a:1):1);") == (0, 0.0)
     assert treecmp.compare(a, "(((a:1,b:1):1,c:1):0.4,(d:1,e:1):0.6);") == (0, 0.0)   # rooted form
+
+
+@pytest.mark.parametrize("n", [10, 80, 300])
+def test_nj_incremental_row_sums_vs_from_scratch(n):
+    """The oracle maintains the row sums incrementally (fixed operation order shared with the GPU
+    kernel). On generic tie-free distances that gives the same topology as recomputing every sum
+    from scratch each iteration, and branch lengths that agree far inside 1e-9."""
+    rng = np.random.default_rng(n)
+    a = rng.random((n, n))
+    d = (a + a.T) / 2
+    np.fill_diagonal(d, 0)
+    names = [f"x{i}" for i in range(n)]
+    m1, l1 = oracle.nj(d)
+    m2, l2 = oracle.nj(d, from_scratch=True)
+    rf, dl = treecmp.compare(merges_to_newick(m1, l1, names, fmt="%.17g"), merges_to_newick(m2, l2, names, fmt="%.17g"))
+    assert rf == 0 and dl < 1e-11
