@@ -185,3 +185,19 @@ def test_site_shards_allreduce_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
     assert all("ok" in o for o in outs)
+
+
+def test_synthetic_vcf_writers_agree_with_restated_converters():
+    from oracle import ref_convert as rc
+    from phyloforge_b200 import synth
+    n, m = 7, 300
+    names = [f"s{i}" for i in range(n)]
+    codes = oracle.synth_codes(n, 0, m, seed=3, miss_ppm=100000)
+    text, ref, alt = synth.snp_vcf_bytes(codes, names)
+    _, seqs, kept = rc.snp_convert(text.decode())
+    want = synth.expected_snp_chars(codes, ref, alt).T
+    assert [s.encode() for s in seqs] == [r.tobytes() for r in want]
+    assert np.array_equal(rc.snp_codes(seqs, kept)[0], codes.T)
+    text, sv = synth.sv_vcf_bytes(codes, names, other_type_every=13)
+    _, seqs = rc.sv_convert(text.decode())
+    assert np.array_equal(rc.sv_codes(seqs), synth.expected_sv_columns(codes, sv))
