@@ -10,8 +10,9 @@ packing all run in libphyloforge_b200.so (csrc/vcf_parse.cu, csrc/pack.cu).
 from __future__ import annotations
 
 import ctypes as C
-import mmap
 import os
+import queue
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -70,21 +71,76 @@ def read_header(path: str):
     return names, size
 
 
-def _chunk_bounds(mm, size: int, chunk_bytes: int):
-    """Cut [0, size) into chunks that end just after a newline."""
-    bounds, start = [], 0
-    while start < size:
-        end = min(size, start + chunk_bytes)
-        if end < size:
-            nl = mm.rfind(b"\n", start, end)
-            if nl < 0:
-                nl = mm.find(b"\n", end)
-                end = size if nl < 0 else nl + 1
-            else:
-                end = nl + 1
-        bounds.append((start, end))
-        start = end
-    return bounds
+class _ChunkReader:
+    """Background reader: fills pinned host buffers with whole lines of the file. A chunk ends just
+    after a newline; the partial line behind it is carried to the front of the next buffer. The
+    read (page cache -> pinned memory) of chunk k+1 overlaps the GPU work on chunk k."""
+
+    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2):
+        self.path, self.size, self.buf_bytes = path, size, buf_bytes
+        self.bufs = [torch.empty(buf_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_bufs)]
+        self.free = queue.Queue()
+        self.full = queue.Queue()
+        for i in range(n_bufs):
+            self.free.put(i)
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            carry = b""
+            done = 0
+            with open(self.path, "rb", buffering=0) as f:
+                while done < self.size or carry:
+                    i = self.free.get()
+                    if i is None:
+                        return
+                    arr = self.bufs[i].numpy()
+                    k = len(carry)
+                    if k >= self.buf_bytes:
+                        raise VcfFormatError(f"{self.path}: a line is longer than the {self.buf_bytes}-byte chunk buffer")
+                    if k:
+                        arr[:k] = np.frombuffer(carry, dtype=np.uint8)
+                    filled = k
+                    mv = memoryview(arr)
+                    while filled < self.buf_bytes and done < self.size:
+                        got = f.readinto(mv[filled:])
+                        if not got:
+                            break
+                        filled += got
+                        done += got
+                    if done >= self.size:
+                        cut = filled                       # last chunk: take everything
+                    else:
+                        tail = arr[max(0, filled - (1 << 20)):filled]
+                        nl = np.flatnonzero(tail == 10)
+                        if nl.size == 0:
+                            nl = np.flatnonzero(arr[:filled] == 10)
+                            if nl.size == 0:
+                                raise VcfFormatError(f"{self.path}: a line is longer than the chunk buffer")
+                            cut = int(nl[-1]) + 1
+                        else:
+                            cut = max(0, filled - (1 << 20)) + int(nl[-1]) + 1
+                    carry = arr[cut:filled].tobytes()
+                    self.full.put((i, cut))
+            self.full.put(None)
+        except BaseException as e:  # noqa: BLE001 - hand the failure to the consumer
+            self.full.put(e)
+
+    def chunks(self):
+        while True:
+            item = self.full.get()
+            if item is None:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+    def release(self, i: int):
+        self.free.put(i)
+
+    def close(self):
+        self.free.put(None)
 
 
 def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, chunk_bytes: int):
@@ -97,51 +153,56 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     if size == 0:
         raise VcfFormatError(f"{path}: empty file")
 
-    f = open(path, "rb")
-    mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
-    view = np.frombuffer(mm, dtype=np.uint8)
+    # A record that yields a matrix column has 9 fixed fields and n sample fields of >= 1 byte, each
+    # followed by a separator: at least 2n + 18 bytes. That bounds the columns of the whole file and
+    # (for well-formed input) the lines of a chunk; blank-line-heavy chunks fall back to counting.
+    min_line = 2 * n + 18
+    buf_bytes = int(min(max(chunk_bytes, 4096), size + 1))
+    n_words_cap = max(1, ((size // min_line + 2) * rpl + 31) // 32)
+    planes = engine.alloc_planes(n, n_words_cap)
+    max_lines = buf_bytes // min_line + 2
+
+    reader = _ChunkReader(path, size, buf_bytes)
+    d_text = torch.empty(buf_bytes, dtype=torch.uint8, device=dev)
+    d_work = torch.empty(int(lib.pf_line_index_work_bytes(buf_bytes)), dtype=torch.uint8, device=dev)
+    carry_rows = 32     # rows [0, 32) of the code buffer carry the sites left over from the previous chunk
+
+    def alloc_line_buffers(cap):
+        return (torch.empty(cap + 1, dtype=torch.int64, device=dev),
+                torch.empty(cap, dtype=torch.int32, device=dev),
+                torch.empty((carry_rows + cap * rpl, ld), dtype=torch.uint8, device=dev),
+                torch.empty((cap * rpl, ld), dtype=torch.uint8, device=dev),
+                torch.empty(carry_rows + cap * rpl, dtype=torch.int64, device=dev),
+                torch.empty(cap * rpl, dtype=torch.int64, device=dev) if keep_chars else None)
+
+    d_lines, d_info, d_codes, d_chars, d_rows, d_rows_all = alloc_line_buffers(max_lines)
+    n_carry = 0            # leftover sites (< 32) waiting in d_codes[0:n_carry]
+    words_done = 0
+    n_lines_total = 0
+    n_unfit_total = 0
+    h2d = 0
+    char_blocks = []
+    summary = (C.c_int64 * 5)()
+    parse = lib.pf_vcf_snp_parse if kind == "snp" else lib.pf_vcf_sv_parse
     try:
-        total_lines_ub = int(np.count_nonzero(view == 10)) + 1
-        n_words_cap = max(1, (total_lines_ub * rpl + 31) // 32)
-        planes = engine.alloc_planes(n, n_words_cap)
-        bounds = _chunk_bounds(mm, size, chunk_bytes)
-        max_chunk = max(e - s for s, e in bounds)
-        max_lines = 0
-        for s, e in bounds:
-            max_lines = max(max_lines, int(np.count_nonzero(view[s:e] == 10)) + 1)
-
-        d_text = torch.empty(max_chunk, dtype=torch.uint8, device=dev)
-        h_pin = torch.empty(max_chunk, dtype=torch.uint8).pin_memory()
-        d_lines = torch.empty(max_lines + 1, dtype=torch.int64, device=dev)
-        d_info = torch.empty(max_lines, dtype=torch.int32, device=dev)
-        d_work = torch.empty(int(lib.pf_line_index_work_bytes(max_chunk)), dtype=torch.uint8, device=dev)
-        # rows [0, 32) of the code buffer carry the sites left over from the previous chunk
-        carry_rows = 32
-        d_codes = torch.empty((carry_rows + max_lines * rpl, ld), dtype=torch.uint8, device=dev)
-        d_chars = torch.empty((max_lines * rpl, ld), dtype=torch.uint8, device=dev)
-        d_rows = torch.empty(carry_rows + max_lines * rpl, dtype=torch.int64, device=dev)
-        d_rows_all = torch.empty(max_lines * rpl, dtype=torch.int64, device=dev) if keep_chars else None
-
-        n_carry = 0            # leftover sites (< 32) waiting in d_codes[0:n_carry]
-        words_done = 0
-        n_lines_total = 0
-        n_unfit_total = 0
-        h2d = 0
-        char_blocks = []
-        line_base = 0
-        summary = (C.c_int64 * 5)()
-        parse = lib.pf_vcf_snp_parse if kind == "snp" else lib.pf_vcf_sv_parse
-        codes_body = d_codes[carry_rows:]
-
-        for (s, e) in bounds:
-            nb = e - s
-            h_pin[:nb].numpy()[:] = view[s:e]
-            d_text[:nb].copy_(h_pin[:nb], non_blocking=True)
+        for (bi, nb) in reader.chunks():
+            h_buf = reader.bufs[bi]
+            d_text[:nb].copy_(h_buf[:nb], non_blocking=True)
             h2d += nb
             n_lines = C.c_int64()
-            check(lib.pf_line_index(d_text.data_ptr(), nb, d_lines.data_ptr(), max_lines + 1, C.byref(n_lines),
-                                    d_work.data_ptr(), stream))
+            rc = lib.pf_line_index(d_text.data_ptr(), nb, d_lines.data_ptr(), max_lines + 1, C.byref(n_lines),
+                                   d_work.data_ptr(), stream)
+            if rc == 3:   # PF_ERR_INPUT: more lines than the bound (blank / short lines): count, grow, retry
+                carried = d_codes[:n_carry].clone()
+                max_lines = int(np.count_nonzero(h_buf[:nb].numpy() == 10)) + 2
+                d_lines, d_info, d_codes, d_chars, d_rows, d_rows_all = alloc_line_buffers(max_lines)
+                d_codes[:n_carry] = carried
+                rc = lib.pf_line_index(d_text.data_ptr(), nb, d_lines.data_ptr(), max_lines + 1, C.byref(n_lines),
+                                       d_work.data_ptr(), stream)
+            check(rc)
+            reader.release(bi)          # pf_line_index synchronised the stream: the H2D copy is done
             nl = n_lines.value
+            codes_body = d_codes[carry_rows:]
             check(parse(d_text.data_ptr(), nb, d_lines.data_ptr(), nl, n, d_chars.data_ptr(),
                         codes_body.data_ptr(), ld, d_info.data_ptr(), stream))
             require_fit = 1 if kind == "snp" else 0
@@ -151,8 +212,8 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
             n_cols, n_err, n_unfit, first_line, first_cls = (int(x) for x in summary)
             if n_err:
                 raise VcfFormatError(
-                    f"{path}: {n_err} record(s) the reference cannot convert; first at body line "
-                    f"{line_base + first_line + 1}: {ERR_TEXT.get(first_cls, first_cls)}")
+                    f"{path}: {n_err} record(s) the reference cannot convert; first at line "
+                    f"{n_lines_total + first_line + 1}: {ERR_TEXT.get(first_cls, first_cls)}")
             if n_unfit and non_biallelic != "skip":
                 raise VcfFormatError(
                     f"{path}: {n_unfit} kept site(s) are not biallelic A/C/G/T and do not fit the 2-bit "
@@ -170,7 +231,9 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                     rows_all = d_rows[carry_rows:carry_rows + n_cols]
                 if n_all:
                     block = engine.transpose_u8(d_chars, n, rows=rows_all, n_rows=n_all)
-                    char_blocks.append(block.cpu().numpy())
+                    host_block = torch.empty(block.shape, dtype=torch.uint8).pin_memory()
+                    host_block.copy_(block, non_blocking=True)
+                    char_blocks.append(host_block)
             # pack: full words now, remainder carried to the next chunk
             d_rows[carry_rows:carry_rows + n_cols] += carry_rows        # rows index into d_codes
             first = carry_rows - n_carry
@@ -178,6 +241,8 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 d_rows[first:carry_rows] = torch.arange(0, n_carry, dtype=torch.int64, device=dev)
             avail = n_carry + n_cols
             full = (avail // 32) * 32
+            if words_done + (avail + 31) // 32 > n_words_cap:
+                raise VcfFormatError(f"{path}: more matrix columns than the file size allows")
             if full:
                 engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done,
                                   rows=d_rows[first:first + full], n_sites=full)
@@ -188,22 +253,19 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 d_codes[:rem] = d_codes.index_select(0, idx)
             n_carry = rem
             n_lines_total += nl
-            line_base += nl
         if n_carry:
             rows = torch.arange(0, n_carry, dtype=torch.int64, device=dev)
             engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done, rows=rows, n_sites=n_carry)
         n_sites = words_done * 32 + n_carry
         torch.cuda.current_stream().synchronize()
     finally:
-        del view                 # the mmap cannot close while a numpy view of it is alive
-        mm.close()
-        f.close()
+        reader.close()
 
     chars = None
     n_columns = n_sites
     if keep_chars:
-        chars = (np.concatenate(char_blocks, axis=1) if char_blocks
-                 else np.zeros((n, 0), dtype=np.uint8))
+        chars = (np.concatenate([b.numpy() for b in char_blocks], axis=1) if len(char_blocks) != 1
+                 else char_blocks[0].numpy()) if char_blocks else np.zeros((n, 0), dtype=np.uint8)
         n_columns = chars.shape[1]
     return PackedGenotypes(names=names, n_samples=n, n_sites=n_sites, n_words=n_words_cap, planes=planes,
                            chars=chars, n_columns=n_columns, n_lines=n_lines_total,
