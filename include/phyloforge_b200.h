@@ -49,6 +49,10 @@ PF_API int pf_microbench_int_pipe(int kind, int iters, double* ops_per_s,
  * and.popc (m16n8k256), 1 b1 xor.popc, 2 s8 (m16n8k32). Synchronous; multiply-accumulates/s. */
 PF_API int pf_microbench_mma(int kind, int iters, double* macs_per_s, void* stream);
 
+/* Self-test of the tcgen05 (kind::i8, TMEM) plumbing used by the tensor-core pair-count variant:
+ * d_c[128][256] (int32) = d_a[128][k] * d_b[256][k]^T for int8 operands, k a multiple of 32, <= 512. */
+PF_API int pf_selftest_umma(const int8_t* d_a, const int8_t* d_b, int32_t* d_c, int k, void* stream);
+
 /* ------------------------------------------------------------------ layout helpers */
 /* number of uint32 words in a planes buffer for n_samples x n_words */
 PF_API int64_t pf_planes_len(int64_t n_samples, int64_t n_words);
