@@ -162,6 +162,17 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
                           int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
                           int variant, void* stream);
 
+/* Tensor-core variant of pf_pair_counts (tcgen05 kind::i8 indicator GEMM; csrc/pair_counts_tc.cu).
+ * Applies when every site of the word range is genotyped in all samples or in none (no mixed
+ * missingness); then it ACCUMULATES the same V / D1 / D2 as pf_pair_counts and sets *h_used = 1.
+ * Otherwise it adds nothing, sets *h_used = 0 and the caller runs pf_pair_counts.
+ * d_work: pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin) bytes of scratch (the
+ * 4-bit operand stream). Synchronises `stream` once (reads the missingness flag). */
+PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_range);
+PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_t n_words,
+                             int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
+                             void* d_work, int64_t work_bytes, int* h_used, void* stream);
+
 /* counts -> fp64 distances, one IEEE divide of exactly converted integers per pair:
  *   metric 0: p-distance D1 / V;  metric 1: IBS distance (D1 + D2) / (2 V).
  * V == 0 -> 1.0 and the pair is counted in *d_n_zero_valid (int32, caller-zeroed).

@@ -114,14 +114,36 @@ class Engine:
                                        out.data_ptr(), out.stride(0), _stream_ptr()))
         return out[:, :n_rows]
 
+    # pair-count kernel variants (include/phyloforge_b200.h): 1 plain popcount, 2 carry-save popcount,
+    # 3 tcgen05 int8 indicator GEMM (falls back to 2 when genotypes are missing in some samples only);
+    # 0 = auto: 3 when the sample count fills a 128 x 256 tensor-core tile reasonably, else 2.
+    TC_MIN_SAMPLES = 192
+
     def pair_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, counts: torch.Tensor,
-                    word_begin: int = 0, word_end: int | None = None, variant: int = 0):
-        """counts[3, n, n] int32 += V / D1 / D2 over words [word_begin, word_end)."""
+                    word_begin: int = 0, word_end: int | None = None, variant: int = 0) -> int:
+        """counts[3, n, n] int32 += V / D1 / D2 over words [word_begin, word_end). Returns the
+        variant that ran."""
         if word_end is None:
             word_end = n_words
         assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
+        if variant == 0:
+            variant = 3 if n_samples >= self.TC_MIN_SAMPLES else 2
+        if variant == 3:
+            need = int(self.lib.pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin))
+            work = getattr(self, "_tc_work", None)
+            if work is None or work.numel() < need:
+                self._tc_work = None
+                work = self._tc_work = torch.empty(need, dtype=torch.uint8, device=self.device)
+            used = C.c_int(0)
+            check(self.lib.pf_pair_counts_tc(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
+                                             counts.data_ptr(), counts.stride(1), work.data_ptr(), work.numel(),
+                                             C.byref(used), _stream_ptr()))
+            if used.value:
+                return 3
+            variant = 2
         check(self.lib.pf_pair_counts(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
+        return variant
 
     def allreduce_counts(self, counts: torch.Tensor):
         """Sum the site shards' count matrices over all ranks (NCCL over NVLink)."""

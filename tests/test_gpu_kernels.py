@@ -65,7 +65,7 @@ def test_pack_with_row_gather_and_word_offset(engine):
     assert (got[:, :2] == 0xFFFFFFFF).all() and (got[:, 8:] == 0xFFFFFFFF).all()
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 @pytest.mark.parametrize("n,m,miss", [
     (2, 10, 0.0), (3, 100, 0.3), (50, 4000, 0.0), (64, 2048, 0.05), (65, 1025, 0.05), (129, 5000, 0.0),
     (130, 3333, 0.5), (70, 40000, 0.001), (200, 70, 1.0),
@@ -206,3 +206,30 @@ def test_host_buffer_path_matches_resident_path(engine):
         got = engine.tree_from_host_codes(host, n, names, chunk_sites=chunk)
         assert torch.equal(got.counts, want.counts) and got.newick == want.newick
         assert np.array_equal(got.dist_host, want.dist.cpu().numpy()) and got.d2h_bytes > 0
+
+
+@pytest.mark.parametrize("n,m", [(2, 40), (130, 5000), (256, 4096), (257, 4100), (300, 70000), (700, 20000)])
+def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
+    """tcgen05 int8 indicator GEMM == oracle on data without mixed missingness (incl. sites missing in
+    every sample and site padding); with mixed missingness it declines and the popcount kernel runs."""
+    rng = np.random.default_rng(n + m)
+    codes = rng.integers(0, 3, size=(m, n), dtype=np.uint8)
+    codes[rng.random(m) < 0.01] = 3                               # whole sites missing: still uniform
+    planes, nw = _pack(engine, codes)
+    counts = engine.alloc_counts(n)
+    ran = engine.pair_counts(planes, n, nw, counts, variant=3)
+    assert ran == 3
+    want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+    # accumulate semantics + word ranges, as the chunked / sharded callers use them
+    parts = engine.alloc_counts(n)
+    cut = max(1, nw // 3)
+    assert engine.pair_counts(planes, n, nw, parts, word_begin=0, word_end=cut, variant=3) == 3
+    assert engine.pair_counts(planes, n, nw, parts, word_begin=cut, word_end=nw, variant=3) == 3
+    assert torch.equal(parts, counts)
+    codes[5, 1] = 3                                               # one genotype missing in one sample
+    planes, nw = _pack(engine, codes)
+    counts = engine.alloc_counts(n)
+    assert engine.pair_counts(planes, n, nw, counts, variant=3) == 2
+    want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
