@@ -50,6 +50,7 @@ UNIT = "pair-sites/s"
 SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
+NCU_TRAFFIC_BYTES_TC = None  # filled from the round's ncu capture of pair_counts_tc_kernel
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
@@ -215,6 +216,7 @@ def run_ours(args):
     counts = eng.alloc_counts(n)
     torch.cuda.synchronize()
 
+    ran_variant = [args.variant]
     stage_ev = {k: [] for k in ("pack", "counts", "allreduce", "normalise", "nj")}
 
     def ev():
@@ -227,7 +229,7 @@ def run_ours(args):
         e0 = ev()
         eng.pack_codes(codes, n, planes, my_words, n_sites=my_sites)
         e1 = ev()
-        eng.pair_counts(planes, n, my_words, counts, variant=args.variant)
+        ran_variant[0] = eng.pair_counts(planes, n, my_words, counts, variant=args.variant)
         e2 = ev()
         eng.allreduce_counts(counts)
         e3 = ev()
@@ -316,33 +318,53 @@ def run_ours(args):
     #   plain popcount (variant 1): 2 LOP3 + 2 POPC without missing data, 4.5 LOP3 + 3 POPC with
     #   carry-save (variant 0/2)  : 4 LOP3 + 1 POPC (+1 IMAD) without missing data; chunks that hold
     #                               missing genotypes run the plain body
-    csa = args.variant != 1
-    if miss == 0:
-        lop_per_pw, popc_per_pw = (4.0, 1.0) if csa else (2.0, 2.0)
-    else:
-        lop_per_pw, popc_per_pw = 4.5, 3.0
-    peak_pw = min(lop3_ops / lop_per_pw, popc_ops / popc_per_pw)
-    binding = "LOP3" if lop3_ops / lop_per_pw < popc_ops / popc_per_pw else "POPC"
-    achieved_pw = pair_words / (counts_ms * 1e-3)
-    plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
-    roofline = {"bound": "int-pipe (%s binding)" % binding, "achieved": achieved_pw * 32 / 1e12,
-                "peak": peak_pw * 32 / 1e12, "unit": "Tpair-sites/s", "frac": achieved_pw / peak_pw,
-                "traffic": NCU_TRAFFIC_BYTES,
-                "kernel": "pair_counts_kernel<%s>" % ("carry-save" if csa else "plain"), "kernel_ms": counts_ms,
-                "ops_per_pair_word": {"lop3": lop_per_pw, "popc": popc_per_pw},
-                "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
-                "peak_source": "pf_microbench_int_pipe measured in this run: POPC %.3g ops/s, LOP3 %.3g ops/s; "
-                               "peak = min(LOP3 rate / %.1f, POPC rate / %.1f) pair-words/s x 32 sites "
-                               "(MEASURED_PEAKS.json has no integer-pipe peak)" % (popc_ops, lop3_ops, lop_per_pw,
-                                                                                  popc_per_pw),
-                "note": "algorithmic pair-words = unordered sample pairs x 32-site words of this rank; "
-                        "frac_of_plain_popcount_roofline is against SURVEY 8(d)'s POPC-only bound "
-                        "(POPC rate / 2 or 3 per pair-word), which the carry-save kernel may exceed"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    achieved_pw = pair_words / (counts_ms * 1e-3)
+    plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
+    variant_ran = ran_variant[0]
+    if variant_ran == 3:
+        # tensor-core indicator GEMM: 2 int8 multiply-accumulates per unordered pair per site
+        bf16 = peaks.get("bf16_tflops", 1590.0)
+        peak_tops = 2.0 * bf16                      # dense int8 = 2 x dense bf16 on the same tensor cores
+        macs = 2.0 * pair_sites(n, my_sites)
+        achieved_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (int8)",
+                    "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES_TC,
+                    "kernel": "pair_counts_tc_kernel (tcgen05 kind::i8) + planes_to_nib4_kernel",
+                    "kernel_ms": counts_ms,
+                    "ops_per_pair_site": {"int8_mac": 2},
+                    "frac_of_popcount_kernel_roofline": achieved_pw / min(lop3_ops / 4.0, popc_ops / 1.0),
+                    "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
+                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no int8 entry; nominal dense "
+                                   "int8 is 4500 TOP/s)" % ("of measured" if peaks else "of fallback 1590"),
+                    "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'); the kernel "
+                            "also computes ~13% redundant pairs in tiles that straddle the diagonal. kernel_ms "
+                            "includes the planes -> 4-bit operand stream conversion and one stream synchronise"}
+    else:
+        csa = variant_ran != 1
+        if miss == 0:
+            lop_per_pw, popc_per_pw = (4.0, 1.0) if csa else (2.0, 2.0)
+        else:
+            lop_per_pw, popc_per_pw = 4.5, 3.0
+        peak_pw = min(lop3_ops / lop_per_pw, popc_ops / popc_per_pw)
+        binding = "LOP3" if lop3_ops / lop_per_pw < popc_ops / popc_per_pw else "POPC"
+        roofline = {"bound": "int-pipe (%s binding)" % binding, "achieved": achieved_pw * 32 / 1e12,
+                    "peak": peak_pw * 32 / 1e12, "unit": "Tpair-sites/s", "frac": achieved_pw / peak_pw,
+                    "traffic": NCU_TRAFFIC_BYTES,
+                    "kernel": "pair_counts_kernel<%s>" % ("carry-save" if csa else "plain"), "kernel_ms": counts_ms,
+                    "ops_per_pair_word": {"lop3": lop_per_pw, "popc": popc_per_pw},
+                    "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
+                    "peak_source": "pf_microbench_int_pipe measured in this run: POPC %.3g ops/s, LOP3 %.3g ops/s; "
+                                   "peak = min(LOP3 rate / %.1f, POPC rate / %.1f) pair-words/s x 32 sites "
+                                   "(MEASURED_PEAKS.json has no integer-pipe peak)" % (popc_ops, lop3_ops, lop_per_pw,
+                                                                                      popc_per_pw),
+                    "note": "algorithmic pair-words = unordered sample pairs x 32-site words of this rank; "
+                            "frac_of_plain_popcount_roofline is against SURVEY 8(d)'s POPC-only bound "
+                            "(POPC rate / 2 or 3 per pair-word), which the carry-save kernel may exceed"}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     pack_bytes = my_sites * ld + my_words * ((n + 63) // 64) * 64 * 8
     roofline_pack = {"bound": "hbm", "achieved": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9, "peak": hbm_peak,
@@ -366,9 +388,9 @@ def run_ours(args):
         "config": {"workload": desc, "samples": n, "sites": m, "miss_ppm": miss, "sites_per_gpu": my_sites,
                    "parallelism": f"sites sharded over {world} GPU(s), int32 counts allreduce (NCCL)",
                    "l2": "inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (my_sites * ld / 1e9),
-                   "pair_counts_variant": args.variant, "seed": SEED},
+                   "pair_counts_variant": ran_variant[0], "pair_counts_variant_requested": args.variant, "seed": SEED},
         "nj_seconds": stages_ms["nj"] * 1e-3, "stages_ms": stages_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * args.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (5 if ran_variant[0] == 3 else 4) * args.steps,
         "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line))
@@ -385,7 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save")
+    ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save popcount, 3 tcgen05 int8 GEMM")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -50,8 +50,14 @@ PF_API int pf_microbench_int_pipe(int kind, int iters, double* ops_per_s,
 PF_API int pf_microbench_mma(int kind, int iters, double* macs_per_s, void* stream);
 
 /* Self-test of the tcgen05 (kind::i8, TMEM) plumbing used by the tensor-core pair-count variant:
- * d_c[128][256] (int32) = d_a[128][k] * d_b[256][k]^T for int8 operands, k a multiple of 32, <= 512. */
-PF_API int pf_selftest_umma(const int8_t* d_a, const int8_t* d_b, int32_t* d_c, int k, void* stream);
+ * d_c[128][256] (int32) = d_a[128][k] * d_b[256][k]^T for int8 operands, k a multiple of 32, <= 256.
+ * a_in_tmem != 0 feeds A through tensor memory (tcgen05.st + the TS form of the MMA). */
+PF_API int pf_selftest_umma(const int8_t* d_a, const int8_t* d_b, int32_t* d_c, int k, int a_in_tmem,
+                            void* stream);
+
+/* Back-to-back kind::i8 MMA issue rate (128 x n x 32 per MMA) with operands resident in shared
+ * memory / TMEM: clock64 ticks per MMA, averaged over one CTA per SM. Synchronous. */
+PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, double* ticks_per_mma, void* stream);
 
 /* ------------------------------------------------------------------ layout helpers */
 /* number of uint32 words in a planes buffer for n_samples x n_words */
@@ -172,6 +178,10 @@ PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_r
 PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_t n_words,
                              int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
                              void* d_work, int64_t work_bytes, int* h_used, void* stream);
+
+/* Diagnostic for the tensor-core kernel: enable/disable role-level wait-cycle accounting and fetch
+ * (then clear) the 16 counters accumulated since the last call; see csrc/pair_counts_tc.cu. */
+PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16);
 
 /* counts -> fp64 distances, one IEEE divide of exactly converted integers per pair:
  *   metric 0: p-distance D1 / V;  metric 1: IBS distance (D1 + D2) / (2 V).

@@ -36,7 +36,8 @@ PROTOTYPES = {
     "pf_device_info": (_i32, [_ip, _ip, _ip, _i64p, _ip]),
     "pf_microbench_int_pipe": (_i32, [_i32, _i32, _dp, _dp, _vp]),
     "pf_microbench_mma": (_i32, [_i32, _i32, _dp, _vp]),
-    "pf_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "pf_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "pf_probe_umma_rate": (_i32, [_i32, _i32, _i32, _dp, _vp]),
     "pf_planes_len": (_i64, [_i64, _i64]),
     "pf_synth_codes": (_i32, [_vp, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _vp]),
     "pf_pack_codes_u8": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
@@ -50,6 +51,7 @@ PROTOTYPES = {
     "pf_pair_counts": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
     "pf_pair_counts_tc_work_bytes": (_i64, [_i64, _i64]),
     "pf_pair_counts_tc": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _ip, _vp]),
+    "pf_pair_counts_tc_profile": (_i32, [_i32, _vp]),
     "pf_normalise": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "pf_nj_work_bytes": (_i64, [_i64]),
     "pf_nj": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),

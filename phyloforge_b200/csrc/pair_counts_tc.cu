@@ -10,32 +10,40 @@
 // is the same number for every pair); pf_pair_counts_tc reports otherwise and the caller uses the
 // popcount kernel. Exact: int8 x int8 products accumulate in int32 in TMEM.
 //
-// Data flow per CTA (one 128 x 256 sample tile pair, a contiguous range of 32-site words):
+// Data flow per CTA (one 128 x 192 sample tile pair, a contiguous range of 32-site words):
 //   "nib4" operand stream (4 bits per genotype, produced once per call by planes_to_nib4):
-//   global --TMA bulk copies--> raw ring --12 expansion warps: PRMT nibble -> int8 (x and h)-->
-//   canonical K-major UMMA tiles in shared memory --tcgen05.mma kind::i8 (1 thread)--> 2 x 256
-//   TMEM columns (all 512) --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
+//   global --TMA bulk copies--> raw ring --10 expansion warps: PRMT nibble -> int8 (x and h)-->
+//   A rows straight into TMEM (tcgen05.st), B rows into canonical K-major UMMA tiles in shared memory
+//   --tcgen05.mma kind::i8, A from TMEM, B from shared memory (1 thread)--> 2 x 192 TMEM accumulator
+//   columns --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
+// The kernel is bound by shared-memory bandwidth (ncu: LSU wavefronts + tensor operand reads), which
+// is why the A operand bypasses shared memory.
 #include "pf_common.cuh"
 #include "umma.cuh"
 
 namespace {
 
-constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M)
-constexpr int TC_J = 256;            // columns (MMA N)
+constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
+constexpr int TC_J = 192;            // columns (MMA N); the B operand is expanded into shared memory
 constexpr int TC_ROWS = TC_I + TC_J; // sample rows expanded per word
+constexpr int TC_PF = TC_ROWS / PF_TILE;  // 64-sample tiles of the operand stream per step: 2 (I) + 3 (J)
 constexpr int STEP_WORDS = 2;        // words per pipeline step (one raw stage feeds one expanded stage)
 constexpr int RAW_WORDS = STEP_WORDS;
-constexpr int RAW_STAGES = 4;
-constexpr int EXP_STAGES = 3;
-constexpr int RAW_STAGE_BYTES = RAW_WORDS * TC_ROWS * 16;      // 12 KB
-constexpr int EXP_WORD_BYTES = TC_ROWS * 32 * 2;               // x and h tiles of A and B for one word: 24 KB
-constexpr int EXP_STAGE_BYTES = STEP_WORDS * EXP_WORD_BYTES;   // 48 KB
-constexpr int EXP_AX = 0, EXP_AH = TC_I * 32, EXP_BX = 2 * TC_I * 32, EXP_BH = 2 * TC_I * 32 + TC_J * 32;
-constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
-constexpr int TC_EXP_WARPS = 12;     // 384 threads: one sample row each
+constexpr int RAW_STAGES = 6;
+constexpr int EXP_STAGES = 4;
+constexpr int RAW_STAGE_BYTES = RAW_WORDS * TC_ROWS * 16;      // 10 KB
+constexpr int EXP_WORD_BYTES = TC_J * 32 * 2;                  // x and h tiles of B for one word: 12 KB
+constexpr int EXP_STAGE_BYTES = STEP_WORDS * EXP_WORD_BYTES;   // 24 KB
+constexpr int EXP_BX = 0, EXP_BH = TC_J * 32;
+// TMEM columns: P accumulators [0, 192), Q accumulators [192, 384), A operand staging [384, 512):
+// per in-flight word 8 columns of x and 8 of h (32 K-bytes per row = 8 x 32-bit columns)
+constexpr int TMEM_P = 0, TMEM_Q = TC_J, TMEM_A = 2 * TC_J;
+constexpr int TC_A_WARPS = TC_I / 32, TC_B_WARPS = TC_J / 32;
+constexpr int TC_EXP_WARPS = TC_A_WARPS + TC_B_WARPS;          // 10: one sample row per thread
 constexpr int TC_THREADS = (TC_EXP_WARPS + 2) * 32;
 constexpr uint32_t POOL_X = 0x000100ffu;  // code 0 -> -1, 1 -> 0, 2 -> +1, 3 -> 0
 constexpr uint32_t POOL_H = 0x00010001u;  // code 0 -> 1, 1 -> 0, 2 -> 1, 3 -> 0
+constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
 
 // ------------------------------------------------------------------ planes -> nib4
 __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> 8 nibbles
@@ -94,6 +102,10 @@ planes_to_nib4_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
 }
 
 // ------------------------------------------------------------------ the GEMM kernel
+// optional role-level cycle accounting (pf_pair_counts_tc_profile): who waits for whom
+__device__ long long g_tc_prof[16];
+bool g_tc_prof_enabled = false;
+
 struct TcParams {
   const uint4* nib4;      // [n_tiles_padded][n_local][64] uint4
   const uint32_t* all_v;  // [n_local] valid-site mask shared by all samples
@@ -108,18 +120,40 @@ struct TcParams {
   const int* flags;       // flags[0] != 0: validity is not uniform -> results must not be used
   const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split
   int64_t hsum_ld;
+  int prof;               // accumulate wait cycles per role into g_tc_prof
 };
+
+// PRMT as the hardware does it (the __byte_perm intrinsic masks the selector first): byte k of the
+// result = byte (nibble k of the low 16 selector bits) of {pool, pool}. Codes are 0..3, so the
+// sign-replicate bit of a selector nibble is never set.
+__device__ __forceinline__ uint32_t prmt(uint32_t pool, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(pool), "r"(sel));
+  return r;
+}
+
+// one sample row x one 32-site word: 16 bytes of nibble codes -> 32 int8 x-values and 32 int8 h-values
+__device__ __forceinline__ void expand_word(const uint4& nb, uint32_t (&xs)[8], uint32_t (&hs)[8]) {
+  const uint32_t q[4] = {nb.x, nb.y, nb.z, nb.w};
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const uint32_t hi = q[m] >> 16;
+    xs[2 * m] = prmt(POOL_X, q[m]);
+    xs[2 * m + 1] = prmt(POOL_X, hi);
+    hs[2 * m] = prmt(POOL_H, q[m]);
+    hs[2 * m + 1] = prmt(POOL_H, hi);
+  }
+}
 
 // byte offset of the 16-byte unit (row r, K half kh) inside a canonical K-major no-swizzle tile
 __device__ __forceinline__ uint32_t unit_off(int r, int kh) {
   return static_cast<uint32_t>((r >> 3) * 256 + kh * 128 + (r & 7) * 16);
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 pair_counts_tc_kernel(const TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* raw = smem;                                        // RAW_STAGES x RAW_STAGE_BYTES
-  uint8_t* exp = smem + RAW_STAGES * RAW_STAGE_BYTES;         // EXP_STAGES x EXP_STAGE_BYTES
   __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
   __shared__ __align__(8) uint64_t exp_full[EXP_STAGES], exp_empty[EXP_STAGES];
   __shared__ __align__(8) uint64_t done_bar;
@@ -128,23 +162,30 @@ pair_counts_tc_kernel(const TcParams P) {
   __shared__ int s_valid_sites;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // shared-window addresses, computed once
+  const uint32_t raw_a = umma::smem_addr(smem);                                   // RAW_STAGES x RAW_STAGE_BYTES
+  const uint32_t exp_a = raw_a + RAW_STAGES * RAW_STAGE_BYTES;                    // EXP_STAGES x EXP_STAGE_BYTES (B tiles)
+  const uint32_t raw_full_a = umma::smem_addr(raw_full), raw_empty_a = umma::smem_addr(raw_empty);
+  const uint32_t exp_full_a = umma::smem_addr(exp_full), exp_empty_a = umma::smem_addr(exp_empty);
+  const uint32_t done_a = umma::smem_addr(&done_bar);
 
-  // work item: (tile pair, split)
+  // work item: (tile pair, split). I-tile ti (128 rows) pairs with the J-tiles (192 columns) that
+  // reach its first row: tj >= floor(128 ti / 192)
   const int pair = blockIdx.x % P.n_tilepairs;
   const int split = blockIdx.x / P.n_tilepairs;
-  int ti = 0, rem = pair;  // I-tile ti pairs with J-tiles tj >= ti / 2
+  int ti = 0, rem = pair;
   while (true) {
-    const int cnt = P.n_jtiles - ti / 2;
+    const int cnt = P.n_jtiles - (2 * ti) / 3;
     if (rem < cnt) break;
     rem -= cnt;
     ++ti;
   }
-  const int tj = ti / 2 + rem;
+  const int tj = (2 * ti) / 3 + rem;
   const int64_t w_begin = static_cast<int64_t>(split) * P.words_per_split;
   const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
   const int n_wordsteps = static_cast<int>(w_end - w_begin);
   if (n_wordsteps <= 0) return;
-  const int n_rawsteps = (n_wordsteps + RAW_WORDS - 1) / RAW_WORDS;
+  const int n_steps = (n_wordsteps + STEP_WORDS - 1) / STEP_WORDS;
 
   if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
   if (tid == 32) {
@@ -159,7 +200,6 @@ pair_counts_tc_kernel(const TcParams P) {
     umma::mbar_init(&done_bar, 1);
     umma::fence_mbar_init();
   }
-  if (tid < TC_ROWS) s_hcount[tid] = 0;
   if (tid == 0) s_valid_sites = 0;
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -167,89 +207,169 @@ pair_counts_tc_kernel(const TcParams P) {
   const uint32_t tmem = s_tmem;
 
   if (warp == TC_EXP_WARPS) {
-    // ===== TMA producer: raw nib4 words of the 2 + 4 sample tiles of this tile pair =====
+    // ===== TMA producer: raw nib4 words of the 2 + 3 sample tiles of this tile pair =====
     if (lane == 0) {
-      for (int rs = 0; rs < n_rawsteps; ++rs) {
-        const int stage = rs % RAW_STAGES;
-        if (rs >= RAW_STAGES) umma::mbar_wait(&raw_empty[stage], ((rs / RAW_STAGES) - 1) & 1);
-        const int64_t w0 = w_begin + static_cast<int64_t>(rs) * RAW_WORDS;
-        const int kw = static_cast<int>(min(static_cast<long long>(RAW_WORDS), static_cast<long long>(w_end - w0)));
-        const uint32_t bytes_per_tile = static_cast<uint32_t>(kw) * 64 * 16;
-        umma::mbar_expect_tx(&raw_full[stage], bytes_per_tile * 6);
-        uint8_t* dst = raw + stage * RAW_STAGE_BYTES;
-        // stage layout: [pf_tile 0..5][word][64 samples][16 B]; pf tiles 0,1 = I rows, 2..5 = J rows
+      long long t_wait = 0;
+      const long long t_start = PROF ? clock64() : 0;
+      const uint4* src_tile[TC_PF];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k) : (4 * static_cast<int64_t>(tj) + (k - 2));
-          umma::bulk_g2s(dst + k * (RAW_WORDS * 64 * 16), P.nib4 + (pft * P.n_local + w0) * 64, bytes_per_tile,
-                         &raw_full[stage]);
+      for (int k = 0; k < TC_PF; ++k) {
+        const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k) : (3 * static_cast<int64_t>(tj) + (k - 2));
+        src_tile[k] = P.nib4 + (pft * P.n_local + w_begin) * 64;
+      }
+      int stage = 0;
+      uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
+      for (int st = 0; st < n_steps; ++st) {
+        if (st >= RAW_STAGES) {
+          const long long t0 = PROF ? clock64() : 0;
+          umma::mbar_wait_a(raw_empty_a + stage * 8, phase);
+          if (PROF) t_wait += clock64() - t0;
         }
+        const int kw = min(RAW_WORDS, n_wordsteps - st * RAW_WORDS);
+        const uint32_t bytes_per_tile = static_cast<uint32_t>(kw) * 64 * 16;
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, bytes_per_tile * TC_PF);
+        const uint32_t dst = raw_a + stage * RAW_STAGE_BYTES;
+        // stage layout: [pf_tile 0..4][word][64 samples][16 B]; pf tiles 0,1 = I rows, 2..4 = J rows
+#pragma unroll
+        for (int k = 0; k < TC_PF; ++k)
+          umma::bulk_g2s_a(dst + k * (RAW_WORDS * 64 * 16), src_tile[k] + static_cast<int64_t>(st) * (RAW_WORDS * 64),
+                           bytes_per_tile, raw_full_a + stage * 8);
+        if (++stage == RAW_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (PROF) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[5]), static_cast<unsigned long long>(t_wait));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[6]), static_cast<unsigned long long>(clock64() - t_start));
       }
     }
   } else if (warp == TC_EXP_WARPS + 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer: D[tmem] += A[tmem] * B[smem], two products per word =====
     if (lane == 0) {
       const uint32_t idesc = umma::idesc_i8(TC_I, TC_J);
-      for (int st = 0; st < n_rawsteps; ++st) {
-        const int e = st % EXP_STAGES;
-        umma::mbar_wait(&exp_full[e], (st / EXP_STAGES) & 1);
+      long long t_wait = 0;
+      const long long t_start = PROF ? clock64() : 0;
+      int e = 0;
+      uint32_t phase = 0;
+      for (int st = 0; st < n_steps; ++st) {
+        const long long t0 = PROF ? clock64() : 0;
+        umma::mbar_wait_a(exp_full_a + e * 8, phase);
+        if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
         const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
-        for (int k = 0; k < kw; ++k) {
-          const uint32_t base = umma::smem_addr(exp + e * EXP_STAGE_BYTES + k * EXP_WORD_BYTES);
-          const uint64_t ax = umma::smem_desc_kmajor_noswizzle(base + EXP_AX, 128, 256);
-          const uint64_t ah = umma::smem_desc_kmajor_noswizzle(base + EXP_AH, 128, 256);
-          const uint64_t bx = umma::smem_desc_kmajor_noswizzle(base + EXP_BX, 128, 256);
-          const uint64_t bh = umma::smem_desc_kmajor_noswizzle(base + EXP_BH, 128, 256);
-          const uint32_t acc = (st > 0 || k > 0) ? 1u : 0u;
-          umma::mma_i8_ss(tmem, ax, bx, idesc, acc);            // P -> columns [0, 256)
-          umma::mma_i8_ss(tmem + TC_J, ah, bh, idesc, acc);     // Q -> columns [256, 512)
+#pragma unroll
+        for (int k = 0; k < STEP_WORDS; ++k) {
+          if (k < kw) {
+            const uint32_t base = exp_a + e * EXP_STAGE_BYTES + k * EXP_WORD_BYTES;
+            const uint64_t bx = umma::smem_desc_kmajor_noswizzle(base + EXP_BX, 128, 256);
+            const uint64_t bh = umma::smem_desc_kmajor_noswizzle(base + EXP_BH, 128, 256);
+            const uint32_t a_col = tmem + TMEM_A + (e * STEP_WORDS + k) * 16;
+            const uint32_t acc = (st > 0 || k > 0) ? 1u : 0u;
+            umma::mma_i8_ts(tmem + TMEM_P, a_col, bx, idesc, acc);
+            umma::mma_i8_ts(tmem + TMEM_Q, a_col + 8, bh, idesc, acc);
+          }
         }
-        umma::commit(&exp_empty[e]);
+        umma::commit_a(exp_empty_a + e * 8);
+        if (++e == EXP_STAGES) {
+          e = 0;
+          phase ^= 1;
+        }
       }
-      umma::commit(&done_bar);
+      umma::commit_a(done_a);
+      if (PROF) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[0]), static_cast<unsigned long long>(t_wait));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[1]), static_cast<unsigned long long>(clock64() - t_start));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[8]), static_cast<unsigned long long>(n_steps));
+      }
     }
   } else {
-    // ===== expansion warps: thread = one sample row (0..127 I rows, 128..383 J rows) =====
-    const int row = tid;                       // 0 .. 383
+    // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, written straight
+    // into TMEM (their lane quadrant); warps 4-9: the 192 B rows, written to shared memory in the
+    // canonical K-major layout =====
+    const int row = tid;                       // 0 .. 319
     const int pf = row >> 6, l = row & 63;     // raw stage sub-tile and sample inside it
     const bool is_a = row < TC_I;
     const int r = is_a ? row : row - TC_I;
-    const uint32_t off_x = is_a ? EXP_AX : EXP_BX;
-    const uint32_t off_h = is_a ? EXP_AH : EXP_BH;
-    for (int st = 0; st < n_rawsteps; ++st) {
-      const int stage = st % RAW_STAGES;
-      const int e = st % EXP_STAGES;
+    const uint32_t a_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A;   // A rows: TMEM lane = row
+    const uint32_t raw_row = raw_a + pf * (RAW_WORDS * 64 * 16) + l * 16;
+    const uint32_t exp_row = exp_a + unit_off(r, 0);                                          // B rows: canonical smem tile
+    long long t_wraw = 0, t_wemp = 0, t_fence = 0;
+    const long long t_start = PROF ? clock64() : 0;
+    int stage = 0, e = 0;
+    uint32_t raw_phase = 0, exp_phase = 1;
+    for (int st = 0; st < n_steps; ++st) {
       if (lane == 0) {
-        umma::mbar_wait(&raw_full[stage], (st / RAW_STAGES) & 1);
-        if (st >= EXP_STAGES) umma::mbar_wait(&exp_empty[e], ((st / EXP_STAGES) - 1) & 1);
-      }
-      __syncwarp();
-      const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
-      const uint8_t* src = raw + stage * RAW_STAGE_BYTES + pf * (RAW_WORDS * 64 * 16) + l * 16;
-      for (int k = 0; k < kw; ++k) {
-        const uint4 nb = *reinterpret_cast<const uint4*>(src + k * (64 * 16));
-        uint8_t* dst = exp + e * EXP_STAGE_BYTES + k * EXP_WORD_BYTES;
-        const uint32_t q[4] = {nb.x, nb.y, nb.z, nb.w};
-        uint32_t xs[8], hs[8];
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          xs[2 * m] = __byte_perm(POOL_X, 0u, q[m]);
-          xs[2 * m + 1] = __byte_perm(POOL_X, 0u, q[m] >> 16);
-          hs[2 * m] = __byte_perm(POOL_H, 0u, q[m]);
-          hs[2 * m + 1] = __byte_perm(POOL_H, 0u, q[m] >> 16);
+        const long long t0 = PROF ? clock64() : 0;
+        umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
+        const long long t1 = PROF ? clock64() : 0;
+        if (st >= EXP_STAGES) umma::mbar_wait_a(exp_empty_a + e * 8, exp_phase);
+        if (PROF) {
+          t_wraw += t1 - t0;
+          t_wemp += clock64() - t1;
         }
-        *reinterpret_cast<uint4*>(dst + off_x + unit_off(r, 0)) = make_uint4(xs[0], xs[1], xs[2], xs[3]);
-        *reinterpret_cast<uint4*>(dst + off_x + unit_off(r, 1)) = make_uint4(xs[4], xs[5], xs[6], xs[7]);
-        *reinterpret_cast<uint4*>(dst + off_h + unit_off(r, 0)) = make_uint4(hs[0], hs[1], hs[2], hs[3]);
-        *reinterpret_cast<uint4*>(dst + off_h + unit_off(r, 1)) = make_uint4(hs[4], hs[5], hs[6], hs[7]);
       }
-      umma::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) {
-        umma::mbar_arrive(&exp_full[e]);
-        umma::mbar_arrive(&raw_empty[stage]);
+      if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+      const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
+      const uint32_t src = raw_row + stage * RAW_STAGE_BYTES;
+      uint4 nb[STEP_WORDS];
+#pragma unroll
+      for (int k = 0; k < STEP_WORDS; ++k) nb[k] = umma::lds128(src + k * (64 * 16));   // stale words of a short last step are unused
+      if (is_a) {
+        const uint32_t a_col = a_base + e * (STEP_WORDS * 16);
+#pragma unroll
+        for (int k = 0; k < STEP_WORDS; ++k) {
+          if (k < kw) {
+            uint32_t xs[8], hs[8];
+            expand_word(nb[k], xs, hs);
+            umma::tmem_st_32x8(a_col + k * 16, xs);
+            umma::tmem_st_32x8(a_col + k * 16 + 8, hs);
+          }
+        }
+      } else {
+        const uint32_t dst = exp_row + e * EXP_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < STEP_WORDS; ++k) {
+          if (k < kw) {
+            uint32_t xs[8], hs[8];
+            expand_word(nb[k], xs, hs);
+            const uint32_t d = dst + k * EXP_WORD_BYTES;
+            umma::sts128(d + EXP_BX, xs[0], xs[1], xs[2], xs[3]);
+            umma::sts128(d + EXP_BX + 128, xs[4], xs[5], xs[6], xs[7]);
+            umma::sts128(d + EXP_BH, hs[0], hs[1], hs[2], hs[3]);
+            umma::sts128(d + EXP_BH + 128, hs[4], hs[5], hs[6], hs[7]);
+          }
+        }
       }
+      const long long tf0 = PROF ? clock64() : 0;
+      if (is_a) {
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+      } else {
+        umma::fence_proxy_async_smem();
+      }
+      __syncwarp();
+      if (PROF) t_fence += clock64() - tf0;
+      if (lane == 0) {
+        umma::mbar_arrive_a(exp_full_a + e * 8);
+        umma::mbar_arrive_a(raw_empty_a + stage * 8);
+      }
+      if (++stage == RAW_STAGES) {
+        stage = 0;
+        raw_phase ^= 1;
+      }
+      if (++e == EXP_STAGES) {
+        e = 0;
+        exp_phase ^= 1;
+      }
+    }
+    if (PROF && lane == 0 && (warp == 0 || warp == 4)) {
+      const int o = warp == 0 ? 2 : 9;   // [2..4] an A-row warp, [9..11] a B-row warp
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o]), static_cast<unsigned long long>(t_wraw));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 1]), static_cast<unsigned long long>(t_wemp));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 13]), static_cast<unsigned long long>(t_fence));
     }
     {
       const int64_t sample = is_a ? (static_cast<int64_t>(ti) * TC_I + r) : (static_cast<int64_t>(tj) * TC_J + r);
@@ -261,14 +381,15 @@ pair_counts_tc_kernel(const TcParams P) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, off);
     if (lane == 0 && vs) atomicAdd(&s_valid_sites, vs);
-    // all expansion warps meet before the epilogue (named barrier 1, 384 threads)
+    // all expansion warps meet before the epilogue (named barrier 1)
     asm volatile("bar.sync 1, %0;" ::"r"(TC_EXP_WARPS * 32) : "memory");
 
     // ===== epilogue: TMEM -> registers -> counts =====
-    umma::mbar_wait(&done_bar, 0);
+    umma::mbar_wait_a(done_a, 0);
     umma::fence_after_thread_sync();
     const int lane_grp = warp & 3;               // TMEM lanes [32 g, 32 g + 32) are visible to warps with w % 4 == g
-    const int col_grp = warp >> 2;               // 3 warps share a lane group: split the 8 column chunks
+    const int grp_rank = warp >> 2;              // rank of this warp among the warps of its lane group
+    const int grp_size = (lane_grp < (TC_EXP_WARPS & 3)) ? (TC_EXP_WARPS / 4 + 1) : (TC_EXP_WARPS / 4);
     const int i_local = lane_grp * 32 + lane;
     const int64_t i = static_cast<int64_t>(ti) * TC_I + i_local;
     const int hi = s_hcount[i_local];
@@ -277,11 +398,11 @@ pair_counts_tc_kernel(const TcParams P) {
     int32_t* V = P.counts;
     int32_t* D1 = P.counts + plane;
     int32_t* D2 = P.counts + 2 * plane;
-    for (int chunk = col_grp; chunk < TC_J / 32; chunk += 3) {
+    for (int chunk = grp_rank; chunk < TC_J / 32; chunk += grp_size) {
       uint32_t pv[32], qv[32];
       const uint32_t taddr = tmem + (static_cast<uint32_t>(lane_grp * 32) << 16) + chunk * 32;
-      umma::tmem_ld_32x32(taddr, pv);
-      umma::tmem_ld_32x32(taddr + TC_J, qv);
+      umma::tmem_ld_32x32(taddr + TMEM_P, pv);
+      umma::tmem_ld_32x32(taddr + TMEM_Q, qv);
       umma::tmem_wait_ld();
       if (i < P.n_samples) {
 #pragma unroll
@@ -332,9 +453,10 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   L.n_tiles = pf_ceil_div(n_samples, PF_TILE);
   L.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, TC_J));
   L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, TC_I));
-  L.n_tiles_padded = static_cast<int64_t>(L.n_jtiles) * (TC_J / PF_TILE);   // multiple of 4 PF tiles
+  L.n_tiles_padded = static_cast<int64_t>(L.n_jtiles) * (TC_J / PF_TILE);   // whole J tiles of operand stream
+  if (L.n_tiles_padded < 2 * static_cast<int64_t>(L.n_itiles)) L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
   L.pairs = 0;
-  for (int ti = 0; ti < L.n_itiles; ++ti) L.pairs += L.n_jtiles - ti / 2;
+  for (int ti = 0; ti < L.n_itiles; ++ti) L.pairs += L.n_jtiles - (2 * ti) / 3;
   // split-K: ~20 waves of one CTA per SM, at least 64 words per CTA, boundaries multiples of HSUM_RUN
   int64_t splits = pf_ceil_div(static_cast<int64_t>(sms) * 20, L.pairs);
   const int64_t max_splits = pf_ceil_div(n_local, 64);
@@ -413,14 +535,29 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   P.hsum = hsum;
   P.hsum_ld = L.hsum_ld;
   P.words_per_split = static_cast<int>(L.words_per_split);
+  P.prof = g_tc_prof_enabled ? 1 : 0;
   const int64_t grid = L.splits * L.pairs;
   if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
   const size_t smem = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES + static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
-  PF_CUDA(cudaFuncSetAttribute(pair_counts_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               static_cast<int>(smem)));
-  pair_counts_tc_kernel<<<static_cast<unsigned>(grid), TC_THREADS, smem, s>>>(P);
+  auto kernel = g_tc_prof_enabled ? pair_counts_tc_kernel<true> : pair_counts_tc_kernel<false>;
+  PF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kernel<<<static_cast<unsigned>(grid), TC_THREADS, smem, s>>>(P);
   PF_CUDA(cudaGetLastError());
   *h_used = 1;
+  return PF_OK;
+  PF_TRY_END
+}
+
+// Diagnostic: enable role-level cycle accounting in the tensor-core kernel and read it back.
+// h_out16: [0] MMA thread cycles waiting for expanded operands, [1] MMA thread total, [2..4] an A-row
+// expansion warp: waiting for raw data / waiting for a free stage / total, [5] TMA producer waiting,
+// [6] producer total, [8] pipeline steps, [9..11] a B-row expansion warp (as [2..4]); summed over CTAs.
+PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16) {
+  PF_TRY_BEGIN
+  if (h_out16) PF_CUDA(cudaMemcpyFromSymbol(h_out16, g_tc_prof, sizeof(long long) * 16));
+  long long zero[16] = {0};
+  PF_CUDA(cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)));
+  g_tc_prof_enabled = enable != 0;
   return PF_OK;
   PF_TRY_END
 }

@@ -126,8 +126,14 @@ class Engine:
         if word_end is None:
             word_end = n_words
         assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
-        if variant == 0:
-            variant = 3 if n_samples >= self.TC_MIN_SAMPLES else 2
+        auto = variant == 0
+        if auto:
+            # after the tensor-core path declined (genotypes missing in some samples only) the next
+            # calls of a chunked run would decline too: skip the attempt for a while
+            skip = getattr(self, "_tc_skip", 0)
+            if skip > 0:
+                self._tc_skip = skip - 1
+            variant = 3 if (n_samples >= self.TC_MIN_SAMPLES and skip == 0) else 2
         if variant == 3:
             need = int(self.lib.pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin))
             work = getattr(self, "_tc_work", None)
@@ -140,6 +146,8 @@ class Engine:
                                              C.byref(used), _stream_ptr()))
             if used.value:
                 return 3
+            if auto:
+                self._tc_skip = 64
             variant = 2
         check(self.lib.pf_pair_counts(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
