@@ -15,8 +15,9 @@ A step = one pass of the hot path over the whole batch:
   value   whole-job sample-pair x sites per second, inputs resident in HBM, CUDA-event timed,
           max over ranks.
   e2e     the same metric through Engine.tree_from_host_codes: genotypes start in pinned host
-          memory, host->device copies (chunked, overlapped with pack + counts) and the
-          device->host read of the result (distance matrix, join list -> Newick) are timed.
+          memory (2-bit site-major rows by default, --e2e-format u8 for one byte per genotype),
+          host->device copies (chunked, overlapped with pack + counts) and the device->host read
+          of the result (distance matrix, join list -> Newick) are timed.
   roofline      the pair-count kernel against the integer-pipe peak measured live by
                 pf_microbench_int_pipe (MEASURED_PEAKS.json has no integer peaks).
   cpu_baseline  the CPU oracle (oracle/pf_oracle.c, all host threads) on a bounded sample,
@@ -50,7 +51,7 @@ UNIT = "pair-sites/s"
 SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
-NCU_TRAFFIC_BYTES_TC = None  # filled from the round's ncu capture of pair_counts_tc_kernel
+NCU_TRAFFIC_BYTES_TC = 50_894_759_000  # r01: 49.27 GB read + 1.63 GB written (profiles/r01_ncu_pair_counts_tc_raw_subset.csv), N=1
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
@@ -277,29 +278,34 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         chunk_sites = args.e2e_chunk_sites
-        host = torch.empty((my_sites, ld), dtype=torch.uint8).pin_memory()
+        packed2 = args.e2e_format == "2bit"
+        ld_host = ((n + 15) // 16 * 4) if packed2 else ld
+        host = torch.empty((my_sites, ld_host), dtype=torch.uint8).pin_memory()
         for c0 in range(0, my_sites, chunk_sites):                 # fill the host buffer (untimed)
             c1 = min(my_sites, c0 + chunk_sites)
             tmp = eng.synth_codes(n, site0 + c0, c1 - c0, seed=SEED, miss_ppm=miss)
-            host[c0:c1].copy_(tmp)
+            host[c0:c1].copy_(eng.to_2bit_rows(tmp, n) if packed2 else tmp)
             del tmp
         torch.cuda.synchronize()
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         res = None
         for _ in range(1):
-            res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant)
+            res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant,
+                                           packed2=packed2)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant)
+            res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant,
+                                           packed2=packed2)
         barrier()
         t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
         e2e = {"value": pair_sites(n, m) / float(t_e2e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(my_sites) * ld, "d2h_bytes_per_step": int(res.d2h_bytes),
+               "h2d_bytes_per_step": int(my_sites) * ld_host, "d2h_bytes_per_step": int(res.d2h_bytes),
+               "host_format": ("site-major 2-bit genotypes, 4 samples per byte" if packed2 else "site-major u8 genotype codes"),
                "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps,
-               "api": "Engine.tree_from_host_codes (pinned host u8 genotypes -> Newick + distance matrix)",
+               "api": "Engine.tree_from_host_codes (pinned host genotype rows -> Newick + distance matrix)",
                "timing": "host wall clock between barriers + cuda synchronize (includes H2D, D2H, host Newick assembly)"}
         del host
 
@@ -411,6 +417,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-format", default="2bit", choices=["2bit", "u8"],
+                    help="host genotype format of the end-to-end path: 2 bits (4 samples per byte) or one byte per genotype")
     ap.add_argument("--e2e-chunk-sites", type=int, default=1 << 19)
     ap.add_argument("--cpu-sample-sites", type=int, default=1 << 18)
     args = ap.parse_args()

@@ -85,6 +85,14 @@ PF_API int pf_pack_codes_u8(const uint8_t* d_codes, int64_t ld, const int64_t* d
                             int64_t n_samples, int64_t n_sites, uint32_t* d_planes,
                             int64_t n_words, int64_t word0, void* stream);
 
+/* Same packer for genotypes that are already 2 bits wide on the host side: site-major rows of ld2
+ * bytes (ld2 % 4 == 0), 4 samples per byte, sample 4b+k in bits 2k..2k+1 of byte b. plink = 0: the
+ * codes are this library's (0 hom-REF, 1 HET, 2 hom-ALT, 3 missing); plink = 1: PLINK .bed codes
+ * (00 hom A1, 01 missing, 10 het, 11 hom A2; the first three magic bytes of a .bed are not data). */
+PF_API int pf_pack_codes_2bit(const uint8_t* d_codes2, int64_t ld2, int64_t n_samples, int64_t n_sites,
+                              uint32_t* d_planes, int64_t n_words, int64_t word0, int plink,
+                              void* stream);
+
 /* planes -> sample-major u8 codes d_out[i * ld_out + s] for s in [0, n_sites) taken from
  * words [word0, ...). Used to emit the reference's on-disk artefacts and by parity tests. */
 PF_API int pf_unpack_codes_u8(const uint32_t* d_planes, int64_t n_words, int64_t word0,

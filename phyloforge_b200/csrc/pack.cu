@@ -90,6 +90,75 @@ pack_kernel(const uint8_t* __restrict__ codes, int64_t ld, const int64_t* __rest
   *reinterpret_cast<uint4*>(base + PF_TILE) = make_uint4(wH[0], wH[1], wH[2], wH[3]);
 }
 
+// ---- site-major 2-bit codes (4 samples per byte, sample 4b+k in bits 2k..2k+1 of byte b) -> planes.
+// A thread owns 16 consecutive samples: one 32-bit load per site row, then a 32 x 32 bit transpose in
+// registers turns "32 sites x (16 samples x 2 bits)" into the L and H words of the 16 samples.
+// plink != 0 reads PLINK .bed genotype codes (00 hom A1, 01 missing, 10 het, 11 hom A2) instead.
+//   algorithmic bytes per genotype: 0.25 read + 0.25 written
+__device__ __forceinline__ void transpose32(uint32_t (&a)[32]) {
+  uint32_t m = 0x0000ffffu;
+#pragma unroll
+  for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+    for (int k = 0; k < 32; k = ((k | j) + 1) & ~j) {
+      const uint32_t t = ((a[k] >> j) ^ a[k | j]) & m;
+      a[k] ^= t << j;
+      a[k | j] ^= t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+pack2_kernel(const uint8_t* __restrict__ codes2, int64_t ld2, int64_t n_samples, int64_t n_sites,
+             uint32_t* __restrict__ planes, int64_t n_words, int64_t word0, int64_t n_groups, int plink) {
+  const int64_t g = static_cast<int64_t>(blockIdx.y) * blockDim.x + threadIdx.x;   // group of 16 samples
+  const int64_t wl = static_cast<int64_t>(blockIdx.x) * blockDim.y + threadIdx.y;  // local word
+  const int64_t n_local_words = pf_ceil_div(n_sites, 32);
+  if (g >= n_groups || wl >= n_local_words) return;
+  const int64_t i0 = g * 16;
+  const uint32_t missing = plink ? 0x55555555u : 0xffffffffu;
+  uint32_t a[32];
+  // samples of this group beyond n_samples read as missing
+  uint32_t keep = 0xffffffffu;
+  if (i0 >= n_samples) keep = 0u;
+  else if (i0 + 16 > n_samples) keep = (1u << (2 * static_cast<int>(n_samples - i0))) - 1u;
+  const bool in_row = (i0 / 4 + 4) <= ld2;   // the 4 bytes of this group lie inside a row
+#pragma unroll
+  for (int b = 0; b < 32; ++b) {
+    const int64_t sidx = wl * 32 + b;
+    uint32_t v = missing;
+    if (sidx < n_sites && keep != 0u) {
+      const uint8_t* p = codes2 + sidx * ld2 + i0 / 4;
+      uint32_t x;
+      if (in_row) {
+        x = *reinterpret_cast<const uint32_t*>(p);
+      } else {
+        x = 0;
+        for (int k = 0; k < 4; ++k)
+          if (i0 / 4 + k < ld2) x |= static_cast<uint32_t>(p[k]) << (8 * k);
+      }
+      v = (x & keep) | (missing & ~keep);
+    }
+    a[b] = v;
+  }
+  transpose32(a);   // a[2j] = low code bits of sample i0+j over the 32 sites, a[2j+1] = high code bits
+  const int64_t tile = i0 / PF_TILE;
+  const int64_t lane = i0 % PF_TILE;
+  uint32_t* base = planes + ((tile * n_words + (word0 + wl)) * 2) * PF_TILE + lane;
+  uint32_t L[16], H[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const uint32_t lo = a[2 * j], hi = a[2 * j + 1];
+    L[j] = plink ? (lo ^ hi) : lo;   // PLINK: het = 10, missing = 01 -> low code bit; hom A2 = 11, missing -> high bit
+    H[j] = plink ? lo : hi;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    *reinterpret_cast<uint4*>(base + 4 * q) = make_uint4(L[4 * q], L[4 * q + 1], L[4 * q + 2], L[4 * q + 3]);
+    *reinterpret_cast<uint4*>(base + PF_TILE + 4 * q) = make_uint4(H[4 * q], H[4 * q + 1], H[4 * q + 2], H[4 * q + 3]);
+  }
+}
+
 // planes -> sample-major byte codes. One CTA per (tile, 32 words): coalesced 512 B reads per
 // word, transposed through shared memory, 1 KB contiguous writes per sample.
 __global__ void __launch_bounds__(256)
@@ -211,6 +280,29 @@ PF_API int pf_transpose_u8(const uint8_t* d_in, int64_t ld_in, const int64_t* d_
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_rows, 64)), static_cast<unsigned>(gy));
   transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, ld_in, d_rows, n_rows, n_cols,
                                                                          d_out, ld_out);
+  PF_CUDA(cudaGetLastError());
+  return PF_OK;
+  PF_TRY_END
+}
+
+PF_API int pf_pack_codes_2bit(const uint8_t* d_codes2, int64_t ld2, int64_t n_samples, int64_t n_sites,
+                              uint32_t* d_planes, int64_t n_words, int64_t word0, int plink, void* stream) {
+  PF_TRY_BEGIN
+  if (!d_codes2 || !d_planes || n_samples <= 0 || n_sites < 0 || ld2 * 4 < n_samples || word0 < 0)
+    return pf_fail("pf_pack_codes_2bit: bad arguments");
+  if (ld2 % 4 != 0 || reinterpret_cast<uintptr_t>(d_codes2) % 4 != 0)
+    return pf_fail("pf_pack_codes_2bit: rows must be 4-byte aligned (ld2 %% 4 == 0)");
+  const int64_t n_local_words = pf_ceil_div(n_sites, 32);
+  if (word0 + n_local_words > n_words) return pf_fail("pf_pack_codes_2bit: word range exceeds n_words");
+  if (n_sites == 0) return PF_OK;
+  const int64_t n_groups = pf_ceil_div(n_samples, PF_TILE) * (PF_TILE / 16);
+  int gx = 4;
+  while (gx < 128 && gx < n_groups) gx *= 2;
+  const int gy = 128 / gx;
+  dim3 block(gx, gy);
+  dim3 grid(static_cast<unsigned>(pf_ceil_div(n_local_words, gy)), static_cast<unsigned>(pf_ceil_div(n_groups, gx)));
+  pack2_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_codes2, ld2, n_samples, n_sites, d_planes,
+                                                                       n_words, word0, n_groups, plink);
   PF_CUDA(cudaGetLastError());
   return PF_OK;
   PF_TRY_END

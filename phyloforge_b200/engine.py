@@ -96,6 +96,26 @@ class Engine:
         check(self.lib.pf_pack_codes_u8(codes.data_ptr(), codes.stride(0), _lib.ptr(rows), n_samples, n_sites,
                                         planes.data_ptr(), n_words, word0, _stream_ptr()))
 
+    def pack_codes_2bit(self, codes2: torch.Tensor, n_samples: int, planes: torch.Tensor, n_words: int,
+                        word0: int = 0, n_sites: int | None = None, plink: bool = False):
+        """codes2: site-major u8 [rows, ld2] holding 4 samples per byte (2 bits each)."""
+        assert codes2.dtype == torch.uint8 and codes2.is_cuda and codes2.stride(1) == 1
+        if n_sites is None:
+            n_sites = codes2.shape[0]
+        check(self.lib.pf_pack_codes_2bit(codes2.data_ptr(), codes2.stride(0), n_samples, n_sites, planes.data_ptr(),
+                                          n_words, word0, 1 if plink else 0, _stream_ptr()))
+
+    @staticmethod
+    def to_2bit_rows(codes: torch.Tensor, n_samples: int) -> torch.Tensor:
+        """Site-major u8 codes [m, >= n] -> site-major 2-bit rows [m, ld2] (ld2 % 4 == 0; padding = code 3).
+        Input-format helper for tests and benchmarks (torch ops, not a timed path)."""
+        m = codes.shape[0]
+        n16 = (n_samples + 15) // 16 * 16
+        c = torch.full((m, n16), 3, dtype=torch.uint8, device=codes.device)
+        c[:, :n_samples] = codes[:, :n_samples] & 3
+        c = c.view(m, n16 // 4, 4)
+        return (c[..., 0] | (c[..., 1] << 2) | (c[..., 2] << 4) | (c[..., 3] << 6)).contiguous()
+
     def unpack_codes(self, planes: torch.Tensor, n_samples: int, n_words: int, n_sites: int,
                      word0: int = 0) -> torch.Tensor:
         """Sample-major u8 codes [n_samples, n_sites]."""
@@ -212,12 +232,14 @@ class Engine:
                           int(nz.item()), dist_host=dist_host)
 
     def tree_from_host_codes(self, host_codes: torch.Tensor, n_samples: int, names, metric="ibs",
-                             chunk_sites: int = 1 << 19, variant: int = 0) -> TreeResult:
+                             chunk_sites: int = 1 << 19, variant: int = 0, packed2: bool = False,
+                             plink: bool = False) -> TreeResult:
         """End-to-end entry for genotypes that live in HOST memory: `host_codes` is a (pinned)
-        site-major u8 matrix [n_sites, ld] holding this rank's site shard. Chunks of sites are
-        copied host->device on a copy stream while the previous chunk is packed and counted; the
-        count matrices are then allreduced over the ranks, normalised and joined, and the result
-        (distance matrix, join list -> Newick) is read back to the host."""
+        site-major u8 matrix holding this rank's site shard — one byte per genotype [n_sites, ld], or,
+        with packed2=True, four genotypes per byte [n_sites, ld2] (plink=True: PLINK .bed codes).
+        Chunks of sites are copied host->device on a copy stream while the previous chunk is packed
+        and counted; the count matrices are then allreduced over the ranks, normalised and joined,
+        and the result (distance matrix, join list -> Newick) is read back to the host."""
         assert host_codes.dtype == torch.uint8 and not host_codes.is_cuda and host_codes.stride(1) == 1
         chunk_sites = max(32, chunk_sites // 32 * 32)
         m, ld = host_codes.shape[0], host_codes.stride(0)
@@ -237,7 +259,10 @@ class Engine:
                 arrived = torch.cuda.Event()
                 arrived.record(copy)
             compute.wait_event(arrived)
-            self.pack_codes(buf, n_samples, bufs["planes"], nw_chunk, n_sites=c1 - c0)
+            if packed2:
+                self.pack_codes_2bit(buf, n_samples, bufs["planes"], nw_chunk, n_sites=c1 - c0, plink=plink)
+            else:
+                self.pack_codes(buf, n_samples, bufs["planes"], nw_chunk, n_sites=c1 - c0)
             self.pair_counts(bufs["planes"], n_samples, nw_chunk, counts, word_end=(c1 - c0 + 31) // 32,
                              variant=variant)
             ev = torch.cuda.Event()

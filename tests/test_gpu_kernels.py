@@ -233,3 +233,38 @@ def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
     assert engine.pair_counts(planes, n, nw, counts, variant=3) == 2
     want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
     assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("n,m", [(2, 33), (16, 64), (17, 100), (63, 257), (64, 32), (130, 1000), (500, 4099)])
+def test_pack_2bit_rows_bit_exact(engine, n, m):
+    """Site-major 2-bit host format (and the PLINK .bed code table) -> the same planes as the byte packer."""
+    rng = np.random.default_rng(n * 31 + m)
+    codes = _random_codes(rng, n, m, 0.1)
+    d = torch.from_numpy(codes).to(engine.device)
+    nw = engine.n_words(m)
+    want = oracle.pack_planes(np.ascontiguousarray(codes.T))
+    rows2 = engine.to_2bit_rows(d, n)
+    planes = engine.alloc_planes(n, nw)
+    planes.fill_(0x5A5A5A5A)
+    engine.pack_codes_2bit(rows2, n, planes, nw)
+    assert np.array_equal(planes.cpu().numpy().view(np.uint32), want)
+    # PLINK .bed codes: 00 hom A1, 01 missing, 10 het, 11 hom A2
+    lut = torch.tensor([0b00, 0b10, 0b11, 0b01], dtype=torch.uint8, device=engine.device)
+    bed = engine.to_2bit_rows(lut[d.long()], n)
+    pad = (-n) % 16
+    if pad:                                   # to_2bit_rows pads with our missing code 3 = 0b11; .bed pads are ignored
+        pass
+    planes.fill_(0x5A5A5A5A)
+    engine.pack_codes_2bit(bed, n, planes, nw, plink=True)
+    assert np.array_equal(planes.cpu().numpy().view(np.uint32), want)
+
+
+def test_host_2bit_path_matches_byte_path(engine):
+    n, m = 260, 20000
+    names = [f"h{i}" for i in range(n)]
+    codes = engine.synth_codes(n, 0, m, seed=6)
+    host_u8 = codes.cpu().pin_memory()
+    host_2b = engine.to_2bit_rows(codes, n).cpu().pin_memory()
+    a = engine.tree_from_host_codes(host_u8, n, names, chunk_sites=4096)
+    b = engine.tree_from_host_codes(host_2b, n, names, chunk_sites=4096, packed2=True)
+    assert torch.equal(a.counts, b.counts) and a.newick == b.newick
