@@ -7,7 +7,9 @@
 Workload (config.workload): BASELINE.json configs[3], "3,000 samples x 10M SNPs", the shape the
 north-star target is quoted on; it fits one B200 (30 GB of site-major byte genotypes + 7.5 GB of
 bit planes), so the same total work is used at every N and the site axis is sharded over the
-ranks ("scaling": "strong").
+ranks. Default "scaling": "weak" — every GPU holds the named configuration's 10M sites (the global
+matrix has N x 10M sites; N = 1 is exactly the named configuration); `--scaling strong` splits the 10M
+sites over the GPUs instead (round-1 measurements of both are in profiles/).
 
 A step = one pass of the hot path over the whole batch:
     pack (byte genotypes -> bit planes) -> all-pairs counts -> [NCCL allreduce of the
@@ -153,6 +155,8 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     n, m, miss, desc = WORKLOADS[args.workload]
+    if args.scaling == "weak":
+        m = m * max(1, args.gpus)          # same global configuration as our arm at this N
     sample = args.cpu_sample_sites
     runs = []
     for i in range(args.warmup + args.steps):
@@ -168,7 +172,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": statistics.mean(r["pack_s"] + r["counts_s"] + r["normalise_s"] for r in runs) * 1e3,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 bit-planes / int64 counts / f64",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 bit-planes / int64 counts / f64",
         "data": "synthetic", "config": {"workload": desc, "samples": n, "sites": m, "miss_ppm": miss},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": runs[0]["threads"], "kind": "port",
                          "sample": (f"{runs[0]['sample_sites']} of {m} sites x all {n} samples per step "
@@ -179,7 +183,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
@@ -204,11 +208,18 @@ def run_ours(args):
 
     n, m, miss, desc = WORKLOADS[args.workload]
     names = [f"S{i:05d}" for i in range(n)]
-    n_words_total = (m + 31) // 32
-    wb, we = sharding.shard_words(n_words_total, world, rank)
-    site0, site1 = wb * 32, min(we * 32, m)
+    if args.scaling == "weak":
+        # every rank holds one full copy's worth of sites of the named configuration: the global
+        # matrix has world x m sites (rank r owns sites [r m, (r + 1) m)); N = 1 is the named config
+        m_total = m * world
+        site0, site1 = rank * m, (rank + 1) * m
+    else:
+        # the named configuration is split: contiguous word-aligned site ranges (phyloforge_b200/sharding.py)
+        m_total = m
+        wb, we = sharding.shard_words((m + 31) // 32, world, rank)
+        site0, site1 = wb * 32, min(we * 32, m)
     my_sites = site1 - site0
-    my_words = we - wb
+    my_words = (my_sites + 31) // 32
     ld = (n + 3) // 4 * 4
 
     # ---- inputs resident in HBM (untimed): this rank's site shard, site-major byte codes
@@ -269,7 +280,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(elapsed_ms.item()) / args.steps
-    value = pair_sites(n, m) / (ms_per_step * 1e-3)
+    value = pair_sites(n, m_total) / (ms_per_step * 1e-3)
     stages_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in stage_ev.items()}
     counts_ms = stages_ms["counts"]
     del codes
@@ -301,7 +312,7 @@ def run_ours(args):
         t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": pair_sites(n, m) / float(t_e2e.item()), "unit": UNIT,
+        e2e = {"value": pair_sites(n, m_total) / float(t_e2e.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(my_sites) * ld_host, "d2h_bytes_per_step": int(res.d2h_bytes),
                "host_format": ("site-major 2-bit genotypes, 4 samples per byte" if packed2 else "site-major u8 genotype codes"),
                "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps,
@@ -389,21 +400,33 @@ def run_ours(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "u32 bit-planes / int32 counts / f64 distances+NJ", "data": "synthetic",
-        "config": {"workload": desc, "samples": n, "sites": m, "miss_ppm": miss, "sites_per_gpu": my_sites,
-                   "parallelism": f"sites sharded over {world} GPU(s), int32 counts allreduce (NCCL)",
+        "config": {"workload": desc + ("" if world == 1 or args.scaling == "strong" else
+                                       f" per GPU: {m_total} sites over {world} GPUs (weak scaling)"),
+                   "samples": n, "sites": m_total, "miss_ppm": miss, "sites_per_gpu": my_sites,
+                   "parallelism": f"sites sharded over {world} GPU(s), int32 counts allreduce (NCCL), NJ replicated",
                    "l2": "inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (my_sites * ld / 1e9),
                    "pair_counts_variant": ran_variant[0], "pair_counts_variant_requested": args.variant, "seed": SEED},
         "nj_seconds": stages_ms["nj"] * 1e-3, "stages_ms": stages_ms,
         "clocks": clocks, "e2e": e2e, "gpu_launches": (5 if ran_variant[0] == 3 else 4) * args.steps,
         "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Keep the process's stdout for the single JSON line: libraries that print to fd 1 (NCCL's version
+    banner) are sent to stderr for the rest of the run. Returns a file object bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    return real
 
 
 def main():
@@ -413,6 +436,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the named configuration's site count (default); "
+                         "strong: the named configuration is split over the GPUs")
     ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save popcount, 3 tcgen05 int8 GEMM")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -424,6 +450,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)
+    args.out = _claim_stdout()
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
