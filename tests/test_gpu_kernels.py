@@ -268,3 +268,61 @@ def test_host_2bit_path_matches_byte_path(engine):
     a = engine.tree_from_host_codes(host_u8, n, names, chunk_sites=4096)
     b = engine.tree_from_host_codes(host_2b, n, names, chunk_sites=4096, packed2=True)
     assert torch.equal(a.counts, b.counts) and a.newick == b.newick
+
+
+def test_kernels_do_not_write_outside_their_buffers(engine):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds stores are looked for with
+    canaries: every output buffer is over-allocated and the padding must stay untouched."""
+    from phyloforge_b200._lib import check
+    n, m = 203, 5000
+    rng = np.random.default_rng(77)
+    codes = _random_codes(rng, n, m, 0.0)
+    d = torch.from_numpy(codes).to(engine.device)
+    nw = engine.n_words(m)
+    st = torch.cuda.current_stream().cuda_stream
+    plen = int(engine.lib.pf_planes_len(n, nw))
+    guard = 4096
+    pbuf = torch.full((plen + 2 * guard,), 0x13572468, dtype=torch.int32, device=engine.device)
+    planes = pbuf[guard:guard + plen]
+    engine.pack_codes(d, n, planes, nw)
+    assert bool((pbuf[:guard] == 0x13572468).all()) and bool((pbuf[guard + plen:] == 0x13572468).all())
+    engine.pack_codes_2bit(engine.to_2bit_rows(d, n), n, planes, nw)
+    assert bool((pbuf[:guard] == 0x13572468).all()) and bool((pbuf[guard + plen:] == 0x13572468).all())
+    ld = n + 5                                                    # counts with a wider leading dimension
+    for variant in (1, 2, 3):
+        cbuf = torch.zeros((3 * n * ld + 2 * guard,), dtype=torch.int32, device=engine.device)
+        cbuf[:guard] = -99
+        cbuf[guard + 3 * n * ld:] = -99
+        cview = cbuf[guard:guard + 3 * n * ld]
+        if variant == 3:
+            work = torch.empty(int(engine.lib.pf_pair_counts_tc_work_bytes(n, nw)) + 2 * guard, dtype=torch.uint8,
+                               device=engine.device)
+            work.fill_(0xA5)
+            import ctypes as C
+            used = C.c_int(0)
+            check(engine.lib.pf_pair_counts_tc(planes.data_ptr(), n, nw, 0, nw, cview.data_ptr(), ld,
+                                               work[guard:].data_ptr(), work.numel() - 2 * guard, C.byref(used), st))
+            assert used.value == 1
+            torch.cuda.synchronize()
+            assert bool((work[:guard] == 0xA5).all()) and bool((work[-guard:] == 0xA5).all())
+        else:
+            check(engine.lib.pf_pair_counts(planes.data_ptr(), n, nw, 0, nw, cview.data_ptr(), ld, variant, st))
+        torch.cuda.synchronize()
+        assert bool((cbuf[:guard] == -99).all()) and bool((cbuf[guard + 3 * n * ld:] == -99).all())
+        got = cview.view(3, n, ld)
+        assert bool((got[:, :, n:] == 0).all())                   # padding columns of the counts are never touched
+        want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
+        assert np.array_equal(got[:, :, :n].cpu().numpy().astype(np.int64), want)
+    # NJ: workspace and outputs
+    dist = torch.rand((n, n), dtype=torch.float64, device=engine.device)
+    dist = (dist + dist.T) / 2
+    dist.fill_diagonal_(0)
+    wbytes = int(engine.lib.pf_nj_work_bytes(n))
+    work = torch.full((wbytes + 2 * guard,), 0x5C, dtype=torch.uint8, device=engine.device)
+    mbuf = torch.full((3 * (n - 2) + 64,), -7, dtype=torch.int32, device=engine.device)
+    lbuf = torch.full((3 * (n - 2) + 64,), -7.0, dtype=torch.float64, device=engine.device)
+    dcopy = dist.clone()
+    check(engine.lib.pf_nj(dcopy.data_ptr(), n, n, mbuf.data_ptr(), lbuf.data_ptr(), work[guard:].data_ptr(), st))
+    torch.cuda.synchronize()
+    assert bool((work[:guard] == 0x5C).all()) and bool((work[guard + wbytes:] == 0x5C).all())
+    assert bool((mbuf[3 * (n - 2):] == -7).all()) and bool((lbuf[3 * (n - 2):] == -7.0).all())
