@@ -56,8 +56,9 @@ PF_API int pf_selftest_umma(const int8_t* d_a, const int8_t* d_b, int32_t* d_c, 
                             void* stream);
 
 /* Back-to-back kind::i8 MMA issue rate (128 x n x 32 per MMA) with operands resident in shared
- * memory / TMEM: clock64 ticks per MMA, averaged over one CTA per SM. Synchronous. */
-PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, double* ticks_per_mma, void* stream);
+ * memory / TMEM: clock64 ticks per MMA, averaged over one CTA per SM. group > 1 (TMEM mode): that many
+ * iterations target one accumulator before switching to the other. Synchronous. */
+PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, int group, double* ticks_per_mma, void* stream);
 
 /* ------------------------------------------------------------------ layout helpers */
 /* number of uint32 words in a planes buffer for n_samples x n_words */

@@ -37,7 +37,7 @@ PROTOTYPES = {
     "pf_microbench_int_pipe": (_i32, [_i32, _i32, _dp, _dp, _vp]),
     "pf_microbench_mma": (_i32, [_i32, _i32, _dp, _vp]),
     "pf_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
-    "pf_probe_umma_rate": (_i32, [_i32, _i32, _i32, _dp, _vp]),
+    "pf_probe_umma_rate": (_i32, [_i32, _i32, _i32, _i32, _dp, _vp]),
     "pf_planes_len": (_i64, [_i64, _i64]),
     "pf_synth_codes": (_i32, [_vp, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _vp]),
     "pf_pack_codes_u8": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),

@@ -105,7 +105,7 @@ PF_API int pf_selftest_umma(const int8_t* d_a, const int8_t* d_b, int32_t* d_c, 
 // ---- MMA throughput probe: back-to-back kind::i8 MMAs on resident operands (no loads in the loop)
 namespace {
 template <int N>
-__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, int a_in_tmem, long long* out_cycles) {
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, int a_in_tmem, int group, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar;
@@ -131,7 +131,18 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, int a_in_tm
       const uint64_t da1 = umma::smem_desc_kmajor_noswizzle(sa + ST_M * 32, 128, 256);
       const uint64_t db0 = umma::smem_desc_kmajor_noswizzle(sb, 128, 256);
       const uint64_t db1 = umma::smem_desc_kmajor_noswizzle(sb + N * 32, 128, 256);
-      if (a_in_tmem) {
+      if (a_in_tmem && group < 0) {
+        // -group independent accumulators used round-robin (A staging sits behind them)
+        const int n_acc = -group;
+        const uint32_t a_col = tmem + n_acc * N;
+        umma::mma_i8_ts(tmem + ((2 * r) % n_acc) * N, a_col, db0, idesc, 1u);
+        umma::mma_i8_ts(tmem + ((2 * r + 1) % n_acc) * N, a_col + 8, db1, idesc, 1u);
+      } else if (a_in_tmem && group > 1) {
+        // `group` consecutive MMAs into the same accumulator before switching to the other one
+        const uint32_t d = ((r / group) & 1) ? tmem + N : tmem;
+        umma::mma_i8_ts(d, tmem + 2 * N, db0, idesc, 1u);
+        umma::mma_i8_ts(d, tmem + 2 * N + 8, db1, idesc, 1u);
+      } else if (a_in_tmem) {
         umma::mma_i8_ts(tmem, tmem + 2 * N, db0, idesc, 1u);
         umma::mma_i8_ts(tmem + N, tmem + 2 * N + 8, db1, idesc, 1u);
       } else {
@@ -150,9 +161,11 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int reps, int a_in_tm
 }  // namespace
 
 // n = 128, 192 or 256 accumulator columns per product; reports SM-clock64 ticks per MMA (mean over CTAs)
-PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, double* ticks_per_mma, void* stream) {
+PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, int group, double* ticks_per_mma, void* stream) {
   PF_TRY_BEGIN
-  if ((n != 128 && n != 192 && n != 256) || reps <= 0 || !ticks_per_mma) return pf_fail("pf_probe_umma_rate: bad arguments");
+  if ((n != 64 && n != 96 && n != 128 && n != 192 && n != 256) || reps <= 0 || !ticks_per_mma)
+    return pf_fail("pf_probe_umma_rate: bad arguments");
+  if (group < 0 && (-group) * n + 16 > 512) return pf_fail("pf_probe_umma_rate: accumulators do not fit in TMEM");
   if (a_in_tmem && n == 256) return pf_fail("pf_probe_umma_rate: no TMEM columns left for A at n = 256");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 0;
@@ -164,10 +177,11 @@ PF_API int pf_probe_umma_rate(int n, int reps, int a_in_tmem, double* ticks_per_
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<sms, 128, smem, s>>>(reps, a_in_tmem, d);
+    kernel<<<sms, 128, smem, s>>>(reps, a_in_tmem, group, d);
     return cudaGetLastError();
   };
-  cudaError_t e = n == 128 ? launch(umma_rate_kernel<128>) : (n == 192 ? launch(umma_rate_kernel<192>) : launch(umma_rate_kernel<256>));
+  cudaError_t e = n == 64 ? launch(umma_rate_kernel<64>) : n == 96 ? launch(umma_rate_kernel<96>) : n == 128 ? launch(umma_rate_kernel<128>)
+                  : (n == 192 ? launch(umma_rate_kernel<192>) : launch(umma_rate_kernel<256>));
   std::vector<long long> h(sms);
   if (e == cudaSuccess) e = cudaMemcpy(h.data(), d, sizeof(long long) * sms, cudaMemcpyDeviceToHost);
   cudaFree(d);
