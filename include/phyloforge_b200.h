@@ -152,6 +152,15 @@ PF_API int pf_vcf_sv_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t
                            int64_t n_lines, int64_t n_samples, uint8_t* d_chars,
                            uint8_t* d_codes, int64_t ld, int32_t* d_line_info, void* stream);
 
+/* Alignment characters -> codes, for callers that hold the character matrix the reference writes
+ * (all_snp.fa: IUPAC; SV.matrix: '0' '1' '.') instead of a VCF — the input of `treebest nj`
+ * (treetool/script.py:359-360). d_chars is SITE-major (row = alignment column; use pf_transpose_u8 on a
+ * sample-major matrix). Per column the two homozygous symbols become 0 and 2 (alphabetical order),
+ * their IUPAC code 1, '-' 'N' '.' 3. d_line_info[s] = 1 | (4 if the column fits 2 bits), so that
+ * pf_vcf_select_rows / pf_pack_codes_u8 apply unchanged. */
+PF_API int pf_chars_to_codes(const uint8_t* d_chars, int64_t ld, int64_t n_sites, int64_t n_samples,
+                             uint8_t* d_codes, int64_t ldc, int32_t* d_line_info, void* stream);
+
 /* Exclusive scan of PF_LINE_COLS over lines -> gather rows. d_rows[c] = source row of matrix
  * column c (SNP: line index; SV: 2*line + which). If require_fit != 0 SNP lines whose
  * FITS2BIT bit is clear are left out (and counted in h_summary[2]).

@@ -154,8 +154,14 @@ class RunCmd:
         tool = self.tree_software
         if tool in ("treebest", "nj"):
             if self._packed is None:
-                print("built_tree with a GPU tree needs the genotypes packed by convert_vcf_to_seq / snp_tree")
-                sys.exit(1)
+                # called on a file alone (the reference's contract): re-read the character matrix
+                from .alignment import load_alignment
+                from .vcf import VcfFormatError
+                try:
+                    self._packed = load_alignment(self.engine(), infile, non_biallelic=self.non_biallelic)
+                except VcfFormatError as e:
+                    print(e)
+                    sys.exit(1)
             out = f"{outpath}/{basename}_treebest.NHX" if tool == "treebest" else f"{outpath}/{basename}.treefile"
             return self.gpu_tree(self._packed, out, basename)
         if tool == "iqtree":

@@ -52,12 +52,29 @@ class PackedGenotypes:
     h2d_bytes: int = 0
 
 
+def _is_gzip(path: str) -> bool:
+    with open(path, "rb") as f:
+        return f.read(2) == b"\x1f\x8b"
+
+
+def _open_bytes(path: str):
+    """Binary reader of the VCF text. gzip / bgzip files (``.vcf.gz``; not accepted by the reference,
+    SURVEY.md §8(f).1) are inflated on the host while the previous chunk is parsed on the GPU."""
+    if _is_gzip(path):
+        import gzip
+        return gzip.open(path, "rb")
+    return open(path, "rb", buffering=0)
+
+
 def read_header(path: str):
     """Sample names from the first line that starts with ``#CHROM`` (vcftree.py:69-73,
-    99-100). Returns (names, file_size)."""
+    99-100). Returns (names, size bound in bytes of the text)."""
     size = os.path.getsize(path)
+    if _is_gzip(path):
+        # uncompressed size is unknown up front: bound it generously (VCF text rarely beats 40:1)
+        size = size * 64 + (1 << 20)
     names = None
-    with open(path, "rb") as f:
+    with _open_bytes(path) as f:
         for raw in f:
             if raw.startswith(b"#CHROM"):
                 names = raw.decode("utf-8", "replace").strip().split()[9:]
@@ -90,8 +107,9 @@ class _ChunkReader:
         try:
             carry = b""
             done = 0
-            with open(self.path, "rb", buffering=0) as f:
-                while done < self.size or carry:
+            eof = False
+            with _open_bytes(self.path) as f:
+                while not eof or carry:
                     i = self.free.get()
                     if i is None:
                         return
@@ -103,13 +121,14 @@ class _ChunkReader:
                         arr[:k] = np.frombuffer(carry, dtype=np.uint8)
                     filled = k
                     mv = memoryview(arr)
-                    while filled < self.buf_bytes and done < self.size:
+                    while filled < self.buf_bytes and not eof:
                         got = f.readinto(mv[filled:])
                         if not got:
+                            eof = True
                             break
                         filled += got
                         done += got
-                    if done >= self.size:
+                    if eof:
                         cut = filled                       # last chunk: take everything
                     else:
                         tail = arr[max(0, filled - (1 << 20)):filled]
