@@ -347,18 +347,22 @@ def run_ours(args):
         # tensor-core indicator GEMM: 2 int8 multiply-accumulates per unordered pair per site
         bf16 = peaks.get("bf16_tflops", 1590.0)
         peak_tops = 2.0 * bf16                      # dense int8 = 2 x dense bf16 on the same tensor cores
-        macs = 2.0 * pair_sites(n, my_sites)
+        launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (VV, HV, VH) ran too
+        macs_per = 5.0 if launches == 2 else 2.0
+        macs = macs_per * pair_sites(n, my_sites)
         achieved_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (int8)",
                     "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES_TC,
                     "kernel": "pair_counts_tc_kernel (tcgen05 kind::i8) + planes_to_nib4_kernel",
                     "kernel_ms": counts_ms,
-                    "ops_per_pair_site": {"int8_mac": 2},
-                    "frac_of_popcount_kernel_roofline": achieved_pw / min(lop3_ops / 4.0, popc_ops / 1.0),
+                    "ops_per_pair_site": {"int8_mac": macs_per}, "gemm_launches": launches,
+                    "frac_of_popcount_kernel_roofline": achieved_pw / (min(lop3_ops / 4.0, popc_ops / 1.0) if miss == 0
+                                                                       else plain_popc_peak_pw),
                     "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
                     "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no int8 entry; nominal dense "
                                    "int8 is 4500 TOP/s)" % ("of measured" if peaks else "of fallback 1590"),
-                    "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'); the kernel "
+                    "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 5 MAC with "
+                            "sample-specific missingness: + v.v', h.v', v.h'); the kernel "
                             "also computes ~13% redundant pairs in tiles that straddle the diagonal. kernel_ms "
                             "includes the planes -> 4-bit operand stream conversion and one stream synchronise"}
     else:
@@ -409,7 +413,7 @@ def run_ours(args):
                    "l2": "inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (my_sites * ld / 1e9),
                    "pair_counts_variant": ran_variant[0], "pair_counts_variant_requested": args.variant, "seed": SEED},
         "nj_seconds": stages_ms["nj"] * 1e-3, "stages_ms": stages_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (5 if ran_variant[0] == 3 else 4) * args.steps,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": ((4 + getattr(eng, "tc_launches", 1)) if ran_variant[0] == 3 else 4) * args.steps,
         "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), file=args.out, flush=True)

@@ -186,16 +186,18 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
                           int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
                           int variant, void* stream);
 
-/* Tensor-core variant of pf_pair_counts (tcgen05 kind::i8 indicator GEMM; csrc/pair_counts_tc.cu).
- * Applies when every site of the word range is genotyped in all samples or in none (no mixed
- * missingness); then it ACCUMULATES the same V / D1 / D2 as pf_pair_counts and sets *h_used = 1.
- * Otherwise it adds nothing, sets *h_used = 0 and the caller runs pf_pair_counts.
+/* Tensor-core variant of pf_pair_counts (tcgen05 kind::i8 indicator GEMMs; csrc/pair_counts_tc.cu).
+ * ACCUMULATES the same V / D1 / D2 as pf_pair_counts. *h_used: 1 = one GEMM launch (every site of the
+ * word range genotyped in all samples or in none), 2 = two launches (genotypes missing in some samples
+ * only; taken when allow_general != 0), 0 = declined (allow_general == 0 and such missingness exists):
+ * nothing was added and the caller runs pf_pair_counts.
  * d_work: pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin) bytes of scratch (the
  * 4-bit operand stream). Synchronises `stream` once (reads the missingness flag). */
 PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_range);
 PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_t n_words,
                              int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
-                             void* d_work, int64_t work_bytes, int* h_used, void* stream);
+                             void* d_work, int64_t work_bytes, int allow_general, int* h_used,
+                             void* stream);
 
 /* Diagnostic for the tensor-core kernel: enable/disable role-level wait-cycle accounting and fetch
  * (then clear) the 16 counters accumulated since the last call; see csrc/pair_counts_tc.cu. */

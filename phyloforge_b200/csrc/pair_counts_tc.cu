@@ -1,21 +1,24 @@
-// Tensor-core variant of the all-pairs genotype counts: an int8 indicator GEMM on tcgen05
+// Tensor-core variant of the all-pairs genotype counts: int8 indicator GEMMs on tcgen05
 // (BASELINE.json north star: "an int8 tcgen05 indicator-GEMM variant kept only if ncu shows it
-// beats popcount"). Same arithmetic as pair_counts.cu, restated as two integer matrix products:
+// beats popcount" — it does, 3.7x on the 3,000 x 10M workload). Same arithmetic as pair_counts.cu,
+// restated as integer matrix products over the site axis. Per genotype:
+//   x = g - 1 in {-1, 0, +1} (0 for het and missing), h = 1 if homozygous, v = 1 if genotyped.
+//   XX = sum x_i x_j = n00 + n22 - n02      HH = sum h_i h_j = n00 + n22 + n02
+//   VV = sum v_i v_j = V                    HV = sum h_i v_j,  VH = sum v_i h_j
+//   D2 = n02 = (HH - XX) / 2                het-vs-hom sites = HV + VH - 2 HH        D1 = that + D2
+// Exact: int8 x int8 products accumulate in int32 in TMEM. Two kernel modes share one body:
+//   mode 0  XX and HH on 128 x 192 tiles. When every site is genotyped in all samples or in none
+//           (no sample-specific missingness) this is all that is needed: HV = |h_i|, VH = |h_j| and V
+//           are per-sample / global numbers the converter already has.
+//   mode 1  VV, HV and VH on 128 x 128 tiles, run in addition when genotypes are missing in some
+//           samples only. The two launches add their linear pieces into the same int32 matrices.
 //
-//   x = g - 1 in {-1, 0, +1} (0 for het and missing),  h = 1 for a homozygous genotype else 0
-//   P = sum_s x_i x_j = n00 + n22 - n02          Q = sum_s h_i h_j = n00 + n22 + n02
-//   D2 = n02 = (Q - P) / 2        het-vs-hom sites = |h_i| + |h_j| - 2 Q        D1 = that + D2
-//
-// valid when every site is genotyped in all samples or in none (the no-missing-data case, where V
-// is the same number for every pair); pf_pair_counts_tc reports otherwise and the caller uses the
-// popcount kernel. Exact: int8 x int8 products accumulate in int32 in TMEM.
-//
-// Data flow per CTA (one 128 x 192 sample tile pair, a contiguous range of 32-site words):
-//   "nib4" operand stream (4 bits per genotype, produced once per call by planes_to_nib4):
-//   global --TMA bulk copies--> raw ring --10 expansion warps: PRMT nibble -> int8 (x and h)-->
-//   A rows straight into TMEM (tcgen05.st), B rows into canonical K-major UMMA tiles in shared memory
-//   --tcgen05.mma kind::i8, A from TMEM, B from shared memory (1 thread)--> 2 x 192 TMEM accumulator
-//   columns --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
+// Data flow per CTA (one sample tile pair, a contiguous range of 32-site words):
+//   "nib4" operand stream (4 bits per genotype, produced once per call by planes_to_nib4; a nibble is
+//   directly a PRMT selector) --TMA bulk copies--> raw ring --expansion warps (thread = sample row):
+//   PRMT nibble -> int8 planes--> A rows straight into TMEM (tcgen05.st), B rows into canonical K-major
+//   UMMA tiles in shared memory --tcgen05.mma kind::i8, A from TMEM, B from shared memory (1 thread)-->
+//   TMEM accumulator columns --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
 // The kernel is bound by shared-memory bandwidth (ncu: LSU wavefronts + tensor operand reads), which
 // is why the A operand bypasses shared memory. (Reading the operand stream straight from global memory
 // with register prefetch instead of the TMA ring was measured 15% slower; kept as a TMA ring.)
@@ -25,26 +28,42 @@
 namespace {
 
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
-constexpr int TC_J = 192;            // columns (MMA N); the B operand is expanded into shared memory
-constexpr int TC_ROWS = TC_I + TC_J; // sample rows expanded per word
-constexpr int TC_PF = TC_ROWS / PF_TILE;  // 64-sample tiles of the operand stream per step: 2 (I) + 3 (J)
 constexpr int STEP_WORDS = 2;        // words per pipeline step (one raw stage feeds one expanded stage)
 constexpr int RAW_WORDS = STEP_WORDS;
 constexpr int RAW_STAGES = 6;
 constexpr int EXP_STAGES = 4;
-constexpr int RAW_STAGE_BYTES = RAW_WORDS * TC_ROWS * 16;      // 10 KB
-constexpr int EXP_WORD_BYTES = TC_J * 32 * 2;                  // x and h tiles of B for one word: 12 KB
-constexpr int EXP_STAGE_BYTES = STEP_WORDS * EXP_WORD_BYTES;   // 24 KB
-constexpr int EXP_BX = 0, EXP_BH = TC_J * 32;
-// TMEM columns: P accumulators [0, 192), Q accumulators [192, 384), A operand staging [384, 512):
-// per in-flight word 8 columns of x and 8 of h (32 K-bytes per row = 8 x 32-bit columns)
-constexpr int TMEM_P = 0, TMEM_Q = TC_J, TMEM_A = 2 * TC_J;
-constexpr int TC_A_WARPS = TC_I / 32, TC_B_WARPS = TC_J / 32;
-constexpr int TC_EXP_WARPS = TC_A_WARPS + TC_B_WARPS;          // 10: one sample row per thread
-constexpr int TC_THREADS = (TC_EXP_WARPS + 2) * 32;
+constexpr int TMEM_A_COLS = 16;      // per in-flight word: 8 columns per A plane (32 K-bytes per row)
 constexpr uint32_t POOL_X = 0x000100ffu;  // code 0 -> -1, 1 -> 0, 2 -> +1, 3 -> 0
 constexpr uint32_t POOL_H = 0x00010001u;  // code 0 -> 1, 1 -> 0, 2 -> 1, 3 -> 0
+constexpr uint32_t POOL_V = 0x00010101u;  // code 0, 1, 2 -> 1, 3 -> 0
 constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
+
+// per-mode geometry: planes 0 / 1 of both operands, accumulator count, tile width
+template <int MODE> struct TcCfg;
+template <> struct TcCfg<0> {   // planes: 0 = x, 1 = h; products XX (acc 0), HH (acc 1)
+  static constexpr int J = 192, NPROD = 2;
+  static constexpr uint32_t POOL0 = POOL_X, POOL1 = POOL_H;
+};
+template <> struct TcCfg<1> {   // planes: 0 = h, 1 = v; products VV (acc 0), HV (acc 1), VH (acc 2)
+  static constexpr int J = 128, NPROD = 3;
+  static constexpr uint32_t POOL0 = POOL_H, POOL1 = POOL_V;
+};
+template <int MODE> struct TcGeo {
+  using C = TcCfg<MODE>;
+  static constexpr int J = C::J;                               // columns (MMA N); B operand in shared memory
+  static constexpr int ROWS = TC_I + J;                        // sample rows expanded per word
+  static constexpr int PF = ROWS / PF_TILE;                    // 64-sample tiles of the stream per step
+  static constexpr int RAW_STAGE_BYTES = RAW_WORDS * ROWS * 16;
+  static constexpr int EXP_WORD_BYTES = J * 32 * 2;            // both planes of B for one word
+  static constexpr int EXP_STAGE_BYTES = STEP_WORDS * EXP_WORD_BYTES;
+  static constexpr int EXP_B0 = 0, EXP_B1 = J * 32;
+  static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
+  static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
+  static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
+  static constexpr size_t SMEM = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES +
+                                 static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
+  static_assert(TMEM_A + EXP_STAGES * STEP_WORDS * TMEM_A_COLS <= 512, "TMEM columns");
+};
 
 // ------------------------------------------------------------------ planes -> nib4
 __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> 8 nibbles
@@ -109,19 +128,18 @@ bool g_tc_prof_enabled = false;
 
 struct TcParams {
   const uint4* nib4;      // [n_tiles_padded][n_local][64] uint4
-  const uint32_t* all_v;  // [n_local] valid-site mask shared by all samples
+  const uint32_t* all_v;  // [n_local] valid-site mask of sample 0 (= of every sample when uniform)
   int64_t n_local;        // words in the range
   int64_t n_samples;
   int32_t* counts;        // [3][n_samples][ld]
   int64_t ld;
   int n_itiles;           // ceil(n_samples / 128)
-  int n_jtiles;           // ceil(n_samples / 256)
+  int n_jtiles;           // ceil(n_samples / J)
   int n_tilepairs;
   int words_per_split;
-  const int* flags;       // flags[0] != 0: validity is not uniform -> results must not be used
-  const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split
+  const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split (mode 0, uniform)
   int64_t hsum_ld;
-  int prof;               // accumulate wait cycles per role into g_tc_prof
+  int general;            // mode 0 only: 1 = sample-specific missingness, mode 1 supplies V and HV + VH
 };
 
 // PRMT as the hardware does it (the __byte_perm intrinsic masks the selector first): byte k of the
@@ -133,16 +151,17 @@ __device__ __forceinline__ uint32_t prmt(uint32_t pool, uint32_t sel) {
   return r;
 }
 
-// one sample row x one 32-site word: 16 bytes of nibble codes -> 32 int8 x-values and 32 int8 h-values
-__device__ __forceinline__ void expand_word(const uint4& nb, uint32_t (&xs)[8], uint32_t (&hs)[8]) {
+// one sample row x one 32-site word: 16 bytes of nibble codes -> 32 int8 values of each of the two planes
+template <uint32_t POOL0, uint32_t POOL1>
+__device__ __forceinline__ void expand_word(const uint4& nb, uint32_t (&p0)[8], uint32_t (&p1)[8]) {
   const uint32_t q[4] = {nb.x, nb.y, nb.z, nb.w};
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     const uint32_t hi = q[m] >> 16;
-    xs[2 * m] = prmt(POOL_X, q[m]);
-    xs[2 * m + 1] = prmt(POOL_X, hi);
-    hs[2 * m] = prmt(POOL_H, q[m]);
-    hs[2 * m + 1] = prmt(POOL_H, hi);
+    p0[2 * m] = prmt(POOL0, q[m]);
+    p0[2 * m + 1] = prmt(POOL0, hi);
+    p1[2 * m] = prmt(POOL1, q[m]);
+    p1[2 * m + 1] = prmt(POOL1, hi);
   }
 }
 
@@ -151,37 +170,40 @@ __device__ __forceinline__ uint32_t unit_off(int r, int kh) {
   return static_cast<uint32_t>((r >> 3) * 256 + kh * 128 + (r & 7) * 16);
 }
 
-template <bool PROF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int MODE, bool PROF>
+__global__ void __launch_bounds__(TcGeo<MODE>::THREADS, 1)
 pair_counts_tc_kernel(const TcParams P) {
+  using G = TcGeo<MODE>;
+  using C = TcCfg<MODE>;
+  constexpr int J = G::J;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
   __shared__ __align__(8) uint64_t exp_full[EXP_STAGES], exp_empty[EXP_STAGES];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t s_tmem;
-  __shared__ int s_hcount[TC_ROWS];
+  __shared__ int s_hcount[G::ROWS];
   __shared__ int s_valid_sites;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // shared-window addresses, computed once
   const uint32_t raw_a = umma::smem_addr(smem);                                   // RAW_STAGES x RAW_STAGE_BYTES
-  const uint32_t exp_a = raw_a + RAW_STAGES * RAW_STAGE_BYTES;                    // EXP_STAGES x EXP_STAGE_BYTES (B tiles)
+  const uint32_t exp_a = raw_a + RAW_STAGES * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (B tiles)
   const uint32_t raw_full_a = umma::smem_addr(raw_full), raw_empty_a = umma::smem_addr(raw_empty);
   const uint32_t exp_full_a = umma::smem_addr(exp_full), exp_empty_a = umma::smem_addr(exp_empty);
   const uint32_t done_a = umma::smem_addr(&done_bar);
 
-  // work item: (tile pair, split). I-tile ti (128 rows) pairs with the J-tiles (192 columns) that
-  // reach its first row: tj >= floor(128 ti / 192)
+  // work item: (tile pair, split). I-tile ti (128 rows) pairs with the J-tiles that reach its first
+  // row: tj >= floor(128 ti / J)
   const int pair = blockIdx.x % P.n_tilepairs;
   const int split = blockIdx.x / P.n_tilepairs;
   int ti = 0, rem = pair;
   while (true) {
-    const int cnt = P.n_jtiles - (2 * ti) / 3;
+    const int cnt = P.n_jtiles - (TC_I * ti) / J;
     if (rem < cnt) break;
     rem -= cnt;
     ++ti;
   }
-  const int tj = (2 * ti) / 3 + rem;
+  const int tj = (TC_I * ti) / J + rem;
   const int64_t w_begin = static_cast<int64_t>(split) * P.words_per_split;
   const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
   const int n_wordsteps = static_cast<int>(w_end - w_begin);
@@ -192,10 +214,10 @@ pair_counts_tc_kernel(const TcParams P) {
   if (tid == 32) {
     for (int s = 0; s < RAW_STAGES; ++s) {
       umma::mbar_init(&raw_full[s], 1);
-      umma::mbar_init(&raw_empty[s], TC_EXP_WARPS);
+      umma::mbar_init(&raw_empty[s], G::EXP_WARPS);
     }
     for (int e = 0; e < EXP_STAGES; ++e) {
-      umma::mbar_init(&exp_full[e], TC_EXP_WARPS);
+      umma::mbar_init(&exp_full[e], G::EXP_WARPS);
       umma::mbar_init(&exp_empty[e], 1);
     }
     umma::mbar_init(&done_bar, 1);
@@ -207,15 +229,16 @@ pair_counts_tc_kernel(const TcParams P) {
   umma::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
 
-  if (warp == TC_EXP_WARPS) {
-    // ===== TMA producer: raw nib4 words of the 2 + 3 sample tiles of this tile pair =====
+  if (warp == G::EXP_WARPS) {
+    // ===== TMA producer: raw nib4 words of the 64-sample tiles of this tile pair =====
     if (lane == 0) {
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
-      const uint4* src_tile[TC_PF];
+      const uint4* src_tile[G::PF];
 #pragma unroll
-      for (int k = 0; k < TC_PF; ++k) {
-        const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k) : (3 * static_cast<int64_t>(tj) + (k - 2));
+      for (int k = 0; k < G::PF; ++k) {
+        const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k)
+                                    : ((J / PF_TILE) * static_cast<int64_t>(tj) + (k - 2));
         src_tile[k] = P.nib4 + (pft * P.n_local + w_begin) * 64;
       }
       int stage = 0;
@@ -228,11 +251,11 @@ pair_counts_tc_kernel(const TcParams P) {
         }
         const int kw = min(RAW_WORDS, n_wordsteps - st * RAW_WORDS);
         const uint32_t bytes_per_tile = static_cast<uint32_t>(kw) * 64 * 16;
-        umma::mbar_expect_tx_a(raw_full_a + stage * 8, bytes_per_tile * TC_PF);
-        const uint32_t dst = raw_a + stage * RAW_STAGE_BYTES;
-        // stage layout: [pf_tile 0..4][word][64 samples][16 B]; pf tiles 0,1 = I rows, 2..4 = J rows
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, bytes_per_tile * G::PF);
+        const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES;
+        // stage layout: [pf_tile][word][64 samples][16 B]; pf tiles 0,1 = I rows, the rest = J rows
 #pragma unroll
-        for (int k = 0; k < TC_PF; ++k)
+        for (int k = 0; k < G::PF; ++k)
           umma::bulk_g2s_a(dst + k * (RAW_WORDS * 64 * 16), src_tile[k] + static_cast<int64_t>(st) * (RAW_WORDS * 64),
                            bytes_per_tile, raw_full_a + stage * 8);
         if (++stage == RAW_STAGES) {
@@ -245,10 +268,10 @@ pair_counts_tc_kernel(const TcParams P) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[6]), static_cast<unsigned long long>(clock64() - t_start));
       }
     }
-  } else if (warp == TC_EXP_WARPS + 1) {
-    // ===== MMA issuer: D[tmem] += A[tmem] * B[smem], two products per word =====
+  } else if (warp == G::EXP_WARPS + 1) {
+    // ===== MMA issuer: D[tmem] += A[tmem] * B[smem] =====
     if (lane == 0) {
-      const uint32_t idesc = umma::idesc_i8(TC_I, TC_J);
+      const uint32_t idesc = umma::idesc_i8(TC_I, J);
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
       int e = 0;
@@ -262,13 +285,19 @@ pair_counts_tc_kernel(const TcParams P) {
 #pragma unroll
         for (int k = 0; k < STEP_WORDS; ++k) {
           if (k < kw) {
-            const uint32_t base = exp_a + e * EXP_STAGE_BYTES + k * EXP_WORD_BYTES;
-            const uint64_t bx = umma::smem_desc_kmajor_noswizzle(base + EXP_BX, 128, 256);
-            const uint64_t bh = umma::smem_desc_kmajor_noswizzle(base + EXP_BH, 128, 256);
-            const uint32_t a_col = tmem + TMEM_A + (e * STEP_WORDS + k) * 16;
+            const uint32_t base = exp_a + e * G::EXP_STAGE_BYTES + k * G::EXP_WORD_BYTES;
+            const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(base + G::EXP_B0, 128, 256);
+            const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(base + G::EXP_B1, 128, 256);
+            const uint32_t a0 = tmem + G::TMEM_A + (e * STEP_WORDS + k) * TMEM_A_COLS, a1 = a0 + 8;
             const uint32_t acc = (st > 0 || k > 0) ? 1u : 0u;
-            umma::mma_i8_ts(tmem + TMEM_P, a_col, bx, idesc, acc);
-            umma::mma_i8_ts(tmem + TMEM_Q, a_col + 8, bh, idesc, acc);
+            if (MODE == 0) {
+              umma::mma_i8_ts(tmem + 0 * J, a0, b0, idesc, acc);   // XX
+              umma::mma_i8_ts(tmem + 1 * J, a1, b1, idesc, acc);   // HH
+            } else {
+              umma::mma_i8_ts(tmem + 0 * J, a1, b1, idesc, acc);   // VV
+              umma::mma_i8_ts(tmem + 1 * J, a0, b1, idesc, acc);   // HV
+              umma::mma_i8_ts(tmem + 2 * J, a1, b0, idesc, acc);   // VH
+            }
           }
         }
         umma::commit_a(exp_empty_a + e * 8);
@@ -286,15 +315,15 @@ pair_counts_tc_kernel(const TcParams P) {
     }
   } else {
     // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, written straight
-    // into TMEM (their lane quadrant); warps 4-9: the 192 B rows, written to shared memory in the
+    // into TMEM (their lane quadrant); the others: the B rows, written to shared memory in the
     // canonical K-major layout =====
-    const int row = tid;                       // 0 .. 319
+    const int row = tid;
     const int pf = row >> 6, l = row & 63;     // raw stage sub-tile and sample inside it
     const bool is_a = row < TC_I;
     const int r = is_a ? row : row - TC_I;
-    const uint32_t a_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TMEM_A;   // A rows: TMEM lane = row
+    const uint32_t a_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A;   // A rows: TMEM lane = row
     const uint32_t raw_row = raw_a + pf * (RAW_WORDS * 64 * 16) + l * 16;
-    const uint32_t exp_row = exp_a + unit_off(r, 0);                                          // B rows: canonical smem tile
+    const uint32_t exp_row = exp_a + unit_off(r, 0);                                             // B rows: canonical smem tile
     long long t_wraw = 0, t_wemp = 0, t_fence = 0;
     const long long t_start = PROF ? clock64() : 0;
     int stage = 0, e = 0;
@@ -313,33 +342,33 @@ pair_counts_tc_kernel(const TcParams P) {
       __syncwarp();
       if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
       const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
-      const uint32_t src = raw_row + stage * RAW_STAGE_BYTES;
+      const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
       uint4 nb[STEP_WORDS];
 #pragma unroll
       for (int k = 0; k < STEP_WORDS; ++k) nb[k] = umma::lds128(src + k * (64 * 16));   // stale words of a short last step are unused
       if (is_a) {
-        const uint32_t a_col = a_base + e * (STEP_WORDS * 16);
+        const uint32_t a_col = a_base + e * (STEP_WORDS * TMEM_A_COLS);
 #pragma unroll
         for (int k = 0; k < STEP_WORDS; ++k) {
           if (k < kw) {
-            uint32_t xs[8], hs[8];
-            expand_word(nb[k], xs, hs);
-            umma::tmem_st_32x8(a_col + k * 16, xs);
-            umma::tmem_st_32x8(a_col + k * 16 + 8, hs);
+            uint32_t p0[8], p1[8];
+            expand_word<C::POOL0, C::POOL1>(nb[k], p0, p1);
+            umma::tmem_st_32x8(a_col + k * TMEM_A_COLS, p0);
+            umma::tmem_st_32x8(a_col + k * TMEM_A_COLS + 8, p1);
           }
         }
       } else {
-        const uint32_t dst = exp_row + e * EXP_STAGE_BYTES;
+        const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < STEP_WORDS; ++k) {
           if (k < kw) {
-            uint32_t xs[8], hs[8];
-            expand_word(nb[k], xs, hs);
-            const uint32_t d = dst + k * EXP_WORD_BYTES;
-            umma::sts128(d + EXP_BX, xs[0], xs[1], xs[2], xs[3]);
-            umma::sts128(d + EXP_BX + 128, xs[4], xs[5], xs[6], xs[7]);
-            umma::sts128(d + EXP_BH, hs[0], hs[1], hs[2], hs[3]);
-            umma::sts128(d + EXP_BH + 128, hs[4], hs[5], hs[6], hs[7]);
+            uint32_t p0[8], p1[8];
+            expand_word<C::POOL0, C::POOL1>(nb[k], p0, p1);
+            const uint32_t d = dst + k * G::EXP_WORD_BYTES;
+            umma::sts128(d + G::EXP_B0, p0[0], p0[1], p0[2], p0[3]);
+            umma::sts128(d + G::EXP_B0 + 128, p0[4], p0[5], p0[6], p0[7]);
+            umma::sts128(d + G::EXP_B1, p1[0], p1[1], p1[2], p1[3]);
+            umma::sts128(d + G::EXP_B1 + 128, p1[4], p1[5], p1[6], p1[7]);
           }
         }
       }
@@ -372,55 +401,80 @@ pair_counts_tc_kernel(const TcParams P) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 13]), static_cast<unsigned long long>(t_fence));
     }
-    {
-      const int64_t sample = is_a ? (static_cast<int64_t>(ti) * TC_I + r) : (static_cast<int64_t>(tj) * TC_J + r);
+    const bool uniform = (MODE == 0) && !P.general;
+    if (uniform) {
+      // |h_i| of this word range from the converter; V = sites genotyped in (all) samples
+      const int64_t sample = is_a ? (static_cast<int64_t>(ti) * TC_I + r) : (static_cast<int64_t>(tj) * J + r);
       s_hcount[row] = (sample < P.n_samples) ? P.hsum[static_cast<int64_t>(split) * P.hsum_ld + sample] : 0;
-    }
-    // valid (genotyped-in-all-samples) sites of this word range: V for every pair
-    int vs = 0;
-    for (int64_t w = w_begin + tid; w < w_end; w += TC_EXP_WARPS * 32) vs += __popc(P.all_v[w]);
+      int vs = 0;
+      for (int64_t w = w_begin + tid; w < w_end; w += G::EXP_WARPS * 32) vs += __popc(P.all_v[w]);
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, off);
-    if (lane == 0 && vs) atomicAdd(&s_valid_sites, vs);
+      for (int off = 16; off >= 1; off >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, off);
+      if (lane == 0 && vs) atomicAdd(&s_valid_sites, vs);
+    }
     // all expansion warps meet before the epilogue (named barrier 1)
-    asm volatile("bar.sync 1, %0;" ::"r"(TC_EXP_WARPS * 32) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"r"(G::EXP_WARPS * 32) : "memory");
 
     // ===== epilogue: TMEM -> registers -> counts =====
     umma::mbar_wait_a(done_a, 0);
     umma::fence_after_thread_sync();
     const int lane_grp = warp & 3;               // TMEM lanes [32 g, 32 g + 32) are visible to warps with w % 4 == g
     const int grp_rank = warp >> 2;              // rank of this warp among the warps of its lane group
-    const int grp_size = (lane_grp < (TC_EXP_WARPS & 3)) ? (TC_EXP_WARPS / 4 + 1) : (TC_EXP_WARPS / 4);
+    const int grp_size = (lane_grp < (G::EXP_WARPS & 3)) ? (G::EXP_WARPS / 4 + 1) : (G::EXP_WARPS / 4);
     const int i_local = lane_grp * 32 + lane;
     const int64_t i = static_cast<int64_t>(ti) * TC_I + i_local;
-    const int hi = s_hcount[i_local];
+    const int hi = uniform ? s_hcount[i_local] : 0;
     const int v_sites = s_valid_sites;
     const int64_t plane = P.n_samples * P.ld;
     int32_t* V = P.counts;
     int32_t* D1 = P.counts + plane;
     int32_t* D2 = P.counts + 2 * plane;
-    for (int chunk = grp_rank; chunk < TC_J / 32; chunk += grp_size) {
-      uint32_t pv[32], qv[32];
+    for (int chunk = grp_rank; chunk < J / 32; chunk += grp_size) {
       const uint32_t taddr = tmem + (static_cast<uint32_t>(lane_grp * 32) << 16) + chunk * 32;
-      umma::tmem_ld_32x32(taddr + TMEM_P, pv);
-      umma::tmem_ld_32x32(taddr + TMEM_Q, qv);
-      umma::tmem_wait_ld();
-      if (i < P.n_samples) {
+      if (MODE == 0) {
+        uint32_t pv[32], qv[32];
+        umma::tmem_ld_32x32(taddr + 0 * J, pv);
+        umma::tmem_ld_32x32(taddr + 1 * J, qv);
+        umma::tmem_wait_ld();
+        if (i < P.n_samples) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const int j_local = chunk * 32 + c;
-          const int64_t j = static_cast<int64_t>(tj) * TC_J + j_local;
-          if (j >= P.n_samples || j < i) continue;       // each unordered pair once: row <= column
-          const int pp = static_cast<int>(pv[c]), qq = static_cast<int>(qv[c]);
-          const int d2 = (qq - pp) >> 1;
-          const int d1 = hi + s_hcount[TC_I + j_local] - 2 * qq + d2;
-          atomicAdd(V + i * P.ld + j, v_sites);
-          atomicAdd(D1 + i * P.ld + j, d1);
-          atomicAdd(D2 + i * P.ld + j, d2);
-          if (j != i) {
-            atomicAdd(V + j * P.ld + i, v_sites);
-            atomicAdd(D1 + j * P.ld + i, d1);
-            atomicAdd(D2 + j * P.ld + i, d2);
+          for (int c = 0; c < 32; ++c) {
+            const int j_local = chunk * 32 + c;
+            const int64_t j = static_cast<int64_t>(tj) * J + j_local;
+            if (j >= P.n_samples || j < i) continue;       // each unordered pair once: row <= column
+            const int xx = static_cast<int>(pv[c]), hh = static_cast<int>(qv[c]);
+            const int d2 = (hh - xx) >> 1;
+            // uniform: D1 = |h_i| + |h_j| - 2 HH + D2; general: HV + VH come from the mode-1 launch
+            const int d1 = (uniform ? hi + s_hcount[TC_I + j_local] : 0) - 2 * hh + d2;
+            if (uniform) atomicAdd(V + i * P.ld + j, v_sites);
+            atomicAdd(D1 + i * P.ld + j, d1);
+            atomicAdd(D2 + i * P.ld + j, d2);
+            if (j != i) {
+              if (uniform) atomicAdd(V + j * P.ld + i, v_sites);
+              atomicAdd(D1 + j * P.ld + i, d1);
+              atomicAdd(D2 + j * P.ld + i, d2);
+            }
+          }
+        }
+      } else {
+        uint32_t vv[32], hv[32], vh[32];
+        umma::tmem_ld_32x32(taddr + 0 * J, vv);
+        umma::tmem_ld_32x32(taddr + 1 * J, hv);
+        umma::tmem_ld_32x32(taddr + 2 * J, vh);
+        umma::tmem_wait_ld();
+        if (i < P.n_samples) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const int64_t j = static_cast<int64_t>(tj) * J + chunk * 32 + c;
+            if (j >= P.n_samples || j < i) continue;
+            const int v = static_cast<int>(vv[c]);
+            const int d1 = static_cast<int>(hv[c]) + static_cast<int>(vh[c]);
+            atomicAdd(V + i * P.ld + j, v);
+            atomicAdd(D1 + i * P.ld + j, d1);
+            if (j != i) {
+              atomicAdd(V + j * P.ld + i, v);
+              atomicAdd(D1 + j * P.ld + i, d1);
+            }
           }
         }
       }
@@ -433,10 +487,14 @@ pair_counts_tc_kernel(const TcParams P) {
 
 constexpr int64_t tc_align(int64_t x) { return (x + 255) / 256 * 256; }
 
+struct TcModePlan {
+  int n_jtiles, pairs;
+  int64_t splits, words_per_split;
+};
 struct TcPlan {
-  int64_t n_local, n_tiles, n_tiles_padded;
-  int n_itiles, n_jtiles, pairs;
-  int64_t splits, words_per_split, hsum_ld;
+  int64_t n_local, n_tiles, n_tiles_padded, hsum_ld;
+  int n_itiles;
+  TcModePlan m[2];
   int64_t nib_bytes, refv_off, flags_off, hsum_off, total;
 };
 
@@ -452,27 +510,43 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   TcPlan L;
   L.n_local = n_local;
   L.n_tiles = pf_ceil_div(n_samples, PF_TILE);
-  L.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, TC_J));
   L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, TC_I));
-  L.n_tiles_padded = static_cast<int64_t>(L.n_jtiles) * (TC_J / PF_TILE);   // whole J tiles of operand stream
-  if (L.n_tiles_padded < 2 * static_cast<int64_t>(L.n_itiles)) L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
-  L.pairs = 0;
-  for (int ti = 0; ti < L.n_itiles; ++ti) L.pairs += L.n_jtiles - (2 * ti) / 3;
-  // split-K: ~20 waves of one CTA per SM, at least 64 words per CTA, boundaries multiples of HSUM_RUN
-  int64_t splits = pf_ceil_div(static_cast<int64_t>(sms) * 20, L.pairs);
-  const int64_t max_splits = pf_ceil_div(n_local, 64);
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  L.words_per_split = pf_ceil_div(pf_ceil_div(n_local, splits), HSUM_RUN) * HSUM_RUN;
-  L.splits = pf_ceil_div(n_local, L.words_per_split);
-  if (L.splits < 1) L.splits = 1;
+  const int widths[2] = {TcCfg<0>::J, TcCfg<1>::J};
+  L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
+  for (int mode = 0; mode < 2; ++mode) {
+    TcModePlan& M = L.m[mode];
+    const int J = widths[mode];
+    M.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, J));
+    const int64_t pf_tiles = static_cast<int64_t>(M.n_jtiles) * (J / PF_TILE);
+    if (pf_tiles > L.n_tiles_padded) L.n_tiles_padded = pf_tiles;      // whole J tiles of operand stream
+    M.pairs = 0;
+    for (int ti = 0; ti < L.n_itiles; ++ti) M.pairs += M.n_jtiles - (TC_I * ti) / J;
+    // split-K: ~20 waves of one CTA per SM, at least 64 words per CTA, boundaries multiples of HSUM_RUN
+    int64_t splits = pf_ceil_div(static_cast<int64_t>(sms) * 20, M.pairs);
+    const int64_t max_splits = pf_ceil_div(n_local, 64);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    M.words_per_split = pf_ceil_div(pf_ceil_div(n_local, splits), HSUM_RUN) * HSUM_RUN;
+    M.splits = pf_ceil_div(n_local, M.words_per_split);
+    if (M.splits < 1) M.splits = 1;
+  }
   L.hsum_ld = L.n_tiles_padded * PF_TILE;
   L.nib_bytes = tc_align(L.n_tiles_padded * n_local * 64 * 16);
   L.refv_off = L.nib_bytes;
   L.flags_off = L.refv_off + tc_align(n_local * 4);
   L.hsum_off = L.flags_off + 256;
-  L.total = L.hsum_off + tc_align(L.splits * L.hsum_ld * 4);
+  L.total = L.hsum_off + tc_align(L.m[0].splits * L.hsum_ld * 4);
   return L;
+}
+
+template <int MODE>
+cudaError_t tc_launch(const TcParams& P, int64_t grid, cudaStream_t s) {
+  using G = TcGeo<MODE>;
+  auto kernel = g_tc_prof_enabled ? pair_counts_tc_kernel<MODE, true> : pair_counts_tc_kernel<MODE, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM));
+  if (e != cudaSuccess) return e;
+  kernel<<<static_cast<unsigned>(grid), G::THREADS, G::SMEM, s>>>(P);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -484,7 +558,7 @@ PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_r
 
 PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_t n_words, int64_t word_begin,
                              int64_t word_end, int32_t* d_counts, int64_t ld, void* d_work, int64_t work_bytes,
-                             int* h_used, void* stream) {
+                             int allow_general, int* h_used, void* stream) {
   PF_TRY_BEGIN
   if (!d_planes || !d_counts || !d_work || !h_used || n_samples <= 0 || ld < n_samples || word_begin < 0 ||
       word_end < word_begin || word_end > n_words)
@@ -508,19 +582,20 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   int* hsum = reinterpret_cast<int*>(w + L.hsum_off);
 
   PF_CUDA(cudaMemsetAsync(flags, 0, 256, s));
-  PF_CUDA(cudaMemsetAsync(hsum, 0, static_cast<size_t>(L.splits * L.hsum_ld) * 4, s));
+  PF_CUDA(cudaMemsetAsync(hsum, 0, static_cast<size_t>(L.m[0].splits * L.hsum_ld) * 4, s));
   {
     const int64_t n_runs = pf_ceil_div(n_local, HSUM_RUN);
     const int64_t threads = L.n_tiles_padded * n_runs * 64;
     planes_to_nib4_kernel<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
         d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded, nib4, ref_v, flags, hsum,
-        L.words_per_split, L.hsum_ld);
+        L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
   }
   int h_flags = 0;
   PF_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, s));
   PF_CUDA(cudaStreamSynchronize(s));
-  if (h_flags != 0) return PF_OK;   // mixed missingness: *h_used stays 0, nothing was added to d_counts
+  const int general = h_flags != 0 ? 1 : 0;     // some genotypes are missing in some samples only
+  if (general && !allow_general) return PF_OK;  // *h_used stays 0, nothing was added to d_counts
 
   TcParams P;
   P.nib4 = nib4;
@@ -530,21 +605,19 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   P.counts = d_counts;
   P.ld = ld;
   P.n_itiles = L.n_itiles;
-  P.n_jtiles = L.n_jtiles;
-  P.n_tilepairs = L.pairs;
-  P.flags = flags;
   P.hsum = hsum;
   P.hsum_ld = L.hsum_ld;
-  P.words_per_split = static_cast<int>(L.words_per_split);
-  P.prof = g_tc_prof_enabled ? 1 : 0;
-  const int64_t grid = L.splits * L.pairs;
-  if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
-  const size_t smem = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES + static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
-  auto kernel = g_tc_prof_enabled ? pair_counts_tc_kernel<true> : pair_counts_tc_kernel<false>;
-  PF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kernel<<<static_cast<unsigned>(grid), TC_THREADS, smem, s>>>(P);
-  PF_CUDA(cudaGetLastError());
-  *h_used = 1;
+  P.general = general;
+  for (int mode = 0; mode < (general ? 2 : 1); ++mode) {
+    const TcModePlan& M = L.m[mode];
+    P.n_jtiles = M.n_jtiles;
+    P.n_tilepairs = M.pairs;
+    P.words_per_split = static_cast<int>(M.words_per_split);
+    const int64_t grid = M.splits * M.pairs;
+    if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
+    PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
+  }
+  *h_used = general ? 2 : 1;
   return PF_OK;
   PF_TRY_END
 }
@@ -552,7 +625,8 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
 // Diagnostic: enable role-level cycle accounting in the tensor-core kernel and read it back.
 // h_out16: [0] MMA thread cycles waiting for expanded operands, [1] MMA thread total, [2..4] an A-row
 // expansion warp: waiting for raw data / waiting for a free stage / total, [5] TMA producer waiting,
-// [6] producer total, [8] pipeline steps, [9..11] a B-row expansion warp (as [2..4]); summed over CTAs.
+// [6] producer total, [8] pipeline steps, [9..11] a B-row expansion warp (as [2..4]), [12] / [13] fence
+// cycles of the A-row / B-row warp; summed over CTAs.
 PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16) {
   PF_TRY_BEGIN
   if (h_out16) PF_CUDA(cudaMemcpyFromSymbol(h_out16, g_tc_prof, sizeof(long long) * 16));

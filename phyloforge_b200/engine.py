@@ -135,25 +135,23 @@ class Engine:
         return out[:, :n_rows]
 
     # pair-count kernel variants (include/phyloforge_b200.h): 1 plain popcount, 2 carry-save popcount,
-    # 3 tcgen05 int8 indicator GEMM (falls back to 2 when genotypes are missing in some samples only);
-    # 0 = auto: 3 when the sample count fills a 128 x 256 tensor-core tile reasonably, else 2.
+    # 3 tcgen05 int8 indicator GEMMs (one launch; a second one when genotypes are missing in some
+    # samples only); 0 = auto: 3 when the sample count fills a 128 x 192 tensor-core tile reasonably,
+    # else 2.
     TC_MIN_SAMPLES = 192
 
     def pair_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, counts: torch.Tensor,
-                    word_begin: int = 0, word_end: int | None = None, variant: int = 0) -> int:
+                    word_begin: int = 0, word_end: int | None = None, variant: int = 0,
+                    tc_general: bool = True) -> int:
         """counts[3, n, n] int32 += V / D1 / D2 over words [word_begin, word_end). Returns the
-        variant that ran."""
+        variant that ran. tc_general=False makes variant 3 decline data with sample-specific
+        missingness (the popcount kernel then runs); self.tc_launches = GEMM launches of the last
+        variant-3 call."""
         if word_end is None:
             word_end = n_words
         assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
-        auto = variant == 0
-        if auto:
-            # after the tensor-core path declined (genotypes missing in some samples only) the next
-            # calls of a chunked run would decline too: skip the attempt for a while
-            skip = getattr(self, "_tc_skip", 0)
-            if skip > 0:
-                self._tc_skip = skip - 1
-            variant = 3 if (n_samples >= self.TC_MIN_SAMPLES and skip == 0) else 2
+        if variant == 0:
+            variant = 3 if n_samples >= self.TC_MIN_SAMPLES else 2
         if variant == 3:
             need = int(self.lib.pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin))
             work = getattr(self, "_tc_work", None)
@@ -163,11 +161,10 @@ class Engine:
             used = C.c_int(0)
             check(self.lib.pf_pair_counts_tc(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                              counts.data_ptr(), counts.stride(1), work.data_ptr(), work.numel(),
-                                             C.byref(used), _stream_ptr()))
+                                             1 if tc_general else 0, C.byref(used), _stream_ptr()))
+            self.tc_launches = used.value
             if used.value:
                 return 3
-            if auto:
-                self._tc_skip = 64
             variant = 2
         check(self.lib.pf_pair_counts(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))

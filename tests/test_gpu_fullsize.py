@@ -98,6 +98,17 @@ def test_config5_10000x5M_missing_row_subset(engine):
     assert bool((D2 <= D1).all()) and bool((D1 <= V).all())
     rows = np.sort(np.random.default_rng(5).choice(n, 40, replace=False))
     _subset_check(engine, n, m, miss, counts, rows)
+    # the two independent implementations (tcgen05 indicator GEMMs, popcount) agree on whole matrices
+    k = 1 << 19
+    codes = engine.synth_codes(n, 12345 * 32, k, seed=42, miss_ppm=miss)
+    nw = k // 32
+    planes = engine.alloc_planes(n, nw)
+    engine.pack_codes(codes, n, planes, nw)
+    a, b = engine.alloc_counts(n), engine.alloc_counts(n)
+    assert engine.pair_counts(planes, n, nw, a, variant=3) == 3 and engine.tc_launches == 2
+    assert engine.pair_counts(planes, n, nw, b, variant=2) == 2
+    assert torch.equal(a, b)
+    del a, b, planes, codes
     names = [f"s{i}" for i in range(n)]
     res = engine.tree_from_counts(counts, names, keep=False)
     tree = treecmp.parse_newick(res.newick)

@@ -227,12 +227,36 @@ def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
     assert engine.pair_counts(planes, n, nw, parts, word_begin=0, word_end=cut, variant=3) == 3
     assert engine.pair_counts(planes, n, nw, parts, word_begin=cut, word_end=nw, variant=3) == 3
     assert torch.equal(parts, counts)
+    assert engine.tc_launches == 1
     codes[5, 1] = 3                                               # one genotype missing in one sample
     planes, nw = _pack(engine, codes)
     counts = engine.alloc_counts(n)
-    assert engine.pair_counts(planes, n, nw, counts, variant=3) == 2
+    assert engine.pair_counts(planes, n, nw, counts, variant=3, tc_general=False) == 2    # declines -> popcount
     want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
     assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+    counts.zero_()
+    assert engine.pair_counts(planes, n, nw, counts, variant=3) == 3 and engine.tc_launches == 2
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+
+
+@pytest.mark.parametrize("n,m,miss", [(2, 100, 0.3), (64, 32, 0.5), (129, 700, 0.1), (193, 3000, 0.02), (257, 5000, 0.2),
+                                      (385, 2048, 0.9), (1000, 40000, 0.05)])
+def test_pair_counts_tensor_core_general_missingness_bit_exact(engine, n, m, miss):
+    """Genotypes missing in some samples only: the XX/HH launch plus the VV/HV/VH launch == oracle,
+    also over word ranges and when accumulated on top of existing counts."""
+    rng = np.random.default_rng(n * 7 + m)
+    codes = _random_codes(rng, n, m, miss)
+    codes[rng.random(m) < 0.01] = 3
+    planes, nw = _pack(engine, codes)
+    want = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
+    counts = engine.alloc_counts(n)
+    assert engine.pair_counts(planes, n, nw, counts, variant=3) == 3 and engine.tc_launches == 2
+    assert np.array_equal(counts.cpu().numpy().astype(np.int64), want)
+    parts = engine.alloc_counts(n)
+    cut = max(1, nw // 2)
+    engine.pair_counts(planes, n, nw, parts, word_begin=0, word_end=cut, variant=3)
+    engine.pair_counts(planes, n, nw, parts, word_begin=cut, word_end=nw, variant=2)     # mixed with the popcount kernel
+    assert torch.equal(parts, counts)
 
 
 @pytest.mark.parametrize("n,m", [(2, 33), (16, 64), (17, 100), (63, 257), (64, 32), (130, 1000), (500, 4099)])
@@ -301,7 +325,7 @@ def test_kernels_do_not_write_outside_their_buffers(engine):
             import ctypes as C
             used = C.c_int(0)
             check(engine.lib.pf_pair_counts_tc(planes.data_ptr(), n, nw, 0, nw, cview.data_ptr(), ld,
-                                               work[guard:].data_ptr(), work.numel() - 2 * guard, C.byref(used), st))
+                                               work[guard:].data_ptr(), work.numel() - 2 * guard, 1, C.byref(used), st))
             assert used.value == 1
             torch.cuda.synchronize()
             assert bool((work[:guard] == 0xA5).all()) and bool((work[-guard:] == 0xA5).all())
