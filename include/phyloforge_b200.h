@@ -225,4 +225,12 @@ PF_API int64_t pf_nj_work_bytes(int64_t n);
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len,
                  void* d_work, void* stream);
 
+/* Diagnostic: phase accounting of the NJ kernels (nanoseconds of CTA 0 summed over iterations) and a
+ * switch that forces the general kernel. enable: bit 0 = run the instrumented kernels in the following
+ * pf_nj calls, bit 1 = use the general kernel (two grid barriers per iteration) also for matrices the
+ * fast kernel would take. h_out8, fast kernel: [0] scan, [1] CTA reduction + publish, [2] exchange,
+ * [3] update; general kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update,
+ * [3] grid barrier 2. Reading resets the counters. */
+PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
+
 #endif /* PHYLOFORGE_B200_H */

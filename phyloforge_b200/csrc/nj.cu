@@ -11,8 +11,24 @@
 //      row sums updated incrementally with the oracle's exact operation order
 // fp64 throughout with explicit round-to-nearest intrinsics (no FMA contraction).
 //
-// Memory-bound scan of the live upper triangle: ~ 4 n^2 bytes per iteration from L2/HBM
-// (DESIGN.md "Kernels"), plus two grid barriers per iteration.
+// The scan of the live upper triangle (4 n^2 bytes per iteration from L2 / HBM) is the only part
+// that scales; everything else is a chain of dependent memory round trips, so the kernel is built to
+// keep that chain short. Two kernels:
+//
+// nj_fast_kernel (n <= NJ_FAST_MAX_N, the row sums and the new node's distances fit in shared memory)
+//   ONE grid-wide exchange per iteration and no grid barrier:
+//   * every CTA keeps the full row-sum vector, the slot -> physical-row map and the distances of the
+//     node merged last (s_du) in shared memory and updates them redundantly (same operations, same bits);
+//   * CTAs publish their argmin candidate as four 64-bit words {tag | 32 data bits} (each word is
+//     written atomically, the tag validates it: no flag, no fence round trip between data and flag)
+//     and poll everybody else's words; the exchange doubles as the barrier that orders this
+//     iteration's scan before the update writes;
+//   * matrix rows are never overwritten while somebody may still read them: the merged node's row
+//     goes to a spare physical row (the row freed one iteration earlier), slot b takes over the last
+//     slot's physical row by remapping. Column entries are written in place. These writes become
+//     visible with the NEXT exchange; the scan in between takes the affected entries from s_du /
+//     the last slot's column instead ("pending" update).
+// nj_kernel (any n): row sums in global memory when they do not fit, two grid barriers per iteration.
 #include "pf_common.cuh"
 
 #include <cooperative_groups.h>
@@ -22,8 +38,8 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int NJ_THREADS = 1024;
 constexpr int NJ_MAX_BLOCKS = 1024;
+constexpr int NJ_NONE = 0x7fffffff;
 
 struct NjRec {
   double q;
@@ -43,11 +59,387 @@ __device__ __forceinline__ void warp_argmin(double& q, double& dab, int& a, int&
     const double d2 = __shfl_xor_sync(0xffffffffu, dab, off);
     const int a2 = __shfl_xor_sync(0xffffffffu, a, off);
     const int b2 = __shfl_xor_sync(0xffffffffu, b, off);
-    if (rec_less(q2, a2, b2, q, a, b)) {
-      q = q2; dab = d2; a = a2; b = b2;
+    const bool take = rec_less(q2, a2, b2, q, a, b);
+    q = take ? q2 : q;
+    dab = take ? d2 : dab;
+    a = take ? a2 : a;
+    b = take ? b2 : b;
+  }
+}
+
+// optional phase accounting (pf_nj_profile): nanoseconds of CTA 0 per phase, summed over iterations
+__device__ unsigned long long g_nj_prof[8];
+bool g_nj_prof_enabled = false;
+__device__ __forceinline__ unsigned long long nj_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define NJ_MARK(slot)                                                  \
+  if (PROF && blockIdx.x == 0 && threadIdx.x == 0) {                   \
+    const unsigned long long now_ = nj_now();                          \
+    g_nj_prof[slot] += now_ - t_prev;                                  \
+    t_prev = now_;                                                     \
+  }
+
+// initial row sums in the fixed order of pfo_rowsum32 (one warp per row, rows spread over the grid)
+__device__ __forceinline__ void nj_initial_row_sums(const double* __restrict__ D, int64_t ld, int n, int gwarp,
+                                                    int nwarps, int lane, double* r_out) {
+  for (int row = gwarp; row < n; row += nwarps) {
+    const double* rp = D + static_cast<int64_t>(row) * ld;
+    double acc = 0.0;
+#pragma unroll 8
+    for (int k = lane; k < n; k += 32) acc = __dadd_rn(acc, __ldcg(rp + k));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    if (lane == 0) r_out[row] = acc;
+  }
+}
+
+// The update of the previous iteration whose global-memory writes are not visible yet (fast kernel):
+// slot a = the merged node (its distances are in s_du), slot b = took over slot `last` (-1: it did not).
+struct NjPending {
+  int a, b, last;
+};
+
+// ---- argmin scan. Work items = (row a, segment of 32 U columns) of the upper triangle, enumerated
+// row-block major so that every thread meets its candidates in ascending (a, b) order: a strict
+// `q < best` then implements the lexicographic tie rule inside a thread. All U loads of an item are
+// issued before the first use (the loop over candidates is branch-free), so an item costs one memory
+// round trip.
+template <int U, bool VIRT, bool R_SMEM>
+__device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld, const double* spare, int n_phys,
+                                        const int* s_phys, const double* rs, const double* s_du, int na, double n2,
+                                        NjPending pend, int gwarp, int nwarps, int lane, double& bq, double& bd,
+                                        int& ba, int& bb) {
+  constexpr int SEG = 32 * U;
+  const int nseg = (na + SEG - 1) / SEG;
+  int rb = 0, base = 0;
+  int rows = min(SEG, na), segs = nseg;
+  int cnt = rows * segs;
+  int total = 0;
+  for (int k = 0; k < nseg; ++k) total += min(SEG, na - k * SEG) * (nseg - k);
+  for (int item = gwarp; item < total; item += nwarps) {
+    while (item >= base + cnt) {
+      base += cnt;
+      ++rb;
+      rows = min(SEG, na - rb * SEG);
+      segs = nseg - rb;
+      cnt = rows * segs;
+    }
+    const int local = item - base;
+    const int ar = local / segs;
+    const int a = rb * SEG + ar;
+    const int c0 = (rb + (local - ar * segs)) * SEG;
+    double dv[U];
+    if (VIRT && a == pend.a) {
+      // row of the node merged last: its distances are in shared memory
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = c0 + u * 32 + lane;
+        dv[u] = (b > a && b < na) ? s_du[b] : CUDART_INF;
+      }
+    } else {
+      int prow = a;
+      if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
+      const double* rp = (VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld;
+      if (VIRT && pend.b >= c0 && pend.b < c0 + SEG) {
+        // column of the slot that took over the last slot: still in the last slot's column
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int b = c0 + u * 32 + lane;
+          const int col = (b == pend.b) ? pend.last : b;
+          dv[u] = (b > a && b < na) ? __ldcg(rp + col) : CUDART_INF;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int b = c0 + u * 32 + lane;
+          dv[u] = (b > a && b < na) ? __ldcg(rp + b) : CUDART_INF;
+        }
+      }
+      if (VIRT && pend.a > a && pend.a >= c0 && pend.a < c0 + SEG) {
+        const double dua = s_du[a];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (c0 + u * 32 + lane == pend.a) dv[u] = dua;
+      }
+    }
+    const double ra = R_SMEM ? rs[a] : __ldcg(rs + a);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int b = c0 + u * 32 + lane;
+      const int bc = min(b, na - 1);
+      const double rbv = R_SMEM ? rs[bc] : __ldcg(rs + bc);
+      double q = __dmul_rn(n2, dv[u]);
+      q = __dsub_rn(q, ra);
+      q = __dsub_rn(q, rbv);
+      const bool take = q < bq;     // +inf for masked entries and NaN never win
+      bq = take ? q : bq;
+      bd = take ? dv[u] : bd;
+      ba = take ? a : ba;
+      bb = take ? b : bb;
     }
   }
 }
+
+// ===================================================================== fast kernel
+constexpr int NJF_THREADS = 512;
+constexpr int NJF_U = 16;            // 512-column scan items
+constexpr int NJF_K = 8;             // slots per thread and batch of the update
+constexpr int64_t NJ_FAST_MAX_N = 11000;   // 20 n bytes of shared memory
+
+struct NjFastParams {
+  double* D;
+  int64_t ld;
+  int n;
+  int32_t* merge;
+  double* len;
+  double* r0;                 // initial row sums
+  double* spare;              // one extra matrix row (physical row index n)
+  int32_t* node;              // slot -> tree node id; touched by CTA 0 only
+  unsigned long long* xchg;   // [2][gridDim.x][4] tagged words
+};
+
+__device__ __forceinline__ void nj_publish(unsigned long long* slot, double q, int a, int b, unsigned tag) {
+  const unsigned long long qb = static_cast<unsigned long long>(__double_as_longlong(q));
+  const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
+  const unsigned long long w0 = t | (qb & 0xffffffffull), w1 = t | (qb >> 32);
+  const unsigned long long w2 = t | static_cast<unsigned>(a), w3 = t | static_cast<unsigned>(b);
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2), "l"(w2), "l"(w3) : "memory");
+}
+__device__ __forceinline__ void nj_peek(const unsigned long long* slot, unsigned long long (&w)[4]) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(slot) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(slot + 2) : "memory");
+}
+
+struct NjWinner {
+  int a, b;
+  double ra, rb;
+};
+
+template <bool PROF>
+__global__ void __launch_bounds__(NJF_THREADS, 1)
+nj_fast_kernel(const NjFastParams P) {
+  cg::grid_group grid = cg::this_grid();
+  extern __shared__ __align__(16) unsigned char nj_dyn[];
+  __shared__ NjRec s_rec[NJF_THREADS / 32];
+  __shared__ NjWinner s_win;
+
+  double* __restrict__ D = P.D;
+  const int64_t ld = P.ld;
+  const int n = P.n;
+  const int n_pad = (n + 1) & ~1;
+  double* s_r = reinterpret_cast<double*>(nj_dyn);
+  double* s_du = s_r + n_pad;
+  int* s_phys = reinterpret_cast<int*>(s_du + n_pad);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int WARPS = NJF_THREADS / 32;
+  const int gwarp = blockIdx.x * WARPS + warp;
+  const int nwarps = gridDim.x * WARPS;
+  const int gthread = blockIdx.x * NJF_THREADS + tid;
+  const int nthreads = gridDim.x * NJF_THREADS;
+  const int n_cta = static_cast<int>(gridDim.x);
+
+  for (int k = gthread; k < 2 * n_cta * 4; k += nthreads) P.xchg[k] = 0ull;
+  if (blockIdx.x == 0)
+    for (int k = tid; k < n; k += NJF_THREADS) P.node[k] = k;
+  nj_initial_row_sums(D, ld, n, gwarp, nwarps, lane, P.r0);
+  grid.sync();
+  for (int k = tid; k < n; k += NJF_THREADS) {
+    s_r[k] = __ldcg(P.r0 + k);
+    s_phys[k] = k;
+  }
+  __syncthreads();
+  unsigned long long t_prev = PROF ? nj_now() : 0;
+
+  NjPending pend{-1, -1, -1};
+  int spare_row = n;     // physical row index of the spare row (n = the workspace row)
+  int na = n, t = 0;
+  while (na > 3) {
+    // ---- scan
+    const double n2 = static_cast<double>(na - 2);
+    double bq = CUDART_INF, bd = 0.0;
+    int ba = NJ_NONE, bb = NJ_NONE;
+    nj_scan<NJF_U, true, true>(D, ld, P.spare, n, s_phys, s_r, s_du, na, n2, pend, gwarp, nwarps, lane, bq, bd, ba,
+                               bb);
+    warp_argmin(bq, bd, ba, bb);
+    if (lane == 0) s_rec[warp] = NjRec{bq, bd, ba, bb};
+    __syncthreads();
+    NJ_MARK(0)   // scan + waiting for this CTA's slowest warp
+    // ---- exchange: warp 0 publishes this CTA's candidate and collects everybody's
+    if (warp == 0) {
+      NjRec v = (lane < WARPS) ? s_rec[lane] : NjRec{CUDART_INF, 0.0, NJ_NONE, NJ_NONE};
+      warp_argmin(v.q, v.dab, v.a, v.b);
+      const unsigned tag = static_cast<unsigned>(t + 1);
+      unsigned long long* mine = P.xchg + (static_cast<int64_t>(t & 1) * n_cta + blockIdx.x) * 4;
+      if (lane == 0) {
+        // release: this CTA's update writes of the previous iteration (ordered before this point by
+        // the __syncthreads above) become visible with the record
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        nj_publish(mine, v.q, v.a, v.b, tag);
+      }
+      NJ_MARK(1)
+      double wq = CUDART_INF, wd = 0.0;
+      int wa = NJ_NONE, wb = NJ_NONE;
+      const unsigned long long* all = P.xchg + static_cast<int64_t>(t & 1) * n_cta * 4;
+      for (int c0 = 0; c0 < n_cta; c0 += 32 * 4) {
+        // up to four records per lane and round, polled together
+        unsigned long long w[4][4];
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + j * 32 + lane;
+            if (c < n_cta) {
+              nj_peek(all + static_cast<int64_t>(c) * 4, w[j]);
+#pragma unroll
+              for (int x = 0; x < 4; ++x) ok = ok && (static_cast<unsigned>(w[j][x] >> 32) == tag);
+            }
+          }
+        } while (!ok);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c0 + j * 32 + lane;
+          if (c < n_cta) {
+            const double q2 = __longlong_as_double(static_cast<long long>((w[j][0] & 0xffffffffull) | (w[j][1] << 32)));
+            const int a2 = static_cast<int>(static_cast<unsigned>(w[j][2]));
+            const int b2 = static_cast<int>(static_cast<unsigned>(w[j][3]));
+            if (rec_less(q2, a2, b2, wq, wa, wb)) {
+              wq = q2; wa = a2; wb = b2;
+            }
+          }
+        }
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: reads below are ordered after the records were seen
+      warp_argmin(wq, wd, wa, wb);
+      if (lane == 0) {
+        if (wa == NJ_NONE) {   // no finite candidate (NaN / inf input): join slots 0 and 1
+          wa = 0; wb = 1;
+        }
+        s_win = NjWinner{wa, wb, s_r[wa], s_r[wb]};
+      }
+    }
+    __syncthreads();
+    NJ_MARK(2)   // exchange (includes waiting for the slowest CTA)
+
+    // ---- update (every CTA: shared-memory state; the owner of a slot: global memory)
+    const int wa = s_win.a, wb = s_win.b;
+    const double rra = s_win.ra, rrb = s_win.rb;
+    const int last = na - 1;
+    const bool move = (wb != last);
+    const int pwa = s_phys[wa], pwb = s_phys[wb], plast = s_phys[last];
+    const double* row_a = (pwa == n) ? P.spare : D + static_cast<int64_t>(pwa) * ld;
+    const double* row_b = (pwb == n) ? P.spare : D + static_cast<int64_t>(pwb) * ld;
+    double* row_u = (spare_row == n) ? P.spare : D + static_cast<int64_t>(spare_row) * ld;
+    const double dab = __ldcg(row_a + wb);
+    int node_a = 0, node_b = 0, node_l = 0;
+    if (gthread == 0) {
+      node_a = __ldcg(P.node + wa);
+      node_b = __ldcg(P.node + wb);
+      node_l = __ldcg(P.node + last);
+    }
+    for (int k0 = tid; k0 < na; k0 += NJF_THREADS * NJF_K) {
+      double dak[NJF_K], dbk[NJF_K], mv[NJF_K];
+      int prow[NJF_K];
+#pragma unroll
+      for (int j = 0; j < NJF_K; ++j) {
+        const int k = k0 + j * NJF_THREADS;
+        const bool live = k < na && k != wa && k != wb;
+        const bool own = live && ((k >> 5) % n_cta) == static_cast<int>(blockIdx.x);
+        dak[j] = live ? __ldcg(row_a + k) : 0.0;
+        dbk[j] = live ? __ldcg(row_b + k) : 0.0;
+        prow[j] = own ? s_phys[k] : -1;
+        mv[j] = 0.0;
+        if (own && move && k != last) {
+          const double* rk_p = (prow[j] == n) ? P.spare : D + static_cast<int64_t>(prow[j]) * ld;
+          mv[j] = __ldcg(rk_p + last);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NJF_K; ++j) {
+        const int k = k0 + j * NJF_THREADS;
+        if (k >= na || k == wb) continue;
+        if (k == wa) {
+          double ru = __dadd_rn(rra, rrb);
+          ru = __dsub_rn(ru, __dmul_rn(static_cast<double>(na), dab));
+          s_r[wa] = __dmul_rn(0.5, ru);
+          s_du[wa] = 0.0;
+          continue;
+        }
+        double d = __dadd_rn(dak[j], dbk[j]);
+        d = __dsub_rn(d, dab);
+        d = __dmul_rn(0.5, d);
+        double rk = __dsub_rn(s_r[k], dak[j]);
+        rk = __dsub_rn(rk, dbk[j]);
+        rk = __dadd_rn(rk, d);
+        const int slot = (move && k == last) ? wb : k;   // the last live slot moves into slot b
+        s_r[slot] = rk;
+        s_du[slot] = d;
+        if (prow[j] >= 0) {
+          double* rk_p = (prow[j] == n) ? P.spare : D + static_cast<int64_t>(prow[j]) * ld;
+          row_u[slot] = d;         // row of the merged node, in the spare physical row
+          rk_p[wa] = d;            // column a of this node's row
+          if (move && k != last) rk_p[wb] = mv[j];   // column b <- column last
+        }
+      }
+    }
+    if (gthread == 0) {
+      double tt = __dsub_rn(rra, rrb);
+      tt = __ddiv_rn(tt, __dmul_rn(2.0, n2));
+      double la = __dmul_rn(0.5, dab);
+      la = __dadd_rn(la, tt);
+      const double lb = __dsub_rn(dab, la);
+      P.merge[3 * t + 0] = node_a;
+      P.merge[3 * t + 1] = node_b;
+      P.merge[3 * t + 2] = 0;
+      P.len[3 * t + 0] = la;
+      P.len[3 * t + 1] = lb;
+      P.len[3 * t + 2] = 0.0;
+      if (move) P.node[wb] = node_l;
+      P.node[wa] = n + t;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_phys[wa] = spare_row;
+      if (move) s_phys[wb] = plast;
+    }
+    // (the scan below does not read s_phys[wa] / s_phys[wb]: those rows are "pending")
+    pend = NjPending{wa, move ? wb : -1, last};
+    spare_row = pwa;       // free from the next iteration on: everybody has read it by the next exchange
+    --na;
+    ++t;
+    NJ_MARK(3)   // update
+  }
+
+  if (gthread == 0) {
+    // the last three nodes; the final update may still be pending, so read through it
+    auto vread = [&](int x, int y) -> double {   // x < y < 3
+      if (x == pend.a) return s_du[y];
+      if (y == pend.a) return s_du[x];
+      const int pr = s_phys[x];   // thread 0 wrote s_phys itself: already remapped
+      const double* rp = (pr == n) ? P.spare : D + static_cast<int64_t>(pr) * ld;
+      return __ldcg(rp + ((y == pend.b) ? pend.last : y));
+    };
+    const double d01 = vread(0, 1), d02 = vread(0, 2), d12 = vread(1, 2);
+    double l0 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d02), d12));
+    double l1 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d12), d02));
+    double l2 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d02, d12), d01));
+    P.merge[3 * t + 0] = P.node[0];
+    P.merge[3 * t + 1] = P.node[1];
+    P.merge[3 * t + 2] = P.node[2];
+    P.len[3 * t + 0] = l0;
+    P.len[3 * t + 1] = l1;
+    P.len[3 * t + 2] = l2;
+  }
+}
+
+// ===================================================================== general kernel
+constexpr int NJ_THREADS = 1024;
+constexpr int NJ_U = 8;   // 256-column scan items (64 registers per thread)
 
 struct NjParams {
   double* D;
@@ -62,8 +454,7 @@ struct NjParams {
   int r_in_smem;  // the row sums of the live nodes fit in dynamic shared memory
 };
 
-constexpr int NJ_SEG = 512;  // columns of one (row, segment) work item of the argmin scan
-
+template <bool PROF>
 __global__ void __launch_bounds__(NJ_THREADS, 1)
 nj_kernel(const NjParams P) {
   cg::grid_group grid = cg::this_grid();
@@ -83,57 +474,32 @@ nj_kernel(const NjParams P) {
   const int gthread = blockIdx.x * NJ_THREADS + tid;
   const int nthreads = gridDim.x * NJ_THREADS;
 
-  // initial row sums in the fixed order of pfo_rowsum32 (one warp per row)
   for (int s = gthread; s < n; s += nthreads) P.node[s] = s;
-  for (int row = gwarp; row < n; row += nwarps) {
-    const double* rp = D + static_cast<int64_t>(row) * ld;
-    double acc = 0.0;
-#pragma unroll 8
-    for (int k = lane; k < n; k += 32) acc = __dadd_rn(acc, __ldcg(rp + k));
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
-    if (lane == 0) P.r0[row] = acc;
-  }
+  nj_initial_row_sums(D, ld, n, gwarp, nwarps, lane, P.r0);
   grid.sync();
+  unsigned long long t_prev = PROF ? nj_now() : 0;
 
   double* cur = P.r0;
   double* nxt = P.r1;
   int na = n;
   int t = 0;
+  const NjPending none{-1, -1, -1};
   while (na > 3) {
-    // ---- B: Q argmin over the upper triangle, work items = (row, 512-column segment)
-    const double* rs = cur;
+    // ---- B: Q argmin over the upper triangle
     if (P.r_in_smem) {
       for (int k = tid; k < na; k += NJ_THREADS) s_r[k] = __ldcg(cur + k);
       __syncthreads();
-      rs = s_r;
     }
     const double n2 = static_cast<double>(na - 2);
     double bq = CUDART_INF;
     double bd = 0.0;
-    int ba = 0x7fffffff, bb = 0x7fffffff;
-    const int nseg = (na + NJ_SEG - 1) / NJ_SEG;
-    const int items = na * nseg;
-    for (int item = gwarp; item < items; item += nwarps) {
-      const int a = item / nseg;
-      const int sgm = item - a * nseg;
-      const int b_lo = max(a + 1, sgm * NJ_SEG);
-      const int b_hi = min(na, (sgm + 1) * NJ_SEG);
-      if (b_lo >= b_hi) continue;
-      const double* rp = D + static_cast<int64_t>(a) * ld;
-      const double ra = P.r_in_smem ? rs[a] : __ldcg(rs + a);
-#pragma unroll 8
-      for (int b = b_lo + lane; b < b_hi; b += 32) {
-        const double d = __ldcg(rp + b);
-        const double rb = P.r_in_smem ? rs[b] : __ldcg(rs + b);
-        double q = __dmul_rn(n2, d);
-        q = __dsub_rn(q, ra);
-        q = __dsub_rn(q, rb);
-        if (rec_less(q, a, b, bq, ba, bb)) {
-          bq = q; bd = d; ba = a; bb = b;
-        }
-      }
-    }
+    int ba = NJ_NONE, bb = NJ_NONE;
+    if (P.r_in_smem)
+      nj_scan<NJ_U, false, true>(D, ld, nullptr, 0, nullptr, s_r, nullptr, na, n2, none, gwarp, nwarps, lane, bq, bd,
+                                 ba, bb);
+    else
+      nj_scan<NJ_U, false, false>(D, ld, nullptr, 0, nullptr, cur, nullptr, na, n2, none, gwarp, nwarps, lane, bq, bd,
+                                  ba, bb);
     warp_argmin(bq, bd, ba, bb);
     if (lane == 0) s_rec[warp] = NjRec{bq, bd, ba, bb};
     __syncthreads();
@@ -142,18 +508,24 @@ nj_kernel(const NjParams P) {
       warp_argmin(v.q, v.dab, v.a, v.b);
       if (lane == 0) P.rec[blockIdx.x] = v;
     }
+    NJ_MARK(0)   // scan + CTA reduction
     grid.sync();
+    NJ_MARK(1)   // barrier 1 (includes waiting for the slowest CTA's scan)
 
     // ---- C: every CTA reduces the per-CTA records to the same winner, then updates
     if (warp == 0) {
-      NjRec v{CUDART_INF, 0.0, 0x7fffffff, 0x7fffffff};
+      NjRec v{CUDART_INF, 0.0, NJ_NONE, NJ_NONE};
       for (int k = lane; k < static_cast<int>(gridDim.x); k += 32) {
         const NjRec* g = P.rec + k;
         const double q2 = __ldcg(&g->q);
         const double d2 = __ldcg(&g->dab);
         const int a2 = __ldcg(&g->a);
         const int b2 = __ldcg(&g->b);
-        if (rec_less(q2, a2, b2, v.q, v.a, v.b)) v = NjRec{q2, d2, a2, b2};
+        const bool take = rec_less(q2, a2, b2, v.q, v.a, v.b);
+        v.q = take ? q2 : v.q;
+        v.dab = take ? d2 : v.dab;
+        v.a = take ? a2 : v.a;
+        v.b = take ? b2 : v.b;
       }
       warp_argmin(v.q, v.dab, v.a, v.b);
       if (lane == 0) s_best = v;
@@ -161,7 +533,7 @@ nj_kernel(const NjParams P) {
     __syncthreads();
     int wa = s_best.a, wb = s_best.b;
     double dab = s_best.dab;
-    if (wa == 0x7fffffff) {  // no finite candidate (NaN/inf input): join slots 0 and 1
+    if (wa == NJ_NONE) {  // no finite candidate (NaN/inf input): join slots 0 and 1
       wa = 0; wb = 1;
       dab = __ldcg(D + 1);
     }
@@ -193,11 +565,15 @@ nj_kernel(const NjParams P) {
         P.node[wa] = n + t;
         continue;
       }
-      const double dak = __ldcg(ra_p + k), dbk = __ldcg(rb_p + k);
+      const double dak = __ldcg(ra_p + k), dbk = __ldcg(rb_p + k), rk0 = __ldcg(cur + k);
+      // row and column of the last slot separately (identical for a symmetric matrix; the oracle
+      // copies both, so an asymmetric input gives the same bits too)
+      const double mv = (move && k != last) ? __ldcg(rl_p + k) : 0.0;
+      const double mvc = (move && k != last) ? __ldcg(D + static_cast<int64_t>(k) * ld + last) : 0.0;
       double d = __dadd_rn(dak, dbk);
       d = __dsub_rn(d, dab);
       d = __dmul_rn(0.5, d);
-      double rk = __dsub_rn(__ldcg(cur + k), dak);
+      double rk = __dsub_rn(rk0, dak);
       rk = __dsub_rn(rk, dbk);
       rk = __dadd_rn(rk, d);
       if (move && k == last) {
@@ -210,13 +586,14 @@ nj_kernel(const NjParams P) {
         D[static_cast<int64_t>(k) * ld + wa] = d;
         nxt[k] = rk;
         if (move) {
-          const double mv = __ldcg(rl_p + k);
           D[static_cast<int64_t>(wb) * ld + k] = mv;
-          D[static_cast<int64_t>(k) * ld + wb] = mv;
+          D[static_cast<int64_t>(k) * ld + wb] = mvc;
         }
       }
     }
+    NJ_MARK(2)   // winner selection + update
     grid.sync();
+    NJ_MARK(3)   // barrier 2
     double* tmp = cur; cur = nxt; nxt = tmp;
     --na;
     ++t;
@@ -238,6 +615,27 @@ nj_kernel(const NjParams P) {
 
 constexpr int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t NJ_MAX_SMEM_R = 200 * 1024;
+int g_nj_force_general = 0;
+
+template <typename K>
+int nj_launch(K kernel, int threads, size_t smem, int64_t want_blocks, int64_t max_blocks, void* params,
+              cudaStream_t s) {
+  int dev = 0, sms = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  PF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) return pf_fail_code(PF_ERR_CUDA, "pf_nj: kernel does not fit on an SM");
+  int64_t blocks = want_blocks;
+  if (blocks > sms) blocks = sms;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  void* args[] = {params};
+  PF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(static_cast<unsigned>(blocks)),
+                                      dim3(threads), args, smem, s));
+  return PF_OK;
+}
 
 }  // namespace
 
@@ -251,40 +649,68 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
   PF_TRY_BEGIN
   if (!d_dist || !d_merge || !d_len || !d_work || n < 3 || ld < n || n > 0x3fffffff)
     return pf_fail("pf_nj: bad arguments (n=%lld, ld=%lld; n must be >= 3)", (long long)n, (long long)ld);
-  int dev = 0, sms = 0, coop = 0;
+  int dev = 0, coop = 0;
   PF_CUDA(cudaGetDevice(&dev));
-  PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop) return pf_fail_code(PF_ERR_CUDA, "pf_nj: device does not support cooperative launch");
-  const int r_in_smem = (8 * n <= NJ_MAX_SMEM_R) ? 1 : 0;
-  const size_t smem = r_in_smem ? static_cast<size_t>(align_up(8 * n, 16)) : 0;
-  PF_CUDA(cudaFuncSetAttribute(nj_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int per_sm = 0;
-  PF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nj_kernel, NJ_THREADS, smem));
-  if (per_sm < 1) return pf_fail_code(PF_ERR_CUDA, "pf_nj: kernel does not fit on an SM");
-  // enough CTAs to give every warp about two (row, segment) items; fewer CTAs make the two grid
-  // barriers of an iteration cheaper when the matrix is small
-  const int64_t items = n * pf_ceil_div(n, NJ_SEG);
-  int64_t blocks = pf_ceil_div(items, (NJ_THREADS / 32) * 2);
-  if (blocks > sms) blocks = sms;
-  if (blocks > NJ_MAX_BLOCKS) blocks = NJ_MAX_BLOCKS;
-  if (blocks < 1) blocks = 1;
-
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* w = static_cast<char*>(d_work);
+  double* w_r0 = reinterpret_cast<double*>(w);
+  double* w_r1 = reinterpret_cast<double*>(w + align_up(8 * n, 256));
+  int32_t* w_node = reinterpret_cast<int32_t*>(w + 2 * align_up(8 * n, 256));
+  void* w_rec = w + 2 * align_up(8 * n, 256) + align_up(4 * n, 256);
+
+  if (n <= NJ_FAST_MAX_N && !g_nj_force_general) {
+    NjFastParams P;
+    P.D = d_dist;
+    P.ld = ld;
+    P.n = static_cast<int>(n);
+    P.merge = d_merge;
+    P.len = d_len;
+    P.r0 = w_r0;
+    P.spare = w_r1;
+    P.node = w_node;
+    P.xchg = reinterpret_cast<unsigned long long*>(w_rec);   // 2 x blocks x 32 bytes, in the record area
+    const int64_t n_pad = (n + 1) & ~int64_t(1);
+    const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
+    // about two 512-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
+    const int64_t items = n * pf_ceil_div(n, 32 * NJF_U) / 2 + 1;
+    const int64_t blocks = pf_ceil_div(items, (NJF_THREADS / 32) * 2);
+    constexpr int64_t max_blocks = static_cast<int64_t>(sizeof(NjRec)) * NJ_MAX_BLOCKS / (2 * 4 * 8);   // xchg fits in rec
+    return g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true>, NJF_THREADS, smem, blocks, max_blocks, &P, s)
+                             : nj_launch(nj_fast_kernel<false>, NJF_THREADS, smem, blocks, max_blocks, &P, s);
+  }
   NjParams P;
   P.D = d_dist;
   P.ld = ld;
   P.n = static_cast<int>(n);
   P.merge = d_merge;
   P.len = d_len;
-  P.r0 = reinterpret_cast<double*>(w);
-  P.r1 = reinterpret_cast<double*>(w + align_up(8 * n, 256));
-  P.node = reinterpret_cast<int32_t*>(w + 2 * align_up(8 * n, 256));
-  P.rec = reinterpret_cast<NjRec*>(w + 2 * align_up(8 * n, 256) + align_up(4 * n, 256));
-  P.r_in_smem = r_in_smem;
-  void* args[] = {&P};
-  PF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(nj_kernel), dim3(static_cast<unsigned>(blocks)),
-                                      dim3(NJ_THREADS), args, smem, static_cast<cudaStream_t>(stream)));
+  P.r0 = w_r0;
+  P.r1 = w_r1;
+  P.node = w_node;
+  P.rec = static_cast<NjRec*>(w_rec);
+  P.r_in_smem = (8 * n <= NJ_MAX_SMEM_R) ? 1 : 0;
+  const size_t smem = P.r_in_smem ? static_cast<size_t>(align_up(8 * n, 16)) : 0;
+  const int64_t items = n * pf_ceil_div(n, 32 * NJ_U) / 2 + 1;
+  const int64_t blocks = pf_ceil_div(items, (NJ_THREADS / 32) * 2);
+  return g_nj_prof_enabled ? nj_launch(nj_kernel<true>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s)
+                           : nj_launch(nj_kernel<false>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s);
+  PF_TRY_END
+}
+
+// Diagnostic: phase accounting of the NJ kernel, and a switch that forces the general (two grid
+// barriers per iteration) kernel for matrices the fast kernel would take. h_out8 = nanoseconds of CTA 0
+// summed over iterations. Fast kernel: [0] scan, [1] CTA reduction + publish, [2] exchange, [3] update.
+// General kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update, [3] grid barrier 2.
+// enable: bit 0 = instrumented kernels, bit 1 = force the general kernel. Reading resets the counters.
+PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {
+  PF_TRY_BEGIN
+  if (h_out8) PF_CUDA(cudaMemcpyFromSymbol(h_out8, g_nj_prof, sizeof(unsigned long long) * 8));
+  unsigned long long zero[8] = {0};
+  PF_CUDA(cudaMemcpyToSymbol(g_nj_prof, zero, sizeof(zero)));
+  g_nj_prof_enabled = (enable & 1) != 0;
+  g_nj_force_general = (enable & 2) != 0;
   return PF_OK;
   PF_TRY_END
 }

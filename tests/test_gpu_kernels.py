@@ -111,39 +111,86 @@ def test_normalise_bit_exact(engine, metric):
     assert int(nz.item()) == want_nz and want_nz > 0
 
 
-def _check_nj(engine, dist):
+def _check_nj(engine, dist, ld=None):
+    """Both NJ kernels (the fast one and, forced through the diagnostic switch, the general one)."""
+    from phyloforge_b200._lib import check
     n = dist.shape[0]
-    d = torch.from_numpy(dist).to(engine.device)
-    merge, length = engine.nj(d)
     want_m, want_l = oracle.nj(dist)
     names = [f"t{i}" for i in range(n)]
-    got_nw = merges_to_newick(merge.cpu().numpy(), length.cpu().numpy(), names)
     want_nw = merges_to_newick(want_m, want_l, names)
-    rf, dl = treecmp.compare(got_nw, want_nw)
-    assert rf == 0                                               # Robinson-Foulds distance 0
-    assert dl <= 1e-9                                            # branch lengths within 1e-9
-    assert np.array_equal(merge.cpu().numpy(), want_m)           # in fact the same join order
-    assert np.array_equal(length.cpu().numpy(), want_l)          # and bit-identical lengths
+    for force_general in (0, 2):
+        check(engine.lib.pf_nj_profile(force_general, None))
+        try:
+            if ld is None:
+                d = torch.from_numpy(dist).to(engine.device)
+            else:                                                  # rows with a wider leading dimension
+                buf = torch.full((n, ld), float("nan"), dtype=torch.float64, device=engine.device)
+                buf[:, :n] = torch.from_numpy(dist).to(engine.device)
+                d = buf[:, :n]
+            merge, length = engine.nj(d)
+            torch.cuda.synchronize()
+        finally:
+            check(engine.lib.pf_nj_profile(0, None))
+        got_nw = merges_to_newick(merge.cpu().numpy(), length.cpu().numpy(), names)
+        rf, dl = treecmp.compare(got_nw, want_nw)
+        which = "general kernel" if force_general else "fast kernel"
+        assert rf == 0, which                                        # Robinson-Foulds distance 0
+        assert dl <= 1e-9, which                                     # branch lengths within 1e-9
+        assert np.array_equal(merge.cpu().numpy(), want_m), which    # in fact the same join order
+        assert np.array_equal(length.cpu().numpy(), want_l), which   # and bit-identical lengths
 
 
-@pytest.mark.parametrize("n", [3, 4, 5, 33, 64, 257])
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 33, 64, 257, 513, 700, 1500])
 def test_nj_random_distances(engine, n):
     rng = np.random.default_rng(n)
     a = rng.random((n, n))
     dist = (a + a.T) / 2
     np.fill_diagonal(dist, 0.0)
     _check_nj(engine, dist)
+    if n in (5, 257):
+        _check_nj(engine, dist, ld=n + 3)
 
 
 def test_nj_many_exact_ties(engine):
     """Rational distances with a common denominator: Q ties are real and must break the same way."""
     rng = np.random.default_rng(99)
-    n = 120
-    a = rng.integers(0, 6, size=(n, n)).astype(np.float64) / 8.0
-    dist = np.triu(a, 1)
-    dist = dist + dist.T
-    _check_nj(engine, dist)
+    for n in (120, 600):
+        a = rng.integers(0, 6, size=(n, n)).astype(np.float64) / 8.0
+        dist = np.triu(a, 1)
+        dist = dist + dist.T
+        _check_nj(engine, dist)
     _check_nj(engine, np.ones((50, 50)) - np.eye(50))            # star: everything ties
+    _check_nj(engine, np.ones((1030, 1030)) - np.eye(1030))      # ... across scan segments and CTAs
+
+
+def test_nj_ultrametric_and_caterpillar_trees(engine):
+    """Tree-like inputs: the node merged last is joined again at once (caterpillar), so the pending
+    update of the fast kernel is read back through shared memory every iteration. The additive
+    matrix is not exactly symmetric in floating point ((x + h_i) + h_j vs (x + h_j) + h_i): the
+    kernels read the same triangle entries as the oracle, so the results are still bit-identical."""
+    n = 400
+    pos = np.cumsum(np.arange(1, n + 1, dtype=np.float64) * 0.01)
+    height = np.linspace(0.5, 1.5, n)
+    dist = np.abs(pos[:, None] - pos[None, :]) + height[:, None] + height[None, :]   # additive (caterpillar) metric
+    np.fill_diagonal(dist, 0.0)
+    _check_nj(engine, dist)
+    rng = np.random.default_rng(1)
+    perm = rng.permutation(n)
+    _check_nj(engine, dist[np.ix_(perm, perm)])
+    levels = np.array([[bin(i ^ j).count("1") and (i ^ j).bit_length() for j in range(256)] for i in range(256)],
+                      dtype=np.float64)                                              # balanced ultrametric tree
+    _check_nj(engine, levels)
+
+
+def test_nj_non_finite_input_does_not_hang(engine):
+    """NaN / inf distances: no candidate ever wins, slots 0 and 1 are joined (as the oracle does)."""
+    n = 40
+    dist = np.full((n, n), np.nan)
+    np.fill_diagonal(dist, 0.0)
+    d = torch.from_numpy(dist).to(engine.device)
+    merge, _ = engine.nj(d)
+    want_m, _ = oracle.nj(dist)
+    assert np.array_equal(merge.cpu().numpy(), want_m)
 
 
 def test_nj_from_genotypes(engine):
