@@ -233,4 +233,10 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
  * [3] grid barrier 2. Reading resets the counters. */
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
 
+/* Diagnostic: latency of the building blocks of the NJ iteration, nanoseconds per step.
+ * kind 0 dependent L2 load chain, 1 store + gpu-scope fence, 2 CTA barrier (512 threads), 3 tagged-word
+ * exchange between n_ctas CTAs, 4 cooperative grid barrier over n_ctas CTAs, 5 as 0 on lines last
+ * written by another SM, 6 a batch of 16 independent L2 loads per step. */
+PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_step, void* stream);
+
 #endif /* PHYLOFORGE_B200_H */

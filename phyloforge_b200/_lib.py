@@ -57,6 +57,7 @@ PROTOTYPES = {
     "pf_normalise": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "pf_nj_work_bytes": (_i64, [_i64]),
     "pf_nj_profile": (_i32, [_i32, _vp]),
+    "pf_probe_latency": (_i32, [_i32, _i32, _i32, _dp, _vp]),
     "pf_nj": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -43,7 +43,6 @@ constexpr int NJ_NONE = 0x7fffffff;
 
 struct NjRec {
   double q;
-  double dab;
   int a;
   int b;
 };
@@ -52,16 +51,14 @@ __device__ __forceinline__ bool rec_less(double q1, int a1, int b1, double q2, i
   return (q1 < q2) || (q1 == q2 && (a1 < a2 || (a1 == a2 && b1 < b2)));
 }
 
-__device__ __forceinline__ void warp_argmin(double& q, double& dab, int& a, int& b) {
+__device__ __forceinline__ void warp_argmin(double& q, int& a, int& b) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
     const double q2 = __shfl_xor_sync(0xffffffffu, q, off);
-    const double d2 = __shfl_xor_sync(0xffffffffu, dab, off);
     const int a2 = __shfl_xor_sync(0xffffffffu, a, off);
     const int b2 = __shfl_xor_sync(0xffffffffu, b, off);
     const bool take = rec_less(q2, a2, b2, q, a, b);
     q = take ? q2 : q;
-    dab = take ? d2 : dab;
     a = take ? a2 : a;
     b = take ? b2 : b;
   }
@@ -105,13 +102,14 @@ struct NjPending {
 // ---- argmin scan. Work items = (row a, segment of 32 U columns) of the upper triangle, enumerated
 // row-block major so that every thread meets its candidates in ascending (a, b) order: a strict
 // `q < best` then implements the lexicographic tie rule inside a thread. All U loads of an item are
-// issued before the first use (the loop over candidates is branch-free), so an item costs one memory
-// round trip.
+// issued before the first use and the loop over candidates is branch-free, so an item costs one memory
+// round trip; items that lie wholly inside the triangle and touch no pending column (almost all of
+// them) take a path without per-element predicates: 9 instructions per candidate.
 template <int U, bool VIRT, bool R_SMEM>
 __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld, const double* spare, int n_phys,
                                         const int* s_phys, const double* rs, const double* s_du, int na, double n2,
-                                        NjPending pend, int gwarp, int nwarps, int lane, double& bq, double& bd,
-                                        int& ba, int& bb) {
+                                        NjPending pend, int gwarp, int nwarps, int lane, double& bq, int& ba,
+                                        int& bb) {
   constexpr int SEG = 32 * U;
   const int nseg = (na + SEG - 1) / SEG;
   int rb = 0, base = 0;
@@ -131,54 +129,68 @@ __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld
     const int ar = local / segs;
     const int a = rb * SEG + ar;
     const int c0 = (rb + (local - ar * segs)) * SEG;
+    const bool pend_in_seg = VIRT && ((pend.a >= c0 && pend.a < c0 + SEG) || (pend.b >= c0 && pend.b < c0 + SEG));
+    const double ra = R_SMEM ? rs[a] : __ldcg(rs + a);
     double dv[U];
-    if (VIRT && a == pend.a) {
-      // row of the node merged last: its distances are in shared memory
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int b = c0 + u * 32 + lane;
-        dv[u] = (b > a && b < na) ? s_du[b] : CUDART_INF;
-      }
-    } else {
+    int iu = -1;     // index u of this item's best candidate so far, if it beats bq
+    if (c0 > a && c0 + SEG <= na && !pend_in_seg && !(VIRT && a == pend.a)) {
       int prow = a;
       if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
-      const double* rp = (VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld;
-      if (VIRT && pend.b >= c0 && pend.b < c0 + SEG) {
-        // column of the slot that took over the last slot: still in the last slot's column
+      const double* rp = ((VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld) + c0 + lane;
+      const double* rsp = rs + c0 + lane;
+#pragma unroll
+      for (int u = 0; u < U; ++u) dv[u] = __ldcg(rp + u * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double rbv = R_SMEM ? rsp[u * 32] : __ldcg(rsp + u * 32);
+        double q = __dmul_rn(n2, dv[u]);
+        q = __dsub_rn(q, ra);
+        q = __dsub_rn(q, rbv);
+        const bool take = q < bq;
+        bq = take ? q : bq;
+        iu = take ? u : iu;
+      }
+    } else {
+      if (VIRT && a == pend.a) {
+        // row of the node merged last: its distances are in shared memory
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int b = c0 + u * 32 + lane;
-          const int col = (b == pend.b) ? pend.last : b;
-          dv[u] = (b > a && b < na) ? __ldcg(rp + col) : CUDART_INF;
+          dv[u] = (b > a && b < na) ? s_du[b] : CUDART_INF;
         }
       } else {
+        int prow = a;
+        if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
+        const double* rp = (VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld;
+        // the column of the slot that took over the last slot is still in the last slot's column
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int b = c0 + u * 32 + lane;
-          dv[u] = (b > a && b < na) ? __ldcg(rp + b) : CUDART_INF;
+          const int col = (VIRT && b == pend.b) ? pend.last : b;
+          dv[u] = (b > a && b < na) ? __ldcg(rp + col) : CUDART_INF;
+        }
+        if (VIRT && pend.a > a && pend.a >= c0 && pend.a < c0 + SEG) {
+          const double dua = s_du[a];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (c0 + u * 32 + lane == pend.a) dv[u] = dua;
         }
       }
-      if (VIRT && pend.a > a && pend.a >= c0 && pend.a < c0 + SEG) {
-        const double dua = s_du[a];
 #pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (c0 + u * 32 + lane == pend.a) dv[u] = dua;
+      for (int u = 0; u < U; ++u) {
+        const int bc = min(c0 + u * 32 + lane, na - 1);
+        const double rbv = R_SMEM ? rs[bc] : __ldcg(rs + bc);
+        double q = __dmul_rn(n2, dv[u]);
+        q = __dsub_rn(q, ra);
+        q = __dsub_rn(q, rbv);
+        const bool take = q < bq;     // +inf for masked entries and NaN never win
+        bq = take ? q : bq;
+        iu = take ? u : iu;
       }
     }
-    const double ra = R_SMEM ? rs[a] : __ldcg(rs + a);
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int b = c0 + u * 32 + lane;
-      const int bc = min(b, na - 1);
-      const double rbv = R_SMEM ? rs[bc] : __ldcg(rs + bc);
-      double q = __dmul_rn(n2, dv[u]);
-      q = __dsub_rn(q, ra);
-      q = __dsub_rn(q, rbv);
-      const bool take = q < bq;     // +inf for masked entries and NaN never win
-      bq = take ? q : bq;
-      bd = take ? dv[u] : bd;
-      ba = take ? a : ba;
-      bb = take ? b : bb;
+    if (iu >= 0) {
+      ba = a;
+      bb = c0 + iu * 32 + lane;
     }
   }
 }
@@ -188,31 +200,21 @@ constexpr int NJF_THREADS = 512;
 constexpr int NJF_U = 16;            // 512-column scan items
 constexpr int NJF_K = 8;             // slots per thread and batch of the update
 constexpr int64_t NJ_FAST_MAX_N = 11000;   // 20 n bytes of shared memory
+constexpr int NJF_SHARDS = 8;        // arrival counters of the exchange, one 128-byte line each
+constexpr int NJF_MAX_CTAS = 256;
+constexpr int64_t NJ_XCHG_BYTES = 32768;   // >= 128 NJF_SHARDS + 2 x NJF_MAX_CTAS x 16, and the general kernel's records
 
 struct NjFastParams {
   double* D;
   int64_t ld;
   int n;
-  int32_t* merge;
-  double* len;
+  int32_t* merge;             // during the iterations: log of (slot a, slot b); node ids at the end
+  double* len;                // during the iterations: log of (r_a, r_b, d_ab); branch lengths at the end
   double* r0;                 // initial row sums
   double* spare;              // one extra matrix row (physical row index n)
-  int32_t* node;              // slot -> tree node id; touched by CTA 0 only
-  unsigned long long* xchg;   // [2][gridDim.x][4] tagged words
+  unsigned* arrive;           // [NJF_SHARDS][32] arrival counters (monotonic)
+  unsigned long long* recs;   // [2][gridDim.x][2]: {q bits, a | b << 32}
 };
-
-__device__ __forceinline__ void nj_publish(unsigned long long* slot, double q, int a, int b, unsigned tag) {
-  const unsigned long long qb = static_cast<unsigned long long>(__double_as_longlong(q));
-  const unsigned long long t = static_cast<unsigned long long>(tag) << 32;
-  const unsigned long long w0 = t | (qb & 0xffffffffull), w1 = t | (qb >> 32);
-  const unsigned long long w2 = t | static_cast<unsigned>(a), w3 = t | static_cast<unsigned>(b);
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
-  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot + 2), "l"(w2), "l"(w3) : "memory");
-}
-__device__ __forceinline__ void nj_peek(const unsigned long long* slot, unsigned long long (&w)[4]) {
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(slot) : "memory");
-  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(slot + 2) : "memory");
-}
 
 struct NjWinner {
   int a, b;
@@ -243,9 +245,7 @@ nj_fast_kernel(const NjFastParams P) {
   const int nthreads = gridDim.x * NJF_THREADS;
   const int n_cta = static_cast<int>(gridDim.x);
 
-  for (int k = gthread; k < 2 * n_cta * 4; k += nthreads) P.xchg[k] = 0ull;
-  if (blockIdx.x == 0)
-    for (int k = tid; k < n; k += NJF_THREADS) P.node[k] = k;
+  for (int k = gthread; k < NJF_SHARDS * 32; k += nthreads) P.arrive[k] = 0u;
   nj_initial_row_sums(D, ld, n, gwarp, nwarps, lane, P.r0);
   grid.sync();
   for (int k = tid; k < n; k += NJF_THREADS) {
@@ -255,67 +255,74 @@ nj_fast_kernel(const NjFastParams P) {
   __syncthreads();
   unsigned long long t_prev = PROF ? nj_now() : 0;
 
+  // exchange bookkeeping of warp 0: lane s < NJF_SHARDS watches arrival counter s, which
+  // (blockIdx % NJF_SHARDS == s) CTAs bump once per iteration
+  unsigned* my_arrive = P.arrive + (blockIdx.x % NJF_SHARDS) * 32;
+  const unsigned shard_ctas = (lane < NJF_SHARDS) ? static_cast<unsigned>((n_cta - lane + NJF_SHARDS - 1) / NJF_SHARDS) : 0u;
+
   NjPending pend{-1, -1, -1};
   int spare_row = n;     // physical row index of the spare row (n = the workspace row)
   int na = n, t = 0;
   while (na > 3) {
     // ---- scan
     const double n2 = static_cast<double>(na - 2);
-    double bq = CUDART_INF, bd = 0.0;
+    double bq = CUDART_INF;
     int ba = NJ_NONE, bb = NJ_NONE;
-    nj_scan<NJF_U, true, true>(D, ld, P.spare, n, s_phys, s_r, s_du, na, n2, pend, gwarp, nwarps, lane, bq, bd, ba,
-                               bb);
-    warp_argmin(bq, bd, ba, bb);
-    if (lane == 0) s_rec[warp] = NjRec{bq, bd, ba, bb};
+    nj_scan<NJF_U, true, true>(D, ld, P.spare, n, s_phys, s_r, s_du, na, n2, pend, gwarp, nwarps, lane, bq, ba, bb);
+    warp_argmin(bq, ba, bb);
+    if (lane == 0) s_rec[warp] = NjRec{bq, ba, bb};
     __syncthreads();
     NJ_MARK(0)   // scan + waiting for this CTA's slowest warp
-    // ---- exchange: warp 0 publishes this CTA's candidate and collects everybody's
+    // ---- exchange: warp 0 publishes this CTA's candidate, waits until every CTA has, reads them all.
+    // It doubles as the barrier that orders this iteration's scan before the update writes.
     if (warp == 0) {
-      NjRec v = (lane < WARPS) ? s_rec[lane] : NjRec{CUDART_INF, 0.0, NJ_NONE, NJ_NONE};
-      warp_argmin(v.q, v.dab, v.a, v.b);
-      const unsigned tag = static_cast<unsigned>(t + 1);
-      unsigned long long* mine = P.xchg + (static_cast<int64_t>(t & 1) * n_cta + blockIdx.x) * 4;
+      NjRec v = (lane < WARPS) ? s_rec[lane] : NjRec{CUDART_INF, NJ_NONE, NJ_NONE};
+      warp_argmin(v.q, v.a, v.b);
+      unsigned long long* recs = P.recs + static_cast<int64_t>(t & 1) * n_cta * 2;
       if (lane == 0) {
-        // release: this CTA's update writes of the previous iteration (ordered before this point by
-        // the __syncthreads above) become visible with the record
+        const unsigned long long w0 = static_cast<unsigned long long>(__double_as_longlong(v.q));
+        const unsigned long long w1 = static_cast<unsigned>(v.a) | (static_cast<unsigned long long>(static_cast<unsigned>(v.b)) << 32);
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(recs + 2 * blockIdx.x), "l"(w0), "l"(w1) : "memory");
+        // release: the record and this CTA's update writes of the previous iteration (ordered before
+        // this point by the __syncthreads above) are visible before the arrival is
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        nj_publish(mine, v.q, v.a, v.b, tag);
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(my_arrive) : "memory");
       }
       NJ_MARK(1)
-      double wq = CUDART_INF, wd = 0.0;
+      const unsigned want = shard_ctas * static_cast<unsigned>(t + 1);
+      bool ok;
+      do {
+        unsigned seen = want;
+        if (lane < NJF_SHARDS)
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.arrive + lane * 32) : "memory");
+        ok = __all_sync(0xffffffffu, seen >= want);
+      } while (!ok);
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: reads below are ordered after the arrivals were seen
+      NJ_MARK(2)
+      double wq = CUDART_INF;
       int wa = NJ_NONE, wb = NJ_NONE;
-      const unsigned long long* all = P.xchg + static_cast<int64_t>(t & 1) * n_cta * 4;
-      for (int c0 = 0; c0 < n_cta; c0 += 32 * 4) {
-        // up to four records per lane and round, polled together
-        unsigned long long w[4][4];
-        bool ok;
-        do {
-          ok = true;
+      for (int c0 = 0; c0 < n_cta; c0 += 32 * 8) {
+        unsigned long long w[8][2];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int c = c0 + j * 32 + lane;
-            if (c < n_cta) {
-              nj_peek(all + static_cast<int64_t>(c) * 4, w[j]);
-#pragma unroll
-              for (int x = 0; x < 4; ++x) ok = ok && (static_cast<unsigned>(w[j][x] >> 32) == tag);
-            }
-          }
-        } while (!ok);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const int c = c0 + j * 32 + lane;
-          if (c < n_cta) {
-            const double q2 = __longlong_as_double(static_cast<long long>((w[j][0] & 0xffffffffull) | (w[j][1] << 32)));
-            const int a2 = static_cast<int>(static_cast<unsigned>(w[j][2]));
-            const int b2 = static_cast<int>(static_cast<unsigned>(w[j][3]));
-            if (rec_less(q2, a2, b2, wq, wa, wb)) {
-              wq = q2; wa = a2; wb = b2;
-            }
-          }
+          w[j][0] = 0x7ff0000000000000ull;   // +inf
+          w[j][1] = 0x7fffffff7fffffffull;
+          if (c < n_cta)
+            asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[j][0]), "=l"(w[j][1]) : "l"(recs + 2 * c) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const double q2 = __longlong_as_double(static_cast<long long>(w[j][0]));
+          const int a2 = static_cast<int>(static_cast<unsigned>(w[j][1]));
+          const int b2 = static_cast<int>(static_cast<unsigned>(w[j][1] >> 32));
+          const bool take = rec_less(q2, a2, b2, wq, wa, wb);
+          wq = take ? q2 : wq;
+          wa = take ? a2 : wa;
+          wb = take ? b2 : wb;
         }
       }
-      asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire: reads below are ordered after the records were seen
-      warp_argmin(wq, wd, wa, wb);
+      warp_argmin(wq, wa, wb);
       if (lane == 0) {
         if (wa == NJ_NONE) {   // no finite candidate (NaN / inf input): join slots 0 and 1
           wa = 0; wb = 1;
@@ -324,7 +331,7 @@ nj_fast_kernel(const NjFastParams P) {
       }
     }
     __syncthreads();
-    NJ_MARK(2)   // exchange (includes waiting for the slowest CTA)
+    NJ_MARK(3)   // exchange (includes waiting for the slowest CTA)
 
     // ---- update (every CTA: shared-memory state; the owner of a slot: global memory)
     const int wa = s_win.a, wb = s_win.b;
@@ -336,12 +343,6 @@ nj_fast_kernel(const NjFastParams P) {
     const double* row_b = (pwb == n) ? P.spare : D + static_cast<int64_t>(pwb) * ld;
     double* row_u = (spare_row == n) ? P.spare : D + static_cast<int64_t>(spare_row) * ld;
     const double dab = __ldcg(row_a + wb);
-    int node_a = 0, node_b = 0, node_l = 0;
-    if (gthread == 0) {
-      node_a = __ldcg(P.node + wa);
-      node_b = __ldcg(P.node + wb);
-      node_l = __ldcg(P.node + last);
-    }
     for (int k0 = tid; k0 < na; k0 += NJF_THREADS * NJF_K) {
       double dak[NJF_K], dbk[NJF_K], mv[NJF_K];
       int prow[NJF_K];
@@ -388,19 +389,12 @@ nj_fast_kernel(const NjFastParams P) {
       }
     }
     if (gthread == 0) {
-      double tt = __dsub_rn(rra, rrb);
-      tt = __ddiv_rn(tt, __dmul_rn(2.0, n2));
-      double la = __dmul_rn(0.5, dab);
-      la = __dadd_rn(la, tt);
-      const double lb = __dsub_rn(dab, la);
-      P.merge[3 * t + 0] = node_a;
-      P.merge[3 * t + 1] = node_b;
-      P.merge[3 * t + 2] = 0;
-      P.len[3 * t + 0] = la;
-      P.len[3 * t + 1] = lb;
-      P.len[3 * t + 2] = 0.0;
-      if (move) P.node[wb] = node_l;
-      P.node[wa] = n + t;
+      // log of the join; node ids and branch lengths are derived after the last iteration
+      P.merge[3 * t + 0] = wa;
+      P.merge[3 * t + 1] = wb;
+      P.len[3 * t + 0] = rra;
+      P.len[3 * t + 1] = rrb;
+      P.len[3 * t + 2] = dab;
     }
     __syncthreads();
     if (tid == 0) {
@@ -412,10 +406,13 @@ nj_fast_kernel(const NjFastParams P) {
     spare_row = pwa;       // free from the next iteration on: everybody has read it by the next exchange
     --na;
     ++t;
-    NJ_MARK(3)   // update
+    NJ_MARK(4)   // update
   }
 
-  if (gthread == 0) {
+  if (blockIdx.x != 0) return;
+  // ---- CTA 0: node ids and branch lengths from the log
+  double d01 = 0.0, d02 = 0.0, d12 = 0.0;
+  if (tid == 0) {
     // the last three nodes; the final update may still be pending, so read through it
     auto vread = [&](int x, int y) -> double {   // x < y < 3
       if (x == pend.a) return s_du[y];
@@ -424,22 +421,60 @@ nj_fast_kernel(const NjFastParams P) {
       const double* rp = (pr == n) ? P.spare : D + static_cast<int64_t>(pr) * ld;
       return __ldcg(rp + ((y == pend.b) ? pend.last : y));
     };
-    const double d01 = vread(0, 1), d02 = vread(0, 2), d12 = vread(1, 2);
+    d01 = vread(0, 1);
+    d02 = vread(0, 2);
+    d12 = vread(1, 2);
+  }
+  __syncthreads();   // the log written by thread 0 is visible to the CTA; s_r / s_du / s_phys are free
+  const int n_iter = t;
+  int2* s_log = reinterpret_cast<int2*>(nj_dyn);   // 8 bytes per iteration over s_r
+  int* s_node = s_phys;
+  for (int i = tid; i < n_iter; i += NJF_THREADS) {
+    s_log[i] = make_int2(__ldcg(P.merge + 3 * i), __ldcg(P.merge + 3 * i + 1));
+    const double rra = __ldcg(P.len + 3 * i), rrb = __ldcg(P.len + 3 * i + 1), dab = __ldcg(P.len + 3 * i + 2);
+    const double n2 = static_cast<double>(n - i - 2);
+    double tt = __dsub_rn(rra, rrb);
+    tt = __ddiv_rn(tt, __dmul_rn(2.0, n2));
+    double la = __dmul_rn(0.5, dab);
+    la = __dadd_rn(la, tt);
+    P.len[3 * i + 0] = la;
+    P.len[3 * i + 1] = __dsub_rn(dab, la);
+    P.len[3 * i + 2] = 0.0;
+    P.merge[3 * i + 2] = 0;
+  }
+  for (int k = tid; k < n; k += NJF_THREADS) s_node[k] = k;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 0; i < n_iter; ++i) {
+      const int2 ab = s_log[i];
+      const int last = n - i - 1;
+      P.merge[3 * i + 0] = s_node[ab.x];
+      P.merge[3 * i + 1] = s_node[ab.y];
+      if (ab.y != last) s_node[ab.y] = s_node[last];
+      s_node[ab.x] = n + i;
+    }
     double l0 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d02), d12));
     double l1 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d12), d02));
     double l2 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d02, d12), d01));
-    P.merge[3 * t + 0] = P.node[0];
-    P.merge[3 * t + 1] = P.node[1];
-    P.merge[3 * t + 2] = P.node[2];
-    P.len[3 * t + 0] = l0;
-    P.len[3 * t + 1] = l1;
-    P.len[3 * t + 2] = l2;
+    P.merge[3 * n_iter + 0] = s_node[0];
+    P.merge[3 * n_iter + 1] = s_node[1];
+    P.merge[3 * n_iter + 2] = s_node[2];
+    P.len[3 * n_iter + 0] = l0;
+    P.len[3 * n_iter + 1] = l1;
+    P.len[3 * n_iter + 2] = l2;
   }
 }
 
 // ===================================================================== general kernel
-constexpr int NJ_THREADS = 1024;
-constexpr int NJ_U = 8;   // 256-column scan items (64 registers per thread)
+constexpr int NJ_THREADS = 512;
+constexpr int NJ_U = 16;  // 512-column scan items
+
+struct NjRecG {   // record of the general kernel: d_ab travels with the candidate, because the
+  double q;       // update overwrites D[a][b] in place while other CTAs may not have read it yet
+  double dab;
+  int a;
+  int b;
+};
 
 struct NjParams {
   double* D;
@@ -450,7 +485,7 @@ struct NjParams {
   double* r0;   // row sums, double-buffered across iterations
   double* r1;
   int32_t* node;
-  NjRec* rec;
+  NjRecG* rec;
   int r_in_smem;  // the row sums of the live nodes fit in dynamic shared memory
 };
 
@@ -460,7 +495,7 @@ nj_kernel(const NjParams P) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ double s_r[];
   __shared__ NjRec s_rec[NJ_THREADS / 32];
-  __shared__ NjRec s_best;
+  __shared__ NjRecG s_best;
 
   double* __restrict__ D = P.D;
   const int64_t ld = P.ld;
@@ -492,21 +527,23 @@ nj_kernel(const NjParams P) {
     }
     const double n2 = static_cast<double>(na - 2);
     double bq = CUDART_INF;
-    double bd = 0.0;
     int ba = NJ_NONE, bb = NJ_NONE;
     if (P.r_in_smem)
-      nj_scan<NJ_U, false, true>(D, ld, nullptr, 0, nullptr, s_r, nullptr, na, n2, none, gwarp, nwarps, lane, bq, bd,
-                                 ba, bb);
+      nj_scan<NJ_U, false, true>(D, ld, nullptr, 0, nullptr, s_r, nullptr, na, n2, none, gwarp, nwarps, lane, bq, ba,
+                                 bb);
     else
-      nj_scan<NJ_U, false, false>(D, ld, nullptr, 0, nullptr, cur, nullptr, na, n2, none, gwarp, nwarps, lane, bq, bd,
-                                  ba, bb);
-    warp_argmin(bq, bd, ba, bb);
-    if (lane == 0) s_rec[warp] = NjRec{bq, bd, ba, bb};
+      nj_scan<NJ_U, false, false>(D, ld, nullptr, 0, nullptr, cur, nullptr, na, n2, none, gwarp, nwarps, lane, bq, ba,
+                                  bb);
+    warp_argmin(bq, ba, bb);
+    if (lane == 0) s_rec[warp] = NjRec{bq, ba, bb};
     __syncthreads();
     if (warp == 0) {
-      NjRec v = s_rec[lane];  // warps_per_block == 32
-      warp_argmin(v.q, v.dab, v.a, v.b);
-      if (lane == 0) P.rec[blockIdx.x] = v;
+      NjRec v = (lane < warps_per_block) ? s_rec[lane] : NjRec{CUDART_INF, NJ_NONE, NJ_NONE};
+      warp_argmin(v.q, v.a, v.b);
+      if (lane == 0) {
+        const double dab = (v.a == NJ_NONE) ? 0.0 : __ldcg(D + static_cast<int64_t>(v.a) * ld + v.b);
+        P.rec[blockIdx.x] = NjRecG{v.q, dab, v.a, v.b};
+      }
     }
     NJ_MARK(0)   // scan + CTA reduction
     grid.sync();
@@ -514,9 +551,9 @@ nj_kernel(const NjParams P) {
 
     // ---- C: every CTA reduces the per-CTA records to the same winner, then updates
     if (warp == 0) {
-      NjRec v{CUDART_INF, 0.0, NJ_NONE, NJ_NONE};
+      NjRecG v{CUDART_INF, 0.0, NJ_NONE, NJ_NONE};
       for (int k = lane; k < static_cast<int>(gridDim.x); k += 32) {
-        const NjRec* g = P.rec + k;
+        const NjRecG* g = P.rec + k;
         const double q2 = __ldcg(&g->q);
         const double d2 = __ldcg(&g->dab);
         const int a2 = __ldcg(&g->a);
@@ -527,8 +564,13 @@ nj_kernel(const NjParams P) {
         v.a = take ? a2 : v.a;
         v.b = take ? b2 : v.b;
       }
-      warp_argmin(v.q, v.dab, v.a, v.b);
-      if (lane == 0) s_best = v;
+      // (q, a, b) is unique per candidate, so d_ab can follow the winner through the shuffles
+      const double q0 = v.q;
+      const int a0 = v.a, b0 = v.b;
+      warp_argmin(v.q, v.a, v.b);
+      const unsigned src = __ballot_sync(0xffffffffu, q0 == v.q && a0 == v.a && b0 == v.b);
+      const double dwin = __shfl_sync(0xffffffffu, v.dab, src ? __ffs(src) - 1 : 0);
+      if (lane == 0) s_best = NjRecG{v.q, dwin, v.a, v.b};
     }
     __syncthreads();
     int wa = s_best.a, wb = s_best.b;
@@ -641,7 +683,7 @@ int nj_launch(K kernel, int threads, size_t smem, int64_t want_blocks, int64_t m
 
 PF_API int64_t pf_nj_work_bytes(int64_t n) {
   if (n < 0) return 0;
-  return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + align_up(sizeof(NjRec) * NJ_MAX_BLOCKS, 256);
+  return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES;
 }
 
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len, void* d_work,
@@ -669,14 +711,16 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
     P.len = d_len;
     P.r0 = w_r0;
     P.spare = w_r1;
-    P.node = w_node;
-    P.xchg = reinterpret_cast<unsigned long long*>(w_rec);   // 2 x blocks x 32 bytes, in the record area
+    P.arrive = reinterpret_cast<unsigned*>(w_rec);
+    P.recs = reinterpret_cast<unsigned long long*>(static_cast<char*>(w_rec) + 128 * NJF_SHARDS);
     const int64_t n_pad = (n + 1) & ~int64_t(1);
     const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
     // about two 512-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
     const int64_t items = n * pf_ceil_div(n, 32 * NJF_U) / 2 + 1;
     const int64_t blocks = pf_ceil_div(items, (NJF_THREADS / 32) * 2);
-    constexpr int64_t max_blocks = static_cast<int64_t>(sizeof(NjRec)) * NJ_MAX_BLOCKS / (2 * 4 * 8);   // xchg fits in rec
+    constexpr int64_t max_blocks = NJF_MAX_CTAS;
+    static_assert(128 * NJF_SHARDS + 2 * NJF_MAX_CTAS * 16 <= NJ_XCHG_BYTES, "exchange area");
+    static_assert(sizeof(NjRecG) * NJ_MAX_BLOCKS <= NJ_XCHG_BYTES, "record area");
     return g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true>, NJF_THREADS, smem, blocks, max_blocks, &P, s)
                              : nj_launch(nj_fast_kernel<false>, NJF_THREADS, smem, blocks, max_blocks, &P, s);
   }
@@ -689,7 +733,7 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
   P.r0 = w_r0;
   P.r1 = w_r1;
   P.node = w_node;
-  P.rec = static_cast<NjRec*>(w_rec);
+  P.rec = static_cast<NjRecG*>(w_rec);
   P.r_in_smem = (8 * n <= NJ_MAX_SMEM_R) ? 1 : 0;
   const size_t smem = P.r_in_smem ? static_cast<size_t>(align_up(8 * n, 16)) : 0;
   const int64_t items = n * pf_ceil_div(n, 32 * NJ_U) / 2 + 1;
@@ -701,7 +745,8 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
 
 // Diagnostic: phase accounting of the NJ kernel, and a switch that forces the general (two grid
 // barriers per iteration) kernel for matrices the fast kernel would take. h_out8 = nanoseconds of CTA 0
-// summed over iterations. Fast kernel: [0] scan, [1] CTA reduction + publish, [2] exchange, [3] update.
+// summed over iterations. Fast kernel: [0] scan, [1] CTA reduction + publish, [2] waiting for the arrivals,
+// [3] reading the records + winner, [4] update.
 // General kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update, [3] grid barrier 2.
 // enable: bit 0 = instrumented kernels, bit 1 = force the general kernel. Reading resets the counters.
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {

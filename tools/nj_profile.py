@@ -10,7 +10,7 @@ from phyloforge_b200._lib import check
 from phyloforge_b200.engine import Engine
 
 eng = Engine(0)
-NAMES = {0: ["scan", "cta-red+publish", "exchange", "update"],
+NAMES = {0: ["scan", "cta-red+publish", "wait", "records+winner", "update"],
          2: ["scan+cta-red", "barrier1", "winner+update", "barrier2"]}
 sizes = [int(x) for x in (sys.argv[1:] or ["1000", "3000", "6000", "10000"])]
 for n in sizes:
@@ -30,7 +30,7 @@ for n in sizes:
         torch.cuda.synchronize()
         out = (C.c_ulonglong * 8)()
         check(eng.lib.pf_nj_profile(0, out))
-        tot = sum(out[:4])
+        tot = sum(out[:5])
         print(f"n={n} {'general' if general else 'fast   '}: {plain*1e3:.1f} ms ({plain/n*1e6:.2f} us/iter); "
               f"instrumented {tot/1e6:.1f} ms: " +
               ", ".join(f"{nm} {out[i]/n/1e3:.2f}" for i, nm in enumerate(NAMES[general])) + " us/iter", flush=True)
