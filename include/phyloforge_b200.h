@@ -239,4 +239,15 @@ PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
  * written by another SM, 6 a batch of 16 independent L2 loads per step. */
 PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_step, void* stream);
 
+/* Diagnostics for the 4-bit tensor-core path (tcgen05.mma kind::mxf4, E2M1 operands, K = 64 per
+ * instruction, all block scale factors 1.0; csrc/umma_fp4_probe.cu).
+ * pf_selftest_umma_fp4: d_c[128][n] (fp32) = d_a[128][k] * d_b[n][k]^T for int8 entries from
+ * {0, +-1, +-2, +-3, +-4, +-6}; n = 128 or 192, k a multiple of 64, at most 1024; a_in_tmem != 0
+ * feeds the A operand from tensor memory (tcgen05.st) instead of shared memory.
+ * pf_probe_umma_fp4_rate: SM clock64 ticks per 128 x n x 64 instruction, operands resident in shared
+ * memory, n_acc accumulators used round-robin. */
+PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c, int n, int k,
+                                int a_in_tmem, void* stream);
+PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, double* ticks_per_mma, void* stream);
+
 #endif /* PHYLOFORGE_B200_H */
