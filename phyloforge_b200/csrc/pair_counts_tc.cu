@@ -1,72 +1,78 @@
-// Tensor-core variant of the all-pairs genotype counts: int8 indicator GEMMs on tcgen05
+// Tensor-core variant of the all-pairs genotype counts: 4-bit indicator GEMMs on tcgen05
 // (BASELINE.json north star: "an int8 tcgen05 indicator-GEMM variant kept only if ncu shows it
-// beats popcount" — it does, 3.7x on the 3,000 x 10M workload). Same arithmetic as pair_counts.cu,
-// restated as integer matrix products over the site axis. Per genotype:
+// beats popcount" — it does; the 4-bit form below is 2.2x the int8 form it replaced, see
+// profiles/r01_mma_probe.md). Same arithmetic as pair_counts.cu, restated as matrix products over
+// the site axis. Per genotype:
 //   x = g - 1 in {-1, 0, +1} (0 for het and missing), h = 1 if homozygous, v = 1 if genotyped.
 //   XX = sum x_i x_j = n00 + n22 - n02      HH = sum h_i h_j = n00 + n22 + n02
 //   VV = sum v_i v_j = V                    HV = sum h_i v_j,  VH = sum v_i h_j
 //   D2 = n02 = (HH - XX) / 2                het-vs-hom sites = HV + VH - 2 HH        D1 = that + D2
-// Exact: int8 x int8 products accumulate in int32 in TMEM. Two kernel modes share one body:
+// The operands are E2M1 (4-bit float) values, tcgen05.mma kind::mxf4 with all block scale factors 1.0:
+// 64 sites per instruction instead of the 32 of kind::i8 at the same instruction time. -1, 0, +1 are
+// exact in E2M1, products are -1 / 0 / +1, and the fp32 accumulators hold integers below 2^24 exactly
+// (a CTA never accumulates more than 2^23 sites), so the counts are bit-exact.
+// Two kernel modes share one body:
 //   mode 0  XX and HH on 128 x 192 tiles. When every site is genotyped in all samples or in none
 //           (no sample-specific missingness) this is all that is needed: HV = |h_i|, VH = |h_j| and V
 //           are per-sample / global numbers the converter already has.
 //   mode 1  VV, HV and VH on 128 x 128 tiles, run in addition when genotypes are missing in some
 //           samples only. The two launches add their linear pieces into the same int32 matrices.
 //
-// Data flow per CTA (one sample tile pair, a contiguous range of 32-site words):
-//   "nib4" operand stream (4 bits per genotype, produced once per call by planes_to_nib4; a nibble is
-//   directly a PRMT selector) --TMA bulk copies--> raw ring --expansion warps (thread = sample row):
-//   PRMT nibble -> int8 planes--> A rows straight into TMEM (tcgen05.st), B rows into canonical K-major
-//   UMMA tiles in shared memory --tcgen05.mma kind::i8, A from TMEM, B from shared memory (1 thread)-->
-//   TMEM accumulator columns --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
-// The kernel is bound by shared-memory bandwidth (ncu: LSU wavefronts + tensor operand reads), which
-// is why the A operand bypasses shared memory. (Reading the operand stream straight from global memory
-// with register prefetch instead of the TMA ring was measured 15% slower; kept as a TMA ring.)
+// Operand stream (produced once per call by planes_to_e2m1): one nibble per genotype that is at the
+// same time the E2M1 code of x and a tag: hom-REF 0xA (-1), het 0x0 (+0), hom-ALT 0x2 (+1),
+// missing 0x8 (-0). h = nibble & 2, v = "nibble != 8". It is stored as 2 KB chunks (64 samples x 64
+// sites) already in the canonical K-major shared-memory order of a UMMA operand, so a TMA bulk copy of
+// the J rows of a chunk row lands as a ready B_x operand.
+// Data flow per CTA (one sample tile pair, a contiguous range of 64-site steps):
+//   stream --TMA bulk copies--> raw ring (A rows | B rows = the B_x operand in mode 0)
+//   --expansion warps (thread = sample row): a few logic ops per 8 genotypes--> A planes straight into
+//   TMEM (tcgen05.st), derived B planes into shared memory
+//   --tcgen05.mma kind::mxf4, A from TMEM, B from shared memory (1 thread)--> fp32 accumulators in TMEM
+//   --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
 #include "pf_common.cuh"
 #include "umma.cuh"
 
 namespace {
 
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
-constexpr int STEP_WORDS = 2;        // words per pipeline step (one raw stage feeds one expanded stage)
-constexpr int RAW_WORDS = STEP_WORDS;
-constexpr int RAW_STAGES = 6;
+constexpr int STEP_WORDS = 2;        // one pipeline step = one MMA K step = 64 sites = two 32-site words
+constexpr int CHUNK_BYTES = 2048;    // 64 samples x 64 sites x 4 bits
+constexpr int RAW_STAGES = 8;
 constexpr int EXP_STAGES = 4;
-constexpr int TMEM_A_COLS = 16;      // per in-flight word: 8 columns per A plane (32 K-bytes per row)
-constexpr uint32_t POOL_X = 0x000100ffu;  // code 0 -> -1, 1 -> 0, 2 -> +1, 3 -> 0
-constexpr uint32_t POOL_H = 0x00010001u;  // code 0 -> 1, 1 -> 0, 2 -> 1, 3 -> 0
-constexpr uint32_t POOL_V = 0x00010101u;  // code 0, 1, 2 -> 1, 3 -> 0
+constexpr int TMEM_A_COLS = 16;      // per expanded stage: 8 columns per A plane (32 K-bytes per row)
+constexpr int TMEM_SF = 448;         // 32 columns of scale factors (all 1.0) behind accumulators and A staging
+constexpr uint32_t NIB_HOM = 0x22222222u;   // bit 1 of a stream nibble: homozygous; as E2M1 that bit alone is +1.0
 constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
+constexpr int64_t MAX_WORDS_PER_CTA = 1 << 18;   // 2^23 sites: fp32 accumulators stay exact
 
-// per-mode geometry: planes 0 / 1 of both operands, accumulator count, tile width
+// per-mode geometry
 template <int MODE> struct TcCfg;
-template <> struct TcCfg<0> {   // planes: 0 = x, 1 = h; products XX (acc 0), HH (acc 1)
-  static constexpr int J = 192, NPROD = 2;
-  static constexpr uint32_t POOL0 = POOL_X, POOL1 = POOL_H;
+template <> struct TcCfg<0> {   // planes: 0 = x (the stream itself), 1 = h; products XX (acc 0), HH (acc 1)
+  static constexpr int J = 192, NPROD = 2, NEXP = 1;   // NEXP = derived B planes written by the expansion warps
 };
 template <> struct TcCfg<1> {   // planes: 0 = h, 1 = v; products VV (acc 0), HV (acc 1), VH (acc 2)
-  static constexpr int J = 128, NPROD = 3;
-  static constexpr uint32_t POOL0 = POOL_H, POOL1 = POOL_V;
+  static constexpr int J = 128, NPROD = 3, NEXP = 2;
 };
 template <int MODE> struct TcGeo {
   using C = TcCfg<MODE>;
   static constexpr int J = C::J;                               // columns (MMA N); B operand in shared memory
-  static constexpr int ROWS = TC_I + J;                        // sample rows expanded per word
-  static constexpr int PF = ROWS / PF_TILE;                    // 64-sample tiles of the stream per step
-  static constexpr int RAW_STAGE_BYTES = RAW_WORDS * ROWS * 16;
-  static constexpr int EXP_WORD_BYTES = J * 32 * 2;            // both planes of B for one word
-  static constexpr int EXP_STAGE_BYTES = STEP_WORDS * EXP_WORD_BYTES;
-  static constexpr int EXP_B0 = 0, EXP_B1 = J * 32;
+  static constexpr int ROWS = TC_I + J;                        // sample rows handled per step
+  static constexpr int PF = ROWS / PF_TILE;                    // 64-sample chunks of the stream per step
+  static constexpr int A_RAW_BYTES = (TC_I / PF_TILE) * CHUNK_BYTES;
+  static constexpr int RAW_STAGE_BYTES = PF * CHUNK_BYTES;     // [A rows | B rows], canonical order
+  static constexpr int EXP_PLANE_BYTES = J * 32;
+  static constexpr int EXP_STAGE_BYTES = C::NEXP * EXP_PLANE_BYTES;
   static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
+  static constexpr int RAW_EMPTY_ARRIVALS = EXP_WARPS + (MODE == 0 ? 1 : 0);   // mode 0: the MMA reads B_x from the raw stage
   static constexpr size_t SMEM = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES +
                                  static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
-  static_assert(TMEM_A + EXP_STAGES * STEP_WORDS * TMEM_A_COLS <= 512, "TMEM columns");
+  static_assert(TMEM_A + EXP_STAGES * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 32 <= 512, "TMEM columns");
 };
 
-// ------------------------------------------------------------------ planes -> nib4
-__device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> 8 nibbles
+// ------------------------------------------------------------------ planes -> E2M1 stream
+__device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> bit 0 of 8 nibbles
   uint32_t x = b;
   x = (x | (x << 12)) & 0x000f000fu;
   x = (x | (x << 6)) & 0x03030303u;
@@ -74,26 +80,30 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> 8 nibble
   return x;
 }
 
-// nib4[((T * n_local + w) * 64 + l) * 4 + q]: nibble j of word q = code of site 32 w + 8 q + j.
+// stream[((T * n_steps + s) * 128 + (l >> 3) * 16 + kh * 8 + (l & 7))] (uint4) = the 32 sites of word
+// 2 s + kh of sample 64 T + l, nibble j of 32-bit word q = site 8 q + j: bit 3 = "hom-REF or missing",
+// bit 1 = "homozygous" (see the file header). A second half-step past the last word is all missing.
 // ref_v[w] = valid-site mask of sample 0; flags[0] is set when any real sample's mask differs from
 // it, i.e. when some site is genotyped in some samples and missing in others.
 // hsum[split][sample] = homozygous genotypes of the sample in the split's word range (|h_i|).
 // One thread = one sample x a run of HSUM_RUN consecutive words (runs never straddle a split).
 __global__ void __launch_bounds__(256)
-planes_to_nib4_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int64_t word_begin, int64_t n_local,
-                      int64_t n_samples, int64_t n_tiles, int64_t n_tiles_padded, uint4* __restrict__ nib4,
+planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int64_t word_begin, int64_t n_local,
+                      int64_t n_samples, int64_t n_tiles, int64_t n_tiles_padded, uint4* __restrict__ stream,
                       uint32_t* __restrict__ ref_v, int* __restrict__ flags, int* __restrict__ hsum,
                       int64_t words_per_split, int64_t hsum_ld) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int l = static_cast<int>(idx & 63);
   const int64_t tr = idx >> 6;
   const int64_t n_runs = (n_local + HSUM_RUN - 1) / HSUM_RUN;
+  const int64_t n_steps = (n_local + 1) / 2;
   const int64_t run = tr % n_runs;
   const int64_t t = tr / n_runs;
   if (t >= n_tiles_padded) return;
   const int64_t w0 = run * HSUM_RUN;
   const int64_t w1 = min(n_local, w0 + HSUM_RUN);
   const bool real = (t * PF_TILE + l) < n_samples;
+  const int unit = (l >> 3) * 16 + (l & 7);
   int hom = 0;
   bool mixed = false;
   for (int64_t w = w0; w < w1; ++w) {
@@ -103,17 +113,20 @@ planes_to_nib4_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
       L = p[l];
       H = p[PF_TILE + l];
     }
+    const uint32_t S = ~(L ^ H), M = ~L;   // code 0 / 3 -> sign bit; code 0 / 2 -> homozygous bit
     uint4 out;
-    out.x = spread8(L & 0xffu) | (spread8(H & 0xffu) << 1);
-    out.y = spread8((L >> 8) & 0xffu) | (spread8((H >> 8) & 0xffu) << 1);
-    out.z = spread8((L >> 16) & 0xffu) | (spread8((H >> 16) & 0xffu) << 1);
-    out.w = spread8(L >> 24) | (spread8(H >> 24) << 1);
-    nib4[(t * n_local + w) * 64 + l] = out;
+    out.x = (spread8(S & 0xffu) << 3) | (spread8(M & 0xffu) << 1);
+    out.y = (spread8((S >> 8) & 0xffu) << 3) | (spread8((M >> 8) & 0xffu) << 1);
+    out.z = (spread8((S >> 16) & 0xffu) << 3) | (spread8((M >> 16) & 0xffu) << 1);
+    out.w = (spread8(S >> 24) << 3) | (spread8(M >> 24) << 1);
+    stream[(t * n_steps + (w >> 1)) * 128 + (w & 1) * 8 + unit] = out;
+    if (w == n_local - 1 && (w & 1) == 0)
+      stream[(t * n_steps + (w >> 1)) * 128 + 8 + unit] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
     const uint32_t* p0 = planes + ((word_begin + w) * 2) * PF_TILE;   // sample 0: tile 0, lane 0
     const uint32_t ref = ~(p0[0] & p0[PF_TILE]);
     if (t == 0 && l == 0) ref_v[w] = ref;
     mixed |= (~(L & H) != ref);
-    hom += __popc(~L);            // homozygous <=> low code bit 0 (missing has it set)
+    hom += __popc(M);             // homozygous <=> low code bit 0 (missing has it set)
   }
   if (real) {
     if (mixed) atomicOr(flags, 1);
@@ -127,41 +140,57 @@ __device__ long long g_tc_prof[16];
 bool g_tc_prof_enabled = false;
 
 struct TcParams {
-  const uint4* nib4;      // [n_tiles_padded][n_local][64] uint4
+  const uint4* stream;    // [n_tiles_padded][n_steps] chunks of 2 KB
   const uint32_t* all_v;  // [n_local] valid-site mask of sample 0 (= of every sample when uniform)
   int64_t n_local;        // words in the range
+  int64_t n_steps;        // 64-site steps in the range
   int64_t n_samples;
   int32_t* counts;        // [3][n_samples][ld]
   int64_t ld;
   int n_itiles;           // ceil(n_samples / 128)
   int n_jtiles;           // ceil(n_samples / J)
   int n_tilepairs;
-  int words_per_split;
+  int words_per_split;    // even
   const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split (mode 0, uniform)
   int64_t hsum_ld;
   int general;            // mode 0 only: 1 = sample-specific missingness, mode 1 supplies V and HV + VH
 };
 
-// PRMT as the hardware does it (the __byte_perm intrinsic masks the selector first): byte k of the
-// result = byte (nibble k of the low 16 selector bits) of {pool, pool}. Codes are 0..3, so the
-// sign-replicate bit of a selector nibble is never set.
-__device__ __forceinline__ uint32_t prmt(uint32_t pool, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(r) : "r"(pool), "r"(sel));
-  return r;
+// block-scaled instruction descriptor (bit layout: CUTLASS cute/arch/mma_sm100_desc.hpp,
+// InstrDescriptorBlockScaled): E2M1 A and B, K-major, UE8M0 scale factors with id 0, dense K = 64
+__host__ __device__ constexpr uint32_t idesc_mxf4(int m, int n) {
+  return (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (1u << 23) |
+         (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// one sample row x one 32-site word: 16 bytes of nibble codes -> 32 int8 values of each of the two planes
-template <uint32_t POOL0, uint32_t POOL1>
-__device__ __forceinline__ void expand_word(const uint4& nb, uint32_t (&p0)[8], uint32_t (&p1)[8]) {
-  const uint32_t q[4] = {nb.x, nb.y, nb.z, nb.w};
+// D[tmem] (+)= A[tmem] * B[smem], E2M1 operands, K = 64, fp32 accumulation; scale factors from TMEM
+__device__ __forceinline__ void mma_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], [%1], %2, %3, [%5], [%6], p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+
+// the two operand planes of one sample row and one 64-site step from its 8 stream words
+template <int MODE>
+__device__ __forceinline__ void make_planes(const uint4& lo, const uint4& hi, uint32_t (&p0)[8], uint32_t (&p1)[8]) {
+  const uint32_t n[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    const uint32_t hi = q[m] >> 16;
-    p0[2 * m] = prmt(POOL0, q[m]);
-    p0[2 * m + 1] = prmt(POOL0, hi);
-    p1[2 * m] = prmt(POOL1, q[m]);
-    p1[2 * m + 1] = prmt(POOL1, hi);
+  for (int m = 0; m < 8; ++m) {
+    const uint32_t h = n[m] & NIB_HOM;
+    if (MODE == 0) {
+      p0[m] = n[m];        // x: the stream nibble is its E2M1 code
+      p1[m] = h;
+    } else {
+      p0[m] = h;
+      p1[m] = (((~n[m]) >> 3 | n[m] >> 1) & 0x11111111u) << 1;   // v: +1.0 unless the nibble is 0x8 (bit 3 set, bit 1 clear)
+    }
   }
 }
 
@@ -174,7 +203,6 @@ template <int MODE, bool PROF>
 __global__ void __launch_bounds__(TcGeo<MODE>::THREADS, 1)
 pair_counts_tc_kernel(const TcParams P) {
   using G = TcGeo<MODE>;
-  using C = TcCfg<MODE>;
   constexpr int J = G::J;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
@@ -187,7 +215,7 @@ pair_counts_tc_kernel(const TcParams P) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // shared-window addresses, computed once
   const uint32_t raw_a = umma::smem_addr(smem);                                   // RAW_STAGES x RAW_STAGE_BYTES
-  const uint32_t exp_a = raw_a + RAW_STAGES * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (B tiles)
+  const uint32_t exp_a = raw_a + RAW_STAGES * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (derived B planes)
   const uint32_t raw_full_a = umma::smem_addr(raw_full), raw_empty_a = umma::smem_addr(raw_empty);
   const uint32_t exp_full_a = umma::smem_addr(exp_full), exp_empty_a = umma::smem_addr(exp_empty);
   const uint32_t done_a = umma::smem_addr(&done_bar);
@@ -206,15 +234,15 @@ pair_counts_tc_kernel(const TcParams P) {
   const int tj = (TC_I * ti) / J + rem;
   const int64_t w_begin = static_cast<int64_t>(split) * P.words_per_split;
   const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
-  const int n_wordsteps = static_cast<int>(w_end - w_begin);
-  if (n_wordsteps <= 0) return;
-  const int n_steps = (n_wordsteps + STEP_WORDS - 1) / STEP_WORDS;
+  if (w_end <= w_begin) return;
+  const int n_steps = static_cast<int>((w_end - w_begin + STEP_WORDS - 1) / STEP_WORDS);
+  const int64_t s_begin = w_begin / STEP_WORDS;
 
   if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
   if (tid == 32) {
     for (int s = 0; s < RAW_STAGES; ++s) {
       umma::mbar_init(&raw_full[s], 1);
-      umma::mbar_init(&raw_empty[s], G::EXP_WARPS);
+      umma::mbar_init(&raw_empty[s], G::RAW_EMPTY_ARRIVALS);
     }
     for (int e = 0; e < EXP_STAGES; ++e) {
       umma::mbar_init(&exp_full[e], G::EXP_WARPS);
@@ -228,9 +256,21 @@ pair_counts_tc_kernel(const TcParams P) {
   __syncthreads();
   umma::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
+  if (warp < TC_I / 32) {
+    // block scale factors: UE8M0 127 = 2^0 everywhere (32 columns cover the A and B factors of any tile shape)
+    uint32_t ones[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ones[j] = 0x7f7f7f7fu;
+#pragma unroll
+    for (int c = 0; c < 32; c += 8) umma::tmem_st_32x8(tmem + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_SF + c, ones);
+    umma::tmem_wait_st();
+  }
+  umma::fence_before_thread_sync();
+  __syncthreads();
+  umma::fence_after_thread_sync();
 
   if (warp == G::EXP_WARPS) {
-    // ===== TMA producer: raw nib4 words of the 64-sample tiles of this tile pair =====
+    // ===== TMA producer: the stream chunks of the 64-sample tiles of this tile pair =====
     if (lane == 0) {
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
@@ -239,7 +279,7 @@ pair_counts_tc_kernel(const TcParams P) {
       for (int k = 0; k < G::PF; ++k) {
         const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k)
                                     : ((J / PF_TILE) * static_cast<int64_t>(tj) + (k - 2));
-        src_tile[k] = P.nib4 + (pft * P.n_local + w_begin) * 64;
+        src_tile[k] = P.stream + (pft * P.n_steps + s_begin) * (CHUNK_BYTES / 16);
       }
       int stage = 0;
       uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
@@ -249,15 +289,12 @@ pair_counts_tc_kernel(const TcParams P) {
           umma::mbar_wait_a(raw_empty_a + stage * 8, phase);
           if (PROF) t_wait += clock64() - t0;
         }
-        const int kw = min(RAW_WORDS, n_wordsteps - st * RAW_WORDS);
-        const uint32_t bytes_per_tile = static_cast<uint32_t>(kw) * 64 * 16;
-        umma::mbar_expect_tx_a(raw_full_a + stage * 8, bytes_per_tile * G::PF);
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, G::PF * CHUNK_BYTES);
         const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES;
-        // stage layout: [pf_tile][word][64 samples][16 B]; pf tiles 0,1 = I rows, the rest = J rows
 #pragma unroll
         for (int k = 0; k < G::PF; ++k)
-          umma::bulk_g2s_a(dst + k * (RAW_WORDS * 64 * 16), src_tile[k] + static_cast<int64_t>(st) * (RAW_WORDS * 64),
-                           bytes_per_tile, raw_full_a + stage * 8);
+          umma::bulk_g2s_a(dst + k * CHUNK_BYTES, src_tile[k] + static_cast<int64_t>(st) * (CHUNK_BYTES / 16), CHUNK_BYTES,
+                           raw_full_a + stage * 8);
         if (++stage == RAW_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -271,40 +308,39 @@ pair_counts_tc_kernel(const TcParams P) {
   } else if (warp == G::EXP_WARPS + 1) {
     // ===== MMA issuer: D[tmem] += A[tmem] * B[smem] =====
     if (lane == 0) {
-      const uint32_t idesc = umma::idesc_i8(TC_I, J);
+      const uint32_t idesc = idesc_mxf4(TC_I, J);
+      const uint32_t tsfa = tmem + TMEM_SF, tsfb = tmem + TMEM_SF + 16;
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
-      int e = 0;
+      int e = 0, stage = 0;
       uint32_t phase = 0;
       for (int st = 0; st < n_steps; ++st) {
         const long long t0 = PROF ? clock64() : 0;
         umma::mbar_wait_a(exp_full_a + e * 8, phase);
         if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
-        const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
-#pragma unroll
-        for (int k = 0; k < STEP_WORDS; ++k) {
-          if (k < kw) {
-            const uint32_t base = exp_a + e * G::EXP_STAGE_BYTES + k * G::EXP_WORD_BYTES;
-            const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(base + G::EXP_B0, 128, 256);
-            const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(base + G::EXP_B1, 128, 256);
-            const uint32_t a0 = tmem + G::TMEM_A + (e * STEP_WORDS + k) * TMEM_A_COLS, a1 = a0 + 8;
-            const uint32_t acc = (st > 0 || k > 0) ? 1u : 0u;
-            if (MODE == 0) {
-              umma::mma_i8_ts(tmem + 0 * J, a0, b0, idesc, acc);   // XX
-              umma::mma_i8_ts(tmem + 1 * J, a1, b1, idesc, acc);   // HH
-            } else {
-              umma::mma_i8_ts(tmem + 0 * J, a1, b1, idesc, acc);   // VV
-              umma::mma_i8_ts(tmem + 1 * J, a0, b1, idesc, acc);   // HV
-              umma::mma_i8_ts(tmem + 2 * J, a1, b0, idesc, acc);   // VH
-            }
-          }
+        const uint32_t a0 = tmem + G::TMEM_A + e * TMEM_A_COLS, a1 = a0 + 8;
+        const uint32_t acc = st > 0 ? 1u : 0u;
+        const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES;
+        if (MODE == 0) {
+          const uint64_t bx = umma::smem_desc_kmajor_noswizzle(raw_a + stage * G::RAW_STAGE_BYTES + G::A_RAW_BYTES, 128, 256);
+          const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
+          mma_mxf4_ts(tmem + 0 * J, a0, bx, idesc, acc, tsfa, tsfb);   // XX
+          mma_mxf4_ts(tmem + 1 * J, a1, bh, idesc, acc, tsfa, tsfb);   // HH
+          umma::commit_a(raw_empty_a + stage * 8);                     // the raw stage held B_x
+        } else {
+          const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
+          const uint64_t bv = umma::smem_desc_kmajor_noswizzle(ebase + G::EXP_PLANE_BYTES, 128, 256);
+          mma_mxf4_ts(tmem + 0 * J, a1, bv, idesc, acc, tsfa, tsfb);   // VV
+          mma_mxf4_ts(tmem + 1 * J, a0, bv, idesc, acc, tsfa, tsfb);   // HV
+          mma_mxf4_ts(tmem + 2 * J, a1, bh, idesc, acc, tsfa, tsfb);   // VH
         }
         umma::commit_a(exp_empty_a + e * 8);
         if (++e == EXP_STAGES) {
           e = 0;
           phase ^= 1;
         }
+        if (++stage == RAW_STAGES) stage = 0;
       }
       umma::commit_a(done_a);
       if (PROF) {
@@ -314,16 +350,16 @@ pair_counts_tc_kernel(const TcParams P) {
       }
     }
   } else {
-    // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, written straight
-    // into TMEM (their lane quadrant); the others: the B rows, written to shared memory in the
-    // canonical K-major layout =====
+    // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, planes written
+    // straight into TMEM (their lane quadrant); the others: the B rows, derived planes written to
+    // shared memory in the canonical K-major layout =====
     const int row = tid;
-    const int pf = row >> 6, l = row & 63;     // raw stage sub-tile and sample inside it
     const bool is_a = row < TC_I;
     const int r = is_a ? row : row - TC_I;
     const uint32_t a_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A;   // A rows: TMEM lane = row
-    const uint32_t raw_row = raw_a + pf * (RAW_WORDS * 64 * 16) + l * 16;
-    const uint32_t exp_row = exp_a + unit_off(r, 0);                                             // B rows: canonical smem tile
+    // both the A part and the B part of a raw stage are canonical tiles, so is the expanded stage
+    const uint32_t raw_row = raw_a + (is_a ? 0 : G::A_RAW_BYTES) + unit_off(r, 0);
+    const uint32_t exp_row = exp_a + unit_off(r, 0);
     long long t_wraw = 0, t_wemp = 0, t_fence = 0;
     const long long t_start = PROF ? clock64() : 0;
     int stage = 0, e = 0;
@@ -341,42 +377,28 @@ pair_counts_tc_kernel(const TcParams P) {
       }
       __syncwarp();
       if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
-      const int kw = min(STEP_WORDS, n_wordsteps - st * STEP_WORDS);
       const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
-      uint4 nb[STEP_WORDS];
-#pragma unroll
-      for (int k = 0; k < STEP_WORDS; ++k) nb[k] = umma::lds128(src + k * (64 * 16));   // stale words of a short last step are unused
-      if (is_a) {
-        const uint32_t a_col = a_base + e * (STEP_WORDS * TMEM_A_COLS);
-#pragma unroll
-        for (int k = 0; k < STEP_WORDS; ++k) {
-          if (k < kw) {
-            uint32_t p0[8], p1[8];
-            expand_word<C::POOL0, C::POOL1>(nb[k], p0, p1);
-            umma::tmem_st_32x8(a_col + k * TMEM_A_COLS, p0);
-            umma::tmem_st_32x8(a_col + k * TMEM_A_COLS + 8, p1);
-          }
-        }
-      } else {
-        const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < STEP_WORDS; ++k) {
-          if (k < kw) {
-            uint32_t p0[8], p1[8];
-            expand_word<C::POOL0, C::POOL1>(nb[k], p0, p1);
-            const uint32_t d = dst + k * G::EXP_WORD_BYTES;
-            umma::sts128(d + G::EXP_B0, p0[0], p0[1], p0[2], p0[3]);
-            umma::sts128(d + G::EXP_B0 + 128, p0[4], p0[5], p0[6], p0[7]);
-            umma::sts128(d + G::EXP_B1, p1[0], p1[1], p1[2], p1[3]);
-            umma::sts128(d + G::EXP_B1 + 128, p1[4], p1[5], p1[6], p1[7]);
-          }
-        }
-      }
+      const uint4 lo = umma::lds128(src), hi = umma::lds128(src + 128);
+      uint32_t p0[8], p1[8];
+      make_planes<MODE>(lo, hi, p0, p1);
       const long long tf0 = PROF ? clock64() : 0;
       if (is_a) {
+        const uint32_t a_col = a_base + e * TMEM_A_COLS;
+        umma::tmem_st_32x8(a_col, p0);
+        umma::tmem_st_32x8(a_col + 8, p1);
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
       } else {
+        const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES;
+        if (MODE == 0) {
+          umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
+          umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
+        } else {
+          umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // h
+          umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
+          umma::sts128(dst + G::EXP_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);   // v
+          umma::sts128(dst + G::EXP_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
+        }
         umma::fence_proxy_async_smem();
       }
       __syncwarp();
@@ -415,7 +437,7 @@ pair_counts_tc_kernel(const TcParams P) {
     // all expansion warps meet before the epilogue (named barrier 1)
     asm volatile("bar.sync 1, %0;" ::"r"(G::EXP_WARPS * 32) : "memory");
 
-    // ===== epilogue: TMEM -> registers -> counts =====
+    // ===== epilogue: TMEM (fp32, integer-valued) -> registers -> counts =====
     umma::mbar_wait_a(done_a, 0);
     umma::fence_after_thread_sync();
     const int lane_grp = warp & 3;               // TMEM lanes [32 g, 32 g + 32) are visible to warps with w % 4 == g
@@ -423,7 +445,7 @@ pair_counts_tc_kernel(const TcParams P) {
     const int grp_size = (lane_grp < (G::EXP_WARPS & 3)) ? (G::EXP_WARPS / 4 + 1) : (G::EXP_WARPS / 4);
     const int i_local = lane_grp * 32 + lane;
     const int64_t i = static_cast<int64_t>(ti) * TC_I + i_local;
-    const int hi = uniform ? s_hcount[i_local] : 0;
+    const int hi_cnt = uniform ? s_hcount[i_local] : 0;
     const int v_sites = s_valid_sites;
     const int64_t plane = P.n_samples * P.ld;
     int32_t* V = P.counts;
@@ -442,10 +464,10 @@ pair_counts_tc_kernel(const TcParams P) {
             const int j_local = chunk * 32 + c;
             const int64_t j = static_cast<int64_t>(tj) * J + j_local;
             if (j >= P.n_samples || j < i) continue;       // each unordered pair once: row <= column
-            const int xx = static_cast<int>(pv[c]), hh = static_cast<int>(qv[c]);
+            const int xx = __float2int_rn(__uint_as_float(pv[c])), hh = __float2int_rn(__uint_as_float(qv[c]));
             const int d2 = (hh - xx) >> 1;
             // uniform: D1 = |h_i| + |h_j| - 2 HH + D2; general: HV + VH come from the mode-1 launch
-            const int d1 = (uniform ? hi + s_hcount[TC_I + j_local] : 0) - 2 * hh + d2;
+            const int d1 = (uniform ? hi_cnt + s_hcount[TC_I + j_local] : 0) - 2 * hh + d2;
             if (uniform) atomicAdd(V + i * P.ld + j, v_sites);
             atomicAdd(D1 + i * P.ld + j, d1);
             atomicAdd(D2 + i * P.ld + j, d2);
@@ -467,8 +489,8 @@ pair_counts_tc_kernel(const TcParams P) {
           for (int c = 0; c < 32; ++c) {
             const int64_t j = static_cast<int64_t>(tj) * J + chunk * 32 + c;
             if (j >= P.n_samples || j < i) continue;
-            const int v = static_cast<int>(vv[c]);
-            const int d1 = static_cast<int>(hv[c]) + static_cast<int>(vh[c]);
+            const int v = __float2int_rn(__uint_as_float(vv[c]));
+            const int d1 = __float2int_rn(__uint_as_float(hv[c])) + __float2int_rn(__uint_as_float(vh[c]));
             atomicAdd(V + i * P.ld + j, v);
             atomicAdd(D1 + i * P.ld + j, d1);
             if (j != i) {
@@ -495,7 +517,7 @@ struct TcPlan {
   int64_t n_local, n_tiles, n_tiles_padded, hsum_ld;
   int n_itiles;
   TcModePlan m[2];
-  int64_t nib_bytes, refv_off, flags_off, hsum_off, total;
+  int64_t n_steps, nib_bytes, refv_off, flags_off, hsum_off, total;
 };
 
 int tc_sm_count() {
@@ -525,13 +547,16 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
     int64_t splits = pf_ceil_div(static_cast<int64_t>(sms) * 20, M.pairs);
     const int64_t max_splits = pf_ceil_div(n_local, 64);
     if (splits > max_splits) splits = max_splits;
+    const int64_t min_splits = pf_ceil_div(n_local, MAX_WORDS_PER_CTA);   // fp32 accumulators stay exact
+    if (splits < min_splits) splits = min_splits;
     if (splits < 1) splits = 1;
     M.words_per_split = pf_ceil_div(pf_ceil_div(n_local, splits), HSUM_RUN) * HSUM_RUN;
     M.splits = pf_ceil_div(n_local, M.words_per_split);
     if (M.splits < 1) M.splits = 1;
   }
   L.hsum_ld = L.n_tiles_padded * PF_TILE;
-  L.nib_bytes = tc_align(L.n_tiles_padded * n_local * 64 * 16);
+  L.n_steps = (n_local + 1) / 2;
+  L.nib_bytes = tc_align(L.n_tiles_padded * L.n_steps * CHUNK_BYTES);
   L.refv_off = L.nib_bytes;
   L.flags_off = L.refv_off + tc_align(n_local * 4);
   L.hsum_off = L.flags_off + 256;
@@ -586,7 +611,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   {
     const int64_t n_runs = pf_ceil_div(n_local, HSUM_RUN);
     const int64_t threads = L.n_tiles_padded * n_runs * 64;
-    planes_to_nib4_kernel<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
+    planes_to_e2m1_kernel<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
         d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded, nib4, ref_v, flags, hsum,
         L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
@@ -598,9 +623,10 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   if (general && !allow_general) return PF_OK;  // *h_used stays 0, nothing was added to d_counts
 
   TcParams P;
-  P.nib4 = nib4;
+  P.stream = nib4;
   P.all_v = ref_v;
   P.n_local = n_local;
+  P.n_steps = L.n_steps;
   P.n_samples = n_samples;
   P.counts = d_counts;
   P.ld = ld;
