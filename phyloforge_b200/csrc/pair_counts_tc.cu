@@ -20,9 +20,9 @@
 //
 // Operand stream (produced once per call by planes_to_e2m1): one nibble per genotype that is at the
 // same time the E2M1 code of x and a tag: hom-REF 0xA (-1), het 0x0 (+0), hom-ALT 0x2 (+1),
-// missing 0x8 (-0). h = nibble & 2, v = "nibble != 8". It is stored as 2 KB chunks (64 samples x 64
-// sites) already in the canonical K-major shared-memory order of a UMMA operand, so a TMA bulk copy of
-// the J rows of a chunk row lands as a ready B_x operand.
+// missing 0x8 (-0). h = nibble & 2, v = "nibble != 8". It is stored step-major as 2 KB chunks (64
+// samples x 64 sites) already in the canonical K-major shared-memory order of a UMMA operand, so ONE
+// TMA bulk copy of the J rows of a step lands as a ready B_x operand.
 // Data flow per CTA (one sample tile pair, a contiguous range of 64-site steps):
 //   stream --TMA bulk copies--> raw ring (A rows | B rows = the B_x operand in mode 0)
 //   --expansion warps (thread = sample row): a few logic ops per 8 genotypes--> A planes straight into
@@ -80,7 +80,7 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> bit 0 of
   return x;
 }
 
-// stream[((T * n_steps + s) * 128 + (l >> 3) * 16 + kh * 8 + (l & 7))] (uint4) = the 32 sites of word
+// stream[((s * n_tiles_padded + T) * 128 + (l >> 3) * 16 + kh * 8 + (l & 7))] (uint4) = the 32 sites of word
 // 2 s + kh of sample 64 T + l, nibble j of 32-bit word q = site 8 q + j: bit 3 = "hom-REF or missing",
 // bit 1 = "homozygous" (see the file header). A second half-step past the last word is all missing.
 // ref_v[w] = valid-site mask of sample 0; flags[0] is set when any real sample's mask differs from
@@ -96,7 +96,6 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
   const int l = static_cast<int>(idx & 63);
   const int64_t tr = idx >> 6;
   const int64_t n_runs = (n_local + HSUM_RUN - 1) / HSUM_RUN;
-  const int64_t n_steps = (n_local + 1) / 2;
   const int64_t run = tr % n_runs;
   const int64_t t = tr / n_runs;
   if (t >= n_tiles_padded) return;
@@ -119,9 +118,9 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
     out.y = (spread8((S >> 8) & 0xffu) << 3) | (spread8((M >> 8) & 0xffu) << 1);
     out.z = (spread8((S >> 16) & 0xffu) << 3) | (spread8((M >> 16) & 0xffu) << 1);
     out.w = (spread8(S >> 24) << 3) | (spread8(M >> 24) << 1);
-    stream[(t * n_steps + (w >> 1)) * 128 + (w & 1) * 8 + unit] = out;
+    stream[((w >> 1) * n_tiles_padded + t) * 128 + (w & 1) * 8 + unit] = out;
     if (w == n_local - 1 && (w & 1) == 0)
-      stream[(t * n_steps + (w >> 1)) * 128 + 8 + unit] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+      stream[((w >> 1) * n_tiles_padded + t) * 128 + 8 + unit] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
     const uint32_t* p0 = planes + ((word_begin + w) * 2) * PF_TILE;   // sample 0: tile 0, lane 0
     const uint32_t ref = ~(p0[0] & p0[PF_TILE]);
     if (t == 0 && l == 0) ref_v[w] = ref;
@@ -138,9 +137,11 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
 // optional role-level cycle accounting (pf_pair_counts_tc_profile): who waits for whom
 __device__ long long g_tc_prof[16];
 bool g_tc_prof_enabled = false;
+int g_tc_debug = 0;
 
 struct TcParams {
-  const uint4* stream;    // [n_tiles_padded][n_steps] chunks of 2 KB
+  const uint4* stream;    // [n_steps][n_tiles_padded] chunks of 2 KB
+  int64_t n_tiles_padded;
   const uint32_t* all_v;  // [n_local] valid-site mask of sample 0 (= of every sample when uniform)
   int64_t n_local;        // words in the range
   int64_t n_steps;        // 64-site steps in the range
@@ -154,6 +155,8 @@ struct TcParams {
   const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split (mode 0, uniform)
   int64_t hsum_ld;
   int general;            // mode 0 only: 1 = sample-specific missingness, mode 1 supplies V and HV + VH
+  int debug;              // timing experiments (results are wrong): 1 = MMAs do not wait for operands,
+                          // 2 = expansion warps do no work, 4 = no MMAs are issued
 };
 
 // block-scaled instruction descriptor (bit layout: CUTLASS cute/arch/mma_sm100_desc.hpp,
@@ -270,17 +273,16 @@ pair_counts_tc_kernel(const TcParams P) {
   umma::fence_after_thread_sync();
 
   if (warp == G::EXP_WARPS) {
-    // ===== TMA producer: the stream chunks of the 64-sample tiles of this tile pair =====
+    // ===== TMA producer: two bulk copies per step. The stream is step-major, so the 64-sample chunks
+    // of the A rows (2) and of the B rows (J / 64) of a step are each one contiguous range. (The TMA
+    // unit takes ~120 clocks per bulk request whatever its size: five 2 KB requests per step capped
+    // the kernel at ~700 clocks per step.) =====
     if (lane == 0) {
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
-      const uint4* src_tile[G::PF];
-#pragma unroll
-      for (int k = 0; k < G::PF; ++k) {
-        const int64_t pft = (k < 2) ? (2 * static_cast<int64_t>(ti) + k)
-                                    : ((J / PF_TILE) * static_cast<int64_t>(tj) + (k - 2));
-        src_tile[k] = P.stream + (pft * P.n_steps + s_begin) * (CHUNK_BYTES / 16);
-      }
+      const int64_t step_stride = P.n_tiles_padded * (CHUNK_BYTES / 16);
+      const uint4* src_a = P.stream + s_begin * step_stride + 2 * static_cast<int64_t>(ti) * (CHUNK_BYTES / 16);
+      const uint4* src_b = P.stream + s_begin * step_stride + (J / PF_TILE) * static_cast<int64_t>(tj) * (CHUNK_BYTES / 16);
       int stage = 0;
       uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
       for (int st = 0; st < n_steps; ++st) {
@@ -289,12 +291,11 @@ pair_counts_tc_kernel(const TcParams P) {
           umma::mbar_wait_a(raw_empty_a + stage * 8, phase);
           if (PROF) t_wait += clock64() - t0;
         }
-        umma::mbar_expect_tx_a(raw_full_a + stage * 8, G::PF * CHUNK_BYTES);
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, G::RAW_STAGE_BYTES);
         const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < G::PF; ++k)
-          umma::bulk_g2s_a(dst + k * CHUNK_BYTES, src_tile[k] + static_cast<int64_t>(st) * (CHUNK_BYTES / 16), CHUNK_BYTES,
-                           raw_full_a + stage * 8);
+        umma::bulk_g2s_a(dst, src_a + st * step_stride, G::A_RAW_BYTES, raw_full_a + stage * 8);
+        umma::bulk_g2s_a(dst + G::A_RAW_BYTES, src_b + st * step_stride, G::RAW_STAGE_BYTES - G::A_RAW_BYTES,
+                         raw_full_a + stage * 8);
         if (++stage == RAW_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -316,9 +317,19 @@ pair_counts_tc_kernel(const TcParams P) {
       uint32_t phase = 0;
       for (int st = 0; st < n_steps; ++st) {
         const long long t0 = PROF ? clock64() : 0;
-        umma::mbar_wait_a(exp_full_a + e * 8, phase);
+        if (!(PROF && (P.debug & 1))) umma::mbar_wait_a(exp_full_a + e * 8, phase);
         if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
+        if (PROF && (P.debug & 4)) {
+          if (MODE == 0) umma::mbar_arrive_a(raw_empty_a + stage * 8);
+          umma::mbar_arrive_a(exp_empty_a + e * 8);
+          if (++e == EXP_STAGES) {
+            e = 0;
+            phase ^= 1;
+          }
+          if (++stage == RAW_STAGES) stage = 0;
+          continue;
+        }
         const uint32_t a0 = tmem + G::TMEM_A + e * TMEM_A_COLS, a1 = a0 + 8;
         const uint32_t acc = st > 0 ? 1u : 0u;
         const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES;
@@ -378,11 +389,17 @@ pair_counts_tc_kernel(const TcParams P) {
       __syncwarp();
       if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
       const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
-      const uint4 lo = umma::lds128(src), hi = umma::lds128(src + 128);
+      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+      const bool idle = PROF && (P.debug & 2);
+      if (!idle) {
+        lo = umma::lds128(src);
+        hi = umma::lds128(src + 128);
+      }
       uint32_t p0[8], p1[8];
       make_planes<MODE>(lo, hi, p0, p1);
       const long long tf0 = PROF ? clock64() : 0;
-      if (is_a) {
+      if (idle) {
+      } else if (is_a) {
         const uint32_t a_col = a_base + e * TMEM_A_COLS;
         umma::tmem_st_32x8(a_col, p0);
         umma::tmem_st_32x8(a_col + 8, p1);
@@ -624,6 +641,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
 
   TcParams P;
   P.stream = nib4;
+  P.n_tiles_padded = L.n_tiles_padded;
   P.all_v = ref_v;
   P.n_local = n_local;
   P.n_steps = L.n_steps;
@@ -634,6 +652,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   P.hsum = hsum;
   P.hsum_ld = L.hsum_ld;
   P.general = general;
+  P.debug = g_tc_prof_enabled ? g_tc_debug : 0;
   for (int mode = 0; mode < (general ? 2 : 1); ++mode) {
     const TcModePlan& M = L.m[mode];
     P.n_jtiles = M.n_jtiles;
@@ -658,7 +677,8 @@ PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16) {
   if (h_out16) PF_CUDA(cudaMemcpyFromSymbol(h_out16, g_tc_prof, sizeof(long long) * 16));
   long long zero[16] = {0};
   PF_CUDA(cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)));
-  g_tc_prof_enabled = enable != 0;
+  g_tc_prof_enabled = (enable & 1) != 0;
+  g_tc_debug = enable >> 4;   // timing experiments, see TcParams::debug
   return PF_OK;
   PF_TRY_END
 }
