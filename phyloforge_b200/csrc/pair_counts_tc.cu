@@ -37,10 +37,12 @@ namespace {
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
 constexpr int STEP_WORDS = 2;        // one pipeline step = one MMA K step = 64 sites = two 32-site words
 constexpr int CHUNK_BYTES = 2048;    // 64 samples x 64 sites x 4 bits
-constexpr int RAW_STAGES = 8;
-constexpr int EXP_STAGES = 4;
-constexpr int TMEM_A_COLS = 16;      // per expanded stage: 8 columns per A plane (32 K-bytes per row)
-constexpr int TMEM_SF = 448;         // 32 columns of scale factors (all 1.0) behind accumulators and A staging
+constexpr int GROUP = 3;             // steps per pipeline stage: the barrier round trips of a stage (~500 clocks
+                                     // for an expansion warp) are paid once per GROUP steps
+constexpr int RAW_STAGES = 4;
+constexpr int EXP_STAGES = 2;
+constexpr int TMEM_A_COLS = 16;      // per step: 8 columns per A plane (32 K-bytes per row)
+constexpr int TMEM_SF = 496;         // 16 columns of scale factors (all 1.0) behind accumulators and A staging
 constexpr uint32_t NIB_HOM = 0x22222222u;   // bit 1 of a stream nibble: homozygous; as E2M1 that bit alone is +1.0
 constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
 constexpr int64_t MAX_WORDS_PER_CTA = 1 << 18;   // 2^23 sites: fp32 accumulators stay exact
@@ -59,16 +61,18 @@ template <int MODE> struct TcGeo {
   static constexpr int ROWS = TC_I + J;                        // sample rows handled per step
   static constexpr int PF = ROWS / PF_TILE;                    // 64-sample chunks of the stream per step
   static constexpr int A_RAW_BYTES = (TC_I / PF_TILE) * CHUNK_BYTES;
-  static constexpr int RAW_STAGE_BYTES = PF * CHUNK_BYTES;     // [A rows | B rows], canonical order
+  static constexpr int RAW_STEP_BYTES = PF * CHUNK_BYTES;      // [A rows | B rows], canonical order
+  static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
   static constexpr int EXP_PLANE_BYTES = J * 32;
-  static constexpr int EXP_STAGE_BYTES = C::NEXP * EXP_PLANE_BYTES;
+  static constexpr int EXP_STEP_BYTES = C::NEXP * EXP_PLANE_BYTES;
+  static constexpr int EXP_STAGE_BYTES = GROUP * EXP_STEP_BYTES;
   static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
   static constexpr int RAW_EMPTY_ARRIVALS = EXP_WARPS + (MODE == 0 ? 1 : 0);   // mode 0: the MMA reads B_x from the raw stage
   static constexpr size_t SMEM = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES +
                                  static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
-  static_assert(TMEM_A + EXP_STAGES * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 32 <= 512, "TMEM columns");
+  static_assert(TMEM_A + EXP_STAGES * GROUP * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
 };
 
 // ------------------------------------------------------------------ planes -> E2M1 stream
@@ -239,6 +243,7 @@ pair_counts_tc_kernel(const TcParams P) {
   const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
   if (w_end <= w_begin) return;
   const int n_steps = static_cast<int>((w_end - w_begin + STEP_WORDS - 1) / STEP_WORDS);
+  const int n_groups = (n_steps + GROUP - 1) / GROUP;
   const int64_t s_begin = w_begin / STEP_WORDS;
 
   if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
@@ -260,12 +265,12 @@ pair_counts_tc_kernel(const TcParams P) {
   umma::fence_after_thread_sync();
   const uint32_t tmem = s_tmem;
   if (warp < TC_I / 32) {
-    // block scale factors: UE8M0 127 = 2^0 everywhere (32 columns cover the A and B factors of any tile shape)
+    // block scale factors: UE8M0 127 = 2^0 everywhere (4 columns for A, 12 for B cover any tile shape)
     uint32_t ones[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) ones[j] = 0x7f7f7f7fu;
 #pragma unroll
-    for (int c = 0; c < 32; c += 8) umma::tmem_st_32x8(tmem + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_SF + c, ones);
+    for (int c = 0; c < 16; c += 8) umma::tmem_st_32x8(tmem + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_SF + c, ones);
     umma::tmem_wait_st();
   }
   umma::fence_before_thread_sync();
@@ -285,17 +290,23 @@ pair_counts_tc_kernel(const TcParams P) {
       const uint4* src_b = P.stream + s_begin * step_stride + (J / PF_TILE) * static_cast<int64_t>(tj) * (CHUNK_BYTES / 16);
       int stage = 0;
       uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
-      for (int st = 0; st < n_steps; ++st) {
-        if (st >= RAW_STAGES) {
+      for (int g = 0; g < n_groups; ++g) {
+        if (g >= RAW_STAGES) {
           const long long t0 = PROF ? clock64() : 0;
           umma::mbar_wait_a(raw_empty_a + stage * 8, phase);
           if (PROF) t_wait += clock64() - t0;
         }
-        umma::mbar_expect_tx_a(raw_full_a + stage * 8, G::RAW_STAGE_BYTES);
-        const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES;
-        umma::bulk_g2s_a(dst, src_a + st * step_stride, G::A_RAW_BYTES, raw_full_a + stage * 8);
-        umma::bulk_g2s_a(dst + G::A_RAW_BYTES, src_b + st * step_stride, G::RAW_STAGE_BYTES - G::A_RAW_BYTES,
-                         raw_full_a + stage * 8);
+        const int kw = min(GROUP, n_steps - g * GROUP);
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          if (j < kw) {
+            const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES;
+            const int64_t off = (static_cast<int64_t>(g) * GROUP + j) * step_stride;
+            umma::bulk_g2s_a(dst, src_a + off, G::A_RAW_BYTES, raw_full_a + stage * 8);
+            umma::bulk_g2s_a(dst + G::A_RAW_BYTES, src_b + off, G::RAW_STEP_BYTES - G::A_RAW_BYTES, raw_full_a + stage * 8);
+          }
+        }
         if (++stage == RAW_STAGES) {
           stage = 0;
           phase ^= 1;
@@ -310,42 +321,41 @@ pair_counts_tc_kernel(const TcParams P) {
     // ===== MMA issuer: D[tmem] += A[tmem] * B[smem] =====
     if (lane == 0) {
       const uint32_t idesc = idesc_mxf4(TC_I, J);
-      const uint32_t tsfa = tmem + TMEM_SF, tsfb = tmem + TMEM_SF + 16;
+      const uint32_t tsfa = tmem + TMEM_SF, tsfb = tmem + TMEM_SF + 4;
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
       int e = 0, stage = 0;
       uint32_t phase = 0;
-      for (int st = 0; st < n_steps; ++st) {
+      for (int g = 0; g < n_groups; ++g) {
         const long long t0 = PROF ? clock64() : 0;
-        if (!(PROF && (P.debug & 1))) umma::mbar_wait_a(exp_full_a + e * 8, phase);
+        umma::mbar_wait_a(exp_full_a + e * 8, phase);
         if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
-        if (PROF && (P.debug & 4)) {
-          if (MODE == 0) umma::mbar_arrive_a(raw_empty_a + stage * 8);
-          umma::mbar_arrive_a(exp_empty_a + e * 8);
-          if (++e == EXP_STAGES) {
-            e = 0;
-            phase ^= 1;
+        const int kw = min(GROUP, n_steps - g * GROUP);
+        if (!(PROF && (P.debug & 4))) {
+#pragma unroll
+          for (int j = 0; j < GROUP; ++j) {
+            if (j < kw) {
+              const uint32_t a0 = tmem + G::TMEM_A + (e * GROUP + j) * TMEM_A_COLS, a1 = a0 + 8;
+              const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
+              const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+              if (MODE == 0) {
+                const uint64_t bx = umma::smem_desc_kmajor_noswizzle(
+                    raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES + G::A_RAW_BYTES, 128, 256);
+                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
+                mma_mxf4_ts(tmem + 0 * J, a0, bx, idesc, acc, tsfa, tsfb);   // XX
+                mma_mxf4_ts(tmem + 1 * J, a1, bh, idesc, acc, tsfa, tsfb);   // HH
+              } else {
+                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
+                const uint64_t bv = umma::smem_desc_kmajor_noswizzle(ebase + G::EXP_PLANE_BYTES, 128, 256);
+                mma_mxf4_ts(tmem + 0 * J, a1, bv, idesc, acc, tsfa, tsfb);   // VV
+                mma_mxf4_ts(tmem + 1 * J, a0, bv, idesc, acc, tsfa, tsfb);   // HV
+                mma_mxf4_ts(tmem + 2 * J, a1, bh, idesc, acc, tsfa, tsfb);   // VH
+              }
+            }
           }
-          if (++stage == RAW_STAGES) stage = 0;
-          continue;
         }
-        const uint32_t a0 = tmem + G::TMEM_A + e * TMEM_A_COLS, a1 = a0 + 8;
-        const uint32_t acc = st > 0 ? 1u : 0u;
-        const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES;
-        if (MODE == 0) {
-          const uint64_t bx = umma::smem_desc_kmajor_noswizzle(raw_a + stage * G::RAW_STAGE_BYTES + G::A_RAW_BYTES, 128, 256);
-          const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
-          mma_mxf4_ts(tmem + 0 * J, a0, bx, idesc, acc, tsfa, tsfb);   // XX
-          mma_mxf4_ts(tmem + 1 * J, a1, bh, idesc, acc, tsfa, tsfb);   // HH
-          umma::commit_a(raw_empty_a + stage * 8);                     // the raw stage held B_x
-        } else {
-          const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
-          const uint64_t bv = umma::smem_desc_kmajor_noswizzle(ebase + G::EXP_PLANE_BYTES, 128, 256);
-          mma_mxf4_ts(tmem + 0 * J, a1, bv, idesc, acc, tsfa, tsfb);   // VV
-          mma_mxf4_ts(tmem + 1 * J, a0, bv, idesc, acc, tsfa, tsfb);   // HV
-          mma_mxf4_ts(tmem + 2 * J, a1, bh, idesc, acc, tsfa, tsfb);   // VH
-        }
+        if (MODE == 0) umma::commit_a(raw_empty_a + stage * 8);   // the raw stage held the B_x operands
         umma::commit_a(exp_empty_a + e * 8);
         if (++e == EXP_STAGES) {
           e = 0;
@@ -375,47 +385,57 @@ pair_counts_tc_kernel(const TcParams P) {
     const long long t_start = PROF ? clock64() : 0;
     int stage = 0, e = 0;
     uint32_t raw_phase = 0, exp_phase = 1;
-    for (int st = 0; st < n_steps; ++st) {
-      if (lane == 0) {
+    const bool idle = PROF && (P.debug & 2);
+    for (int g = 0; g < n_groups; ++g) {
+      {
+        // lane 0 waits for the raw data, lane 1 for the free expanded stage, concurrently
         const long long t0 = PROF ? clock64() : 0;
-        umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
-        const long long t1 = PROF ? clock64() : 0;
-        if (st >= EXP_STAGES) umma::mbar_wait_a(exp_empty_a + e * 8, exp_phase);
-        if (PROF) {
-          t_wraw += t1 - t0;
-          t_wemp += clock64() - t1;
-        }
+        if (lane == 0) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
+        if (lane == 1 && g >= EXP_STAGES) umma::mbar_wait_a(exp_empty_a + e * 8, exp_phase);
+        if (PROF && lane == 0) t_wraw += clock64() - t0;
       }
       __syncwarp();
       if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+      const int kw = min(GROUP, n_steps - g * GROUP);
       const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
-      uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
-      const bool idle = PROF && (P.debug & 2);
-      if (!idle) {
-        lo = umma::lds128(src);
-        hi = umma::lds128(src + 128);
+      uint4 lo[GROUP], hi[GROUP];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) {
+        lo[j] = make_uint4(0, 0, 0, 0);
+        hi[j] = lo[j];
+        if (j < kw && !idle) {
+          lo[j] = umma::lds128(src + j * G::RAW_STEP_BYTES);
+          hi[j] = umma::lds128(src + j * G::RAW_STEP_BYTES + 128);
+        }
       }
-      uint32_t p0[8], p1[8];
-      make_planes<MODE>(lo, hi, p0, p1);
       const long long tf0 = PROF ? clock64() : 0;
-      if (idle) {
-      } else if (is_a) {
-        const uint32_t a_col = a_base + e * TMEM_A_COLS;
-        umma::tmem_st_32x8(a_col, p0);
-        umma::tmem_st_32x8(a_col + 8, p1);
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) {
+        if (j < kw && !idle) {
+          uint32_t p0[8], p1[8];
+          make_planes<MODE>(lo[j], hi[j], p0, p1);
+          if (is_a) {
+            const uint32_t a_col = a_base + (e * GROUP + j) * TMEM_A_COLS;
+            umma::tmem_st_32x8(a_col, p0);
+            umma::tmem_st_32x8(a_col + 8, p1);
+          } else {
+            const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+            if (MODE == 0) {
+              umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
+              umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
+            } else {
+              umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // h
+              umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
+              umma::sts128(dst + G::EXP_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);   // v
+              umma::sts128(dst + G::EXP_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
+            }
+          }
+        }
+      }
+      if (is_a) {
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
       } else {
-        const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES;
-        if (MODE == 0) {
-          umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
-          umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
-        } else {
-          umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // h
-          umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
-          umma::sts128(dst + G::EXP_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);   // v
-          umma::sts128(dst + G::EXP_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
-        }
         umma::fence_proxy_async_smem();
       }
       __syncwarp();
