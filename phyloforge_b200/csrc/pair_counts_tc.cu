@@ -24,7 +24,8 @@
 // samples x 64 sites) already in the canonical K-major shared-memory order of a UMMA operand, so ONE
 // TMA bulk copy of the J rows of a step lands as a ready B_x operand.
 // Data flow per CTA (one sample tile pair, a contiguous range of 64-site steps):
-//   stream --TMA bulk copies--> raw ring (A rows | B rows = the B_x operand in mode 0)
+//   stream --TMA bulk copy per step--> raw ring (the B rows of a step = the B_x operand in mode 0);
+//   the A rows go from the stream to registers of their expansion threads, one stage ahead
 //   --expansion warps (thread = sample row): a few logic ops per 8 genotypes--> A planes straight into
 //   TMEM (tcgen05.st), derived B planes into shared memory
 //   --tcgen05.mma kind::mxf4, A from TMEM, B from shared memory (1 thread)--> fp32 accumulators in TMEM
@@ -60,8 +61,7 @@ template <int MODE> struct TcGeo {
   static constexpr int J = C::J;                               // columns (MMA N); B operand in shared memory
   static constexpr int ROWS = TC_I + J;                        // sample rows handled per step
   static constexpr int PF = ROWS / PF_TILE;                    // 64-sample chunks of the stream per step
-  static constexpr int A_RAW_BYTES = (TC_I / PF_TILE) * CHUNK_BYTES;
-  static constexpr int RAW_STEP_BYTES = PF * CHUNK_BYTES;      // [A rows | B rows], canonical order
+  static constexpr int RAW_STEP_BYTES = (J / PF_TILE) * CHUNK_BYTES;   // the B rows of a step, canonical order
   static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
   static constexpr int EXP_PLANE_BYTES = J * 32;
   static constexpr int EXP_STEP_BYTES = C::NEXP * EXP_PLANE_BYTES;
@@ -69,7 +69,7 @@ template <int MODE> struct TcGeo {
   static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
-  static constexpr int RAW_EMPTY_ARRIVALS = EXP_WARPS + (MODE == 0 ? 1 : 0);   // mode 0: the MMA reads B_x from the raw stage
+  static constexpr int RAW_EMPTY_ARRIVALS = J / 32 + (MODE == 0 ? 1 : 0);   // B-row warps; mode 0: the MMA reads B_x from the raw stage
   static constexpr size_t SMEM = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES +
                                  static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
   static_assert(TMEM_A + EXP_STAGES * GROUP * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
@@ -278,15 +278,14 @@ pair_counts_tc_kernel(const TcParams P) {
   umma::fence_after_thread_sync();
 
   if (warp == G::EXP_WARPS) {
-    // ===== TMA producer: two bulk copies per step. The stream is step-major, so the 64-sample chunks
-    // of the A rows (2) and of the B rows (J / 64) of a step are each one contiguous range. (The TMA
-    // unit takes ~120 clocks per bulk request whatever its size: five 2 KB requests per step capped
-    // the kernel at ~700 clocks per step.) =====
+    // ===== TMA producer: one bulk copy per step. The stream is step-major, so the 64-sample chunks of
+    // the B rows (J / 64) of a step are one contiguous range. (The TMA unit takes ~120 clocks per bulk
+    // request whatever its size: five 2 KB requests per step capped the kernel at ~700 clocks per step;
+    // the A rows are therefore loaded by their expansion threads directly.) =====
     if (lane == 0) {
       long long t_wait = 0;
       const long long t_start = PROF ? clock64() : 0;
       const int64_t step_stride = P.n_tiles_padded * (CHUNK_BYTES / 16);
-      const uint4* src_a = P.stream + s_begin * step_stride + 2 * static_cast<int64_t>(ti) * (CHUNK_BYTES / 16);
       const uint4* src_b = P.stream + s_begin * step_stride + (J / PF_TILE) * static_cast<int64_t>(tj) * (CHUNK_BYTES / 16);
       int stage = 0;
       uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
@@ -300,12 +299,10 @@ pair_counts_tc_kernel(const TcParams P) {
         umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
 #pragma unroll
         for (int j = 0; j < GROUP; ++j) {
-          if (j < kw) {
-            const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES;
-            const int64_t off = (static_cast<int64_t>(g) * GROUP + j) * step_stride;
-            umma::bulk_g2s_a(dst, src_a + off, G::A_RAW_BYTES, raw_full_a + stage * 8);
-            umma::bulk_g2s_a(dst + G::A_RAW_BYTES, src_b + off, G::RAW_STEP_BYTES - G::A_RAW_BYTES, raw_full_a + stage * 8);
-          }
+          if (j < kw)
+            umma::bulk_g2s_a(raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES,
+                             src_b + (static_cast<int64_t>(g) * GROUP + j) * step_stride, G::RAW_STEP_BYTES,
+                             raw_full_a + stage * 8);
         }
         if (++stage == RAW_STAGES) {
           stage = 0;
@@ -341,7 +338,7 @@ pair_counts_tc_kernel(const TcParams P) {
               const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
               if (MODE == 0) {
                 const uint64_t bx = umma::smem_desc_kmajor_noswizzle(
-                    raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES + G::A_RAW_BYTES, 128, 256);
+                    raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
                 const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
                 mma_mxf4_ts(tmem + 0 * J, a0, bx, idesc, acc, tsfa, tsfb);   // XX
                 mma_mxf4_ts(tmem + 1 * J, a1, bh, idesc, acc, tsfa, tsfb);   // HH
@@ -371,41 +368,63 @@ pair_counts_tc_kernel(const TcParams P) {
       }
     }
   } else {
-    // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, planes written
-    // straight into TMEM (their lane quadrant); the others: the B rows, derived planes written to
-    // shared memory in the canonical K-major layout =====
+    // ===== expansion warps: thread = one sample row. Warps 0-3: the 128 A rows, loaded from the
+    // stream one stage ahead into registers, planes written straight into TMEM (their lane quadrant);
+    // the others: the B rows, read from the raw ring, derived planes written to shared memory in the
+    // canonical K-major layout =====
     const int row = tid;
     const bool is_a = row < TC_I;
     const int r = is_a ? row : row - TC_I;
     const uint32_t a_base = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A;   // A rows: TMEM lane = row
-    // both the A part and the B part of a raw stage are canonical tiles, so is the expanded stage
-    const uint32_t raw_row = raw_a + (is_a ? 0 : G::A_RAW_BYTES) + unit_off(r, 0);
+    const uint32_t raw_row = raw_a + unit_off(r, 0);     // raw and expanded stages are canonical tiles
     const uint32_t exp_row = exp_a + unit_off(r, 0);
+    const int64_t step_stride = P.n_tiles_padded * (CHUNK_BYTES / 16);
+    // A rows: this thread's two 16-byte units of a step inside the chunk of its 64-sample tile
+    const uint4* a_src = P.stream + s_begin * step_stride + (2 * static_cast<int64_t>(ti) + (r >> 6)) * (CHUNK_BYTES / 16) +
+                         ((r & 63) >> 3) * 16 + (r & 7);
     long long t_wraw = 0, t_wemp = 0, t_fence = 0;
     const long long t_start = PROF ? clock64() : 0;
     int stage = 0, e = 0;
     uint32_t raw_phase = 0, exp_phase = 1;
     const bool idle = PROF && (P.debug & 2);
-    for (int g = 0; g < n_groups; ++g) {
-      {
-        // lane 0 waits for the raw data, lane 1 for the free expanded stage, concurrently
-        const long long t0 = PROF ? clock64() : 0;
-        if (lane == 0) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
-        if (lane == 1 && g >= EXP_STAGES) umma::mbar_wait_a(exp_empty_a + e * 8, exp_phase);
-        if (PROF && lane == 0) t_wraw += clock64() - t0;
-      }
-      __syncwarp();
-      if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
-      const int kw = min(GROUP, n_steps - g * GROUP);
-      const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
-      uint4 lo[GROUP], hi[GROUP];
+    uint4 lo[GROUP], hi[GROUP];
+    auto load_a_rows = [&](int g) {
 #pragma unroll
       for (int j = 0; j < GROUP; ++j) {
         lo[j] = make_uint4(0, 0, 0, 0);
         hi[j] = lo[j];
-        if (j < kw && !idle) {
-          lo[j] = umma::lds128(src + j * G::RAW_STEP_BYTES);
-          hi[j] = umma::lds128(src + j * G::RAW_STEP_BYTES + 128);
+        const int st = g * GROUP + j;
+        if (st < n_steps && !idle) {
+          lo[j] = __ldg(a_src + st * step_stride);
+          hi[j] = __ldg(a_src + st * step_stride + 8);
+        }
+      }
+    };
+    if (is_a) load_a_rows(0);
+    for (int g = 0; g < n_groups; ++g) {
+      {
+        // B rows: lane 0 waits for the raw data, lane 1 for the free expanded stage, concurrently
+        const long long t0 = PROF ? clock64() : 0;
+        if (!is_a && lane == 0) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
+        if (lane == 1 && g >= EXP_STAGES) umma::mbar_wait_a(exp_empty_a + e * 8, exp_phase);
+        if (PROF && lane < 2) {
+          if (lane == 0) t_wraw += clock64() - t0;
+          else t_wemp += clock64() - t0;
+        }
+      }
+      __syncwarp();
+      if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+      const int kw = min(GROUP, n_steps - g * GROUP);
+      if (!is_a) {
+        const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < GROUP; ++j) {
+          lo[j] = make_uint4(0, 0, 0, 0);
+          hi[j] = lo[j];
+          if (j < kw && !idle) {
+            lo[j] = umma::lds128(src + j * G::RAW_STEP_BYTES);
+            hi[j] = umma::lds128(src + j * G::RAW_STEP_BYTES + 128);
+          }
         }
       }
       const long long tf0 = PROF ? clock64() : 0;
@@ -433,6 +452,7 @@ pair_counts_tc_kernel(const TcParams P) {
         }
       }
       if (is_a) {
+        load_a_rows(g + 1);     // next stage's rows are in flight while this stage's MMAs run
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
       } else {
@@ -442,7 +462,7 @@ pair_counts_tc_kernel(const TcParams P) {
       if (PROF) t_fence += clock64() - tf0;
       if (lane == 0) {
         umma::mbar_arrive_a(exp_full_a + e * 8);
-        umma::mbar_arrive_a(raw_empty_a + stage * 8);
+        if (!is_a) umma::mbar_arrive_a(raw_empty_a + stage * 8);
       }
       if (++stage == RAW_STAGES) {
         stage = 0;
@@ -453,6 +473,7 @@ pair_counts_tc_kernel(const TcParams P) {
         exp_phase ^= 1;
       }
     }
+    t_wemp = __shfl_sync(0xffffffffu, t_wemp, 1);
     if (PROF && lane == 0 && (warp == 0 || warp == 4)) {
       const int o = warp == 0 ? 2 : 9;   // [2..4] an A-row warp, [9..11] a B-row warp
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o]), static_cast<unsigned long long>(t_wraw));
