@@ -344,26 +344,29 @@ def run_ours(args):
     plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
     variant_ran = ran_variant[0]
     if variant_ran == 3:
-        # tensor-core indicator GEMM: 2 int8 multiply-accumulates per unordered pair per site
+        # tensor-core indicator GEMMs on 4-bit (E2M1) operands: 2 multiply-accumulates per unordered pair
+        # per site (5 with sample-specific missingness)
         bf16 = peaks.get("bf16_tflops", 1590.0)
-        peak_tops = 2.0 * bf16                      # dense int8 = 2 x dense bf16 on the same tensor cores
+        peak_tops = 4.0 * bf16                      # dense fp4 = 4 x dense bf16 on the same tensor cores (9 vs 2.25 PFLOP/s nominal)
         launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (VV, HV, VH) ran too
         macs_per = 5.0 if launches == 2 else 2.0
         macs = macs_per * pair_sites(n, my_sites)
         achieved_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (int8)",
+        roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (fp4)",
                     "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES_TC,
-                    "kernel": "pair_counts_tc_kernel (tcgen05 kind::i8) + planes_to_nib4_kernel",
+                    "kernel": "pair_counts_tc_kernel (tcgen05 kind::mxf4, E2M1 operands) + planes_to_e2m1_kernel",
                     "kernel_ms": counts_ms,
-                    "ops_per_pair_site": {"int8_mac": macs_per}, "gemm_launches": launches,
+                    "ops_per_pair_site": {"fp4_mac": macs_per}, "gemm_launches": launches,
                     "frac_of_popcount_kernel_roofline": achieved_pw / (min(lop3_ops / 4.0, popc_ops / 1.0) if miss == 0
                                                                        else plain_popc_peak_pw),
                     "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
-                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no int8 entry; nominal dense "
-                                   "int8 is 4500 TOP/s)" % ("of measured" if peaks else "of fallback 1590"),
+                    "frac_of_int8_tensor_peak": achieved_tops / (2.0 * bf16),
+                    "peak_source": "4 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no fp4 entry; nominal dense "
+                                   "fp4 is 9000 TOP/s, 4 x the 2250 of bf16)" % ("of measured" if peaks else "of fallback 1590"),
                     "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 5 MAC with "
-                            "sample-specific missingness: + v.v', h.v', v.h'); the kernel "
-                            "also computes ~13% redundant pairs in tiles that straddle the diagonal. kernel_ms "
+                            "sample-specific missingness: + v.v', h.v', v.h'); the kernel also computes ~13% redundant "
+                            "pairs in tiles that straddle the diagonal, and a 128 x 192 x 64 instruction takes the "
+                            "time of a 128 x 256 x 64 one (73% of the instruction-level peak). kernel_ms "
                             "includes the planes -> 4-bit operand stream conversion and one stream synchronise"}
     else:
         csa = variant_ran != 1
@@ -443,7 +446,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU gets the named configuration's site count (default); "
                          "strong: the named configuration is split over the GPUs")
-    ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save popcount, 3 tcgen05 int8 GEMM")
+    ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save popcount, 3 tcgen05 4-bit (E2M1) GEMMs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
