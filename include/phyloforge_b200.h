@@ -236,7 +236,9 @@ PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
 /* Diagnostic: latency of the building blocks of the NJ iteration, nanoseconds per step.
  * kind 0 dependent L2 load chain, 1 store + gpu-scope fence, 2 CTA barrier (512 threads), 3 tagged-word
  * exchange between n_ctas CTAs, 4 cooperative grid barrier over n_ctas CTAs, 5 as 0 on lines last
- * written by another SM, 6 a batch of 16 independent L2 loads per step. */
+ * written by another SM, 6 a batch of 16 independent L2 loads per step, 7 tcgen05.commit to mbarrier wait,
+ * 8 one 6 KB cp.async.bulk from issue to completion, 9 the same with 8 copies in flight (per copy),
+ * 10 mbarrier arrive to try_wait wake-up between two warps (per hop). */
 PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_step, void* stream);
 
 /* Diagnostics for the 4-bit tensor-core path (tcgen05.mma kind::mxf4, E2M1 operands, K = 64 per

@@ -2,6 +2,7 @@
 // trip, one gpu-scope fence, one CTA barrier, one tagged-word exchange between CTAs and one cooperative
 // grid barrier cost on this GPU. Diagnostic only (tools/probe_latency.py).
 #include "pf_common.cuh"
+#include "umma.cuh"
 
 #include <cooperative_groups.h>
 
@@ -22,6 +23,10 @@ __device__ __forceinline__ unsigned long long probe_now() {
 // kind 4: cooperative grid.sync per step
 // kind 5: as 0, but the chain is first written by another CTA (lines last written remotely)
 // kind 6: 16 independent ld.global.cg per step (one batch), one warp
+// kind 7: tcgen05.commit (no MMA outstanding) -> mbarrier wait round trip, one thread
+// kind 8: cp.async.bulk of 6 KB global -> shared, issue to completion (mbarrier wait), one thread
+// kind 9: cp.async.bulk of 6 KB: 7 copies in flight per wait
+// kind 10: mbarrier arrive by thread 32 -> try_wait wake-up of thread 0 and back (ping-pong), per hop
 __global__ void __launch_bounds__(512, 1)
 probe_kernel(int kind, int iters, unsigned* buf, int buf_len, unsigned long long* xchg, unsigned long long* out_ns,
              unsigned* sink) {
@@ -95,8 +100,52 @@ probe_kernel(int kind, int iters, unsigned* buf, int buf_len, unsigned long long
       acc = p;
     }
   }
+  if (kind >= 7 && kind <= 10 && blockIdx.x == 0) {
+    __shared__ __align__(1024) unsigned char s_buf[7 * 6144];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmem;
+    if (kind == 7 && warp == 0) umma::tmem_alloc(&s_tmem, 32);
+    if (tid == 0) {
+      umma::mbar_init(&s_bar[0], 1);
+      umma::mbar_init(&s_bar[1], 1);
+      umma::fence_mbar_init();
+    }
+    __syncthreads();
+    t0 = probe_now();
+    if (kind == 7 && tid == 0) {
+      for (int i = 0; i < iters; ++i) {
+        umma::commit(&s_bar[0]);
+        umma::mbar_wait(&s_bar[0], i & 1);
+      }
+    } else if (kind == 8 && tid == 0) {
+      for (int i = 0; i < iters; ++i) {
+        umma::mbar_expect_tx(&s_bar[0], 6144);
+        umma::bulk_g2s(s_buf, reinterpret_cast<const unsigned char*>(buf) + (i & 7) * 6144, 6144, &s_bar[0]);
+        umma::mbar_wait(&s_bar[0], i & 1);
+      }
+    } else if (kind == 9 && tid == 0) {
+      for (int i = 0, k = 0; i < iters; i += 7, ++k) {
+        umma::mbar_expect_tx(&s_bar[0], 7 * 6144);
+        for (int j = 0; j < 7; ++j)
+          umma::bulk_g2s(s_buf + j * 6144, reinterpret_cast<const unsigned char*>(buf) + j * 6144, 6144, &s_bar[0]);
+        umma::mbar_wait(&s_bar[0], k & 1);
+      }
+    } else if (kind == 10 && (tid == 0 || tid == 32)) {
+      for (int i = 0; i < iters; ++i) {
+        if (tid == 0) {
+          umma::mbar_arrive(&s_bar[0]);
+          umma::mbar_wait(&s_bar[1], i & 1);
+        } else {
+          umma::mbar_wait(&s_bar[0], i & 1);
+          umma::mbar_arrive(&s_bar[1]);
+        }
+      }
+    }
+    __syncthreads();
+    if (kind == 7 && warp == 0) umma::tmem_dealloc(s_tmem, 32);
+  }
   unsigned long long t1 = probe_now();
-  if (blockIdx.x == 0 && tid == 0) *out_ns = t1 - t0;
+  if (blockIdx.x == 0 && tid == 0) *out_ns = (kind == 10) ? (t1 - t0) / 2 : (t1 - t0);
   if (acc == 0xdeadbeefu) *sink = acc;
 }
 
@@ -105,7 +154,7 @@ probe_kernel(int kind, int iters, unsigned* buf, int buf_len, unsigned long long
 // See include/phyloforge_b200.h
 PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_step, void* stream) {
   PF_TRY_BEGIN
-  if (kind < 0 || kind > 6 || iters <= 0 || n_ctas <= 0 || !h_ns_per_step)
+  if (kind < 0 || kind > 10 || iters <= 0 || n_ctas <= 0 || !h_ns_per_step)
     return pf_fail("pf_probe_latency: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 0;

@@ -60,7 +60,6 @@ template <int MODE> struct TcGeo {
   using C = TcCfg<MODE>;
   static constexpr int J = C::J;                               // columns (MMA N); B operand in shared memory
   static constexpr int ROWS = TC_I + J;                        // sample rows handled per step
-  static constexpr int PF = ROWS / PF_TILE;                    // 64-sample chunks of the stream per step
   static constexpr int RAW_STEP_BYTES = (J / PF_TILE) * CHUNK_BYTES;   // the B rows of a step, canonical order
   static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
   static constexpr int EXP_PLANE_BYTES = J * 32;

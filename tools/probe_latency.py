@@ -11,8 +11,13 @@ from phyloforge_b200.engine import Engine
 eng = Engine(0)
 st = torch.cuda.current_stream().cuda_stream
 KINDS = ["L2 load chain", "store + fence.acq_rel.gpu", "__syncthreads (512 thr)", "tagged-word exchange",
-         "cooperative grid.sync", "L2 load chain, remotely written lines", "batch of 16 L2 loads"]
+         "cooperative grid.sync", "L2 load chain, remotely written lines", "batch of 16 L2 loads",
+         "tcgen05.commit -> mbarrier wait", "cp.async.bulk 6 KB, issue to completion", "cp.async.bulk 6 KB, 7 in flight (per copy)",
+         "mbarrier arrive -> try_wait wake-up (per hop)"]
+only = [int(x) for x in sys.argv[1:]]
 for kind, name in enumerate(KINDS):
+    if only and kind not in only:
+        continue
     for n_ctas in ((2, 32, 148) if kind in (3, 4) else (2,)):
         out = C.c_double(0)
         check(eng.lib.pf_probe_latency(kind, 2000, n_ctas, C.byref(out), st))
