@@ -247,9 +247,11 @@ PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_st
  * {0, +-1, +-2, +-3, +-4, +-6}; n = 128 or 192, k a multiple of 64, at most 1024; a_in_tmem != 0
  * feeds the A operand from tensor memory (tcgen05.st) instead of shared memory.
  * pf_probe_umma_fp4_rate: SM clock64 ticks per 128 x n x 64 instruction, operands resident in shared
- * memory, n_acc accumulators used round-robin. */
+ * memory (a_in_tmem: the A operand in tensor memory), n_acc accumulators used round-robin, the B
+ * operand rotating over n_bufs different tiles. */
 PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c, int n, int k,
                                 int a_in_tmem, void* stream);
-PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, double* ticks_per_mma, void* stream);
+PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs,
+                                  double* ticks_per_mma, void* stream);
 
 #endif /* PHYLOFORGE_B200_H */

@@ -26,8 +26,8 @@
 // Data flow per CTA (one sample tile pair, a contiguous range of 64-site steps):
 //   stream --TMA bulk copy per step--> raw ring (the B rows of a step = the B_x operand in mode 0);
 //   the A rows go from the stream to registers of their expansion threads, one stage ahead
-//   --expansion warps (thread = sample row): a few logic ops per 8 genotypes--> A planes straight into
-//   TMEM (tcgen05.st), derived B planes into shared memory
+//   --expansion warps (thread = sample row): a few logic ops per 8 genotypes--> one A plane straight into
+//   TMEM (tcgen05.st), the other A plane and the derived B planes into shared memory
 //   --tcgen05.mma kind::mxf4, A from TMEM, B from shared memory (1 thread)--> fp32 accumulators in TMEM
 //   --tcgen05.ld--> epilogue --> int32 RED atomics (split-K, bit-exact).
 #include "pf_common.cuh"
@@ -38,11 +38,13 @@ namespace {
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
 constexpr int STEP_WORDS = 2;        // one pipeline step = one MMA K step = 64 sites = two 32-site words
 constexpr int CHUNK_BYTES = 2048;    // 64 samples x 64 sites x 4 bits
-constexpr int GROUP = 3;             // steps per pipeline stage: the barrier round trips of a stage (~500 clocks
+constexpr int GROUP = 5;             // steps per pipeline stage: the barrier round trips of a stage (~500 clocks
                                      // for an expansion warp) are paid once per GROUP steps
-constexpr int RAW_STAGES = 4;
-constexpr int EXP_STAGES = 2;
-constexpr int TMEM_A_COLS = 16;      // per step: 8 columns per A plane (32 K-bytes per row)
+constexpr int RAW_STAGES = 3;
+constexpr int EXP_STAGES = 2;        // a barrier hand-over costs ~230 clocks (profiles/r01_mma_probe.md): the ring
+                                     // must cover MMA time + three hand-overs + the expansion itself
+constexpr int TMEM_A_COLS = 8;       // per step: the 8 columns (32 K-bytes per row) of the A plane kept in TMEM;
+                                     // the other A plane goes through shared memory so that four stages fit
 constexpr int TMEM_SF = 496;         // 16 columns of scale factors (all 1.0) behind accumulators and A staging
 constexpr uint32_t NIB_HOM = 0x22222222u;   // bit 1 of a stream nibble: homozygous; as E2M1 that bit alone is +1.0
 constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
@@ -63,7 +65,8 @@ template <int MODE> struct TcGeo {
   static constexpr int RAW_STEP_BYTES = (J / PF_TILE) * CHUNK_BYTES;   // the B rows of a step, canonical order
   static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
   static constexpr int EXP_PLANE_BYTES = J * 32;
-  static constexpr int EXP_STEP_BYTES = C::NEXP * EXP_PLANE_BYTES;
+  static constexpr int A_PLANE_BYTES = TC_I * 32;              // the A plane that goes through shared memory, in front
+  static constexpr int EXP_STEP_BYTES = A_PLANE_BYTES + C::NEXP * EXP_PLANE_BYTES;
   static constexpr int EXP_STAGE_BYTES = GROUP * EXP_STEP_BYTES;
   static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
@@ -180,6 +183,20 @@ __device__ __forceinline__ void mma_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "}\n"
       :
       : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
+      : "memory");
+}
+
+// as above with the A operand from shared memory
+__device__ __forceinline__ void mma_mxf4_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate, uint32_t tsfa, uint32_t tsfb) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb)
       : "memory");
 }
 
@@ -332,21 +349,23 @@ pair_counts_tc_kernel(const TcParams P) {
 #pragma unroll
           for (int j = 0; j < GROUP; ++j) {
             if (j < kw) {
-              const uint32_t a0 = tmem + G::TMEM_A + (e * GROUP + j) * TMEM_A_COLS, a1 = a0 + 8;
+              const uint32_t a_t = tmem + G::TMEM_A + (e * GROUP + j) * TMEM_A_COLS;    // A plane 1 (h / v) in TMEM
               const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
               const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+              const uint64_t a_s = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);    // A plane 0 (x / h) in shared memory
+              const uint32_t bbase = ebase + G::A_PLANE_BYTES;
               if (MODE == 0) {
                 const uint64_t bx = umma::smem_desc_kmajor_noswizzle(
                     raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
-                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
-                mma_mxf4_ts(tmem + 0 * J, a0, bx, idesc, acc, tsfa, tsfb);   // XX
-                mma_mxf4_ts(tmem + 1 * J, a1, bh, idesc, acc, tsfa, tsfb);   // HH
+                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
+                mma_mxf4_ss(tmem + 0 * J, a_s, bx, idesc, acc, tsfa, tsfb);   // XX
+                mma_mxf4_ts(tmem + 1 * J, a_t, bh, idesc, acc, tsfa, tsfb);   // HH
               } else {
-                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
-                const uint64_t bv = umma::smem_desc_kmajor_noswizzle(ebase + G::EXP_PLANE_BYTES, 128, 256);
-                mma_mxf4_ts(tmem + 0 * J, a1, bv, idesc, acc, tsfa, tsfb);   // VV
-                mma_mxf4_ts(tmem + 1 * J, a0, bv, idesc, acc, tsfa, tsfb);   // HV
-                mma_mxf4_ts(tmem + 2 * J, a1, bh, idesc, acc, tsfa, tsfb);   // VH
+                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
+                const uint64_t bv = umma::smem_desc_kmajor_noswizzle(bbase + G::EXP_PLANE_BYTES, 128, 256);
+                mma_mxf4_ts(tmem + 0 * J, a_t, bv, idesc, acc, tsfa, tsfb);   // VV
+                mma_mxf4_ss(tmem + 1 * J, a_s, bv, idesc, acc, tsfa, tsfb);   // HV
+                mma_mxf4_ts(tmem + 2 * J, a_t, bh, idesc, acc, tsfa, tsfb);   // VH
               }
             }
           }
@@ -433,11 +452,13 @@ pair_counts_tc_kernel(const TcParams P) {
           uint32_t p0[8], p1[8];
           make_planes<MODE>(lo[j], hi[j], p0, p1);
           if (is_a) {
-            const uint32_t a_col = a_base + (e * GROUP + j) * TMEM_A_COLS;
-            umma::tmem_st_32x8(a_col, p0);
-            umma::tmem_st_32x8(a_col + 8, p1);
-          } else {
+            // plane 0 (x / h) to the A tile in shared memory, plane 1 (h / v) to TMEM
             const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+            umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);
+            umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
+            umma::tmem_st_32x8(a_base + (e * GROUP + j) * TMEM_A_COLS, p1);
+          } else {
+            const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES + G::A_PLANE_BYTES;
             if (MODE == 0) {
               umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
               umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
@@ -451,18 +472,19 @@ pair_counts_tc_kernel(const TcParams P) {
         }
       }
       if (is_a) {
-        load_a_rows(g + 1);     // next stage's rows are in flight while this stage's MMAs run
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
-      } else {
-        umma::fence_proxy_async_smem();
       }
+      umma::fence_proxy_async_smem();
       __syncwarp();
       if (PROF) t_fence += clock64() - tf0;
       if (lane == 0) {
         umma::mbar_arrive_a(exp_full_a + e * 8);
         if (!is_a) umma::mbar_arrive_a(raw_empty_a + stage * 8);
       }
+      // next stage's rows: in flight while this stage's MMAs run (issued after the fences, which
+      // would otherwise wait for these loads)
+      if (is_a) load_a_rows(g + 1);
       if (++stage == RAW_STAGES) {
         stage = 0;
         raw_phase ^= 1;

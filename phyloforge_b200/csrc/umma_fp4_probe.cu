@@ -147,7 +147,8 @@ umma_fp4_selftest_kernel(const int8_t* __restrict__ A, const int8_t* __restrict_
 }
 
 template <int N>
-__global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_acc, long long* out_cycles) {
+__global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_acc, int a_in_tmem, int n_bufs,
+                                                               long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
   __shared__ __align__(8) uint64_t s_bar;
@@ -157,7 +158,7 @@ __global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_a
     umma::mbar_init(&s_bar, 1);
     umma::fence_mbar_init();
   }
-  for (int i = tid; i < (F4_M + N) * 32 * 2 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x22222222u;
+  for (int i = tid; i < (F4_M * 2 + N * n_bufs) * 32 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x22222222u;
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -170,14 +171,25 @@ __global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_a
   if (tid == 0) {
     const uint32_t idesc = idesc_mxf4(F4_M, N, 0, 0);
     const uint32_t sa = umma::smem_addr(smem), sb = sa + F4_M * 32 * 2;
+    const uint32_t a_col = tmem + n_acc * N;        // A staging behind the accumulators (contents irrelevant)
     const long long t0 = clock64();
+    int buf = 0;
     for (int r = 0; r < reps; ++r) {
+      // two products per iteration, like the pair-count kernel; the B tile changes every instruction
       const uint64_t da0 = umma::smem_desc_kmajor_noswizzle(sa, 128, 256);
       const uint64_t da1 = umma::smem_desc_kmajor_noswizzle(sa + F4_M * 32, 128, 256);
-      const uint64_t db0 = umma::smem_desc_kmajor_noswizzle(sb, 128, 256);
-      const uint64_t db1 = umma::smem_desc_kmajor_noswizzle(sb + N * 32, 128, 256);
-      mma_mxf4_ss(tmem + ((2 * r) % n_acc) * N, da0, db0, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
-      mma_mxf4_ss(tmem + ((2 * r + 1) % n_acc) * N, da1, db1, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
+      const uint64_t db0 = umma::smem_desc_kmajor_noswizzle(sb + buf * N * 32, 128, 256);
+      if (++buf == n_bufs) buf = 0;
+      const uint64_t db1 = umma::smem_desc_kmajor_noswizzle(sb + buf * N * 32, 128, 256);
+      if (++buf == n_bufs) buf = 0;
+      const uint32_t d0 = tmem + ((2 * r) % n_acc) * N, d1 = tmem + ((2 * r + 1) % n_acc) * N;
+      if (a_in_tmem) {
+        mma_mxf4_ts(d0, a_col, db0, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
+        mma_mxf4_ts(d1, a_col + 8, db1, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
+      } else {
+        mma_mxf4_ss(d0, da0, db0, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
+        mma_mxf4_ss(d1, da1, db1, idesc, 1u, tmem + F4_SF_COL, tmem + F4_SF_COL + 16);
+      }
     }
     umma::commit(&s_bar);
     umma::mbar_wait(&s_bar, 0);
@@ -211,9 +223,11 @@ PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c
 }
 
 // SM-clock64 ticks per kind::mxf4 MMA (128 x n x 64), operands resident in shared memory, n_acc accumulators round-robin
-PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, double* ticks_per_mma, void* stream) {
+PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs, double* ticks_per_mma,
+                                  void* stream) {
   PF_TRY_BEGIN
-  if ((n != 128 && n != 192 && n != 256) || reps <= 0 || n_acc < 1 || n_acc * n > F4_SF_COL || !ticks_per_mma)
+  if ((n != 128 && n != 192 && n != 256) || reps <= 0 || n_acc < 1 || n_acc * n + (a_in_tmem ? 16 : 0) > F4_SF_COL ||
+      n_bufs < 1 || n_bufs > 16 || !ticks_per_mma)
     return pf_fail("pf_probe_umma_fp4_rate: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int dev = 0, sms = 0;
@@ -221,11 +235,11 @@ PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, double* ticks_per_
   PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long* d = nullptr;
   PF_CUDA(cudaMalloc(&d, sizeof(long long) * sms));
-  const size_t smem = static_cast<size_t>(F4_M + n) * 32 * 2;
+  const size_t smem = static_cast<size_t>(F4_M * 2 + n * n_bufs) * 32;
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<sms, 128, smem, s>>>(reps, n_acc, d);
+    kernel<<<sms, 128, smem, s>>>(reps, n_acc, a_in_tmem, n_bufs, d);
     return cudaGetLastError();
   };
   cudaError_t e = n == 128 ? launch(umma_fp4_rate_kernel<128>) : n == 192 ? launch(umma_fp4_rate_kernel<192>) : launch(umma_fp4_rate_kernel<256>);
