@@ -186,18 +186,23 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
                           int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
                           int variant, void* stream);
 
-/* Tensor-core variant of pf_pair_counts (tcgen05 kind::i8 indicator GEMMs; csrc/pair_counts_tc.cu).
- * ACCUMULATES the same V / D1 / D2 as pf_pair_counts. *h_used: 1 = one GEMM launch (every site of the
- * word range genotyped in all samples or in none), 2 = two launches (genotypes missing in some samples
- * only; taken when allow_general != 0), 0 = declined (allow_general == 0 and such missingness exists):
- * nothing was added and the caller runs pf_pair_counts.
- * d_work: pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin) bytes of scratch (the
- * 4-bit operand stream). Synchronises `stream` once (reads the missingness flag). */
+/* Tensor-core variant of pf_pair_counts (tcgen05 kind::mxf4 indicator GEMMs on 4-bit E2M1 operands;
+ * csrc/pair_counts_tc.cu). ACCUMULATES the same V / D1 / D2 as pf_pair_counts.
+ * allow_general != 0: fully asynchronous; *h_used = 1. A second GEMM launch (VV, HV, VH) does its work only
+ * when the converter finds genotypes missing in some samples only (pf_pair_counts_tc_was_general tells).
+ * allow_general == 0: synchronises `stream` once to read that flag; *h_used = 0 = declined (such
+ * missingness exists): nothing was added and the caller runs pf_pair_counts.
+ * d_work: pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin) bytes of scratch (the 4-bit
+ * operand stream). */
 PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_range);
 PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_t n_words,
                              int64_t word_begin, int64_t word_end, int32_t* d_counts, int64_t ld,
                              void* d_work, int64_t work_bytes, int allow_general, int* h_used,
                              void* stream);
+/* After a pf_pair_counts_tc call on `stream` with the same d_work / sizes: *h_general = 1 if that call
+ * found sample-specific missingness (the second launch worked), else 0. Synchronises `stream`. */
+PF_API int pf_pair_counts_tc_was_general(const void* d_work, int64_t n_samples, int64_t n_words_range,
+                                         int* h_general, void* stream);
 
 /* Diagnostic for the tensor-core kernel: enable/disable role-level wait-cycle accounting and fetch
  * (then clear) the 16 counters accumulated since the last call; see csrc/pair_counts_tc.cu. */

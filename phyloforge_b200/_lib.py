@@ -52,6 +52,7 @@ PROTOTYPES = {
     "pf_vcf_select_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i64p, _vp]),
     "pf_pair_counts": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
     "pf_pair_counts_tc_work_bytes": (_i64, [_i64, _i64]),
+    "pf_pair_counts_tc_was_general": (_i32, [_vp, _i64, _i64, _ip, _vp]),
     "pf_pair_counts_tc": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i32, _ip, _vp]),
     "pf_pair_counts_tc_profile": (_i32, [_i32, _vp]),
     "pf_normalise": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),

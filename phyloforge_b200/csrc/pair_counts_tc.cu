@@ -160,7 +160,8 @@ struct TcParams {
   int words_per_split;    // even
   const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split (mode 0, uniform)
   int64_t hsum_ld;
-  int general;            // mode 0 only: 1 = sample-specific missingness, mode 1 supplies V and HV + VH
+  const int* flags;       // flags[0] != 0: sample-specific missingness (set by the converter). Mode 0 then leaves
+                          // V and HV + VH to the mode-1 launch; mode 1 exits at once when it is 0.
   int debug;              // timing experiments (results are wrong): 1 = MMAs do not wait for operands,
                           // 2 = expansion warps do no work, 4 = no MMAs are issued
 };
@@ -236,6 +237,8 @@ pair_counts_tc_kernel(const TcParams P) {
   __shared__ int s_valid_sites;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool general = __ldg(P.flags) != 0;
+  if (MODE == 1 && !general) return;
   // shared-window addresses, computed once
   const uint32_t raw_a = umma::smem_addr(smem);                                   // RAW_STAGES x RAW_STAGE_BYTES
   const uint32_t exp_a = raw_a + RAW_STAGES * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (derived B planes)
@@ -502,7 +505,7 @@ pair_counts_tc_kernel(const TcParams P) {
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 13]), static_cast<unsigned long long>(t_fence));
     }
-    const bool uniform = (MODE == 0) && !P.general;
+    const bool uniform = (MODE == 0) && !general;
     if (uniform) {
       // |h_i| of this word range from the converter; V = sites genotyped in (all) samples
       const int64_t sample = is_a ? (static_cast<int64_t>(ti) * TC_I + r) : (static_cast<int64_t>(tj) * J + r);
@@ -695,11 +698,13 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
         L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
   }
-  int h_flags = 0;
-  PF_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PF_CUDA(cudaStreamSynchronize(s));
-  const int general = h_flags != 0 ? 1 : 0;     // some genotypes are missing in some samples only
-  if (general && !allow_general) return PF_OK;  // *h_used stays 0, nothing was added to d_counts
+  if (!allow_general) {
+    // the caller wants to fall back to the popcount kernel: the decision needs the flag on the host
+    int h_flags = 0;
+    PF_CUDA(cudaMemcpyAsync(&h_flags, flags, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PF_CUDA(cudaStreamSynchronize(s));
+    if (h_flags != 0) return PF_OK;  // *h_used stays 0, nothing was added to d_counts
+  }
 
   TcParams P;
   P.stream = nib4;
@@ -713,9 +718,11 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   P.n_itiles = L.n_itiles;
   P.hsum = hsum;
   P.hsum_ld = L.hsum_ld;
-  P.general = general;
+  P.flags = flags;
   P.debug = g_tc_prof_enabled ? g_tc_debug : 0;
-  for (int mode = 0; mode < (general ? 2 : 1); ++mode) {
+  // mode 1 is launched unconditionally (it returns at once unless the converter found sample-specific
+  // missingness), so that the call never waits for the device
+  for (int mode = 0; mode < (allow_general ? 2 : 1); ++mode) {
     const TcModePlan& M = L.m[mode];
     P.n_jtiles = M.n_jtiles;
     P.n_tilepairs = M.pairs;
@@ -724,7 +731,23 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
     PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }
-  *h_used = general ? 2 : 1;
+  *h_used = 1;
+  return PF_OK;
+  PF_TRY_END
+}
+
+// After the work of a pf_pair_counts_tc call on `stream` has finished: did that call find genotypes
+// missing in some samples only (1: the VV / HV / VH launch did the work too) or not (0)? Synchronises.
+PF_API int pf_pair_counts_tc_was_general(const void* d_work, int64_t n_samples, int64_t n_words_range, int* h_general,
+                                         void* stream) {
+  PF_TRY_BEGIN
+  if (!d_work || !h_general || n_samples <= 0 || n_words_range <= 0) return pf_fail("pf_pair_counts_tc_was_general: bad arguments");
+  const TcPlan L = tc_plan(n_samples, n_words_range, tc_sm_count());
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int h_flags = 0;
+  PF_CUDA(cudaMemcpyAsync(&h_flags, static_cast<const char*>(d_work) + L.flags_off, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PF_CUDA(cudaStreamSynchronize(s));
+  *h_general = h_flags != 0 ? 1 : 0;
   return PF_OK;
   PF_TRY_END
 }

@@ -145,8 +145,8 @@ class Engine:
                     tc_general: bool = True) -> int:
         """counts[3, n, n] int32 += V / D1 / D2 over words [word_begin, word_end). Returns the
         variant that ran. tc_general=False makes variant 3 decline data with sample-specific
-        missingness (the popcount kernel then runs); self.tc_launches = GEMM launches of the last
-        variant-3 call."""
+        missingness (the popcount kernel then runs, and the call waits for the device once);
+        self.tc_launches = GEMM launches that did work in the last variant-3 call."""
         if word_end is None:
             word_end = n_words
         assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
@@ -162,13 +162,25 @@ class Engine:
             check(self.lib.pf_pair_counts_tc(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                              counts.data_ptr(), counts.stride(1), work.data_ptr(), work.numel(),
                                              1 if tc_general else 0, C.byref(used), _stream_ptr()))
-            self.tc_launches = used.value
+            self._tc_last = (n_samples, word_end - word_begin) if used.value else None
             if used.value:
                 return 3
             variant = 2
         check(self.lib.pf_pair_counts(planes.data_ptr(), n_samples, n_words, word_begin, word_end,
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
         return variant
+
+    @property
+    def tc_launches(self) -> int:
+        """GEMM launches that did work in the last variant-3 call: 2 when it met genotypes missing in
+        some samples only, else 1 (0: the call declined). Synchronises the current stream."""
+        last = getattr(self, "_tc_last", None)
+        if last is None or last[1] <= 0:
+            return 0 if last is None else 1
+        g = C.c_int(0)
+        check(self.lib.pf_pair_counts_tc_was_general(self._tc_work.data_ptr(), last[0], last[1], C.byref(g),
+                                                     _stream_ptr()))
+        return 2 if g.value else 1
 
     def allreduce_counts(self, counts: torch.Tensor):
         """Sum the site shards' count matrices over all ranks (NCCL over NVLink)."""
@@ -213,7 +225,25 @@ class Engine:
                          fetch_dist: bool = False) -> TreeResult:
         n = counts.shape[1]
         dist_m, nz = self.normalise(counts, metric)
-        dist_host = dist_m.cpu().numpy() if fetch_dist else None
+        dist_host = None
+        fetched = None
+        if fetch_dist:
+            # device -> pinned host buffer on the copy stream, overlapping the NJ kernel. The array
+            # returned is a view of that buffer: valid until the next call that fetches distances.
+            pinned = getattr(self, "_dist_pinned", None)
+            if pinned is None or pinned.shape[0] != n:
+                pinned = self._dist_pinned = torch.empty((n, n), dtype=torch.float64).pin_memory()
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream())
+            copy = self._copy_stream()
+            with torch.cuda.stream(copy):
+                copy.wait_event(ready)
+                pinned.copy_(dist_m, non_blocking=True)
+                fetched = torch.cuda.Event()
+                fetched.record(copy)
+            dist_host = pinned.numpy()
+        if n <= 2 and fetched is not None:
+            fetched.synchronize()
         if n == 1:
             return TreeResult(f"{names[0]};", np.zeros((0, 3), np.int32), np.zeros((0, 3)), dist_m, counts,
                               dist_host=dist_host)
@@ -221,10 +251,14 @@ class Engine:
             d = float(dist_m[0, 1].item())
             return TreeResult(two_leaf_newick(names, d), np.zeros((0, 3), np.int32), np.zeros((0, 3)),
                               dist_m, counts, int(nz.item()), dist_host=dist_host)
+        if fetched is not None and not keep:
+            torch.cuda.current_stream().wait_event(fetched)     # NJ overwrites the matrix in place
         merge, length = self.nj(dist_m, destroy=not keep)
         merge_h = merge.cpu().numpy()
         length_h = length.cpu().numpy()
         newick = merges_to_newick(merge_h, length_h, list(names))
+        if fetched is not None:
+            fetched.synchronize()
         return TreeResult(newick, merge_h, length_h, dist_m if keep else None, counts if keep else None,
                           int(nz.item()), dist_host=dist_host)
 
