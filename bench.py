@@ -53,7 +53,7 @@ UNIT = "pair-sites/s"
 SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
-NCU_TRAFFIC_BYTES_TC = 50_894_759_000  # r01: 49.27 GB read + 1.63 GB written (profiles/r01_ncu_pair_counts_tc_raw_subset.csv), N=1
+NCU_TRAFFIC_BYTES_TC = 75_751_410_000  # r01: 74.15 GB read + 1.61 GB written per launch (profiles/r01_ncu_pair_counts_tc_raw_subset.csv), N=1
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 

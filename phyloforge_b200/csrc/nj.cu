@@ -51,17 +51,25 @@ __device__ __forceinline__ bool rec_less(double q1, int a1, int b1, double q2, i
   return (q1 < q2) || (q1 == q2 && (a1 < a2 || (a1 == a2 && b1 < b2)));
 }
 
+// lexicographic (q, a, b) minimum over the warp with four integer REDUX steps: q through its
+// order-preserving 64-bit key (high word, then low word among the lanes that hold the minimal high
+// word), then a among the lanes that hold the minimal q, then b. q is never NaN here (a NaN candidate
+// never replaces a thread's best); -0.0 is folded into +0.0 so that key equality is double equality.
 __device__ __forceinline__ void warp_argmin(double& q, int& a, int& b) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const double q2 = __shfl_xor_sync(0xffffffffu, q, off);
-    const int a2 = __shfl_xor_sync(0xffffffffu, a, off);
-    const int b2 = __shfl_xor_sync(0xffffffffu, b, off);
-    const bool take = rec_less(q2, a2, b2, q, a, b);
-    q = take ? q2 : q;
-    a = take ? a2 : a;
-    b = take ? b2 : b;
-  }
+  const unsigned full = 0xffffffffu;
+  const long long bits = __double_as_longlong(__dadd_rn(q, 0.0));
+  const unsigned long long key = static_cast<unsigned long long>(bits) ^ ((bits < 0) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
+  const unsigned mhi = __reduce_min_sync(full, hi);
+  const unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xffffffffu);
+  const bool is_min = hi == mhi && lo == mlo;
+  const unsigned ma = __reduce_min_sync(full, is_min ? static_cast<unsigned>(a) : 0xffffffffu);
+  const unsigned mb = __reduce_min_sync(full, (is_min && static_cast<unsigned>(a) == ma) ? static_cast<unsigned>(b) : 0xffffffffu);
+  const unsigned long long mkey = (static_cast<unsigned long long>(mhi) << 32) | mlo;
+  const unsigned long long mbits = (mkey & 0x8000000000000000ull) ? (mkey ^ 0x8000000000000000ull) : ~mkey;
+  q = __longlong_as_double(static_cast<long long>(mbits));
+  a = static_cast<int>(ma);
+  b = static_cast<int>(mb);
 }
 
 // optional phase accounting (pf_nj_profile): nanoseconds of CTA 0 per phase, summed over iterations
@@ -101,10 +109,11 @@ struct NjPending {
 
 // ---- argmin scan. Work items = (row a, segment of 32 U columns) of the upper triangle, enumerated
 // row-block major so that every thread meets its candidates in ascending (a, b) order: a strict
-// `q < best` then implements the lexicographic tie rule inside a thread. All U loads of an item are
-// issued before the first use and the loop over candidates is branch-free, so an item costs one memory
-// round trip; items that lie wholly inside the triangle and touch no pending column (almost all of
-// them) take a path without per-element predicates: 9 instructions per candidate.
+// `q < best` then implements the lexicographic tie rule inside a thread. The U loads of an item are
+// issued together, and the loads of a warp's NEXT item are issued before the candidates of the current
+// one are evaluated (two register buffers), so the memory round trip of an item is hidden behind the
+// arithmetic of the previous one. Items that lie wholly inside the triangle and touch no pending
+// column (almost all of them) load without per-element predicates.
 template <int U, bool VIRT, bool R_SMEM>
 __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld, const double* spare, int n_phys,
                                         const int* s_phys, const double* rs, const double* s_du, int na, double n2,
@@ -112,34 +121,63 @@ __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld
                                         int& bb) {
   constexpr int SEG = 32 * U;
   const int nseg = (na + SEG - 1) / SEG;
-  int rb = 0, base = 0;
-  int rows = min(SEG, na), segs = nseg;
-  int cnt = rows * segs;
   int total = 0;
   for (int k = 0; k < nseg; ++k) total += min(SEG, na - k * SEG) * (nseg - k);
-  for (int item = gwarp; item < total; item += nwarps) {
+  if (gwarp >= total) return;
+  // enumeration state; decode() is called with increasing item numbers
+  int rb = 0, base = 0;
+  int segs = nseg;
+  int cnt = min(SEG, na) * segs;
+  // kind: 0 = interior item (no predicates), 1 = general, 2 = the row of the node merged last (in s_du)
+  auto decode = [&](int item, int& a, int& c0, int& kind, const double*& rp) {
     while (item >= base + cnt) {
       base += cnt;
       ++rb;
-      rows = min(SEG, na - rb * SEG);
       segs = nseg - rb;
-      cnt = rows * segs;
+      cnt = min(SEG, na - rb * SEG) * segs;
     }
     const int local = item - base;
     const int ar = local / segs;
-    const int a = rb * SEG + ar;
-    const int c0 = (rb + (local - ar * segs)) * SEG;
+    a = rb * SEG + ar;
+    c0 = (rb + (local - ar * segs)) * SEG;
     const bool pend_in_seg = VIRT && ((pend.a >= c0 && pend.a < c0 + SEG) || (pend.b >= c0 && pend.b < c0 + SEG));
-    const double ra = R_SMEM ? rs[a] : __ldcg(rs + a);
-    double dv[U];
-    int iu = -1;     // index u of this item's best candidate so far, if it beats bq
-    if (c0 > a && c0 + SEG <= na && !pend_in_seg && !(VIRT && a == pend.a)) {
-      int prow = a;
-      if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
-      const double* rp = ((VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld) + c0 + lane;
-      const double* rsp = rs + c0 + lane;
+    int prow = a;
+    if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
+    rp = (VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld;
+    kind = (VIRT && a == pend.a) ? 2 : ((c0 > a && c0 + SEG <= na && !pend_in_seg) ? 0 : 1);
+  };
+  auto load = [&](double (&dv)[U], int a, int c0, int kind, const double* rp) {
+    if (kind == 0) {
+      const double* p = rp + c0 + lane;
 #pragma unroll
-      for (int u = 0; u < U; ++u) dv[u] = __ldcg(rp + u * 32);
+      for (int u = 0; u < U; ++u) dv[u] = __ldcg(p + u * 32);
+    } else if (kind == 1) {
+      // the column of the slot that took over the last slot is still in the last slot's column
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = c0 + u * 32 + lane;
+        const int col = (VIRT && b == pend.b) ? pend.last : b;
+        dv[u] = (b > a && b < na) ? __ldcg(rp + col) : CUDART_INF;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = c0 + u * 32 + lane;
+        dv[u] = (b > a && b < na) ? s_du[b] : CUDART_INF;
+      }
+    }
+  };
+  auto compute = [&](double (&dv)[U], int a, int c0, int kind) {
+    if (VIRT && kind == 1 && pend.a > a && pend.a >= c0 && pend.a < c0 + SEG) {
+      const double dua = s_du[a];      // the column of the node merged last
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (c0 + u * 32 + lane == pend.a) dv[u] = dua;
+    }
+    const double ra = R_SMEM ? rs[a] : __ldcg(rs + a);
+    int iu = -1;     // index u of this item's best candidate, if it beats bq
+    if (kind == 0) {
+      const double* rsp = rs + c0 + lane;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const double rbv = R_SMEM ? rsp[u * 32] : __ldcg(rsp + u * 32);
@@ -151,31 +189,6 @@ __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld
         iu = take ? u : iu;
       }
     } else {
-      if (VIRT && a == pend.a) {
-        // row of the node merged last: its distances are in shared memory
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int b = c0 + u * 32 + lane;
-          dv[u] = (b > a && b < na) ? s_du[b] : CUDART_INF;
-        }
-      } else {
-        int prow = a;
-        if (VIRT) prow = s_phys[(a == pend.b) ? pend.last : a];
-        const double* rp = (VIRT && prow == n_phys) ? spare : D + static_cast<int64_t>(prow) * ld;
-        // the column of the slot that took over the last slot is still in the last slot's column
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int b = c0 + u * 32 + lane;
-          const int col = (VIRT && b == pend.b) ? pend.last : b;
-          dv[u] = (b > a && b < na) ? __ldcg(rp + col) : CUDART_INF;
-        }
-        if (VIRT && pend.a > a && pend.a >= c0 && pend.a < c0 + SEG) {
-          const double dua = s_du[a];
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (c0 + u * 32 + lane == pend.a) dv[u] = dua;
-        }
-      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int bc = min(c0 + u * 32 + lane, na - 1);
@@ -192,12 +205,37 @@ __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld
       ba = a;
       bb = c0 + iu * 32 + lane;
     }
+  };
+
+  double dv0[U], dv1[U];
+  int a0, c00, k0, a1 = 0, c01 = 0, k1 = 0;
+  const double *p0, *p1 = nullptr;
+  int item = gwarp;
+  decode(item, a0, c00, k0, p0);
+  load(dv0, a0, c00, k0, p0);
+  while (true) {
+    item += nwarps;
+    const bool more1 = item < total;
+    if (more1) {
+      decode(item, a1, c01, k1, p1);
+      load(dv1, a1, c01, k1, p1);
+    }
+    compute(dv0, a0, c00, k0);
+    if (!more1) break;
+    item += nwarps;
+    const bool more0 = item < total;
+    if (more0) {
+      decode(item, a0, c00, k0, p0);
+      load(dv0, a0, c00, k0, p0);
+    }
+    compute(dv1, a1, c01, k1);
+    if (!more0) break;
   }
 }
 
 // ===================================================================== fast kernel
 constexpr int NJF_THREADS = 512;
-constexpr int NJF_U = 16;            // 512-column scan items
+constexpr int NJF_U = 8;             // 256-column scan items, two in flight per warp
 constexpr int NJF_K = 8;             // slots per thread and batch of the update
 constexpr int64_t NJ_FAST_MAX_N = 11000;   // 20 n bytes of shared memory
 constexpr int NJF_SHARDS = 8;        // arrival counters of the exchange, one 128-byte line each
@@ -343,6 +381,9 @@ nj_fast_kernel(const NjFastParams P) {
     const double* row_b = (pwb == n) ? P.spare : D + static_cast<int64_t>(pwb) * ld;
     double* row_u = (spare_row == n) ? P.spare : D + static_cast<int64_t>(spare_row) * ld;
     const double dab = __ldcg(row_a + wb);
+    // the global-memory side of slot k belongs to one CTA: contiguous, 32-aligned ranges of slots
+    const int own_span = ((na + n_cta - 1) / n_cta + 31) & ~31;
+    const int own_lo = static_cast<int>(blockIdx.x) * own_span, own_hi = own_lo + own_span;
     for (int k0 = tid; k0 < na; k0 += NJF_THREADS * NJF_K) {
       double dak[NJF_K], dbk[NJF_K], mv[NJF_K];
       int prow[NJF_K];
@@ -350,7 +391,7 @@ nj_fast_kernel(const NjFastParams P) {
       for (int j = 0; j < NJF_K; ++j) {
         const int k = k0 + j * NJF_THREADS;
         const bool live = k < na && k != wa && k != wb;
-        const bool own = live && ((k >> 5) % n_cta) == static_cast<int>(blockIdx.x);
+        const bool own = live && k >= own_lo && k < own_hi;
         dak[j] = live ? __ldcg(row_a + k) : 0.0;
         dbk[j] = live ? __ldcg(row_b + k) : 0.0;
         prow[j] = own ? s_phys[k] : -1;
@@ -467,7 +508,7 @@ nj_fast_kernel(const NjFastParams P) {
 
 // ===================================================================== general kernel
 constexpr int NJ_THREADS = 512;
-constexpr int NJ_U = 16;  // 512-column scan items
+constexpr int NJ_U = 8;   // 256-column scan items, two in flight per warp
 
 struct NjRecG {   // record of the general kernel: d_ab travels with the candidate, because the
   double q;       // update overwrites D[a][b] in place while other CTAs may not have read it yet
@@ -715,7 +756,7 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
     P.recs = reinterpret_cast<unsigned long long*>(static_cast<char*>(w_rec) + 128 * NJF_SHARDS);
     const int64_t n_pad = (n + 1) & ~int64_t(1);
     const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
-    // about two 512-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
+    // about four 256-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
     const int64_t items = n * pf_ceil_div(n, 32 * NJF_U) / 2 + 1;
     const int64_t blocks = pf_ceil_div(items, (NJF_THREADS / 32) * 2);
     constexpr int64_t max_blocks = NJF_MAX_CTAS;
