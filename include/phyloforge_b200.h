@@ -253,10 +253,11 @@ PF_API int pf_probe_latency(int kind, int iters, int n_ctas, double* h_ns_per_st
  * feeds the A operand from tensor memory (tcgen05.st) instead of shared memory.
  * pf_probe_umma_fp4_rate: SM clock64 ticks per 128 x n x 64 instruction, operands resident in shared
  * memory (a_in_tmem: the A operand in tensor memory), n_acc accumulators used round-robin, the B
- * operand rotating over n_bufs different tiles. */
+ * operand rotating over n_bufs different tiles; noise > 0: three other warps each do one LDS.128 +
+ * one STS.128 (512 B each way) every `noise` clocks beside the MMAs. */
 PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c, int n, int k,
                                 int a_in_tmem, void* stream);
-PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs,
+PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs, int noise,
                                   double* ticks_per_mma, void* stream);
 
 #endif /* PHYLOFORGE_B200_H */

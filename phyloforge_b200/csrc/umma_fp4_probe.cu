@@ -148,17 +148,19 @@ umma_fp4_selftest_kernel(const int8_t* __restrict__ A, const int8_t* __restrict_
 
 template <int N>
 __global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_acc, int a_in_tmem, int n_bufs,
-                                                               long long* out_cycles) {
+                                                               int noise, long long* out_cycles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint32_t s_tmem;
+  __shared__ int s_stop;
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
   if (tid == 0) {
+    s_stop = 0;
     umma::mbar_init(&s_bar, 1);
     umma::fence_mbar_init();
   }
-  for (int i = tid; i < (F4_M * 2 + N * n_bufs) * 32 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x22222222u;
+  for (int i = tid; i < ((F4_M * 2 + N * n_bufs) * 32 + 4096) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x22222222u;
   umma::fence_proxy_async_smem();
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -194,6 +196,18 @@ __global__ void __launch_bounds__(128, 1) umma_fp4_rate_kernel(int reps, int n_a
     umma::commit(&s_bar);
     umma::mbar_wait(&s_bar, 0);
     out_cycles[blockIdx.x] = clock64() - t0;
+    *reinterpret_cast<volatile int*>(&s_stop) = 1;
+  } else if (warp >= 1 && noise > 0) {
+    // shared-memory traffic beside the MMAs: every `noise` clocks per warp one LDS.128 + one STS.128
+    // (512 B each way per warp), on a region the MMAs do not read
+    const uint32_t base = umma::smem_addr(smem) + (F4_M * 2 + N * n_bufs) * 32 + (warp - 1) * 1024 + (tid & 31) * 16;
+    uint4 v = make_uint4(tid, 0, 0, 0);
+    while (*reinterpret_cast<volatile int*>(&s_stop) == 0) {
+      const long long t = clock64();
+      const uint4 w = umma::lds128(base + 512);
+      umma::sts128(base, v.x ^ w.x, v.y, v.z, v.w);
+      while (clock64() - t < noise) {}
+    }
   }
   umma::fence_before_thread_sync();
   __syncthreads();
@@ -223,8 +237,8 @@ PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c
 }
 
 // SM-clock64 ticks per kind::mxf4 MMA (128 x n x 64), operands resident in shared memory, n_acc accumulators round-robin
-PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs, double* ticks_per_mma,
-                                  void* stream) {
+PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs, int noise,
+                                  double* ticks_per_mma, void* stream) {
   PF_TRY_BEGIN
   if ((n != 128 && n != 192 && n != 256) || reps <= 0 || n_acc < 1 || n_acc * n + (a_in_tmem ? 16 : 0) > F4_SF_COL ||
       n_bufs < 1 || n_bufs > 16 || !ticks_per_mma)
@@ -235,11 +249,11 @@ PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int
   PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   long long* d = nullptr;
   PF_CUDA(cudaMalloc(&d, sizeof(long long) * sms));
-  const size_t smem = static_cast<size_t>(F4_M * 2 + n * n_bufs) * 32;
+  const size_t smem = static_cast<size_t>(F4_M * 2 + n * n_bufs) * 32 + 4096;
   auto launch = [&](auto kernel) -> cudaError_t {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return e;
-    kernel<<<sms, 128, smem, s>>>(reps, n_acc, a_in_tmem, n_bufs, d);
+    kernel<<<sms, 128, smem, s>>>(reps, n_acc, a_in_tmem, n_bufs, noise, d);
     return cudaGetLastError();
   };
   cudaError_t e = n == 128 ? launch(umma_fp4_rate_kernel<128>) : n == 192 ? launch(umma_fp4_rate_kernel<192>) : launch(umma_fp4_rate_kernel<256>);

@@ -28,8 +28,10 @@ for n, k, vals in ((128, 64, (-1, 0, 1)), (192, 256, (-1, 0, 1)), (128, 1024, (-
               f"max|diff|={np.abs(got - want).max()}", flush=True)
         if not ok:
             print(" got[0,:8]", got[0, :8], "want", want[0, :8])
-for n, acc, ts, bufs in ((128, 1, 0, 2), (192, 1, 0, 2), (256, 1, 0, 2), (192, 2, 0, 2), (192, 2, 0, 8), (192, 2, 1, 2), (192, 2, 1, 8),
-                         (128, 3, 1, 8), (256, 1, 0, 8), (256, 1, 1, 8)):
+for n, acc, ts, bufs, noise in ((128, 1, 0, 2, 0), (192, 2, 0, 8, 0), (192, 2, 1, 8, 0), (256, 1, 1, 8, 0),
+                                (192, 2, 1, 8, 400), (192, 2, 1, 8, 200), (192, 2, 1, 8, 100), (192, 2, 1, 8, 50), (192, 2, 1, 8, 25),
+                                (192, 2, 0, 8, 100), (192, 2, 0, 8, 50)):
     v = C.c_double()
-    check(eng.lib.pf_probe_umma_fp4_rate(n, 4000, acc, ts, bufs, C.byref(v), st))
-    print(f"mxf4 128x{n}x64 A-in-{'TMEM' if ts else 'smem'}, {acc} accumulators, {bufs} B tiles: {v.value:.1f} clocks per MMA", flush=True)
+    check(eng.lib.pf_probe_umma_fp4_rate(n, 4000, acc, ts, bufs, noise, C.byref(v), st))
+    extra = f", LDS+STS noise {3 * 1024 / noise:.0f} B/clk" if noise else ""
+    print(f"mxf4 128x{n}x64 A-in-{'TMEM' if ts else 'smem'}, {acc} accumulators, {bufs} B tiles{extra}: {v.value:.1f} clocks per MMA", flush=True)
