@@ -230,6 +230,20 @@ PF_API int64_t pf_nj_work_bytes(int64_t n);
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len,
                  void* d_work, void* stream);
 
+/* Block bootstrap (csrc/bootstrap.cu; the reproducible counterpart of the `-b 1000` the reference passes to
+ * `treebest nj`, treetool/script.py:359-360). The caller keeps the count matrices of n_blocks contiguous
+ * site blocks (pf_pair_counts / pf_pair_counts_tc on word ranges into separate [3][n][ld] buffers,
+ * elems_per_block = 3 n ld apart).
+ * pf_bootstrap_weights: d_weights[r][b] (int32, n_reps x n_blocks) = multiplicity of block b among the
+ * n_blocks draws with replacement of replicate replicate0 + r (counter-based hash of seed, replicate, draw).
+ * pf_bootstrap_counts: d_out[r][e] = sum_b d_weights[r][b] * d_blocks[b][e] for up to 8 replicates per call;
+ * elems_per_block a multiple of 4, buffers 16-byte aligned. Normalise and join each replicate with
+ * pf_normalise / pf_nj. */
+PF_API int pf_bootstrap_weights(uint64_t seed, int64_t replicate0, int n_reps, int n_blocks,
+                                int32_t* d_weights, void* stream);
+PF_API int pf_bootstrap_counts(const int32_t* d_blocks, int n_blocks, int64_t elems_per_block,
+                               const int32_t* d_weights, int n_reps, int32_t* d_out, void* stream);
+
 /* Diagnostic: phase accounting of the NJ kernels (nanoseconds of CTA 0 summed over iterations) and a
  * switch that forces the general kernel. enable: bit 0 = run the instrumented kernels in the following
  * pf_nj calls, bit 1 = use the general kernel (two grid barriers per iteration) also for matrices the

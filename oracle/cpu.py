@@ -54,6 +54,18 @@ def synth_codes(n_samples: int, site0: int, n_sites: int, seed: int = 42, n_pops
     return out
 
 
+def bootstrap_weights(seed: int, replicate0: int, n_reps: int, n_blocks: int) -> np.ndarray:
+    """[n_reps, n_blocks] int32 block multiplicities (same draws as pf_bootstrap_weights)."""
+    out = np.zeros((n_reps, n_blocks), dtype=np.int32)
+    lib().pfo_bootstrap_weights(C.c_uint64(seed), C.c_int64(replicate0), C.c_int(n_reps), C.c_int(n_blocks), _p(out))
+    return out
+
+
+def bootstrap_counts(blocks: np.ndarray, weights: np.ndarray) -> np.ndarray:
+    """blocks [B, 3, n, n] (int), weights [R, B] -> replicate count matrices [R, 3, n, n] int64."""
+    return np.tensordot(weights.astype(np.int64), blocks.astype(np.int64), axes=(1, 0))
+
+
 def synth_rows(rows, n_samples: int, site0: int, n_sites: int, seed: int = 42,
                n_pops: int | None = None, miss_ppm: int = 0) -> np.ndarray:
     """Sample-major codes [len(rows), n_sites] for a subset of samples."""

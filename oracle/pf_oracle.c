@@ -70,6 +70,17 @@ static inline uint8_t pfo_synth_code(uint64_t seed, int64_t site, int64_t i, int
   return (uint8_t)g;
 }
 
+/* Block bootstrap (mirrors phyloforge_b200/csrc/bootstrap.cu): weights[r * n_blocks + b] = multiplicity of
+ * block b among the n_blocks draws with replacement of replicate replicate0 + r. */
+PFO_API void pfo_bootstrap_weights(uint64_t seed, int64_t replicate0, int n_reps, int n_blocks, int32_t* weights) {
+  for (int64_t k = 0; k < (int64_t)n_reps * n_blocks; ++k) weights[k] = 0;
+  for (int r = 0; r < n_reps; ++r)
+    for (int t = 0; t < n_blocks; ++t) {
+      uint32_t h = pfo_hash3(seed ^ 0xb007573a9b007573ULL, (uint64_t)(replicate0 + r), (uint32_t)t);
+      weights[(int64_t)r * n_blocks + (h % (uint32_t)n_blocks)] += 1;
+    }
+}
+
 /* site-major: codes[(s - site0) * ld + i] */
 PFO_API void pfo_synth_codes(uint8_t* codes, int64_t n_samples, int64_t ld, int64_t site0,
                              int64_t n_sites, uint64_t seed, int n_pops, uint32_t miss_ppm) {

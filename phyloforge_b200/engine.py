@@ -182,6 +182,69 @@ class Engine:
                                                      _stream_ptr()))
         return 2 if g.value else 1
 
+    # ------------------------------------------------------------------ bootstrap support
+    def block_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, n_blocks: int,
+                     word_end: int | None = None, variant: int = 0) -> torch.Tensor:
+        """Count matrices of n_blocks contiguous word ranges: int32 [n_blocks, 3, n, n]."""
+        from .sharding import shard_words
+        if word_end is None:
+            word_end = n_words
+        blocks = torch.zeros((n_blocks, 3, n_samples, n_samples), dtype=torch.int32, device=self.device)
+        for b in range(n_blocks):
+            wb, we = shard_words(word_end, n_blocks, b)
+            if we > wb:
+                self.pair_counts(planes, n_samples, n_words, blocks[b], word_begin=wb, word_end=we, variant=variant)
+        return blocks
+
+    def bootstrap_weights(self, seed: int, replicate0: int, n_reps: int, n_blocks: int) -> torch.Tensor:
+        w = torch.empty((n_reps, n_blocks), dtype=torch.int32, device=self.device)
+        check(self.lib.pf_bootstrap_weights(seed, replicate0, n_reps, n_blocks, w.data_ptr(), _stream_ptr()))
+        return w
+
+    def bootstrap_counts(self, blocks: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """blocks [B, 3, n, n] int32, weights [R <= 8, B] int32 -> [R, 3, n, n] int32 weighted sums."""
+        n_blocks = blocks.shape[0]
+        elems = blocks[0].numel()
+        assert blocks.is_contiguous() and weights.is_contiguous() and weights.shape[1] == n_blocks
+        pad = (-elems) % 4                     # the kernel works on groups of four elements
+        src = blocks.reshape(n_blocks, elems)
+        if pad:
+            src = torch.nn.functional.pad(src, (0, pad)).contiguous()
+        out = torch.empty((weights.shape[0], elems + pad), dtype=torch.int32, device=self.device)
+        check(self.lib.pf_bootstrap_counts(src.data_ptr(), n_blocks, elems + pad, weights.data_ptr(), weights.shape[0],
+                                           out.data_ptr(), _stream_ptr()))
+        return out[:, :elems].reshape((weights.shape[0],) + tuple(blocks.shape[1:]))
+
+    def bootstrap_tree(self, planes: torch.Tensor, n_samples: int, n_words: int, names, replicates: int = 100,
+                       seed: int = 1, n_blocks: int = 256, metric="ibs", variant: int = 0,
+                       n_sites: int | None = None, max_block_bytes: int = 48 << 30):
+        """NJ tree of all sites with block-bootstrap support on its internal edges.
+        Returns (TreeResult of the main tree with support labels in .newick, support [n-3] in percent,
+        replicate join lists [replicates, n-2, 3] int32)."""
+        from .bootstrap import split_support
+        word_end = n_words if n_sites is None else (n_sites + 31) // 32
+        per_block = 12 * n_samples * n_samples
+        n_blocks = int(max(1, min(n_blocks, word_end, max_block_bytes // max(1, per_block))))
+        blocks = self.block_counts(planes, n_samples, n_words, n_blocks, word_end=word_end, variant=variant)
+        ones = torch.ones((1, n_blocks), dtype=torch.int32, device=self.device)
+        total = self.bootstrap_counts(blocks, ones)[0].contiguous()
+        main = self.tree_from_counts(total, names, metric=metric, keep=True)
+        if n_samples < 4 or replicates <= 0:
+            return main, np.zeros((0,)), np.zeros((0, max(0, n_samples - 2), 3), dtype=np.int32)
+        merges = []
+        for r0 in range(0, replicates, 8):
+            k = min(8, replicates - r0)
+            w = self.bootstrap_weights(seed, r0, k, n_blocks)
+            rep = self.bootstrap_counts(blocks, w)
+            for j in range(k):
+                dist_m, _ = self.normalise(rep[j].contiguous(), metric)
+                merge, _ = self.nj(dist_m, destroy=True)
+                merges.append(merge)
+        rep_merges = torch.stack(merges).cpu().numpy()
+        support = split_support(main.merge, rep_merges, n_samples)
+        main.newick = merges_to_newick(main.merge, main.length, list(names), support=support)
+        return main, support, rep_merges
+
     def allreduce_counts(self, counts: torch.Tensor):
         """Sum the site shards' count matrices over all ranks (NCCL over NVLink)."""
         from .sharding import allreduce_counts

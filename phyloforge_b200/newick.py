@@ -19,8 +19,10 @@ def quote_label(name: str) -> str:
     return "'" + name.replace("'", "''") + "'"
 
 
-def merges_to_newick(merge, length, names: Sequence[str], fmt: str = "%.10g") -> str:
+def merges_to_newick(merge, length, names: Sequence[str], fmt: str = "%.10g", support=None) -> str:
     """Serialise the pf_nj merge list as an unrooted Newick string with a trifurcating root.
+    support[t] (optional, one value per row t < n-3) is written as the label of internal node n+t,
+    i.e. of the edge above it (bootstrap support in percent).
 
     merge[t] = (a, b, 0) for t < n-3 (node n+t has children a, b with branch lengths
     length[t][0..1]); merge[n-3] = the three nodes of the final join, length[n-3] their
@@ -51,7 +53,8 @@ def merges_to_newick(merge, length, names: Sequence[str], fmt: str = "%.10g") ->
             continue
         (a, la), (b, lb) = children[v]
         if a in text and b in text:
-            text[v] = f"({text.pop(a)}:{fmt % la},{text.pop(b)}:{fmt % lb})"
+            label = "" if support is None else ("%g" % float(support[v - n]))
+            text[v] = f"({text.pop(a)}:{fmt % la},{text.pop(b)}:{fmt % lb}){label}"
             stack.pop()
         else:
             if a not in text:

@@ -42,6 +42,8 @@ class RunCmd:
         self.out_path = os.getcwd()
         self.distance = "ibs"                   # new optional key
         self.non_biallelic = "error"            # new optional key
+        self.bootstrap = 0                      # new optional key: block-bootstrap replicates (the reference asks
+        self.bootstrap_seed = 1                 # treebest for -b 1000, script.py:360); 0 = no support values
         self._engine = None
         self._packed = None
         self.report = {}
@@ -87,6 +89,14 @@ class RunCmd:
         if self.non_biallelic not in ("error", "skip"):
             print(f"non_biallelic: {self.non_biallelic} is not recognized (error or skip), please check it")
             sys.exit()
+        try:
+            self.bootstrap = int(self.bootstrap)
+            self.bootstrap_seed = int(self.bootstrap_seed)
+            if self.bootstrap < 0:
+                raise ValueError
+        except ValueError:
+            print(f"bootstrap: {self.bootstrap} / bootstrap_seed: {self.bootstrap_seed} must be non-negative integers")
+            sys.exit()
 
     # ------------------------------------------------------------------ config
     def get_config(self, opt_cfg, opt):
@@ -127,8 +137,16 @@ class RunCmd:
             print("At least two samples are needed to build a tree")
             sys.exit(1)
         t0 = time.perf_counter()
-        res = eng.tree_from_planes(packed.planes, packed.n_samples, packed.n_words, packed.names,
-                                   metric=self.distance, n_sites=packed.n_sites)
+        if self.bootstrap > 0 and packed.n_samples >= 4:
+            # main tree + seeded block-bootstrap support on its internal edges (labels in percent)
+            res, support, _ = eng.bootstrap_tree(packed.planes, packed.n_samples, packed.n_words, packed.names,
+                                                 replicates=self.bootstrap, seed=self.bootstrap_seed,
+                                                 metric=self.distance, n_sites=packed.n_sites)
+            self.report.update({"bootstrap_replicates": self.bootstrap, "bootstrap_seed": self.bootstrap_seed,
+                                "bootstrap_mean_support": float(support.mean()) if support.size else None})
+        else:
+            res = eng.tree_from_planes(packed.planes, packed.n_samples, packed.n_words, packed.names,
+                                       metric=self.distance, n_sites=packed.n_sites)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         with open(out_file, "w") as f:
