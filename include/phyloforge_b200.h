@@ -229,6 +229,11 @@ PF_API int pf_normalise(const int32_t* d_counts, int64_t n_samples, int64_t ld, 
 PF_API int64_t pf_nj_work_bytes(int64_t n);
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len,
                  void* d_work, void* stream);
+/* n_mat matrices of the same size in one call (bootstrap replicates): matrix m at d_dist + m * mat_stride
+ * doubles, outputs at d_merge / d_len + m * 3 (n - 2), workspace n_mat * pf_nj_work_bytes(n) bytes. The
+ * matrices are joined concurrently, each by its own group of CTAs of one cooperative launch. */
+PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
+                       int32_t* d_merge, double* d_len, void* d_work, void* stream);
 
 /* Block bootstrap (csrc/bootstrap.cu; the reproducible counterpart of the `-b 1000` the reference passes to
  * `treebest nj`, treetool/script.py:359-360). The caller keeps the count matrices of n_blocks contiguous

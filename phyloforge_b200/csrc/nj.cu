@@ -251,7 +251,12 @@ struct NjFastParams {
   double* r0;                 // initial row sums
   double* spare;              // one extra matrix row (physical row index n)
   unsigned* arrive;           // [NJF_SHARDS][32] arrival counters (monotonic)
-  unsigned long long* recs;   // [2][gridDim.x][2]: {q bits, a | b << 32}
+  unsigned long long* recs;   // [2][CTAs of the matrix][2]: {q bits, a | b << 32}
+  // batch: the grid is n_mat groups of ctas_per_mat CTAs, group g joins matrix g; all pointers above
+  // belong to matrix 0 and move by these strides per matrix
+  int n_mat, ctas_per_mat;
+  int64_t mat_stride;         // doubles between distance matrices
+  int64_t work_stride;        // bytes between the workspaces (r0, spare, arrive, recs)
 };
 
 struct NjWinner {
@@ -261,15 +266,30 @@ struct NjWinner {
 
 template <bool PROF>
 __global__ void __launch_bounds__(NJF_THREADS, 1)
-nj_fast_kernel(const NjFastParams P) {
+nj_fast_kernel(const NjFastParams P_in) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char nj_dyn[];
   __shared__ NjRec s_rec[NJF_THREADS / 32];
   __shared__ NjWinner s_win;
 
+  NjFastParams P = P_in;
+  const int n = P.n;
+  // this CTA's matrix (batch) and its rank among the CTAs of that matrix
+  const int n_cta = P.ctas_per_mat;
+  const int mat = static_cast<int>(blockIdx.x) / n_cta;
+  const int cta = static_cast<int>(blockIdx.x) - mat * n_cta;
+  {
+    const int64_t out3 = 3 * static_cast<int64_t>(n - 2);
+    P.D += mat * P.mat_stride;
+    P.merge += mat * out3;
+    P.len += mat * out3;
+    P.r0 = reinterpret_cast<double*>(reinterpret_cast<char*>(P.r0) + mat * P.work_stride);
+    P.spare = reinterpret_cast<double*>(reinterpret_cast<char*>(P.spare) + mat * P.work_stride);
+    P.arrive = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(P.arrive) + mat * P.work_stride);
+    P.recs = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(P.recs) + mat * P.work_stride);
+  }
   double* __restrict__ D = P.D;
   const int64_t ld = P.ld;
-  const int n = P.n;
   const int n_pad = (n + 1) & ~1;
   double* s_r = reinterpret_cast<double*>(nj_dyn);
   double* s_du = s_r + n_pad;
@@ -277,11 +297,10 @@ nj_fast_kernel(const NjFastParams P) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int WARPS = NJF_THREADS / 32;
-  const int gwarp = blockIdx.x * WARPS + warp;
-  const int nwarps = gridDim.x * WARPS;
-  const int gthread = blockIdx.x * NJF_THREADS + tid;
-  const int nthreads = gridDim.x * NJF_THREADS;
-  const int n_cta = static_cast<int>(gridDim.x);
+  const int gwarp = cta * WARPS + warp;
+  const int nwarps = n_cta * WARPS;
+  const int gthread = cta * NJF_THREADS + tid;
+  const int nthreads = n_cta * NJF_THREADS;
 
   for (int k = gthread; k < NJF_SHARDS * 32; k += nthreads) P.arrive[k] = 0u;
   nj_initial_row_sums(D, ld, n, gwarp, nwarps, lane, P.r0);
@@ -295,7 +314,7 @@ nj_fast_kernel(const NjFastParams P) {
 
   // exchange bookkeeping of warp 0: lane s < NJF_SHARDS watches arrival counter s, which
   // (blockIdx % NJF_SHARDS == s) CTAs bump once per iteration
-  unsigned* my_arrive = P.arrive + (blockIdx.x % NJF_SHARDS) * 32;
+  unsigned* my_arrive = P.arrive + (cta % NJF_SHARDS) * 32;
   const unsigned shard_ctas = (lane < NJF_SHARDS) ? static_cast<unsigned>((n_cta - lane + NJF_SHARDS - 1) / NJF_SHARDS) : 0u;
 
   NjPending pend{-1, -1, -1};
@@ -320,7 +339,7 @@ nj_fast_kernel(const NjFastParams P) {
       if (lane == 0) {
         const unsigned long long w0 = static_cast<unsigned long long>(__double_as_longlong(v.q));
         const unsigned long long w1 = static_cast<unsigned>(v.a) | (static_cast<unsigned long long>(static_cast<unsigned>(v.b)) << 32);
-        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(recs + 2 * blockIdx.x), "l"(w0), "l"(w1) : "memory");
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(recs + 2 * cta), "l"(w0), "l"(w1) : "memory");
         // release: the record and this CTA's update writes of the previous iteration (ordered before
         // this point by the __syncthreads above) are visible before the arrival is
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -383,7 +402,7 @@ nj_fast_kernel(const NjFastParams P) {
     const double dab = __ldcg(row_a + wb);
     // the global-memory side of slot k belongs to one CTA: contiguous, 32-aligned ranges of slots
     const int own_span = ((na + n_cta - 1) / n_cta + 31) & ~31;
-    const int own_lo = static_cast<int>(blockIdx.x) * own_span, own_hi = own_lo + own_span;
+    const int own_lo = cta * own_span, own_hi = own_lo + own_span;
     for (int k0 = tid; k0 < na; k0 += NJF_THREADS * NJF_K) {
       double dak[NJF_K], dbk[NJF_K], mv[NJF_K];
       int prow[NJF_K];
@@ -450,8 +469,8 @@ nj_fast_kernel(const NjFastParams P) {
     NJ_MARK(4)   // update
   }
 
-  if (blockIdx.x != 0) return;
-  // ---- CTA 0: node ids and branch lengths from the log
+  if (cta != 0) return;
+  // ---- CTA 0 of the matrix: node ids and branch lengths from the log
   double d01 = 0.0, d02 = 0.0, d12 = 0.0;
   if (tid == 0) {
     // the last three nodes; the final update may still be pending, so read through it
@@ -727,60 +746,103 @@ PF_API int64_t pf_nj_work_bytes(int64_t n) {
   return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES;
 }
 
+namespace {
+
+// n_mat matrices of the same size, mat_stride doubles apart; outputs 3 (n - 2) apart; workspaces
+// pf_nj_work_bytes(n) apart
+int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride, int32_t* d_merge, double* d_len,
+           void* d_work, cudaStream_t s) {
+  int dev = 0, coop = 0, sms = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!coop) return pf_fail_code(PF_ERR_CUDA, "pf_nj: device does not support cooperative launch");
+  const int64_t work_stride = 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES;
+  const int64_t out3 = 3 * (n - 2);
+
+  if (n <= NJ_FAST_MAX_N && !g_nj_force_general) {
+    int done = 0;
+    while (done < n_mat) {
+      // as many matrices per launch as keep at least 8 CTAs each (one CTA per SM, cooperative launch)
+      int batch = n_mat - done;
+      if (batch > sms / 8) batch = sms / 8;
+      if (batch < 1) batch = 1;
+      char* w = static_cast<char*>(d_work) + done * work_stride;
+      NjFastParams P;
+      P.D = d_dist + done * mat_stride;
+      P.ld = ld;
+      P.n = static_cast<int>(n);
+      P.merge = d_merge + done * out3;
+      P.len = d_len + done * out3;
+      P.r0 = reinterpret_cast<double*>(w);
+      P.spare = reinterpret_cast<double*>(w + align_up(8 * n, 256));
+      char* w_rec = w + 2 * align_up(8 * n, 256) + align_up(4 * n, 256);
+      P.arrive = reinterpret_cast<unsigned*>(w_rec);
+      P.recs = reinterpret_cast<unsigned long long*>(w_rec + 128 * NJF_SHARDS);
+      P.n_mat = batch;
+      P.mat_stride = mat_stride;
+      P.work_stride = work_stride;
+      const int64_t n_pad = (n + 1) & ~int64_t(1);
+      const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
+      // about four 256-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
+      const int64_t items = n * pf_ceil_div(n, 32 * NJF_U) / 2 + 1;
+      int64_t per_mat = pf_ceil_div(items, (NJF_THREADS / 32) * 2);
+      if (per_mat > sms / batch) per_mat = sms / batch;
+      if (per_mat > NJF_MAX_CTAS) per_mat = NJF_MAX_CTAS;
+      if (per_mat < 1) per_mat = 1;
+      P.ctas_per_mat = static_cast<int>(per_mat);
+      static_assert(128 * NJF_SHARDS + 2 * NJF_MAX_CTAS * 16 <= NJ_XCHG_BYTES, "exchange area");
+      static_assert(sizeof(NjRecG) * NJ_MAX_BLOCKS <= NJ_XCHG_BYTES, "record area");
+      const int64_t blocks = per_mat * batch;
+      const int rc = g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true>, NJF_THREADS, smem, blocks, blocks, &P, s)
+                                       : nj_launch(nj_fast_kernel<false>, NJF_THREADS, smem, blocks, blocks, &P, s);
+      if (rc != PF_OK) return rc;
+      done += batch;
+    }
+    return PF_OK;
+  }
+  for (int m = 0; m < n_mat; ++m) {
+    char* w = static_cast<char*>(d_work) + m * work_stride;
+    NjParams P;
+    P.D = d_dist + m * mat_stride;
+    P.ld = ld;
+    P.n = static_cast<int>(n);
+    P.merge = d_merge + m * out3;
+    P.len = d_len + m * out3;
+    P.r0 = reinterpret_cast<double*>(w);
+    P.r1 = reinterpret_cast<double*>(w + align_up(8 * n, 256));
+    P.node = reinterpret_cast<int32_t*>(w + 2 * align_up(8 * n, 256));
+    P.rec = reinterpret_cast<NjRecG*>(w + 2 * align_up(8 * n, 256) + align_up(4 * n, 256));
+    P.r_in_smem = (8 * n <= NJ_MAX_SMEM_R) ? 1 : 0;
+    const size_t smem = P.r_in_smem ? static_cast<size_t>(align_up(8 * n, 16)) : 0;
+    const int64_t items = n * pf_ceil_div(n, 32 * NJ_U) / 2 + 1;
+    const int64_t blocks = pf_ceil_div(items, (NJ_THREADS / 32) * 2);
+    const int rc = g_nj_prof_enabled ? nj_launch(nj_kernel<true>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s)
+                                     : nj_launch(nj_kernel<false>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s);
+    if (rc != PF_OK) return rc;
+  }
+  return PF_OK;
+}
+
+}  // namespace
+
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len, void* d_work,
                  void* stream) {
   PF_TRY_BEGIN
   if (!d_dist || !d_merge || !d_len || !d_work || n < 3 || ld < n || n > 0x3fffffff)
     return pf_fail("pf_nj: bad arguments (n=%lld, ld=%lld; n must be >= 3)", (long long)n, (long long)ld);
-  int dev = 0, coop = 0;
-  PF_CUDA(cudaGetDevice(&dev));
-  PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-  if (!coop) return pf_fail_code(PF_ERR_CUDA, "pf_nj: device does not support cooperative launch");
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  char* w = static_cast<char*>(d_work);
-  double* w_r0 = reinterpret_cast<double*>(w);
-  double* w_r1 = reinterpret_cast<double*>(w + align_up(8 * n, 256));
-  int32_t* w_node = reinterpret_cast<int32_t*>(w + 2 * align_up(8 * n, 256));
-  void* w_rec = w + 2 * align_up(8 * n, 256) + align_up(4 * n, 256);
+  return nj_run(d_dist, n, ld, 1, 0, d_merge, d_len, d_work, static_cast<cudaStream_t>(stream));
+  PF_TRY_END
+}
 
-  if (n <= NJ_FAST_MAX_N && !g_nj_force_general) {
-    NjFastParams P;
-    P.D = d_dist;
-    P.ld = ld;
-    P.n = static_cast<int>(n);
-    P.merge = d_merge;
-    P.len = d_len;
-    P.r0 = w_r0;
-    P.spare = w_r1;
-    P.arrive = reinterpret_cast<unsigned*>(w_rec);
-    P.recs = reinterpret_cast<unsigned long long*>(static_cast<char*>(w_rec) + 128 * NJF_SHARDS);
-    const int64_t n_pad = (n + 1) & ~int64_t(1);
-    const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
-    // about four 256-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
-    const int64_t items = n * pf_ceil_div(n, 32 * NJF_U) / 2 + 1;
-    const int64_t blocks = pf_ceil_div(items, (NJF_THREADS / 32) * 2);
-    constexpr int64_t max_blocks = NJF_MAX_CTAS;
-    static_assert(128 * NJF_SHARDS + 2 * NJF_MAX_CTAS * 16 <= NJ_XCHG_BYTES, "exchange area");
-    static_assert(sizeof(NjRecG) * NJ_MAX_BLOCKS <= NJ_XCHG_BYTES, "record area");
-    return g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true>, NJF_THREADS, smem, blocks, max_blocks, &P, s)
-                             : nj_launch(nj_fast_kernel<false>, NJF_THREADS, smem, blocks, max_blocks, &P, s);
-  }
-  NjParams P;
-  P.D = d_dist;
-  P.ld = ld;
-  P.n = static_cast<int>(n);
-  P.merge = d_merge;
-  P.len = d_len;
-  P.r0 = w_r0;
-  P.r1 = w_r1;
-  P.node = w_node;
-  P.rec = static_cast<NjRecG*>(w_rec);
-  P.r_in_smem = (8 * n <= NJ_MAX_SMEM_R) ? 1 : 0;
-  const size_t smem = P.r_in_smem ? static_cast<size_t>(align_up(8 * n, 16)) : 0;
-  const int64_t items = n * pf_ceil_div(n, 32 * NJ_U) / 2 + 1;
-  const int64_t blocks = pf_ceil_div(items, (NJ_THREADS / 32) * 2);
-  return g_nj_prof_enabled ? nj_launch(nj_kernel<true>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s)
-                           : nj_launch(nj_kernel<false>, NJ_THREADS, smem, blocks, NJ_MAX_BLOCKS, &P, s);
+PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride, int32_t* d_merge,
+                       double* d_len, void* d_work, void* stream) {
+  PF_TRY_BEGIN
+  if (!d_dist || !d_merge || !d_len || !d_work || n < 3 || ld < n || n > 0x3fffffff || n_mat < 1 ||
+      (n_mat > 1 && mat_stride < n * ld))
+    return pf_fail("pf_nj_batch: bad arguments (n=%lld, ld=%lld, n_mat=%d, mat_stride=%lld)", (long long)n,
+                   (long long)ld, n_mat, (long long)mat_stride);
+  return nj_run(d_dist, n, ld, n_mat, mat_stride, d_merge, d_len, d_work, static_cast<cudaStream_t>(stream));
   PF_TRY_END
 }
 

@@ -236,11 +236,10 @@ class Engine:
             k = min(8, replicates - r0)
             w = self.bootstrap_weights(seed, r0, k, n_blocks)
             rep = self.bootstrap_counts(blocks, w)
-            for j in range(k):
-                dist_m, _ = self.normalise(rep[j].contiguous(), metric)
-                merge, _ = self.nj(dist_m, destroy=True)
-                merges.append(merge)
-        rep_merges = torch.stack(merges).cpu().numpy()
+            dists = torch.stack([self.normalise(rep[j].contiguous(), metric)[0] for j in range(k)])
+            merge, _ = self.nj_batch(dists)          # the replicates of a batch are joined concurrently
+            merges.append(merge)
+        rep_merges = torch.cat(merges).cpu().numpy()
         support = split_support(main.merge, rep_merges, n_samples)
         main.newick = merges_to_newick(main.merge, main.length, list(names), support=support)
         return main, support, rep_merges
@@ -269,6 +268,18 @@ class Engine:
         work = torch.empty(int(self.lib.pf_nj_work_bytes(n)), dtype=torch.uint8, device=self.device)
         check(self.lib.pf_nj(work_d.data_ptr(), n, work_d.stride(0), merge.data_ptr(), length.data_ptr(),
                              work.data_ptr(), _stream_ptr()))
+        return merge, length
+
+    def nj_batch(self, dist_b: torch.Tensor):
+        """fp64 [k, n, n] (overwritten) -> (merge int32 [k, n-2, 3], length fp64 [k, n-2, 3]): k trees
+        joined concurrently, each by its own group of CTAs."""
+        k, n = dist_b.shape[0], dist_b.shape[1]
+        assert dist_b.dtype == torch.float64 and dist_b.is_contiguous() and n >= 3
+        merge = torch.zeros((k, n - 2, 3), dtype=torch.int32, device=self.device)
+        length = torch.zeros((k, n - 2, 3), dtype=torch.float64, device=self.device)
+        work = torch.empty(k * int(self.lib.pf_nj_work_bytes(n)), dtype=torch.uint8, device=self.device)
+        check(self.lib.pf_nj_batch(dist_b.data_ptr(), n, n, k, n * n, merge.data_ptr(), length.data_ptr(),
+                                   work.data_ptr(), _stream_ptr()))
         return merge, length
 
     # ------------------------------------------------------------------ composed path

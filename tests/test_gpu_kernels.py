@@ -151,6 +151,24 @@ def test_nj_random_distances(engine, n):
         _check_nj(engine, dist, ld=n + 3)
 
 
+@pytest.mark.parametrize("k,n", [(1, 30), (5, 100), (20, 40), (3, 700)])
+def test_nj_batch_matches_oracle_tree_by_tree(engine, k, n):
+    """pf_nj_batch: several matrices joined concurrently by groups of CTAs of one launch."""
+    rng = np.random.default_rng(k * 1000 + n)
+    mats = []
+    for _ in range(k):
+        a = rng.random((n, n))
+        d = (a + a.T) / 2
+        np.fill_diagonal(d, 0.0)
+        mats.append(d)
+    merge, length = engine.nj_batch(torch.from_numpy(np.stack(mats)).to(engine.device))
+    torch.cuda.synchronize()
+    for j in range(k):
+        want_m, want_l = oracle.nj(mats[j])
+        assert np.array_equal(merge[j].cpu().numpy(), want_m), j
+        assert np.array_equal(length[j].cpu().numpy(), want_l), j
+
+
 def test_nj_many_exact_ties(engine):
     """Rational distances with a common denominator: Q ties are real and must break the same way."""
     rng = np.random.default_rng(99)
