@@ -36,33 +36,33 @@ def merges_to_newick(merge, length, names: Sequence[str], fmt: str = "%.10g", su
     n_steps = n - 2
     if len(merge) != n_steps:
         raise ValueError(f"expected {n_steps} merge rows, got {len(merge)}")
-    children: dict[int, tuple] = {}
-    for t in range(n_steps - 1):
-        a, b = int(merge[t][0]), int(merge[t][1])
-        children[n + t] = ((a, float(length[t][0])), (b, float(length[t][1])))
-    root = tuple((int(merge[n_steps - 1][k]), float(length[n_steps - 1][k])) for k in range(3))
-
-    # iterative post-order so that 10^4-leaf caterpillar trees do not hit the recursion limit
-    text: dict[int, str] = {}
-    stack = [c for c, _ in root]
+    mg = merge.tolist() if hasattr(merge, "tolist") else [list(r) for r in merge]
+    ln = length.tolist() if hasattr(length, "tolist") else [list(r) for r in length]
+    sup = None if support is None else [("%g" % float(x)) for x in support]
+    # one pass over a token stack (no recursion, no repeated copying of subtree strings: 10^4-leaf
+    # caterpillar trees stay linear); a stack item is a finished piece of text or a node to expand
+    out = []
+    root = mg[n_steps - 1]
+    rl = ln[n_steps - 1]
+    stack = [");", int(root[2]), f":{fmt % rl[1]},", int(root[1]), f":{fmt % rl[0]},", int(root[0]), "("]
     while stack:
-        v = stack[-1]
-        if v < n:
-            text[v] = quote_label(names[v])
-            stack.pop()
-            continue
-        (a, la), (b, lb) = children[v]
-        if a in text and b in text:
-            label = "" if support is None else ("%g" % float(support[v - n]))
-            text[v] = f"({text.pop(a)}:{fmt % la},{text.pop(b)}:{fmt % lb}){label}"
-            stack.pop()
+        x = stack.pop()
+        if x.__class__ is str:
+            out.append(x)
+        elif x < n:
+            out.append(quote_label(names[x]))
         else:
-            if a not in text:
-                stack.append(a)
-            if b not in text:
-                stack.append(b)
-    parts = [f"{text[c]}:{fmt % l}" for c, l in root]
-    return "(" + ",".join(parts) + ");"
+            t = x - n
+            a, b = mg[t][0], mg[t][1]
+            la, lb = ln[t][0], ln[t][1]
+            stack.append(f":{fmt % lb})" if sup is None else f":{fmt % lb}){sup[t]}")
+            stack.append(int(b))
+            stack.append(f":{fmt % la},")
+            stack.append(int(a))
+            stack.append("(")
+    text = "".join(out)
+    # the root's third branch length sits before the closing parenthesis
+    return text[:-2] + f":{fmt % rl[2]});"
 
 
 def two_leaf_newick(names: Sequence[str], d: float, fmt: str = "%.10g") -> str:
