@@ -235,6 +235,16 @@ PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double
 PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
                        int32_t* d_merge, double* d_len, void* d_work, void* stream);
 
+/* Host-side: the join list of pf_nj (copied to the host) as unrooted Newick text with a trifurcating root,
+ * branch lengths "%.10g" — what `treebest nj` prints into SNP_treebest.NHX (treetool/script.py:359-360).
+ * names[i] = label of leaf i, already quoted where Newick needs it; h_support: NULL or one value
+ * per row t < n - 3, written as the label of internal node n + t. Returns the text length (without the
+ * terminating 0) or -1 on error; the text is written when h_out != NULL and capacity > length, so a first
+ * call with h_out = NULL sizes the buffer. */
+PF_API int64_t pf_newick_from_merges(const int32_t* h_merge, const double* h_len, int64_t n,
+                                     const char* const* names, const double* h_support, char* h_out,
+                                     int64_t capacity);
+
 /* Block bootstrap (csrc/bootstrap.cu; the reproducible counterpart of the `-b 1000` the reference passes to
  * `treebest nj`, treetool/script.py:359-360). The caller keeps the count matrices of n_blocks contiguous
  * site blocks (pf_pair_counts / pf_pair_counts_tc on word ranges into separate [3][n][ld] buffers,

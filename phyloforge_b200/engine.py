@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from ._lib import PhyloForgeError, check
-from .newick import merges_to_newick, two_leaf_newick
+from .newick import merges_to_newick, merges_to_newick_native, two_leaf_newick
 
 TILE = 64
 METRICS = {"p": 0, "pdist": 0, "p-distance": 0, 0: 0, "ibs": 1, "IBS": 1, 1: 1}
@@ -241,7 +241,7 @@ class Engine:
             merges.append(merge)
         rep_merges = torch.cat(merges).cpu().numpy()
         support = split_support(main.merge, rep_merges, n_samples)
-        main.newick = merges_to_newick(main.merge, main.length, list(names), support=support)
+        main.newick = merges_to_newick_native(self.lib, main.merge, main.length, list(names), support=support)
         return main, support, rep_merges
 
     def allreduce_counts(self, counts: torch.Tensor):
@@ -330,7 +330,7 @@ class Engine:
         merge, length = self.nj(dist_m, destroy=not keep)
         merge_h = merge.cpu().numpy()
         length_h = length.cpu().numpy()
-        newick = merges_to_newick(merge_h, length_h, list(names))
+        newick = merges_to_newick_native(self.lib, merge_h, length_h, list(names))
         if fetched is not None:
             fetched.synchronize()
         return TreeResult(newick, merge_h, length_h, dist_m if keep else None, counts if keep else None,

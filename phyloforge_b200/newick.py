@@ -65,6 +65,39 @@ def merges_to_newick(merge, length, names: Sequence[str], fmt: str = "%.10g", su
     return text[:-2] + f":{fmt % rl[2]});"
 
 
+def merges_to_newick_native(lib, merge, length, names: Sequence[str], support=None) -> str:
+    """merges_to_newick(fmt="%.10g") through the library's host-side serialiser
+    (pf_newick_from_merges): same text, a few times faster for thousands of leaves."""
+    import ctypes as C
+
+    import numpy as np
+    n = len(names)
+    if n < 3:
+        return merges_to_newick(merge, length, names, support=support)
+    mg = np.ascontiguousarray(merge, dtype=np.int32)
+    ln = np.ascontiguousarray(length, dtype=np.float64)
+    if mg.shape != (n - 2, 3) or ln.shape != (n - 2, 3):
+        raise ValueError(f"expected {n - 2} merge rows")
+    enc = [quote_label(x).encode() for x in names]
+    labels = (C.c_char_p * n)(*enc)
+    sup = None
+    if support is not None:
+        sup = np.ascontiguousarray(support, dtype=np.float64)
+        if sup.shape[0] < n - 3:
+            raise ValueError("one support value per internal edge expected")
+    sup_p = sup.ctypes.data if sup is not None else None
+    cap = 48 * n + sum(map(len, enc)) + 64
+    buf = C.create_string_buffer(cap)
+    need = lib.pf_newick_from_merges(mg.ctypes.data, ln.ctypes.data, n, labels, sup_p, buf, cap)
+    if need >= cap:
+        cap = need + 1
+        buf = C.create_string_buffer(cap)
+        need = lib.pf_newick_from_merges(mg.ctypes.data, ln.ctypes.data, n, labels, sup_p, buf, cap)
+    if need < 0:
+        raise ValueError(lib.pf_last_error().decode())
+    return buf.raw[:need].decode()
+
+
 def two_leaf_newick(names: Sequence[str], d: float, fmt: str = "%.10g") -> str:
     """Degenerate NJ on two samples: one edge of length d split evenly."""
     h = fmt % (d / 2.0)

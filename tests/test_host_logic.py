@@ -201,3 +201,43 @@ def test_synthetic_vcf_writers_agree_with_restated_converters():
     text, sv = synth.sv_vcf_bytes(codes, names, other_type_every=13)
     _, seqs = rc.sv_convert(text.decode())
     assert np.array_equal(rc.sv_codes(seqs), synth.expected_sv_columns(codes, sv))
+
+
+def test_native_newick_serialiser_matches_the_python_one():
+    """pf_newick_from_merges (host-side C++ in the library, no GPU needed) == merges_to_newick."""
+    import time
+    from phyloforge_b200 import _lib
+    from phyloforge_b200.newick import merges_to_newick, merges_to_newick_native
+    from oracle import cpu as oracle
+    lib = _lib.load()
+    rng = np.random.default_rng(17)
+    for n in (3, 4, 5, 17, 400):
+        a = rng.random((n, n))
+        d = (a + a.T) / 2 - 0.05                       # some negative branch lengths
+        np.fill_diagonal(d, 0.0)
+        m, l = oracle.nj(d)
+        names = [f"s{i}" for i in range(n)]
+        names[0] = "odd name(1)"
+        names[-1] = "it's:quoted"
+        if n > 4:
+            names[2] = "ünï"
+        assert merges_to_newick_native(lib, m, l, names) == merges_to_newick(m, l, names)
+        if n > 3:
+            sup = rng.integers(0, 101, size=n - 3).astype(np.float64)
+            sup[0] = 12.5
+            assert merges_to_newick_native(lib, m, l, names, support=sup) == merges_to_newick(m, l, names, support=sup)
+    # caterpillar: depth ~ n, must stay linear
+    n = 3000
+    pos = np.cumsum(np.arange(1, n + 1, dtype=np.float64) * 0.01)
+    d = np.abs(pos[:, None] - pos[None, :]) + 1.0
+    np.fill_diagonal(d, 0.0)
+    m, l = oracle.nj(d)
+    names = [f"S{i:05d}" for i in range(n)]
+    t0 = time.perf_counter()
+    text = merges_to_newick_native(lib, m, l, names)
+    t1 = time.perf_counter()
+    assert text == merges_to_newick(m, l, names) and t1 - t0 < 0.5
+    bad = m.copy()
+    bad[0, 0] = n + 5                                   # refers to a node that does not exist yet
+    with pytest.raises(ValueError):
+        merges_to_newick_native(lib, bad, l, names)
