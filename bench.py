@@ -345,11 +345,11 @@ def run_ours(args):
     variant_ran = ran_variant[0]
     if variant_ran == 3:
         # tensor-core indicator GEMMs on 4-bit (E2M1) operands: 2 multiply-accumulates per unordered pair
-        # per site (5 with sample-specific missingness)
+        # per site (4 with sample-specific missingness)
         bf16 = peaks.get("bf16_tflops", 1590.0)
         peak_tops = 4.0 * bf16                      # dense fp4 = 4 x dense bf16 on the same tensor cores (9 vs 2.25 PFLOP/s nominal)
-        launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (VV, HV, VH) ran too
-        macs_per = 5.0 if launches == 2 else 2.0
+        launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (TT, VV) ran too
+        macs_per = 4.0 if launches == 2 else 2.0
         macs = macs_per * pair_sites(n, my_sites)
         achieved_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (fp4)",
@@ -363,8 +363,8 @@ def run_ours(args):
                     "frac_of_int8_tensor_peak": achieved_tops / (2.0 * bf16),
                     "peak_source": "4 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no fp4 entry; nominal dense "
                                    "fp4 is 9000 TOP/s, 4 x the 2250 of bf16)" % ("of measured" if peaks else "of fallback 1590"),
-                    "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 5 MAC with "
-                            "sample-specific missingness: + v.v', h.v', v.h'); the kernel also computes ~13% redundant "
+                    "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 4 MAC with "
+                            "sample-specific missingness: + t.t', v.v'); the kernel also computes ~13% redundant "
                             "pairs in tiles that straddle the diagonal, and a 128 x 192 x 64 instruction takes the "
                             "time of a 128 x 256 x 64 one (73% of the instruction-level peak). kernel_ms "
                             "includes the planes -> 4-bit operand stream conversion and one stream synchronise"}

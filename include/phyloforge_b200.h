@@ -188,7 +188,7 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
 
 /* Tensor-core variant of pf_pair_counts (tcgen05 kind::mxf4 indicator GEMMs on 4-bit E2M1 operands;
  * csrc/pair_counts_tc.cu). ACCUMULATES the same V / D1 / D2 as pf_pair_counts.
- * allow_general != 0: fully asynchronous; *h_used = 1. A second GEMM launch (VV, HV, VH) does its work only
+ * allow_general != 0: fully asynchronous; *h_used = 1. A second GEMM launch (TT, VV) does its work only
  * when the converter finds genotypes missing in some samples only (pf_pair_counts_tc_was_general tells).
  * allow_general == 0: synchronises `stream` once to read that flag; *h_used = 0 = declined (such
  * missingness exists): nothing was added and the caller runs pf_pair_counts.

@@ -5,22 +5,22 @@
 // the site axis. Per genotype:
 //   x = g - 1 in {-1, 0, +1} (0 for het and missing), h = 1 if homozygous, v = 1 if genotyped.
 //   XX = sum x_i x_j = n00 + n22 - n02      HH = sum h_i h_j = n00 + n22 + n02
-//   VV = sum v_i v_j = V                    HV = sum h_i v_j,  VH = sum v_i h_j
-//   D2 = n02 = (HH - XX) / 2                het-vs-hom sites = HV + VH - 2 HH        D1 = that + D2
+//   VV = sum v_i v_j = V                    TT = sum t_i t_j, t = v - h = 1 if heterozygous
+//   D2 = n02 = (HH - XX) / 2                equal genotypes = (XX + HH) / 2 + TT     D1 = VV - that
 // The operands are E2M1 (4-bit float) values, tcgen05.mma kind::mxf4 with all block scale factors 1.0:
 // 64 sites per instruction instead of the 32 of kind::i8 at the same instruction time. -1, 0, +1 are
 // exact in E2M1, products are -1 / 0 / +1, and the fp32 accumulators hold integers below 2^24 exactly
 // (a CTA never accumulates more than 2^23 sites), so the counts are bit-exact.
 // Two kernel modes share one body:
 //   mode 0  XX and HH on 128 x 192 tiles. When every site is genotyped in all samples or in none
-//           (no sample-specific missingness) this is all that is needed: HV = |h_i|, VH = |h_j| and V
+//           (no sample-specific missingness) this is all that is needed: the het-vs-hom counts |h_i|, |h_j| and V
 //           are per-sample / global numbers the converter already has.
-//   mode 1  VV, HV and VH on 128 x 128 tiles, run in addition when genotypes are missing in some
-//           samples only. The two launches add their linear pieces into the same int32 matrices.
+//   mode 1  TT and VV on the same tiles, run in addition when genotypes are missing in some samples only.
+//           The two launches add their linear pieces into the same int32 matrices.
 //
 // Operand stream (produced once per call by planes_to_e2m1): one nibble per genotype that is at the
 // same time the E2M1 code of x and a tag: hom-REF 0xA (-1), het 0x0 (+0), hom-ALT 0x2 (+1),
-// missing 0x8 (-0). h = nibble & 2, v = "nibble != 8". It is stored step-major as 2 KB chunks (64
+// missing 0x8 (-0). h = nibble & 2, v = "nibble != 8", t = "nibble == 0". It is stored step-major as 2 KB chunks (64
 // samples x 64 sites) already in the canonical K-major shared-memory order of a UMMA operand, so ONE
 // TMA bulk copy of the J rows of a step lands as a ready B_x operand.
 // Data flow per CTA (one sample tile pair, a contiguous range of 64-site steps):
@@ -38,9 +38,7 @@ namespace {
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
 constexpr int STEP_WORDS = 2;        // one pipeline step = one MMA K step = 64 sites = two 32-site words
 constexpr int CHUNK_BYTES = 2048;    // 64 samples x 64 sites x 4 bits
-constexpr int GROUP = 5;             // steps per pipeline stage: the barrier round trips of a stage (~500 clocks
-                                     // for an expansion warp) are paid once per GROUP steps
-constexpr int RAW_STAGES = 3;
+constexpr int MAX_RAW_STAGES = 4;
 constexpr int EXP_STAGES = 2;        // a barrier hand-over costs ~230 clocks (profiles/r01_mma_probe.md): the ring
                                      // must cover MMA time + three hand-overs + the expansion itself
 constexpr int TMEM_A_COLS = 8;       // per step: the 8 columns (32 K-bytes per row) of the A plane kept in TMEM;
@@ -50,17 +48,21 @@ constexpr uint32_t NIB_HOM = 0x22222222u;   // bit 1 of a stream nibble: homozyg
 constexpr int HSUM_RUN = 16;         // words per thread of the converter; split boundaries are multiples of it
 constexpr int64_t MAX_WORDS_PER_CTA = 1 << 18;   // 2^23 sites: fp32 accumulators stay exact
 
-// per-mode geometry
+// per-mode geometry. GROUP = steps per pipeline stage: the barrier round trips and fences of a stage
+// (~500 clocks for an expansion warp) are paid once per GROUP steps; RAW = stages of the TMA ring.
 template <int MODE> struct TcCfg;
 template <> struct TcCfg<0> {   // planes: 0 = x (the stream itself), 1 = h; products XX (acc 0), HH (acc 1)
   static constexpr int J = 192, NPROD = 2, NEXP = 1;   // NEXP = derived B planes written by the expansion warps
+  static constexpr int GROUP = 5, RAW = 3;
 };
-template <> struct TcCfg<1> {   // planes: 0 = h, 1 = v; products VV (acc 0), HV (acc 1), VH (acc 2)
-  static constexpr int J = 128, NPROD = 3, NEXP = 2;
+template <> struct TcCfg<1> {   // planes: 0 = t (heterozygous), 1 = v (genotyped); products TT (acc 0), VV (acc 1)
+  static constexpr int J = 192, NPROD = 2, NEXP = 2;
+  static constexpr int GROUP = 4, RAW = 3;
 };
 template <int MODE> struct TcGeo {
   using C = TcCfg<MODE>;
   static constexpr int J = C::J;                               // columns (MMA N); B operand in shared memory
+  static constexpr int GROUP = C::GROUP, RAW = C::RAW;
   static constexpr int ROWS = TC_I + J;                        // sample rows handled per step
   static constexpr int RAW_STEP_BYTES = (J / PF_TILE) * CHUNK_BYTES;   // the B rows of a step, canonical order
   static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
@@ -72,9 +74,10 @@ template <int MODE> struct TcGeo {
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
   static constexpr int RAW_EMPTY_ARRIVALS = J / 32 + (MODE == 0 ? 1 : 0);   // B-row warps; mode 0: the MMA reads B_x from the raw stage
-  static constexpr size_t SMEM = static_cast<size_t>(RAW_STAGES) * RAW_STAGE_BYTES +
+  static constexpr size_t SMEM = static_cast<size_t>(RAW) * RAW_STAGE_BYTES +
                                  static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
   static_assert(TMEM_A + EXP_STAGES * GROUP * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
+  static_assert(RAW <= MAX_RAW_STAGES && SMEM + 2048 <= 227 * 1024, "shared memory");
 };
 
 // ------------------------------------------------------------------ planes -> E2M1 stream
@@ -171,7 +174,7 @@ struct TcParams {
   const int* hsum;        // [splits][hsum_ld] homozygous counts per sample and split (mode 0, uniform)
   int64_t hsum_ld;
   const int* flags;       // flags[0] != 0: sample-specific missingness (set by the converter). Mode 0 then leaves
-                          // V and HV + VH to the mode-1 launch; mode 1 exits at once when it is 0.
+                          // V and VV - TT to the mode-1 launch; mode 1 exits at once when it is 0.
   int debug;              // timing experiments (results are wrong): 1 = MMAs do not wait for operands,
                           // 2 = expansion warps do no work, 4 = no MMAs are issued
 };
@@ -217,13 +220,13 @@ __device__ __forceinline__ void make_planes(const uint4& lo, const uint4& hi, ui
   const uint32_t n[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    const uint32_t h = n[m] & NIB_HOM;
     if (MODE == 0) {
       p0[m] = n[m];        // x: the stream nibble is its E2M1 code
-      p1[m] = h;
+      p1[m] = n[m] & NIB_HOM;
     } else {
-      p0[m] = h;
-      p1[m] = (((~n[m]) >> 3 | n[m] >> 1) & 0x11111111u) << 1;   // v: +1.0 unless the nibble is 0x8 (bit 3 set, bit 1 clear)
+      const uint32_t s1 = n[m] >> 3, m1 = n[m] >> 1;              // bit 0 of each nibble: sign bit / homozygous bit
+      p0[m] = (~(s1 | m1) & 0x11111111u) << 1;                    // t: +1.0 for a heterozygous genotype (nibble 0x0)
+      p1[m] = ((~s1 | m1) & 0x11111111u) << 1;                    // v: +1.0 unless the nibble is 0x8 (bit 3 set, bit 1 clear)
     }
   }
 }
@@ -239,7 +242,7 @@ pair_counts_tc_kernel(const TcParams P) {
   using G = TcGeo<MODE>;
   constexpr int J = G::J;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t raw_full[RAW_STAGES], raw_empty[RAW_STAGES];
+  __shared__ __align__(8) uint64_t raw_full[MAX_RAW_STAGES], raw_empty[MAX_RAW_STAGES];
   __shared__ __align__(8) uint64_t exp_full[EXP_STAGES], exp_empty[EXP_STAGES];
   __shared__ __align__(8) uint64_t done_bar;
   __shared__ uint32_t s_tmem;
@@ -250,8 +253,8 @@ pair_counts_tc_kernel(const TcParams P) {
   const bool general = __ldg(P.flags) != 0;
   if (MODE == 1 && !general) return;
   // shared-window addresses, computed once
-  const uint32_t raw_a = umma::smem_addr(smem);                                   // RAW_STAGES x RAW_STAGE_BYTES
-  const uint32_t exp_a = raw_a + RAW_STAGES * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (derived B planes)
+  const uint32_t raw_a = umma::smem_addr(smem);                                   // G::RAW x RAW_STAGE_BYTES
+  const uint32_t exp_a = raw_a + G::RAW * G::RAW_STAGE_BYTES;                 // EXP_STAGES x EXP_STAGE_BYTES (derived B planes)
   const uint32_t raw_full_a = umma::smem_addr(raw_full), raw_empty_a = umma::smem_addr(raw_empty);
   const uint32_t exp_full_a = umma::smem_addr(exp_full), exp_empty_a = umma::smem_addr(exp_empty);
   const uint32_t done_a = umma::smem_addr(&done_bar);
@@ -272,12 +275,12 @@ pair_counts_tc_kernel(const TcParams P) {
   const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
   if (w_end <= w_begin) return;
   const int n_steps = static_cast<int>((w_end - w_begin + STEP_WORDS - 1) / STEP_WORDS);
-  const int n_groups = (n_steps + GROUP - 1) / GROUP;
+  const int n_groups = (n_steps + G::GROUP - 1) / G::GROUP;
   const int64_t s_begin = w_begin / STEP_WORDS;
 
   if (warp == 0) umma::tmem_alloc(&s_tmem, 512);
   if (tid == 32) {
-    for (int s = 0; s < RAW_STAGES; ++s) {
+    for (int s = 0; s < G::RAW; ++s) {
       umma::mbar_init(&raw_full[s], 1);
       umma::mbar_init(&raw_empty[s], G::RAW_EMPTY_ARRIVALS);
     }
@@ -319,21 +322,21 @@ pair_counts_tc_kernel(const TcParams P) {
       int stage = 0;
       uint32_t phase = 1;        // parity of the "previous use" of a stage: first pass must not block
       for (int g = 0; g < n_groups; ++g) {
-        if (g >= RAW_STAGES) {
+        if (g >= G::RAW) {
           const long long t0 = PROF ? clock64() : 0;
           umma::mbar_wait_a(raw_empty_a + stage * 8, phase);
           if (PROF) t_wait += clock64() - t0;
         }
-        const int kw = min(GROUP, n_steps - g * GROUP);
+        const int kw = min(G::GROUP, n_steps - g * G::GROUP);
         umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
 #pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
+        for (int j = 0; j < G::GROUP; ++j) {
           if (j < kw)
             umma::bulk_g2s_a(raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES,
-                             src_b + (static_cast<int64_t>(g) * GROUP + j) * step_stride, G::RAW_STEP_BYTES,
+                             src_b + (static_cast<int64_t>(g) * G::GROUP + j) * step_stride, G::RAW_STEP_BYTES,
                              raw_full_a + stage * 8);
         }
-        if (++stage == RAW_STAGES) {
+        if (++stage == G::RAW) {
           stage = 0;
           phase ^= 1;
         }
@@ -357,12 +360,12 @@ pair_counts_tc_kernel(const TcParams P) {
         umma::mbar_wait_a(exp_full_a + e * 8, phase);
         if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
-        const int kw = min(GROUP, n_steps - g * GROUP);
+        const int kw = min(G::GROUP, n_steps - g * G::GROUP);
         if (!(PROF && (P.debug & 4))) {
 #pragma unroll
-          for (int j = 0; j < GROUP; ++j) {
+          for (int j = 0; j < G::GROUP; ++j) {
             if (j < kw) {
-              const uint32_t a_t = tmem + G::TMEM_A + (e * GROUP + j) * TMEM_A_COLS;    // A plane 1 (h / v) in TMEM
+              const uint32_t a_t = tmem + G::TMEM_A + (e * G::GROUP + j) * TMEM_A_COLS;    // A plane 1 (h / v) in TMEM
               const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
               const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
               const uint64_t a_s = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);    // A plane 0 (x / h) in shared memory
@@ -374,11 +377,10 @@ pair_counts_tc_kernel(const TcParams P) {
                 mma_mxf4_ss(tmem + 0 * J, a_s, bx, idesc, acc, tsfa, tsfb);   // XX
                 mma_mxf4_ts(tmem + 1 * J, a_t, bh, idesc, acc, tsfa, tsfb);   // HH
               } else {
-                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
+                const uint64_t bt = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
                 const uint64_t bv = umma::smem_desc_kmajor_noswizzle(bbase + G::EXP_PLANE_BYTES, 128, 256);
-                mma_mxf4_ts(tmem + 0 * J, a_t, bv, idesc, acc, tsfa, tsfb);   // VV
-                mma_mxf4_ss(tmem + 1 * J, a_s, bv, idesc, acc, tsfa, tsfb);   // HV
-                mma_mxf4_ts(tmem + 2 * J, a_t, bh, idesc, acc, tsfa, tsfb);   // VH
+                mma_mxf4_ss(tmem + 0 * J, a_s, bt, idesc, acc, tsfa, tsfb);   // TT
+                mma_mxf4_ts(tmem + 1 * J, a_t, bv, idesc, acc, tsfa, tsfb);   // VV
               }
             }
           }
@@ -389,7 +391,7 @@ pair_counts_tc_kernel(const TcParams P) {
           e = 0;
           phase ^= 1;
         }
-        if (++stage == RAW_STAGES) stage = 0;
+        if (++stage == G::RAW) stage = 0;
       }
       umma::commit_a(done_a);
       if (PROF) {
@@ -418,13 +420,13 @@ pair_counts_tc_kernel(const TcParams P) {
     int stage = 0, e = 0;
     uint32_t raw_phase = 0, exp_phase = 1;
     const bool idle = PROF && (P.debug & 2);
-    uint4 lo[GROUP], hi[GROUP];
+    uint4 lo[G::GROUP], hi[G::GROUP];
     auto load_a_rows = [&](int g) {
 #pragma unroll
-      for (int j = 0; j < GROUP; ++j) {
+      for (int j = 0; j < G::GROUP; ++j) {
         lo[j] = make_uint4(0, 0, 0, 0);
         hi[j] = lo[j];
-        const int st = g * GROUP + j;
+        const int st = g * G::GROUP + j;
         if (st < n_steps && !idle) {
           lo[j] = __ldg(a_src + st * step_stride);
           hi[j] = __ldg(a_src + st * step_stride + 8);
@@ -445,11 +447,11 @@ pair_counts_tc_kernel(const TcParams P) {
       }
       __syncwarp();
       if (is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
-      const int kw = min(GROUP, n_steps - g * GROUP);
+      const int kw = min(G::GROUP, n_steps - g * G::GROUP);
       if (!is_a) {
         const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
 #pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
+        for (int j = 0; j < G::GROUP; ++j) {
           lo[j] = make_uint4(0, 0, 0, 0);
           hi[j] = lo[j];
           if (j < kw && !idle) {
@@ -460,7 +462,7 @@ pair_counts_tc_kernel(const TcParams P) {
       }
       const long long tf0 = PROF ? clock64() : 0;
 #pragma unroll
-      for (int j = 0; j < GROUP; ++j) {
+      for (int j = 0; j < G::GROUP; ++j) {
         if (j < kw && !idle) {
           uint32_t p0[8], p1[8];
           make_planes<MODE>(lo[j], hi[j], p0, p1);
@@ -469,14 +471,14 @@ pair_counts_tc_kernel(const TcParams P) {
             const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
             umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);
             umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
-            umma::tmem_st_32x8(a_base + (e * GROUP + j) * TMEM_A_COLS, p1);
+            umma::tmem_st_32x8(a_base + (e * G::GROUP + j) * TMEM_A_COLS, p1);
           } else {
             const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES + G::A_PLANE_BYTES;
             if (MODE == 0) {
               umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
               umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
             } else {
-              umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // h
+              umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // t
               umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
               umma::sts128(dst + G::EXP_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);   // v
               umma::sts128(dst + G::EXP_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
@@ -498,7 +500,7 @@ pair_counts_tc_kernel(const TcParams P) {
       // next stage's rows: in flight while this stage's MMAs run (issued after the fences, which
       // would otherwise wait for these loads)
       if (is_a) load_a_rows(g + 1);
-      if (++stage == RAW_STAGES) {
+      if (++stage == G::RAW) {
         stage = 0;
         raw_phase ^= 1;
       }
@@ -558,8 +560,10 @@ pair_counts_tc_kernel(const TcParams P) {
             if (j >= P.n_samples || j < i) continue;       // each unordered pair once: row <= column
             const int xx = __float2int_rn(__uint_as_float(pv[c])), hh = __float2int_rn(__uint_as_float(qv[c]));
             const int d2 = (hh - xx) >> 1;
-            // uniform: D1 = |h_i| + |h_j| - 2 HH + D2; general: HV + VH come from the mode-1 launch
-            const int d1 = (uniform ? hi_cnt + s_hcount[TC_I + j_local] : 0) - 2 * hh + d2;
+            // D1 = (valid sites) - (sites with equal genotypes). Uniform: |h_i| + |h_j| - 2 HH + D2.
+            // General: VV - TT - (XX + HH) / 2, VV - TT coming from the mode-1 launch; XX + HH is twice the
+            // number of equal homozygous sites of this CTA's site range, so the halving is exact.
+            const int d1 = uniform ? (hi_cnt + s_hcount[TC_I + j_local] - 2 * hh + d2) : -((xx + hh) >> 1);
             if (uniform) atomicAdd(V + i * P.ld + j, v_sites);
             atomicAdd(D1 + i * P.ld + j, d1);
             atomicAdd(D2 + i * P.ld + j, d2);
@@ -571,10 +575,9 @@ pair_counts_tc_kernel(const TcParams P) {
           }
         }
       } else {
-        uint32_t vv[32], hv[32], vh[32];
-        umma::tmem_ld_32x32(taddr + 0 * J, vv);
-        umma::tmem_ld_32x32(taddr + 1 * J, hv);
-        umma::tmem_ld_32x32(taddr + 2 * J, vh);
+        uint32_t tt[32], vv[32];
+        umma::tmem_ld_32x32(taddr + 0 * J, tt);
+        umma::tmem_ld_32x32(taddr + 1 * J, vv);
         umma::tmem_wait_ld();
         if (i < P.n_samples) {
 #pragma unroll
@@ -582,7 +585,7 @@ pair_counts_tc_kernel(const TcParams P) {
             const int64_t j = static_cast<int64_t>(tj) * J + chunk * 32 + c;
             if (j >= P.n_samples || j < i) continue;
             const int v = __float2int_rn(__uint_as_float(vv[c]));
-            const int d1 = __float2int_rn(__uint_as_float(hv[c])) + __float2int_rn(__uint_as_float(vh[c]));
+            const int d1 = v - __float2int_rn(__uint_as_float(tt[c]));
             atomicAdd(V + i * P.ld + j, v);
             atomicAdd(D1 + i * P.ld + j, d1);
             if (j != i) {
@@ -762,7 +765,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
 }
 
 // After the work of a pf_pair_counts_tc call on `stream` has finished: did that call find genotypes
-// missing in some samples only (1: the VV / HV / VH launch did the work too) or not (0)? Synchronises.
+// missing in some samples only (1: the TT / VV launch did the work too) or not (0)? Synchronises.
 PF_API int pf_pair_counts_tc_was_general(const void* d_work, int64_t n_samples, int64_t n_words_range, int* h_general,
                                          void* stream) {
   PF_TRY_BEGIN

@@ -307,7 +307,7 @@ def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
 @pytest.mark.parametrize("n,m,miss", [(2, 100, 0.3), (64, 32, 0.5), (129, 700, 0.1), (193, 3000, 0.02), (257, 5000, 0.2),
                                       (385, 2048, 0.9), (1000, 40000, 0.05)])
 def test_pair_counts_tensor_core_general_missingness_bit_exact(engine, n, m, miss):
-    """Genotypes missing in some samples only: the XX/HH launch plus the VV/HV/VH launch == oracle,
+    """Genotypes missing in some samples only: the XX/HH launch plus the TT/VV launch == oracle,
     also over word ranges and when accumulated on top of existing counts."""
     rng = np.random.default_rng(n * 7 + m)
     codes = _random_codes(rng, n, m, miss)
