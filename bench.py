@@ -416,7 +416,7 @@ def run_ours(args):
                    "l2": "inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (my_sites * ld / 1e9),
                    "pair_counts_variant": ran_variant[0], "pair_counts_variant_requested": args.variant, "seed": SEED},
         "nj_seconds": stages_ms["nj"] * 1e-3, "stages_ms": stages_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (6 if ran_variant[0] == 3 else 4) * args.steps,   # pack, (stream conversion, 2 GEMM launches | popcount), normalise, NJ
+        "clocks": clocks, "e2e": e2e, "gpu_launches": (7 if ran_variant[0] == 3 else 4) * args.steps,   # pack, (2 stream conversions, 2 GEMM launches | popcount), normalise, NJ
         "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), file=args.out, flush=True)

@@ -18,7 +18,8 @@
 //   mode 1  TT and VV on the same tiles, run in addition when genotypes are missing in some samples only.
 //           The two launches add their linear pieces into the same int32 matrices.
 //
-// Operand stream (produced once per call by planes_to_e2m1): one nibble per genotype that is at the
+// Operand streams (produced once per call by planes_to_e2m1; the second one, for mode 1, only when it is
+// needed: nibble = E2M1 code of t, het 0x2, missing 0x8, else 0x0; v = "sign bit clear"). Stream 0: one nibble per genotype that is at the
 // same time the E2M1 code of x and a tag: hom-REF 0xA (-1), het 0x0 (+0), hom-ALT 0x2 (+1),
 // missing 0x8 (-0). h = nibble & 2, v = "nibble != 8", t = "nibble == 0". It is stored step-major as 2 KB chunks (64
 // samples x 64 sites) already in the canonical K-major shared-memory order of a UMMA operand, so ONE
@@ -51,13 +52,13 @@ constexpr int64_t MAX_WORDS_PER_CTA = 1 << 18;   // 2^23 sites: fp32 accumulator
 // per-mode geometry. GROUP = steps per pipeline stage: the barrier round trips and fences of a stage
 // (~500 clocks for an expansion warp) are paid once per GROUP steps; RAW = stages of the TMA ring.
 template <int MODE> struct TcCfg;
-template <> struct TcCfg<0> {   // planes: 0 = x (the stream itself), 1 = h; products XX (acc 0), HH (acc 1)
+template <> struct TcCfg<0> {   // stream 0: plane 0 = x (the stream itself), plane 1 = h; products XX (acc 0), HH (acc 1)
   static constexpr int J = 192, NPROD = 2, NEXP = 1;   // NEXP = derived B planes written by the expansion warps
   static constexpr int GROUP = 5, RAW = 3;
 };
-template <> struct TcCfg<1> {   // planes: 0 = t (heterozygous), 1 = v (genotyped); products TT (acc 0), VV (acc 1)
-  static constexpr int J = 192, NPROD = 2, NEXP = 2;
-  static constexpr int GROUP = 4, RAW = 3;
+template <> struct TcCfg<1> {   // stream 1: plane 0 = t (the stream itself), plane 1 = v; products TT (acc 0), VV (acc 1)
+  static constexpr int J = 192, NPROD = 2, NEXP = 1;
+  static constexpr int GROUP = 5, RAW = 3;
 };
 template <int MODE> struct TcGeo {
   using C = TcCfg<MODE>;
@@ -73,7 +74,7 @@ template <int MODE> struct TcGeo {
   static constexpr int TMEM_A = C::NPROD * J;                  // accumulators first, then A staging
   static constexpr int EXP_WARPS = TC_I / 32 + J / 32;         // one sample row per thread
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;         // + TMA producer warp + MMA issuer warp
-  static constexpr int RAW_EMPTY_ARRIVALS = J / 32 + (MODE == 0 ? 1 : 0);   // B-row warps; mode 0: the MMA reads B_x from the raw stage
+  static constexpr int RAW_EMPTY_ARRIVALS = J / 32 + 1;   // B-row warps + the MMA, which reads the plane-0 B operand from the raw stage
   static constexpr size_t SMEM = static_cast<size_t>(RAW) * RAW_STAGE_BYTES +
                                  static_cast<size_t>(EXP_STAGES) * EXP_STAGE_BYTES;
   static_assert(TMEM_A + EXP_STAGES * GROUP * TMEM_A_COLS <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
@@ -91,11 +92,13 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> bit 0 of
 
 // stream[((s * n_tiles_padded + T) * 128 + (l >> 3) * 16 + kh * 8 + (l & 7))] (uint4) = the 32 sites of word
 // 2 s + kh of sample 64 T + l, nibble j of 32-bit word q = site 8 q + j: bit 3 = "hom-REF or missing",
-// bit 1 = "homozygous" (see the file header). A second half-step past the last word is all missing.
+// bit 1 = "homozygous" (see the file header; stream 1: bit 3 = "missing", bit 1 = "heterozygous"). A second
+// half-step past the last word is all missing.
 // ref_v[w] = valid-site mask of sample 0; flags[0] is set when any real sample's mask differs from
 // it, i.e. when some site is genotyped in some samples and missing in others.
 // hsum[split][sample] = homozygous genotypes of the sample in the split's word range (|h_i|).
 // One thread = one sample x a run of HSUM_RUN consecutive words (runs never straddle a split).
+template <int STREAM>
 __global__ void __launch_bounds__(256)
 planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int64_t word_begin, int64_t n_local,
                       int64_t n_samples, int64_t n_tiles, int64_t n_tiles_padded, uint4* __restrict__ stream,
@@ -105,6 +108,7 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
   // homozygous plane): 20 instructions per word instead of ~110 of shift-and-mask spreading, which made
   // this kernel ALU-bound
   __shared__ uint32_t s_lut_s[256], s_lut_m[256];
+  if (STREAM == 1 && __ldg(flags) == 0) return;   // stream 1 is needed only with sample-specific missingness
   {
     const uint32_t sp = spread8(threadIdx.x);
     s_lut_s[threadIdx.x] = sp << 3;
@@ -131,7 +135,9 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
       L = p[l];
       H = p[PF_TILE + l];
     }
-    const uint32_t S = ~(L ^ H), M = ~L;   // code 0 / 3 -> sign bit; code 0 / 2 -> homozygous bit
+    // stream 0: code 0 / 3 -> sign bit; code 0 / 2 -> bit 1 (x = -1 / +0 / +1 / -0 for codes 0 / 1 / 2 / 3)
+    // stream 1: code 3 -> sign bit; code 1 -> bit 1       (t =  0 / +1 /  0 / -0)
+    const uint32_t S = STREAM == 0 ? ~(L ^ H) : (L & H), M = STREAM == 0 ? ~L : (L & ~H);
     uint4 out;
     out.x = s_lut_s[S & 0xffu] | s_lut_m[M & 0xffu];
     out.y = s_lut_s[(S >> 8) & 0xffu] | s_lut_m[(M >> 8) & 0xffu];
@@ -140,13 +146,15 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
     stream[((w >> 1) * n_tiles_padded + t) * 128 + (w & 1) * 8 + unit] = out;
     if (w == n_local - 1 && (w & 1) == 0)
       stream[((w >> 1) * n_tiles_padded + t) * 128 + 8 + unit] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
-    const uint32_t* p0 = planes + ((word_begin + w) * 2) * PF_TILE;   // sample 0: tile 0, lane 0
-    const uint32_t ref = ~(p0[0] & p0[PF_TILE]);
-    if (t == 0 && l == 0) ref_v[w] = ref;
-    mixed |= (~(L & H) != ref);
-    hom += __popc(M);             // homozygous <=> low code bit 0 (missing has it set)
+    if (STREAM == 0) {
+      const uint32_t* p0 = planes + ((word_begin + w) * 2) * PF_TILE;   // sample 0: tile 0, lane 0
+      const uint32_t ref = ~(p0[0] & p0[PF_TILE]);
+      if (t == 0 && l == 0) ref_v[w] = ref;
+      mixed |= (~(L & H) != ref);
+      hom += __popc(M);             // homozygous <=> low code bit 0 (missing has it set)
+    }
   }
-  if (real) {
+  if (STREAM == 0 && real) {
     if (mixed) atomicOr(flags, 1);
     if (hom) atomicAdd(hsum + (w0 / words_per_split) * hsum_ld + t * PF_TILE + l, hom);
   }
@@ -159,7 +167,7 @@ bool g_tc_prof_enabled = false;
 int g_tc_debug = 0;
 
 struct TcParams {
-  const uint4* stream;    // [n_steps][n_tiles_padded] chunks of 2 KB
+  const uint4* stream;    // [n_steps][n_tiles_padded] chunks of 2 KB: stream 0 (x) for mode 0, stream 1 (t) for mode 1
   int64_t n_tiles_padded;
   const uint32_t* all_v;  // [n_local] valid-site mask of sample 0 (= of every sample when uniform)
   int64_t n_local;        // words in the range
@@ -220,14 +228,9 @@ __device__ __forceinline__ void make_planes(const uint4& lo, const uint4& hi, ui
   const uint32_t n[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
-    if (MODE == 0) {
-      p0[m] = n[m];        // x: the stream nibble is its E2M1 code
-      p1[m] = n[m] & NIB_HOM;
-    } else {
-      const uint32_t s1 = n[m] >> 3, m1 = n[m] >> 1;              // bit 0 of each nibble: sign bit / homozygous bit
-      p0[m] = (~(s1 | m1) & 0x11111111u) << 1;                    // t: +1.0 for a heterozygous genotype (nibble 0x0)
-      p1[m] = ((~s1 | m1) & 0x11111111u) << 1;                    // v: +1.0 unless the nibble is 0x8 (bit 3 set, bit 1 clear)
-    }
+    p0[m] = n[m];          // x / t: the stream nibble is its E2M1 code
+    if (MODE == 0) p1[m] = n[m] & NIB_HOM;                              // h: bit 1 alone is +1.0
+    else p1[m] = ((~n[m] >> 3) & 0x11111111u) << 1;                     // v: +1.0 unless the sign bit is set (nibble 0x8)
   }
 }
 
@@ -370,22 +373,15 @@ pair_counts_tc_kernel(const TcParams P) {
               const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
               const uint64_t a_s = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);    // A plane 0 (x / h) in shared memory
               const uint32_t bbase = ebase + G::A_PLANE_BYTES;
-              if (MODE == 0) {
-                const uint64_t bx = umma::smem_desc_kmajor_noswizzle(
-                    raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
-                const uint64_t bh = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
-                mma_mxf4_ss(tmem + 0 * J, a_s, bx, idesc, acc, tsfa, tsfb);   // XX
-                mma_mxf4_ts(tmem + 1 * J, a_t, bh, idesc, acc, tsfa, tsfb);   // HH
-              } else {
-                const uint64_t bt = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
-                const uint64_t bv = umma::smem_desc_kmajor_noswizzle(bbase + G::EXP_PLANE_BYTES, 128, 256);
-                mma_mxf4_ss(tmem + 0 * J, a_s, bt, idesc, acc, tsfa, tsfb);   // TT
-                mma_mxf4_ts(tmem + 1 * J, a_t, bv, idesc, acc, tsfa, tsfb);   // VV
-              }
+              const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(
+                  raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
+              const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(bbase, 128, 256);
+              mma_mxf4_ss(tmem + 0 * J, a_s, b0, idesc, acc, tsfa, tsfb);   // XX / TT
+              mma_mxf4_ts(tmem + 1 * J, a_t, b1, idesc, acc, tsfa, tsfb);   // HH / VV
             }
           }
         }
-        if (MODE == 0) umma::commit_a(raw_empty_a + stage * 8);   // the raw stage held the B_x operands
+        umma::commit_a(raw_empty_a + stage * 8);   // the raw stage held the plane-0 B operands
         umma::commit_a(exp_empty_a + e * 8);
         if (++e == EXP_STAGES) {
           e = 0;
@@ -474,15 +470,8 @@ pair_counts_tc_kernel(const TcParams P) {
             umma::tmem_st_32x8(a_base + (e * G::GROUP + j) * TMEM_A_COLS, p1);
           } else {
             const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES + G::A_PLANE_BYTES;
-            if (MODE == 0) {
-              umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h (x is read from the raw stage)
-              umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
-            } else {
-              umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);           // t
-              umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
-              umma::sts128(dst + G::EXP_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);   // v
-              umma::sts128(dst + G::EXP_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
-            }
+            umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h / v (plane 0 is read from the raw stage)
+            umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
           }
         }
       }
@@ -612,7 +601,7 @@ struct TcPlan {
   int64_t n_local, n_tiles, n_tiles_padded, hsum_ld;
   int n_itiles;
   TcModePlan m[2];
-  int64_t n_steps, nib_bytes, refv_off, flags_off, hsum_off, total;
+  int64_t n_steps, nib_bytes, stream1_off, refv_off, flags_off, hsum_off, total;
 };
 
 int tc_sm_count() {
@@ -667,7 +656,8 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   L.hsum_ld = L.n_tiles_padded * PF_TILE;
   L.n_steps = (n_local + 1) / 2;
   L.nib_bytes = tc_align(L.n_tiles_padded * L.n_steps * CHUNK_BYTES);
-  L.refv_off = L.nib_bytes;
+  L.stream1_off = L.nib_bytes;          // second operand stream (t), written only with sample-specific missingness
+  L.refv_off = 2 * L.nib_bytes;
   L.flags_off = L.refv_off + tc_align(n_local * 4);
   L.hsum_off = L.flags_off + 256;
   L.total = L.hsum_off + tc_align(L.m[0].splits * L.hsum_ld * 4);
@@ -721,10 +711,17 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   {
     const int64_t n_runs = pf_ceil_div(n_local, HSUM_RUN);
     const int64_t threads = L.n_tiles_padded * n_runs * 64;
-    planes_to_e2m1_kernel<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
+    planes_to_e2m1_kernel<0><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
         d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded, nib4, ref_v, flags, hsum,
         L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
+    if (allow_general) {
+      // returns at once unless the first pass found sample-specific missingness
+      planes_to_e2m1_kernel<1><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
+          d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded,
+          reinterpret_cast<uint4*>(w + L.stream1_off), ref_v, flags, hsum, L.m[0].words_per_split, L.hsum_ld);
+      PF_CUDA(cudaGetLastError());
+    }
   }
   if (!allow_general) {
     // the caller wants to fall back to the popcount kernel: the decision needs the flag on the host
@@ -752,6 +749,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   // missingness), so that the call never waits for the device
   for (int mode = 0; mode < (allow_general ? 2 : 1); ++mode) {
     const TcModePlan& M = L.m[mode];
+    P.stream = mode == 0 ? nib4 : reinterpret_cast<const uint4*>(w + L.stream1_off);
     P.n_jtiles = M.n_jtiles;
     P.n_tilepairs = M.pairs;
     P.words_per_split = static_cast<int>(M.words_per_split);
