@@ -650,6 +650,7 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
     if (splits < min_splits) splits = min_splits;
     if (splits < 1) splits = 1;
     M.words_per_split = pf_ceil_div(pf_ceil_div(n_local, splits), HSUM_RUN) * HSUM_RUN;
+    if (M.words_per_split < HSUM_RUN) M.words_per_split = HSUM_RUN;   // empty word range: no division by zero below
     M.splits = pf_ceil_div(n_local, M.words_per_split);
     if (M.splits < 1) M.splits = 1;
   }
@@ -677,7 +678,7 @@ cudaError_t tc_launch(const TcParams& P, int64_t grid, cudaStream_t s) {
 }  // namespace
 
 PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_range) {
-  if (n_samples <= 0 || n_words_range < 0) return 0;
+  if (n_samples <= 0 || n_words_range <= 0) return 256;   // an empty range needs no scratch (non-zero: callers allocate it)
   return tc_plan(n_samples, n_words_range, tc_sm_count()).total;
 }
 

@@ -241,3 +241,15 @@ def test_native_newick_serialiser_matches_the_python_one():
     bad[0, 0] = n + 5                                   # refers to a node that does not exist yet
     with pytest.raises(ValueError):
         merges_to_newick_native(lib, bad, l, names)
+
+
+def test_tensor_path_workspace_size_of_degenerate_ranges():
+    """pf_pair_counts_tc_work_bytes is pure host arithmetic: empty and tiny word ranges must not divide by zero
+    (found by tools/fuzz_gpu.py: an empty range raised SIGFPE)."""
+    from phyloforge_b200 import _lib
+    lib = _lib.load()
+    assert lib.pf_pair_counts_tc_work_bytes(300, 0) > 0
+    assert lib.pf_pair_counts_tc_work_bytes(0, 10) > 0
+    sizes = [lib.pf_pair_counts_tc_work_bytes(300, w) for w in (1, 2, 15, 16, 17, 63, 64, 65, 1000)]
+    assert all(b > 0 for b in sizes) and sizes == sorted(sizes)
+    assert lib.pf_pair_counts_tc_work_bytes(10000, 156250) > 2 * 25_000_000_000 // 2      # two operand streams at C5
