@@ -208,6 +208,12 @@ PF_API int pf_pair_counts_tc_was_general(const void* d_work, int64_t n_samples, 
  * (then clear) the 16 counters accumulated since the last call; see csrc/pair_counts_tc.cu. */
 PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16);
 
+/* Diagnostic / A-B switch for pf_pair_counts_tc: impl 1 = the single-CTA GEMM kernel (128 x 192 sample
+ * tiles), impl 2 = the CTA-pair kernel (cluster of two CTAs, tcgen05.mma.cta_group::2, 256 x 240 tiles;
+ * the default); cfg 0..3 = pipeline geometry of the pair kernel. The workspace layout depends on impl:
+ * query pf_pair_counts_tc_work_bytes again after changing it. Results are identical. */
+PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg);
+
 /* counts -> fp64 distances, one IEEE divide of exactly converted integers per pair:
  *   metric 0: p-distance D1 / V;  metric 1: IBS distance (D1 + D2) / (2 V).
  * V == 0 -> 1.0 and the pair is counted in *d_n_zero_valid (int32, caller-zeroed).
@@ -288,5 +294,14 @@ PF_API int pf_selftest_umma_fp4(const int8_t* d_a, const int8_t* d_b, float* d_c
                                 int a_in_tmem, void* stream);
 PF_API int pf_probe_umma_fp4_rate(int n, int reps, int n_acc, int a_in_tmem, int n_bufs, int noise,
                                   double* ticks_per_mma, void* stream);
+
+/* Diagnostics for the CTA-pair form of that path (tcgen05.mma.cta_group::2 on a cluster of two CTAs;
+ * csrc/umma_fp4_2cta_probe.cu). pf_selftest_umma_fp4_2cta: d_c[256][n] (fp32) = d_a[256][k] * d_b[n][k]^T,
+ * n a multiple of 16 in [32, 256], k a multiple of 64, at most 1024. pf_probe_umma_fp4_2cta_rate: SM
+ * clock64 ticks per 256 x n x 64 instruction (n <= 240, two accumulators), on every CTA pair of the
+ * device at once; *h_pairs = number of pairs. */
+PF_API int pf_selftest_umma_fp4_2cta(const int8_t* d_a, const int8_t* d_b, float* d_c, int n, int k, void* stream);
+PF_API int pf_probe_umma_fp4_2cta_rate(int n, int reps, int n_bufs, double* ticks_per_mma, int* h_pairs,
+                                       void* stream);
 
 #endif /* PHYLOFORGE_B200_H */

@@ -591,6 +591,429 @@ pair_counts_tc_kernel(const TcParams P) {
   if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------ the CTA-pair GEMM kernel
+// tcgen05.mma.cta_group::2: a cluster of two CTAs (the two SMs of a TPC) works on one 256 x 240 sample tile
+// pair. Each CTA holds 128 A rows and 120 B rows of every step in its own shared memory and accumulates its
+// 128 rows x 240 columns in its own tensor memory; the leader CTA (cluster rank 0) issues the instructions
+// for both. Measured (pf_probe_umma_fp4_2cta_rate): the pair instruction takes 0.5 clocks per B column (120
+// clocks for 256 x 240 x 64) where the single-CTA one takes 147 clocks for any N <= 256, and every SM
+// expands 248 sample rows per 128 x 240 x 64 MACs instead of 320 per 128 x 192 x 64 and reads 7.75 KB
+// instead of 10 KB per step from L2.
+// Per CTA: warps 0-3 = the 128 A rows (stream -> registers, two stages ahead -> both A planes to shared
+// memory), warps 4-7 = the 120 B rows (raw ring -> derived plane to shared memory), warp 8 = TMA producer
+// (its B rows), warp 9 = MMA issuer (leader only).
+// Hand-over. Operands ready: every expansion warp of both CTAs arrives on the LEADER's exp_full barrier after
+// its operand writes and a generic->async proxy fence; the peer's warps use a remote arrive. Stage consumed:
+// ONE multicast commit per stage on a ring of stage_done barriers in both CTAs; the expansion warps (reuse of
+// the expanded stage EXP stages later) and the TMA producer (reuse of the raw stage RAW stages later) wait on
+// the same ring, whose depth max(RAW, EXP) keeps a waiter at most one phase behind. (A commit costs the
+// issuing thread ~200 clocks during which no MMA is issued; the first version had two per stage.)
+// Memory-model note: the remote arrive is the default `mbarrier.arrive.shared::cluster` (release at CTA
+// scope), as in CUTLASS's ClusterBarrier::arrive. The PTX model would ask for `.release.cluster`; that
+// compiles to MEMBAR.ALL.GPU, which stalls the SM's whole memory pipeline: with it in every expansion warp
+// the kernel runs at 665 instead of ~400 clocks per step. The data in question is shared memory written by
+// STS and made visible to the async proxy by FENCE.VIEW.ASYNC before the arrive leaves the SM, so nothing is
+// in flight that the heavier fence could order; TcParams::debug bit 0 selects the strict form for A/B runs
+// (tests/test_gpu_kernels.py runs both and compares them bit for bit).
+// B tiles of A block ti start at its first row (256 ti + 240 k), so only the first tile of a block straddles
+// the diagonal.
+constexpr int TC2_I = 256, TC2_IH = 128;     // rows per pair / per CTA
+// Geometry. J = columns of the pair's tile (each CTA supplies J / 2 B rows). Shared-memory bandwidth is what
+// bounds this kernel (ncu, J = 240 with both A planes in shared memory: LSU wavefronts 46 % + tensor-core
+// operand reads 27 % of the peak, tensor pipe 53 % active at 423 clocks per step), so with AH_TMEM the
+// derived A plane (h / v) goes to TENSOR memory (tcgen05.st, no shared-memory write, no operand read): the
+// 16 accumulator + 16 scale-factor columns leave 512 - 2 J - 16 columns for EXP x GROUP steps of 8 columns,
+// which is what limits J to 208 there.
+template <int CFG> struct Tc2Cfg;
+template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true; };
+template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false; };
+template <> struct Tc2Cfg<2> { static constexpr int J = 208, GROUP = 3, RAW = 5, EXP = 3; static constexpr bool AH_TMEM = true; };
+template <> struct Tc2Cfg<3> { static constexpr int J = 224, GROUP = 3, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true; };
+constexpr int tc2_cols(int cfg) { return cfg == 1 ? Tc2Cfg<1>::J : cfg == 2 ? Tc2Cfg<2>::J : cfg == 3 ? Tc2Cfg<3>::J : Tc2Cfg<0>::J; }
+template <int CFG> struct Tc2Geo {
+  using C = Tc2Cfg<CFG>;
+  static constexpr int J = C::J, JH = C::J / 2;
+  static constexpr bool AH_TMEM = C::AH_TMEM;
+  static constexpr int GROUP = C::GROUP, RAW = C::RAW, EXP = C::EXP;
+  static constexpr int DONE = RAW > EXP ? RAW : EXP;                        // depth of the stage_done ring
+  static constexpr int RAW_STEP_BYTES = JH * 32;
+  static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
+  static constexpr int A_PLANE_BYTES = TC2_IH * 32;                         // 4096
+  static constexpr int A_PLANES_SMEM = AH_TMEM ? 1 : 2;
+  static constexpr int EXP_STEP_BYTES = A_PLANES_SMEM * A_PLANE_BYTES + RAW_STEP_BYTES;   // A plane(s), then B plane 1
+  static constexpr int EXP_STAGE_BYTES = GROUP * EXP_STEP_BYTES;
+  static constexpr int TMEM_A = 2 * J;                                       // A plane 1 staging behind the accumulators
+  static constexpr int B_WARPS = (JH + 31) / 32;
+  static constexpr int EXP_WARPS = 4 + B_WARPS;
+  static constexpr int THREADS = (EXP_WARPS + 2) * 32;
+  static constexpr size_t SMEM = static_cast<size_t>(RAW) * RAW_STAGE_BYTES + static_cast<size_t>(EXP) * EXP_STAGE_BYTES;
+  static_assert(J % 16 == 0 && JH % 8 == 0, "tile width");
+  static_assert(2 * J + (AH_TMEM ? EXP * GROUP * TMEM_A_COLS : 0) <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
+  static_assert(RAW <= 8 && EXP <= 8 && SMEM + 4096 <= 227 * 1024, "shared memory");
+};
+
+// work item -> (A block ti, first column of the B tile)
+__device__ __forceinline__ void tc2_tile(int pair, int64_t n_samples, int J, int& ti, int64_t& b_start) {
+  ti = 0;
+  int rem = pair;
+  while (true) {
+    const int cnt = static_cast<int>((n_samples - static_cast<int64_t>(TC2_I) * ti + J - 1) / J);
+    if (rem < cnt) break;
+    rem -= cnt;
+    ++ti;
+  }
+  b_start = static_cast<int64_t>(TC2_I) * ti + static_cast<int64_t>(J) * rem;
+}
+
+// position in a ring of N barriers: slot and the parity of the phase that use completes
+template <int N> struct RingPos {
+  int slot = 0;
+  uint32_t parity = 0;
+  __device__ __forceinline__ void advance() {
+    if (++slot == N) {
+      slot = 0;
+      parity ^= 1;
+    }
+  }
+};
+
+template <int MODE, int CFG, bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Geo<CFG>::THREADS, 1)
+pair_counts_tc2_kernel(const TcParams P) {
+  using G = Tc2Geo<CFG>;
+  constexpr int J = G::J, JH = G::JH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t raw_full[G::RAW], exp_full[G::EXP], stage_done[G::DONE];
+  __shared__ __align__(8) uint64_t done_bar;
+  __shared__ uint32_t s_tmem;
+  __shared__ int s_hcount[TC2_IH + J];
+  __shared__ int s_valid_sites;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool general = __ldg(P.flags) != 0;
+  if (MODE == 1 && !general) return;
+  const uint32_t rank = umma::cluster_ctarank();
+  const uint32_t raw_a = umma::smem_addr(smem);
+  const uint32_t exp_a = raw_a + G::RAW * G::RAW_STAGE_BYTES;
+  const uint32_t raw_full_a = umma::smem_addr(raw_full), exp_full_a = umma::smem_addr(exp_full);
+  const uint32_t stage_done_a = umma::smem_addr(stage_done);
+  const uint32_t done_a = umma::smem_addr(&done_bar);
+  const uint32_t exp_full_leader = umma::mapa(exp_full_a, 0);      // the leader's barrier, cluster address
+  const bool strict = (P.debug & 1) != 0;
+
+  const int item = static_cast<int>(blockIdx.x >> 1);
+  const int pair = item % P.n_tilepairs;
+  const int split = item / P.n_tilepairs;
+  int ti;
+  int64_t b_start;
+  tc2_tile(pair, P.n_samples, J, ti, b_start);
+  const int64_t w_begin = static_cast<int64_t>(split) * P.words_per_split;
+  const int64_t w_end = min(P.n_local, w_begin + P.words_per_split);
+  if (w_end <= w_begin) return;                 // same decision in both CTAs of the pair
+  const int n_steps = static_cast<int>((w_end - w_begin + STEP_WORDS - 1) / STEP_WORDS);
+  const int n_groups = (n_steps + G::GROUP - 1) / G::GROUP;
+  const int64_t s_begin = w_begin / STEP_WORDS;
+  const int64_t a_row0 = static_cast<int64_t>(TC2_I) * ti + TC2_IH * rank;   // first A sample of this CTA
+  const int64_t b_row0 = b_start + JH * rank;                                 // first B sample of this CTA
+
+  if (warp == 0) umma::tmem_alloc_2cta(&s_tmem, 512);
+  if (tid == 32) {
+    for (int s = 0; s < G::RAW; ++s) umma::mbar_init(&raw_full[s], 1);
+    for (int e = 0; e < G::EXP; ++e) umma::mbar_init(&exp_full[e], 2 * G::EXP_WARPS);   // used in the leader
+    for (int d = 0; d < G::DONE; ++d) umma::mbar_init(&stage_done[d], 1);
+    umma::mbar_init(&done_bar, 1);
+    umma::fence_mbar_init();
+  }
+  if (tid == 0) s_valid_sites = 0;
+  umma::fence_before_thread_sync();
+  umma::cluster_sync();                          // barriers of both CTAs exist before any remote arrival
+  umma::fence_after_thread_sync();
+  const uint32_t tmem = s_tmem;
+  if (warp < 4) {
+    uint32_t ones[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ones[j] = 0x7f7f7f7fu;
+#pragma unroll
+    for (int c = 0; c < 16; c += 8) umma::tmem_st_32x8(tmem + (static_cast<uint32_t>(warp * 32) << 16) + TMEM_SF + c, ones);
+    umma::tmem_wait_st();
+  }
+  umma::fence_before_thread_sync();
+  umma::cluster_sync();                          // scale factors of both CTAs are in place
+  umma::fence_after_thread_sync();
+
+  const int64_t step_stride = P.n_tiles_padded * (CHUNK_BYTES / 16);
+  if (warp == G::EXP_WARPS) {
+    // ===== TMA producer: the J / 2 B rows of this CTA, one bulk copy per step =====
+    if (lane == 0) {
+      const uint4* src_b = P.stream + s_begin * step_stride + (b_row0 >> 3) * 16;
+      int stage = 0;
+      RingPos<G::DONE> freed;                    // stage g - RAW, whose MMAs must have completed
+      for (int g = 0; g < n_groups; ++g) {
+        if (g >= G::RAW) {
+          umma::mbar_wait_a(stage_done_a + freed.slot * 8, freed.parity);
+          freed.advance();
+        }
+        const int kw = min(G::GROUP, n_steps - g * G::GROUP);
+        umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          if (j < kw)
+            umma::bulk_g2s_a(raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES,
+                             src_b + (static_cast<int64_t>(g) * G::GROUP + j) * step_stride, G::RAW_STEP_BYTES,
+                             raw_full_a + stage * 8);
+        }
+        if (++stage == G::RAW) stage = 0;
+      }
+    }
+  } else if (warp == G::EXP_WARPS + 1) {
+    // ===== MMA issuer (leader CTA only): D[tmem of both CTAs] += A * B over the pair =====
+    if (rank == 0 && lane == 0) {
+      const uint32_t idesc = idesc_mxf4(TC2_I, J);
+      const uint32_t tsfa = tmem + TMEM_SF, tsfb = tmem + TMEM_SF + 4;
+      long long t_wait = 0;
+      const long long t_start = PROF ? clock64() : 0;
+      int e = 0, stage = 0, d = 0;
+      uint32_t phase = 0;
+      for (int g = 0; g < n_groups; ++g) {
+        const long long t0 = PROF ? clock64() : 0;
+        umma::mbar_wait_cluster_a(exp_full_a + e * 8, phase);
+        if (PROF) t_wait += clock64() - t0;
+        umma::fence_after_thread_sync();
+        const int kw = min(G::GROUP, n_steps - g * G::GROUP);
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          if (j < kw) {
+            const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
+            const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+            const uint64_t a0 = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
+            const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(
+                raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
+            const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(ebase + G::A_PLANES_SMEM * G::A_PLANE_BYTES, 128, 256);
+            umma::mma_mxf4_ss_2cta(tmem + 0 * J, a0, b0, idesc, acc, tsfa, tsfb);       // XX / TT
+            if (G::AH_TMEM) {
+              umma::mma_mxf4_ts_2cta(tmem + 1 * J, tmem + G::TMEM_A + (e * G::GROUP + j) * TMEM_A_COLS, b1, idesc, acc, tsfa, tsfb);
+            } else {
+              const uint64_t a1 = umma::smem_desc_kmajor_noswizzle(ebase + G::A_PLANE_BYTES, 128, 256);
+              umma::mma_mxf4_ss_2cta(tmem + 1 * J, a1, b1, idesc, acc, tsfa, tsfb);     // HH / VV
+            }
+          }
+        }
+        umma::commit_2cta_a(stage_done_a + d * 8, 3);          // both CTAs: raw and expanded stage of g are free
+        if (++e == G::EXP) {
+          e = 0;
+          phase ^= 1;
+        }
+        if (++stage == G::RAW) stage = 0;
+        if (++d == G::DONE) d = 0;
+      }
+      umma::commit_2cta_a(done_a, 3);
+      if (PROF) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[0]), static_cast<unsigned long long>(t_wait));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[1]), static_cast<unsigned long long>(clock64() - t_start));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[8]), static_cast<unsigned long long>(n_steps));
+      }
+    }
+  } else {
+    // ===== expansion warps: thread = one sample row of this CTA =====
+    const int row = tid;
+    const bool is_a = row < TC2_IH;
+    const int r = is_a ? row : row - TC2_IH;
+    const bool active = is_a || r < JH;               // the last B-row warp may have rows to spare
+    const uint32_t a_tmem = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A;   // A rows: TMEM lane = row
+    const uint32_t raw_row = raw_a + unit_off(r, 0);
+    const uint32_t exp_row = exp_a + unit_off(r, 0) + (is_a ? 0 : G::A_PLANES_SMEM * G::A_PLANE_BYTES);
+    const int64_t a_sample = a_row0 + r;
+    const uint4* a_src = P.stream + s_begin * step_stride + (a_sample >> 3) * 16 + (a_sample & 7);
+    long long t_wraw = 0, t_wemp = 0, t_work = 0, t_fence = 0, t_arrive = 0, t_post = 0;
+    const long long t_start = PROF ? clock64() : 0;
+    int stage = 0, e = 0;
+    uint32_t raw_phase = 0;
+    RingPos<G::DONE> freed;                      // stage g - EXP, whose MMAs must have completed
+    // A rows come straight from the stream into registers TWO stages ahead (two register sets): the loads of
+    // a stage are issued a full stage period (~1,500 clocks) before they are used; one stage ahead left the
+    // A-row warps waiting for L2 / HBM
+    uint4 lo0[G::GROUP], hi0[G::GROUP], lo1[G::GROUP], hi1[G::GROUP];
+    auto load_a_rows = [&](int g, uint4 (&lo)[G::GROUP], uint4 (&hi)[G::GROUP]) {
+#pragma unroll
+      for (int j = 0; j < G::GROUP; ++j) {
+        lo[j] = make_uint4(0, 0, 0, 0);
+        hi[j] = lo[j];
+        const int st = g * G::GROUP + j;
+        if (st < n_steps && !(P.debug & 32)) {
+          lo[j] = __ldg(a_src + st * step_stride);
+          hi[j] = __ldg(a_src + st * step_stride + 8);
+        }
+      }
+    };
+    auto do_stage = [&](int g, uint4 (&lo)[G::GROUP], uint4 (&hi)[G::GROUP]) {
+      {
+        const long long t0 = PROF ? clock64() : 0;
+        if (!is_a && lane == 0) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
+        if (lane == 1 && g >= G::EXP) umma::mbar_wait_a(stage_done_a + freed.slot * 8, freed.parity);
+        if (PROF && lane < 2) {
+          if (lane == 0) t_wraw += clock64() - t0;
+          else t_wemp += clock64() - t0;
+        }
+      }
+      if (g >= G::EXP) freed.advance();
+      __syncwarp();
+      const long long tw0 = PROF ? clock64() : 0;
+      if (G::AH_TMEM && is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+      const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+      if (!is_a) {
+        const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          lo[j] = make_uint4(0, 0, 0, 0);
+          hi[j] = lo[j];
+          if (j < kw && active) {
+            lo[j] = umma::lds128(src + j * G::RAW_STEP_BYTES);
+            hi[j] = umma::lds128(src + j * G::RAW_STEP_BYTES + 128);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < G::GROUP; ++j) {
+        if (j < kw && active) {
+          uint32_t p0[8], p1[8];
+          make_planes<MODE>(lo[j], hi[j], p0, p1);
+          const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
+          if (is_a) {
+            umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);                             // x / t
+            umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
+            if (G::AH_TMEM) {
+              umma::tmem_st_32x8(a_tmem + (e * G::GROUP + j) * TMEM_A_COLS, p1);       // h / v
+            } else {
+              umma::sts128(dst + G::A_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);
+              umma::sts128(dst + G::A_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
+            }
+          } else {
+            umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h / v (plane 0 is read from the raw stage)
+            umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
+          }
+        }
+      }
+      const long long tf0 = PROF ? clock64() : 0;
+      if (G::AH_TMEM && is_a) {
+        umma::tmem_wait_st();
+        umma::fence_before_thread_sync();
+      }
+      umma::fence_proxy_async_smem();    // generic-proxy operand writes -> the tensor cores' async proxy
+      __syncwarp();
+      long long tf1 = 0;
+      if (PROF) {
+        tf1 = clock64();
+        t_work += tf0 - tw0;
+        t_fence += tf1 - tf0;
+      }
+      if (lane == 0) {
+        if (strict) umma::mbar_arrive_cluster(exp_full_leader + e * 8);
+        else if (rank == 0) umma::mbar_arrive_a(exp_full_a + e * 8);
+        else umma::mbar_arrive_remote(exp_full_leader + e * 8);
+      }
+      __syncwarp();
+      const long long tp1 = PROF ? clock64() : 0;
+      if (PROF) t_arrive += tp1 - tf1;
+      if (is_a) load_a_rows(g + 2, lo, hi);
+      if (PROF) t_post += clock64() - tp1;
+      if (++stage == G::RAW) {
+        stage = 0;
+        raw_phase ^= 1;
+      }
+      if (++e == G::EXP) e = 0;
+    };
+    if (is_a) {
+      load_a_rows(0, lo0, hi0);
+      load_a_rows(1, lo1, hi1);
+    }
+    for (int g = 0; g < n_groups; g += 2) {
+      do_stage(g, lo0, hi0);
+      if (g + 1 < n_groups) do_stage(g + 1, lo1, hi1);
+    }
+    t_wemp = __shfl_sync(0xffffffffu, t_wemp, 1);
+    if (PROF && lane == 0 && (warp == 0 || warp == 4) && rank == ((P.debug >> 6) & 1)) {   // debug bit 6: which CTA of the pair reports
+      const int o = warp == 0 ? 2 : 9;
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o]), static_cast<unsigned long long>(t_wraw));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 1]), static_cast<unsigned long long>(t_wemp));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 5 : 6]), static_cast<unsigned long long>(t_arrive));
+      if (warp == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[7]), static_cast<unsigned long long>(t_post));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 14]), static_cast<unsigned long long>(t_work));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 13 : 15]), static_cast<unsigned long long>(t_fence));
+    }
+    const bool uniform = (MODE == 0) && !general;
+    if (uniform) {
+      // |h| of this CTA's 128 A rows and of all J B columns of the pair, for this word range
+      for (int k = tid; k < TC2_IH + J; k += G::EXP_WARPS * 32) {
+        const int64_t sample = k < TC2_IH ? a_row0 + k : b_start + (k - TC2_IH);
+        s_hcount[k] = (sample < P.n_samples) ? P.hsum[static_cast<int64_t>(split) * P.hsum_ld + sample] : 0;
+      }
+      int vs = 0;
+      for (int64_t w = w_begin + tid; w < w_end; w += G::EXP_WARPS * 32) vs += __popc(P.all_v[w]);
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, off);
+      if (lane == 0 && vs) atomicAdd(&s_valid_sites, vs);
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(G::EXP_WARPS * 32) : "memory");
+
+    // ===== epilogue: this CTA's 128 rows x J columns, TMEM -> registers -> counts =====
+    umma::mbar_wait_a(done_a, 0);
+    umma::fence_after_thread_sync();
+    const int lane_grp = warp & 3;               // TMEM lanes [32 g, 32 g + 32) are visible to warps with w % 4 == g
+    const int grp_rank = warp >> 2;              // rank of this warp among the warps of its lane group
+    const int grp_size = (lane_grp < (G::EXP_WARPS & 3)) ? (G::EXP_WARPS / 4 + 1) : (G::EXP_WARPS / 4);
+    const int i_local = lane_grp * 32 + lane;
+    const int64_t i = a_row0 + i_local;
+    const int hi_cnt = uniform ? s_hcount[i_local] : 0;
+    const int v_sites = s_valid_sites;
+    const int64_t plane = P.n_samples * P.ld;
+    int32_t* V = P.counts;
+    int32_t* D1 = P.counts + plane;
+    int32_t* D2 = P.counts + 2 * plane;
+    for (int chunk = grp_rank; chunk < J / 16; chunk += grp_size) {
+      const uint32_t taddr = tmem + (static_cast<uint32_t>(lane_grp * 32) << 16) + chunk * 16;
+      uint32_t pv[16], qv[16];
+      umma::tmem_ld_32x16(taddr + 0 * J, pv);
+      umma::tmem_ld_32x16(taddr + 1 * J, qv);
+      umma::tmem_wait_ld();
+      if (i < P.n_samples) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int j_local = chunk * 16 + c;
+          const int64_t j = b_start + j_local;
+          if (j >= P.n_samples || j < i) continue;       // each unordered pair once: row <= column
+          const int p = __float2int_rn(__uint_as_float(pv[c])), q = __float2int_rn(__uint_as_float(qv[c]));
+          if (MODE == 0) {
+            const int xx = p, hh = q;
+            const int d2 = (hh - xx) >> 1;
+            const int d1 = uniform ? (hi_cnt + s_hcount[TC2_IH + j_local] - 2 * hh + d2) : -((xx + hh) >> 1);
+            if (uniform) atomicAdd(V + i * P.ld + j, v_sites);
+            atomicAdd(D1 + i * P.ld + j, d1);
+            atomicAdd(D2 + i * P.ld + j, d2);
+            if (j != i) {
+              if (uniform) atomicAdd(V + j * P.ld + i, v_sites);
+              atomicAdd(D1 + j * P.ld + i, d1);
+              atomicAdd(D2 + j * P.ld + i, d2);
+            }
+          } else {
+            const int v = q, d1 = q - p;                 // VV, VV - TT
+            atomicAdd(V + i * P.ld + j, v);
+            atomicAdd(D1 + i * P.ld + j, d1);
+            if (j != i) {
+              atomicAdd(V + j * P.ld + i, v);
+              atomicAdd(D1 + j * P.ld + i, d1);
+            }
+          }
+        }
+      }
+    }
+    umma::fence_before_thread_sync();
+  }
+  __syncwarp();
+  umma::cluster_sync();        // neither CTA leaves (or frees tensor memory) while its peer may still use its memory
+  if (warp == 0) umma::tmem_dealloc_2cta(tmem, 512);
+}
+
 constexpr int64_t tc_align(int64_t x) { return (x + 255) / 256 * 256; }
 
 struct TcModePlan {
@@ -612,21 +1035,42 @@ int tc_sm_count() {
   return sms;
 }
 
+// which GEMM kernel pf_pair_counts_tc launches: 1 = one CTA per 128 x 192 tile pair, 2 = a CTA pair (cluster of
+// two, tcgen05.mma.cta_group::2) per 256 x 240 tile pair; g_tc_cfg = pipeline geometry of the pair kernel
+int g_tc_impl = 2;
+int g_tc_cfg = 1;
+
 TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   TcPlan L;
   L.n_local = n_local;
   L.n_tiles = pf_ceil_div(n_samples, PF_TILE);
-  L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, TC_I));
+  const bool pair_kernel = g_tc_impl == 2;
+  L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, pair_kernel ? TC2_I : TC_I));
   const int widths[2] = {TcCfg<0>::J, TcCfg<1>::J};
   L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
+  if (pair_kernel) {
+    // A blocks of 256 rows; the B tiles of block ti start at its first row, so the last one ends before n + J
+    const int64_t rows = static_cast<int64_t>(TC2_I) * L.n_itiles;
+    const int J2 = tc2_cols(g_tc_cfg);
+    L.n_tiles_padded = pf_ceil_div(rows > n_samples + J2 ? rows : n_samples + J2, PF_TILE);
+    sms /= 2;                                    // work items run on CTA pairs
+    if (sms < 1) sms = 1;
+  }
   for (int mode = 0; mode < 2; ++mode) {
     TcModePlan& M = L.m[mode];
     const int J = widths[mode];
-    M.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, J));
-    const int64_t pf_tiles = static_cast<int64_t>(M.n_jtiles) * (J / PF_TILE);
-    if (pf_tiles > L.n_tiles_padded) L.n_tiles_padded = pf_tiles;      // whole J tiles of operand stream
     M.pairs = 0;
-    for (int ti = 0; ti < L.n_itiles; ++ti) M.pairs += M.n_jtiles - (TC_I * ti) / J;
+    if (pair_kernel) {
+      const int J2 = tc2_cols(g_tc_cfg);
+      M.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, J2));
+      for (int ti = 0; ti < L.n_itiles; ++ti)
+        M.pairs += static_cast<int>(pf_ceil_div(n_samples - static_cast<int64_t>(TC2_I) * ti, J2));
+    } else {
+      M.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, J));
+      const int64_t pf_tiles = static_cast<int64_t>(M.n_jtiles) * (J / PF_TILE);
+      if (pf_tiles > L.n_tiles_padded) L.n_tiles_padded = pf_tiles;      // whole J tiles of operand stream
+      for (int ti = 0; ti < L.n_itiles; ++ti) M.pairs += M.n_jtiles - (TC_I * ti) / J;
+    }
     // split-K: ~20 waves of one CTA per SM, at least 64 words per CTA, boundaries multiples of HSUM_RUN.
     // All CTAs do the same work, so the time is waves x (work per CTA): among the next few split counts
     // take the one whose last wave is fullest (e.g. 208 tile pairs on 148 SMs: 15 splits = 21.08 waves,
@@ -675,7 +1119,36 @@ cudaError_t tc_launch(const TcParams& P, int64_t grid, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+template <int MODE, int CFG>
+cudaError_t tc2_launch_cfg(const TcParams& P, int64_t items, cudaStream_t s) {
+  using G = Tc2Geo<CFG>;
+  auto kernel = g_tc_prof_enabled ? pair_counts_tc2_kernel<MODE, CFG, true> : pair_counts_tc2_kernel<MODE, CFG, false>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM));
+  if (e != cudaSuccess) return e;
+  kernel<<<static_cast<unsigned>(2 * items), G::THREADS, G::SMEM, s>>>(P);   // __cluster_dims__(2): one pair per item
+  return cudaGetLastError();
+}
+template <int MODE>
+cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s) {
+  switch (g_tc_cfg) {
+    case 1: return tc2_launch_cfg<MODE, 1>(P, items, s);
+    case 2: return tc2_launch_cfg<MODE, 2>(P, items, s);
+    case 3: return tc2_launch_cfg<MODE, 3>(P, items, s);
+    default: return tc2_launch_cfg<MODE, 0>(P, items, s);
+  }
+}
+
 }  // namespace
+
+// Diagnostic / A-B switch: impl 1 = single-CTA GEMM kernel (128 x 192 tiles), 2 = CTA-pair kernel (256 x 240
+// tiles, default); cfg = pipeline geometry of the pair kernel (0..3). Affects later pf_pair_counts_tc* calls
+// (the workspace layout depends on it: query pf_pair_counts_tc_work_bytes again).
+PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg) {
+  if ((impl != 1 && impl != 2) || cfg < 0 || cfg > 3) return pf_fail("pf_pair_counts_tc_set_impl: bad arguments");
+  g_tc_impl = impl;
+  g_tc_cfg = cfg;
+  return PF_OK;
+}
 
 PF_API int64_t pf_pair_counts_tc_work_bytes(int64_t n_samples, int64_t n_words_range) {
   if (n_samples <= 0 || n_words_range <= 0) return 256;   // an empty range needs no scratch (non-zero: callers allocate it)
@@ -745,7 +1218,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   P.hsum = hsum;
   P.hsum_ld = L.hsum_ld;
   P.flags = flags;
-  P.debug = g_tc_prof_enabled ? g_tc_debug : 0;
+  P.debug = g_tc_debug;
   // mode 1 is launched unconditionally (it returns at once unless the converter found sample-specific
   // missingness), so that the call never waits for the device
   for (int mode = 0; mode < (allow_general ? 2 : 1); ++mode) {
@@ -755,8 +1228,9 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     P.n_tilepairs = M.pairs;
     P.words_per_split = static_cast<int>(M.words_per_split);
     const int64_t grid = M.splits * M.pairs;
-    if (grid > 0x7fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
-    PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
+    if (grid > 0x3fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
+    if (g_tc_impl == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
+    else PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }
   *h_used = 1;
   return PF_OK;

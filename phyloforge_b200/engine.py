@@ -170,6 +170,14 @@ class Engine:
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
         return variant
 
+    def set_tc_impl(self, impl: int = 2, cfg: int = 1, strict: bool = False) -> None:
+        """A/B switch of the tensor-core pair-count kernel (results are identical): impl 1 = one CTA per
+        128 x 192 tile pair, impl 2 = a CTA pair (tcgen05.mma.cta_group::2) per 256-row tile pair (default);
+        cfg = tile width / pipeline geometry of the pair kernel; strict = cluster-scope release on every
+        operand hand-over (the slow, formally scoped form; see csrc/pair_counts_tc.cu)."""
+        check(self.lib.pf_pair_counts_tc_set_impl(impl, cfg))
+        check(self.lib.pf_pair_counts_tc_profile((1 << 4) if strict else 0, None))
+
     @property
     def tc_launches(self) -> int:
         """GEMM launches that did work in the last variant-3 call: 2 when it met genotypes missing in

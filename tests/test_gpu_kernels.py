@@ -273,8 +273,19 @@ def test_host_buffer_path_matches_resident_path(engine):
         assert np.array_equal(got.dist_host, want.dist.cpu().numpy()) and got.d2h_bytes > 0
 
 
+@pytest.fixture(params=[(2, 0, False), (2, 1, False), (2, 2, False), (2, 3, False), (2, 0, True), (1, 0, False)],
+                ids=["pair", "pair-j240-smem", "pair-deep", "pair-j224", "pair-strict", "single-cta"])
+def tc_impl(engine, request):
+    """Every GEMM kernel behind pf_pair_counts_tc: the CTA-pair kernel (default geometry, the alternatives, and
+    with cluster-scope release on the hand-over) and the single-CTA kernel."""
+    impl, cfg, strict = request.param
+    engine.set_tc_impl(impl, cfg, strict)
+    yield request.param
+    engine.set_tc_impl()
+
+
 @pytest.mark.parametrize("n,m", [(2, 40), (130, 5000), (256, 4096), (257, 4100), (300, 70000), (700, 20000)])
-def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
+def test_pair_counts_tensor_core_variant_bit_exact(engine, tc_impl, n, m):
     """tcgen05 int8 indicator GEMM == oracle on data without mixed missingness (incl. sites missing in
     every sample and site padding); with mixed missingness it declines and the popcount kernel runs."""
     rng = np.random.default_rng(n + m)
@@ -306,7 +317,7 @@ def test_pair_counts_tensor_core_variant_bit_exact(engine, n, m):
 
 @pytest.mark.parametrize("n,m,miss", [(2, 100, 0.3), (64, 32, 0.5), (129, 700, 0.1), (193, 3000, 0.02), (257, 5000, 0.2),
                                       (385, 2048, 0.9), (1000, 40000, 0.05)])
-def test_pair_counts_tensor_core_general_missingness_bit_exact(engine, n, m, miss):
+def test_pair_counts_tensor_core_general_missingness_bit_exact(engine, tc_impl, n, m, miss):
     """Genotypes missing in some samples only: the XX/HH launch plus the TT/VV launch == oracle,
     also over word ranges and when accumulated on top of existing counts."""
     rng = np.random.default_rng(n * 7 + m)
