@@ -625,32 +625,57 @@ constexpr int TC2_I = 256, TC2_IH = 128;     // rows per pair / per CTA
 // 16 accumulator + 16 scale-factor columns leave 512 - 2 J - 16 columns for EXP x GROUP steps of 8 columns,
 // which is what limits J to 208 there.
 template <int CFG> struct Tc2Cfg;
-template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true; };
-template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false; };
-template <> struct Tc2Cfg<2> { static constexpr int J = 208, GROUP = 3, RAW = 5, EXP = 3; static constexpr bool AH_TMEM = true; };
-template <> struct Tc2Cfg<3> { static constexpr int J = 224, GROUP = 3, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true; };
+// SPLIT: two threads per sample row (one per 32-site half of a step) instead of one: the per-stage latency
+// chain of an expansion warp (wake-up, loads, stores, fences, arrive) is what the MMAs wait for, and it
+// halves when a warp handles half the bytes
+// A_TMA: the A rows arrive by TMA too (a second bulk copy per step) and plane 0 of A is read by the MMAs straight
+// from the raw ring; the A-row warps then only derive plane 1 (LDS -> tensor or shared memory) and never have
+// global loads in flight across a proxy fence (fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
+// and the MEMBAR waits for the register prefetch of the following stages).
+template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true; };
+template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = false, A_TMA = false; };
+template <> struct Tc2Cfg<2> { static constexpr int J = 240, GROUP = 5, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = true, A_TMA = true; };
+template <> struct Tc2Cfg<3> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = false; };
 constexpr int tc2_cols(int cfg) { return cfg == 1 ? Tc2Cfg<1>::J : cfg == 2 ? Tc2Cfg<2>::J : cfg == 3 ? Tc2Cfg<3>::J : Tc2Cfg<0>::J; }
 template <int CFG> struct Tc2Geo {
   using C = Tc2Cfg<CFG>;
   static constexpr int J = C::J, JH = C::J / 2;
-  static constexpr bool AH_TMEM = C::AH_TMEM;
+  static constexpr bool AH_TMEM = C::AH_TMEM, SPLIT = C::SPLIT;
+  static constexpr int NU = SPLIT ? 1 : 2;                                  // 16-byte units of a row and step per thread
   static constexpr int GROUP = C::GROUP, RAW = C::RAW, EXP = C::EXP;
   static constexpr int DONE = RAW > EXP ? RAW : EXP;                        // depth of the stage_done ring
-  static constexpr int RAW_STEP_BYTES = JH * 32;
-  static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
+  static constexpr bool A_TMA = C::A_TMA;
   static constexpr int A_PLANE_BYTES = TC2_IH * 32;                         // 4096
-  static constexpr int A_PLANES_SMEM = AH_TMEM ? 1 : 2;
-  static constexpr int EXP_STEP_BYTES = A_PLANES_SMEM * A_PLANE_BYTES + RAW_STEP_BYTES;   // A plane(s), then B plane 1
+  static constexpr int B_STEP_BYTES = JH * 32;                              // the B rows of a step
+  static constexpr int RAW_B_OFF = A_TMA ? A_PLANE_BYTES : 0;               // raw step: [A rows (A_TMA)][B rows]
+  static constexpr int RAW_STEP_BYTES = RAW_B_OFF + B_STEP_BYTES;
+  static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
+  static constexpr int A_PLANES_SMEM = (A_TMA ? 0 : 1) + (AH_TMEM ? 0 : 1);   // A planes the expansion warps write to shared memory
+  static constexpr int EXP_A1_OFF = A_TMA ? 0 : A_PLANE_BYTES;              // expanded step: [A plane 0 (!A_TMA)][A plane 1 (!AH_TMEM)][B plane 1]
+  static constexpr int EXP_STEP_BYTES = A_PLANES_SMEM * A_PLANE_BYTES + B_STEP_BYTES;
   static constexpr int EXP_STAGE_BYTES = GROUP * EXP_STEP_BYTES;
   static constexpr int TMEM_A = 2 * J;                                       // A plane 1 staging behind the accumulators
-  static constexpr int B_WARPS = (JH + 31) / 32;
-  static constexpr int EXP_WARPS = 4 + B_WARPS;
+  static constexpr int A_WARPS = 4 * (2 / NU);
+  static constexpr int A_THREADS = A_WARPS * 32;
+  static constexpr int B_WARPS = (JH * (2 / NU) + 31) / 32;
+  static constexpr int EXP_WARPS = A_WARPS + B_WARPS;
   static constexpr int THREADS = (EXP_WARPS + 2) * 32;
   static constexpr size_t SMEM = static_cast<size_t>(RAW) * RAW_STAGE_BYTES + static_cast<size_t>(EXP) * EXP_STAGE_BYTES;
   static_assert(J % 16 == 0 && JH % 8 == 0, "tile width");
   static_assert(2 * J + (AH_TMEM ? EXP * GROUP * TMEM_A_COLS : 0) <= TMEM_SF && TMEM_SF + 16 <= 512, "TMEM columns");
   static_assert(RAW <= 8 && EXP <= 8 && SMEM + 4096 <= 227 * 1024, "shared memory");
 };
+
+// planes of one 16-byte unit (32 sites of one sample row): p0 = the stream itself (x / t), p1 = h / v
+template <int MODE>
+__device__ __forceinline__ void make_unit_planes(const uint4& n, uint4& p1) {
+  if (MODE == 0) {
+    p1 = make_uint4(n.x & NIB_HOM, n.y & NIB_HOM, n.z & NIB_HOM, n.w & NIB_HOM);
+  } else {
+    p1 = make_uint4(((~n.x >> 3) & 0x11111111u) << 1, ((~n.y >> 3) & 0x11111111u) << 1, ((~n.z >> 3) & 0x11111111u) << 1,
+                    ((~n.w >> 3) & 0x11111111u) << 1);
+  }
+}
 
 // work item -> (A block ti, first column of the B tile)
 __device__ __forceinline__ void tc2_tile(int pair, int64_t n_samples, int J, int& ti, int64_t& b_start) {
@@ -719,7 +744,7 @@ pair_counts_tc2_kernel(const TcParams P) {
   if (warp == 0) umma::tmem_alloc_2cta(&s_tmem, 512);
   if (tid == 32) {
     for (int s = 0; s < G::RAW; ++s) umma::mbar_init(&raw_full[s], 1);
-    for (int e = 0; e < G::EXP; ++e) umma::mbar_init(&exp_full[e], 2 * G::EXP_WARPS);   // used in the leader
+    for (int e = 0; e < G::EXP; ++e) umma::mbar_init(&exp_full[e], 2);                    // one arrival per CTA (used in the leader)
     for (int d = 0; d < G::DONE; ++d) umma::mbar_init(&stage_done[d], 1);
     umma::mbar_init(&done_bar, 1);
     umma::fence_mbar_init();
@@ -743,9 +768,10 @@ pair_counts_tc2_kernel(const TcParams P) {
 
   const int64_t step_stride = P.n_tiles_padded * (CHUNK_BYTES / 16);
   if (warp == G::EXP_WARPS) {
-    // ===== TMA producer: the J / 2 B rows of this CTA, one bulk copy per step =====
+    // ===== TMA producer: the J / 2 B rows of this CTA (A_TMA: and its 128 A rows), one bulk copy each per step =====
     if (lane == 0) {
       const uint4* src_b = P.stream + s_begin * step_stride + (b_row0 >> 3) * 16;
+      const uint4* src_a = P.stream + s_begin * step_stride + (a_row0 >> 3) * 16;
       int stage = 0;
       RingPos<G::DONE> freed;                    // stage g - RAW, whose MMAs must have completed
       for (int g = 0; g < n_groups; ++g) {
@@ -757,10 +783,12 @@ pair_counts_tc2_kernel(const TcParams P) {
         umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
 #pragma unroll
         for (int j = 0; j < G::GROUP; ++j) {
-          if (j < kw)
-            umma::bulk_g2s_a(raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES,
-                             src_b + (static_cast<int64_t>(g) * G::GROUP + j) * step_stride, G::RAW_STEP_BYTES,
-                             raw_full_a + stage * 8);
+          if (j < kw) {
+            const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES;
+            const int64_t off = (static_cast<int64_t>(g) * G::GROUP + j) * step_stride;
+            if (G::A_TMA) umma::bulk_g2s_a(dst, src_a + off, G::A_PLANE_BYTES, raw_full_a + stage * 8);
+            umma::bulk_g2s_a(dst + G::RAW_B_OFF, src_b + off, G::B_STEP_BYTES, raw_full_a + stage * 8);
+          }
         }
         if (++stage == G::RAW) stage = 0;
       }
@@ -774,30 +802,37 @@ pair_counts_tc2_kernel(const TcParams P) {
       const long long t_start = PROF ? clock64() : 0;
       int e = 0, stage = 0, d = 0;
       uint32_t phase = 0;
+      // Shared-memory descriptors differ only in the start-address field (bits [0, 14) of the low word, in
+      // 16-byte units; all addresses are below 256 KB, so adding an offset never carries out of the field):
+      // one 32-bit add per operand instead of rebuilding 64-bit descriptors. The issuing thread's own
+      // instruction stream was the limit with the tensor-memory A plane (293 clocks per step for 208 of MMAs).
+      const uint64_t desc0 = umma::smem_desc_kmajor_noswizzle(0, 128, 256);
+      const uint32_t desc_hi = static_cast<uint32_t>(desc0 >> 32), desc_lo = static_cast<uint32_t>(desc0);
+      auto desc_at = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+      auto issue_stage = [&](const bool full, int kw, uint32_t first_acc) {
+        const uint32_t e_lo = desc_lo + ((exp_a + e * G::EXP_STAGE_BYTES) >> 4);
+        const uint32_t r_lo = desc_lo + ((raw_a + stage * G::RAW_STAGE_BYTES) >> 4);
+        const uint32_t ta = tmem + G::TMEM_A + e * G::GROUP * TMEM_A_COLS;
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          if (full || j < kw) {
+            const uint32_t acc = j > 0 ? 1u : first_acc;
+            const uint32_t ex = e_lo + j * (G::EXP_STEP_BYTES >> 4), rw = r_lo + j * (G::RAW_STEP_BYTES >> 4);
+            umma::mma_mxf4_ss_2cta(tmem + 0 * J, desc_at(G::A_TMA ? rw : ex), desc_at(rw + (G::RAW_B_OFF >> 4)), idesc, acc, tsfa, tsfb);   // XX / TT
+            const uint64_t b1 = desc_at(ex + ((G::A_PLANES_SMEM * G::A_PLANE_BYTES) >> 4));
+            if (G::AH_TMEM) umma::mma_mxf4_ts_2cta(tmem + 1 * J, ta + j * TMEM_A_COLS, b1, idesc, acc, tsfa, tsfb);
+            else umma::mma_mxf4_ss_2cta(tmem + 1 * J, desc_at(ex + (G::EXP_A1_OFF >> 4)), b1, idesc, acc, tsfa, tsfb);                   // HH / VV
+          }
+        }
+      };
       for (int g = 0; g < n_groups; ++g) {
         const long long t0 = PROF ? clock64() : 0;
         umma::mbar_wait_cluster_a(exp_full_a + e * 8, phase);
         if (PROF) t_wait += clock64() - t0;
         umma::fence_after_thread_sync();
         const int kw = min(G::GROUP, n_steps - g * G::GROUP);
-#pragma unroll
-        for (int j = 0; j < G::GROUP; ++j) {
-          if (j < kw) {
-            const uint32_t acc = (g > 0 || j > 0) ? 1u : 0u;
-            const uint32_t ebase = exp_a + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
-            const uint64_t a0 = umma::smem_desc_kmajor_noswizzle(ebase, 128, 256);
-            const uint64_t b0 = umma::smem_desc_kmajor_noswizzle(
-                raw_a + stage * G::RAW_STAGE_BYTES + j * G::RAW_STEP_BYTES, 128, 256);
-            const uint64_t b1 = umma::smem_desc_kmajor_noswizzle(ebase + G::A_PLANES_SMEM * G::A_PLANE_BYTES, 128, 256);
-            umma::mma_mxf4_ss_2cta(tmem + 0 * J, a0, b0, idesc, acc, tsfa, tsfb);       // XX / TT
-            if (G::AH_TMEM) {
-              umma::mma_mxf4_ts_2cta(tmem + 1 * J, tmem + G::TMEM_A + (e * G::GROUP + j) * TMEM_A_COLS, b1, idesc, acc, tsfa, tsfb);
-            } else {
-              const uint64_t a1 = umma::smem_desc_kmajor_noswizzle(ebase + G::A_PLANE_BYTES, 128, 256);
-              umma::mma_mxf4_ss_2cta(tmem + 1 * J, a1, b1, idesc, acc, tsfa, tsfb);     // HH / VV
-            }
-          }
-        }
+        if (kw == G::GROUP) issue_stage(true, kw, g > 0 ? 1u : 0u);
+        else issue_stage(false, kw, g > 0 ? 1u : 0u);
         umma::commit_2cta_a(stage_done_a + d * 8, 3);          // both CTAs: raw and expanded stage of g are free
         if (++e == G::EXP) {
           e = 0;
@@ -814,132 +849,214 @@ pair_counts_tc2_kernel(const TcParams P) {
       }
     }
   } else {
-    // ===== expansion warps: thread = one sample row of this CTA =====
-    const int row = tid;
-    const bool is_a = row < TC2_IH;
-    const int r = is_a ? row : row - TC2_IH;
-    const bool active = is_a || r < JH;               // the last B-row warp may have rows to spare
-    const uint32_t a_tmem = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A;   // A rows: TMEM lane = row
-    const uint32_t raw_row = raw_a + unit_off(r, 0);
-    const uint32_t exp_row = exp_a + unit_off(r, 0) + (is_a ? 0 : G::A_PLANES_SMEM * G::A_PLANE_BYTES);
-    const int64_t a_sample = a_row0 + r;
-    const uint4* a_src = P.stream + s_begin * step_stride + (a_sample >> 3) * 16 + (a_sample & 7);
-    long long t_wraw = 0, t_wemp = 0, t_work = 0, t_fence = 0, t_arrive = 0, t_post = 0;
+    // ===== expansion warps: thread = one sample row of this CTA (SPLIT: one 32-site half of it). The A-row
+    // and the B-row warps run separate, branch-free instruction streams (a stage of six steps was ~365
+    // instructions per warp when both roles shared one predicated body, and an in-order warp needs ~3 clocks
+    // per instruction: the expansion warps, not the memory system, were what the MMAs waited for) =====
+    constexpr int NU = G::NU;
+    constexpr int NR = G::GROUP * NU;
+    long long t_wait = 0;
     const long long t_start = PROF ? clock64() : 0;
+    // Stage hand-over inside a CTA goes through hardware named barriers: ONE thread polls the mbarriers (raw
+    // data landed, stage slot free) and ONE thread arrives on the leader's exp_full. With every expansion warp
+    // polling and arriving on the mbarriers themselves (30 arrivals per stage on one barrier word that the
+    // MMA thread polls) an arrive took ~400 clocks.
+    constexpr int EXP_THREADS = G::EXP_WARPS * 32;
     int stage = 0, e = 0;
     uint32_t raw_phase = 0;
     RingPos<G::DONE> freed;                      // stage g - EXP, whose MMAs must have completed
-    // A rows come straight from the stream into registers TWO stages ahead (two register sets): the loads of
-    // a stage are issued a full stage period (~1,500 clocks) before they are used; one stage ahead left the
-    // A-row warps waiting for L2 / HBM
-    uint4 lo0[G::GROUP], hi0[G::GROUP], lo1[G::GROUP], hi1[G::GROUP];
-    auto load_a_rows = [&](int g, uint4 (&lo)[G::GROUP], uint4 (&hi)[G::GROUP]) {
-#pragma unroll
-      for (int j = 0; j < G::GROUP; ++j) {
-        lo[j] = make_uint4(0, 0, 0, 0);
-        hi[j] = lo[j];
-        const int st = g * G::GROUP + j;
-        if (st < n_steps && !(P.debug & 32)) {
-          lo[j] = __ldg(a_src + st * step_stride);
-          hi[j] = __ldg(a_src + st * step_stride + 8);
-        }
+    auto stage_begin = [&](int g) {
+      const long long t0 = PROF ? clock64() : 0;
+      if (tid == 0) {
+        if (!(P.debug & 256)) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
+        if (g >= G::EXP) umma::mbar_wait_a(stage_done_a + freed.slot * 8, freed.parity);
       }
-    };
-    auto do_stage = [&](int g, uint4 (&lo)[G::GROUP], uint4 (&hi)[G::GROUP]) {
-      {
-        const long long t0 = PROF ? clock64() : 0;
-        if (!is_a && lane == 0) umma::mbar_wait_a(raw_full_a + stage * 8, raw_phase);
-        if (lane == 1 && g >= G::EXP) umma::mbar_wait_a(stage_done_a + freed.slot * 8, freed.parity);
-        if (PROF && lane < 2) {
-          if (lane == 0) t_wraw += clock64() - t0;
-          else t_wemp += clock64() - t0;
-        }
-      }
+      asm volatile("bar.sync 2, %0;" ::"r"(EXP_THREADS) : "memory");
+      if (PROF) t_wait += clock64() - t0;
       if (g >= G::EXP) freed.advance();
-      __syncwarp();
-      const long long tw0 = PROF ? clock64() : 0;
-      if (G::AH_TMEM && is_a) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
-      const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
-      if (!is_a) {
-        const uint32_t src = raw_row + stage * G::RAW_STAGE_BYTES;
-#pragma unroll
-        for (int j = 0; j < G::GROUP; ++j) {
-          lo[j] = make_uint4(0, 0, 0, 0);
-          hi[j] = lo[j];
-          if (j < kw && active) {
-            lo[j] = umma::lds128(src + j * G::RAW_STEP_BYTES);
-            hi[j] = umma::lds128(src + j * G::RAW_STEP_BYTES + 128);
-          }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < G::GROUP; ++j) {
-        if (j < kw && active) {
-          uint32_t p0[8], p1[8];
-          make_planes<MODE>(lo[j], hi[j], p0, p1);
-          const uint32_t dst = exp_row + e * G::EXP_STAGE_BYTES + j * G::EXP_STEP_BYTES;
-          if (is_a) {
-            umma::sts128(dst, p0[0], p0[1], p0[2], p0[3]);                             // x / t
-            umma::sts128(dst + 128, p0[4], p0[5], p0[6], p0[7]);
-            if (G::AH_TMEM) {
-              umma::tmem_st_32x8(a_tmem + (e * G::GROUP + j) * TMEM_A_COLS, p1);       // h / v
-            } else {
-              umma::sts128(dst + G::A_PLANE_BYTES, p1[0], p1[1], p1[2], p1[3]);
-              umma::sts128(dst + G::A_PLANE_BYTES + 128, p1[4], p1[5], p1[6], p1[7]);
-            }
-          } else {
-            umma::sts128(dst, p1[0], p1[1], p1[2], p1[3]);           // h / v (plane 0 is read from the raw stage)
-            umma::sts128(dst + 128, p1[4], p1[5], p1[6], p1[7]);
-          }
-        }
-      }
-      const long long tf0 = PROF ? clock64() : 0;
-      if (G::AH_TMEM && is_a) {
+    };
+    auto stage_end = [&](bool wrote_smem, bool wrote_tmem) {     // operands of the stage in slot e are written
+      if (wrote_tmem) {
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
       }
-      umma::fence_proxy_async_smem();    // generic-proxy operand writes -> the tensor cores' async proxy
-      __syncwarp();
-      long long tf1 = 0;
-      if (PROF) {
-        tf1 = clock64();
-        t_work += tf0 - tw0;
-        t_fence += tf1 - tf0;
-      }
-      if (lane == 0) {
+      if (wrote_smem) umma::fence_proxy_async_smem();    // generic-proxy operand writes -> the tensor cores' async proxy
+      asm volatile("bar.sync 3, %0;" ::"r"(EXP_THREADS) : "memory");
+      if (tid == 0) {
         if (strict) umma::mbar_arrive_cluster(exp_full_leader + e * 8);
         else if (rank == 0) umma::mbar_arrive_a(exp_full_a + e * 8);
         else umma::mbar_arrive_remote(exp_full_leader + e * 8);
       }
-      __syncwarp();
-      const long long tp1 = PROF ? clock64() : 0;
-      if (PROF) t_arrive += tp1 - tf1;
-      if (is_a) load_a_rows(g + 2, lo, hi);
-      if (PROF) t_post += clock64() - tp1;
       if (++stage == G::RAW) {
         stage = 0;
         raw_phase ^= 1;
       }
       if (++e == G::EXP) e = 0;
     };
-    if (is_a) {
-      load_a_rows(0, lo0, hi0);
-      load_a_rows(1, lo1, hi1);
+    if (warp < G::A_WARPS && G::A_TMA) {
+      // ---- A rows, from the raw ring: plane 1 to tensor or shared memory (plane 0 is read from the raw ring by the MMAs)
+      const int r = G::SPLIT ? (warp & 3) * 32 + lane : tid;     // TMEM lane = row: warps w and w + 4 share a lane quadrant
+      const int kh = G::SPLIT ? (warp >> 2) : 0;
+      const uint32_t a_tmem = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A + kh * 4;
+      const uint32_t raw_row = raw_a + unit_off(r, kh);
+      const uint32_t exp_row = exp_a + unit_off(r, kh);
+      auto derive_stage = [&](const bool full, int kw) {
+        const uint32_t src0 = raw_row + stage * G::RAW_STAGE_BYTES;
+        const uint32_t dst0 = exp_row + e * G::EXP_STAGE_BYTES;
+        const uint32_t ta0 = a_tmem + e * G::GROUP * TMEM_A_COLS;
+        uint4 u[NR];
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+#pragma unroll
+          for (int q = 0; q < NU; ++q)
+            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_STEP_BYTES + q * 128);
+        }
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          if (full || j < kw) {
+            uint4 p1[NU];
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+              make_unit_planes<MODE>(u[j * NU + q], p1[q]);
+              if (!G::AH_TMEM) umma::sts128(dst0 + j * G::EXP_STEP_BYTES + q * 128, p1[q].x, p1[q].y, p1[q].z, p1[q].w);
+            }
+            if (G::AH_TMEM) {
+              if (NU == 2) {
+                const uint32_t v[8] = {p1[0].x, p1[0].y, p1[0].z, p1[0].w, p1[NU - 1].x, p1[NU - 1].y, p1[NU - 1].z, p1[NU - 1].w};
+                umma::tmem_st_32x8(ta0 + j * TMEM_A_COLS, v);
+              } else {
+                umma::tmem_st_32x4(ta0 + j * TMEM_A_COLS, p1[0].x, p1[0].y, p1[0].z, p1[0].w);
+              }
+            }
+          }
+        }
+      };
+      for (int g = 0; g < n_groups; ++g) {
+        stage_begin(g);
+        if (g >= G::EXP && G::AH_TMEM) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+        const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+        if (kw == G::GROUP) derive_stage(true, kw);
+        else derive_stage(false, kw);
+        stage_end(!G::AH_TMEM, G::AH_TMEM);     // tensor-memory stores need no proxy fence
+      }
+    } else if (warp < G::A_WARPS) {
+      // ---- A rows: stream -> registers (two stages ahead) -> plane 0 to shared memory, plane 1 to shared or tensor memory
+      const int r = G::SPLIT ? (warp & 3) * 32 + lane : tid;     // TMEM lane = row: warps w and w + 4 share a lane quadrant
+      const int kh = G::SPLIT ? (warp >> 2) : 0;
+      const uint32_t a_tmem = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + G::TMEM_A + kh * 4;
+      const uint32_t exp_row = exp_a + unit_off(r, kh);
+      const int64_t a_sample = a_row0 + r;
+      const int64_t step_bytes = step_stride * 16;
+      const char* a_ptr = reinterpret_cast<const char*>(P.stream + s_begin * step_stride + (a_sample >> 3) * 16 + (a_sample & 7) + kh * 8);
+      uint4 u0[NR], u1[NR];
+      auto load_rows = [&](int g, uint4 (&u)[NR]) {
+        const char* p = a_ptr + static_cast<int64_t>(g) * G::GROUP * step_bytes;
+        if ((g + 1) * G::GROUP <= n_steps) {
+#pragma unroll
+          for (int j = 0; j < G::GROUP; ++j) {
+#pragma unroll
+            for (int q = 0; q < NU; ++q) u[j * NU + q] = __ldg(reinterpret_cast<const uint4*>(p + j * step_bytes) + q * 8);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < G::GROUP; ++j) {
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+              u[j * NU + q] = make_uint4(0, 0, 0, 0);
+              if (g * G::GROUP + j < n_steps) u[j * NU + q] = __ldg(reinterpret_cast<const uint4*>(p + j * step_bytes) + q * 8);
+            }
+          }
+        }
+      };
+      auto write_stage = [&](const bool full, int kw, uint4 (&u)[NR]) {
+        const uint32_t dst0 = exp_row + e * G::EXP_STAGE_BYTES;
+        const uint32_t ta0 = a_tmem + e * G::GROUP * TMEM_A_COLS;
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+          if (full || j < kw) {
+            const uint32_t dst = dst0 + j * G::EXP_STEP_BYTES;
+            uint4 p1[NU];
+#pragma unroll
+            for (int q = 0; q < NU; ++q) {
+              const uint4& x = u[j * NU + q];
+              make_unit_planes<MODE>(x, p1[q]);
+              umma::sts128(dst + q * 128, x.x, x.y, x.z, x.w);                          // x / t
+              if (!G::AH_TMEM) umma::sts128(dst + G::A_PLANE_BYTES + q * 128, p1[q].x, p1[q].y, p1[q].z, p1[q].w);   // h / v
+            }
+            if (G::AH_TMEM) {
+              if (NU == 2) {
+                const uint32_t v[8] = {p1[0].x, p1[0].y, p1[0].z, p1[0].w, p1[NU - 1].x, p1[NU - 1].y, p1[NU - 1].z, p1[NU - 1].w};
+                umma::tmem_st_32x8(ta0 + j * TMEM_A_COLS, v);
+              } else {
+                umma::tmem_st_32x4(ta0 + j * TMEM_A_COLS, p1[0].x, p1[0].y, p1[0].z, p1[0].w);
+              }
+            }
+          }
+        }
+      };
+      auto do_stage = [&](int g, uint4 (&u)[NR]) {
+        stage_begin(g);
+        if (g >= G::EXP && G::AH_TMEM) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
+        const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+        if (kw == G::GROUP) write_stage(true, kw, u);    // inlined twice: the full-stage copy has no per-step predicates
+        else write_stage(false, kw, u);
+        stage_end(true, G::AH_TMEM);
+        if (!(P.debug & 32)) load_rows(g + 2, u);
+      };
+      load_rows(0, u0);
+      load_rows(1, u1);
+      for (int g = 0; g < n_groups; g += 2) {
+        do_stage(g, u0);
+        if (g + 1 < n_groups) do_stage(g + 1, u1);
+      }
+    } else {
+      // ---- B rows: raw ring -> registers -> plane 1 to shared memory (plane 0 is read from the raw ring by the MMAs)
+      const int t = tid - G::A_THREADS;
+      int r = G::SPLIT ? t % JH : t;
+      int kh = G::SPLIT ? t / JH : 0;
+      const bool active = G::SPLIT ? (kh < 2) : (r < JH);         // the last B-row warp may have threads to spare
+      if (!active) {
+        r = 0;
+        kh = 0;
+      }
+      const uint32_t raw_row = raw_a + G::RAW_B_OFF + unit_off(r, kh);
+      const uint32_t exp_row = exp_a + unit_off(r, kh) + G::A_PLANES_SMEM * G::A_PLANE_BYTES;
+      auto expand_stage = [&](const bool full, int kw) {
+        const uint32_t src0 = raw_row + stage * G::RAW_STAGE_BYTES;
+        const uint32_t dst0 = exp_row + e * G::EXP_STAGE_BYTES;
+        uint4 u[NR];
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+#pragma unroll
+          for (int q = 0; q < NU; ++q)
+            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_STEP_BYTES + q * 128);
+        }
+#pragma unroll
+        for (int j = 0; j < G::GROUP; ++j) {
+#pragma unroll
+          for (int q = 0; q < NU; ++q) {
+            if (full || j < kw) {
+              uint4 p1;
+              make_unit_planes<MODE>(u[j * NU + q], p1);
+              umma::sts128(dst0 + j * G::EXP_STEP_BYTES + q * 128, p1.x, p1.y, p1.z, p1.w);
+            }
+          }
+        }
+      };
+      for (int g = 0; g < n_groups; ++g) {
+        stage_begin(g);
+        const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+        if (active) {
+          if (kw == G::GROUP) expand_stage(true, kw);
+          else expand_stage(false, kw);
+        }
+        stage_end(true, false);
+      }
     }
-    for (int g = 0; g < n_groups; g += 2) {
-      do_stage(g, lo0, hi0);
-      if (g + 1 < n_groups) do_stage(g + 1, lo1, hi1);
-    }
-    t_wemp = __shfl_sync(0xffffffffu, t_wemp, 1);
-    if (PROF && lane == 0 && (warp == 0 || warp == 4) && rank == ((P.debug >> 6) & 1)) {   // debug bit 6: which CTA of the pair reports
-      const int o = warp == 0 ? 2 : 9;
-      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o]), static_cast<unsigned long long>(t_wraw));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 1]), static_cast<unsigned long long>(t_wemp));
+    if (PROF && lane == 0 && (warp == 0 || warp == G::A_WARPS) && rank == ((P.debug >> 6) & 1)) {   // debug bit 6: which CTA of the pair reports
+      const int o = warp == 0 ? 2 : 9;           // [3], [4]: an A-row warp waiting / total; [10], [11]: a B-row warp
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 1]), static_cast<unsigned long long>(t_wait));
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 5 : 6]), static_cast<unsigned long long>(t_arrive));
-      if (warp == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[7]), static_cast<unsigned long long>(t_post));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 14]), static_cast<unsigned long long>(t_work));
-      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 13 : 15]), static_cast<unsigned long long>(t_fence));
     }
     const bool uniform = (MODE == 0) && !general;
     if (uniform) {
@@ -1038,7 +1155,7 @@ int tc_sm_count() {
 // which GEMM kernel pf_pair_counts_tc launches: 1 = one CTA per 128 x 192 tile pair, 2 = a CTA pair (cluster of
 // two, tcgen05.mma.cta_group::2) per 256 x 240 tile pair; g_tc_cfg = pipeline geometry of the pair kernel
 int g_tc_impl = 2;
-int g_tc_cfg = 1;
+int g_tc_cfg = 0;
 
 TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   TcPlan L;

@@ -170,7 +170,7 @@ class Engine:
                                       counts.data_ptr(), counts.stride(1), variant, _stream_ptr()))
         return variant
 
-    def set_tc_impl(self, impl: int = 2, cfg: int = 1, strict: bool = False) -> None:
+    def set_tc_impl(self, impl: int = 2, cfg: int = 0, strict: bool = False) -> None:
         """A/B switch of the tensor-core pair-count kernel (results are identical): impl 1 = one CTA per
         128 x 192 tile pair, impl 2 = a CTA pair (tcgen05.mma.cta_group::2) per 256-row tile pair (default);
         cfg = tile width / pipeline geometry of the pair kernel; strict = cluster-scope release on every

@@ -84,6 +84,5 @@ for impl, cfg, dbg in cfgs:
     v = list(buf)
     steps = max(v[8], 1)
     print(f"impl={impl} cfg={cfg} dbg={dbg} n={n} m={m}: counts (conversion + GEMM) {min(ts):.2f} ms (all {[round(t, 2) for t in ts]}), same as first={same}; "
-          f"MMA thread {v[1] / steps:.0f} clk/step, waiting {v[0] / steps:.0f}; A warp wait-free {v[3] / steps:.0f}; "
-          f"B warp wait-raw {v[9] / steps:.0f} wait-free {v[10] / steps:.0f}; per step (CTA rank {(dbg >> 6) & 1}): A warp total {v[4] / steps:.0f} work {v[12] / steps:.0f} "
-          f"fence {v[13] / steps:.0f} arrive {v[5] / steps:.0f} loads {v[7] / steps:.0f}; B warp total {v[11] / steps:.0f} work {v[14] / steps:.0f} fence {v[15] / steps:.0f} arrive {v[6] / steps:.0f}", flush=True)
+          f"per step: MMA thread {v[1] / steps:.0f} clk, waiting {v[0] / steps:.0f}; A warp {v[4] / steps:.0f}, waiting {v[3] / steps:.0f}; "
+          f"B warp {v[11] / steps:.0f}, waiting {v[10] / steps:.0f} (expansion warps of CTA rank {(dbg >> 6) & 1})", flush=True)
