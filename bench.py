@@ -53,7 +53,7 @@ UNIT = "pair-sites/s"
 SEED = 42
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
-NCU_TRAFFIC_BYTES_TC = 75_751_410_000  # r01: 74.15 GB read + 1.61 GB written per launch (profiles/r01_ncu_pair_counts_tc_raw_subset.csv), N=1
+NCU_TRAFFIC_BYTES_TC = 54_051_894_000  # r01: 52.15 GB read + 1.90 GB written per launch of pair_counts_tc2_kernel (profiles/r01_ncu_pair_counts_tc2_raw_subset.csv), N=1
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
@@ -284,6 +284,23 @@ def run_ours(args):
     stages_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in stage_ev.items()}
     counts_ms = stages_ms["counts"]
     del codes
+    # split of the counts stage into its two kernels (untimed extra passes, CUDA events on the launching stream
+    # recorded inside pf_pair_counts_tc): operand-stream conversion and the tensor-core GEMM launch(es)
+    tc_split = None
+    if ran_variant[0] == 3:
+        import ctypes as C
+        from phyloforge_b200._lib import check
+        check(eng.lib.pf_pair_counts_tc_timing(1, None))
+        conv, gemm = [], []
+        for _ in range(3):
+            counts.zero_()
+            eng.pair_counts(planes, n, my_words, counts, variant=args.variant)
+            ms2 = (C.c_float * 2)()
+            check(eng.lib.pf_pair_counts_tc_timing(1, ms2))
+            conv.append(float(ms2[0]))
+            gemm.append(float(ms2[1]))
+        check(eng.lib.pf_pair_counts_tc_timing(0, None))
+        tc_split = {"conversion_ms": statistics.mean(conv), "gemm_ms": statistics.mean(gemm)}
 
     # ---- end to end from pinned host memory through the public host-buffer API
     e2e = None
@@ -351,11 +368,14 @@ def run_ours(args):
         launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (TT, VV) ran too
         macs_per = 4.0 if launches == 2 else 2.0
         macs = macs_per * pair_sites(n, my_sites)
-        achieved_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
+        gemm_ms = tc_split["gemm_ms"] if tc_split else counts_ms
+        achieved_tops = 2.0 * macs / (gemm_ms * 1e-3) / 1e12
+        stage_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (fp4)",
                     "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES_TC,
-                    "kernel": "pair_counts_tc_kernel (tcgen05 kind::mxf4, E2M1 operands) + planes_to_e2m1_kernel",
-                    "kernel_ms": counts_ms,
+                    "kernel": "pair_counts_tc2_kernel (tcgen05.mma.cta_group::2 kind::mxf4 on CTA pairs, E2M1 operands)",
+                    "kernel_ms": gemm_ms, "stream_conversion_ms": tc_split["conversion_ms"] if tc_split else None,
+                    "counts_stage_ms": counts_ms, "frac_of_counts_stage": stage_tops / peak_tops,
                     "ops_per_pair_site": {"fp4_mac": macs_per}, "gemm_launches": launches,
                     "frac_of_popcount_kernel_roofline": achieved_pw / (min(lop3_ops / 4.0, popc_ops / 1.0) if miss == 0
                                                                        else plain_popc_peak_pw),
@@ -364,10 +384,11 @@ def run_ours(args):
                     "peak_source": "4 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no fp4 entry; nominal dense "
                                    "fp4 is 9000 TOP/s, 4 x the 2250 of bf16)" % ("of measured" if peaks else "of fallback 1590"),
                     "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 4 MAC with "
-                            "sample-specific missingness: + t.t', v.v'); the kernel also computes ~13% redundant "
-                            "pairs in tiles that straddle the diagonal, and a 128 x 192 x 64 instruction takes the "
-                            "time of a 128 x 256 x 64 one (73% of the instruction-level peak). kernel_ms "
-                            "includes the planes -> 4-bit operand stream conversion and one stream synchronise"}
+                            "sample-specific missingness: + t.t', v.v'); the kernel also computes ~16% redundant "
+                            "pairs in the 256 x 208 tiles that straddle the diagonal. frac = the GEMM kernel alone "
+                            "(kernel_ms, CUDA events around its launch inside pf_pair_counts_tc, untimed extra passes); "
+                            "frac_of_counts_stage also charges the planes -> 4-bit operand stream conversion "
+                            "(planes_to_e2m1_kernel, stream_conversion_ms) to it, as the timed step does"}
     else:
         csa = variant_ran != 1
         if miss == 0:

@@ -214,6 +214,11 @@ PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16);
  * query pf_pair_counts_tc_work_bytes again after changing it. Results are identical. */
 PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg);
 
+/* Diagnostic: enable != 0 makes later pf_pair_counts_tc calls record CUDA events on their stream around the
+ * operand-stream conversion and around the GEMM launch(es). With h_ms2 != NULL the call first waits for the
+ * last recorded call and returns h_ms2[0] = conversion ms, h_ms2[1] = GEMM ms (bench.py's roofline). */
+PF_API int pf_pair_counts_tc_timing(int enable, float* h_ms2);
+
 /* counts -> fp64 distances, one IEEE divide of exactly converted integers per pair:
  *   metric 0: p-distance D1 / V;  metric 1: IBS distance (D1 + D2) / (2 V).
  * V == 0 -> 1.0 and the pair is counted in *d_n_zero_valid (int32, caller-zeroed).

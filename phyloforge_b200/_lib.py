@@ -65,6 +65,7 @@ PROTOTYPES = {
     "pf_selftest_umma_fp4": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pf_probe_umma_fp4_rate": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _dp, _vp]),
     "pf_pair_counts_tc_set_impl": (_i32, [_i32, _i32]),
+    "pf_pair_counts_tc_timing": (_i32, [_i32, _vp]),
     "pf_selftest_umma_fp4_2cta": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "pf_probe_umma_fp4_2cta_rate": (_i32, [_i32, _i32, _i32, _dp, _vp, _vp]),
     "pf_nj_batch": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),

@@ -1152,6 +1152,10 @@ int tc_sm_count() {
   return sms;
 }
 
+// optional split timing of a pf_pair_counts_tc call (pf_pair_counts_tc_timing): events around the conversion and the GEMM launches
+bool g_tc_timing = false;
+cudaEvent_t g_tc_ev[3] = {nullptr, nullptr, nullptr};
+
 // which GEMM kernel pf_pair_counts_tc launches: 1 = one CTA per 128 x 192 tile pair, 2 = a CTA pair (cluster of
 // two, tcgen05.mma.cta_group::2) per 256 x 240 tile pair; g_tc_cfg = pipeline geometry of the pair kernel
 int g_tc_impl = 2;
@@ -1297,6 +1301,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   int* flags = reinterpret_cast<int*>(w + L.flags_off);
   int* hsum = reinterpret_cast<int*>(w + L.hsum_off);
 
+  if (g_tc_timing) PF_CUDA(cudaEventRecord(g_tc_ev[0], s));
   PF_CUDA(cudaMemsetAsync(flags, 0, 256, s));
   PF_CUDA(cudaMemsetAsync(hsum, 0, static_cast<size_t>(L.m[0].splits * L.hsum_ld) * 4, s));
   {
@@ -1322,6 +1327,7 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     if (h_flags != 0) return PF_OK;  // *h_used stays 0, nothing was added to d_counts
   }
 
+  if (g_tc_timing) PF_CUDA(cudaEventRecord(g_tc_ev[1], s));
   TcParams P;
   P.stream = nib4;
   P.n_tiles_padded = L.n_tiles_padded;
@@ -1349,7 +1355,26 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     if (g_tc_impl == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
     else PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }
+  if (g_tc_timing) PF_CUDA(cudaEventRecord(g_tc_ev[2], s));
   *h_used = 1;
+  return PF_OK;
+  PF_TRY_END
+}
+
+// Diagnostic: enable != 0 makes later pf_pair_counts_tc calls record CUDA events on their stream around the
+// operand-stream conversion and around the GEMM launch(es); with h_ms2 != NULL the call first waits for the
+// last recorded call and returns h_ms2[0] = conversion ms, h_ms2[1] = GEMM ms (both launches when two ran).
+PF_API int pf_pair_counts_tc_timing(int enable, float* h_ms2) {
+  PF_TRY_BEGIN
+  if (h_ms2) {
+    if (!g_tc_ev[0]) return pf_fail("pf_pair_counts_tc_timing: timing was never enabled");
+    PF_CUDA(cudaEventSynchronize(g_tc_ev[2]));
+    PF_CUDA(cudaEventElapsedTime(&h_ms2[0], g_tc_ev[0], g_tc_ev[1]));
+    PF_CUDA(cudaEventElapsedTime(&h_ms2[1], g_tc_ev[1], g_tc_ev[2]));
+  }
+  if (enable && !g_tc_ev[0])
+    for (int i = 0; i < 3; ++i) PF_CUDA(cudaEventCreate(&g_tc_ev[i]));
+  g_tc_timing = enable != 0;
   return PF_OK;
   PF_TRY_END
 }
