@@ -34,6 +34,8 @@
 #include "pf_common.cuh"
 #include "umma.cuh"
 
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
 namespace {
 
 constexpr int TC_I = 128;            // rows of the accumulator tile (MMA M); the A operand lives in TMEM
@@ -185,6 +187,10 @@ struct TcParams {
                           // V and VV - TT to the mode-1 launch; mode 1 exits at once when it is 0.
   int debug;              // timing experiments (results are wrong): 1 = MMAs do not wait for operands,
                           // 2 = expansion warps do no work, 4 = no MMAs are issued
+  // CTA-pair kernel with TMAP: the stream as a 3-D tensor [step][row group of 8 samples][256 bytes]; boxes of
+  // GROUP steps x 16 (A) / J / 16 (B) row groups, so that ONE request per operand fetches a whole stage
+  alignas(64) CUtensorMap tm_a;
+  alignas(64) CUtensorMap tm_b;
 };
 
 // block-scaled instruction descriptor (bit layout: CUTLASS cute/arch/mma_sm100_desc.hpp,
@@ -632,11 +638,18 @@ template <int CFG> struct Tc2Cfg;
 // from the raw ring; the A-row warps then only derive plane 1 (LDS -> tensor or shared memory) and never have
 // global loads in flight across a proxy fence (fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
 // and the MEMBAR waits for the register prefetch of the following stages).
-template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true; };
-template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = false, A_TMA = false; };
-template <> struct Tc2Cfg<2> { static constexpr int J = 240, GROUP = 5, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = true, A_TMA = true; };
-template <> struct Tc2Cfg<3> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = false; };
-constexpr int tc2_cols(int cfg) { return cfg == 1 ? Tc2Cfg<1>::J : cfg == 2 ? Tc2Cfg<2>::J : cfg == 3 ? Tc2Cfg<3>::J : Tc2Cfg<0>::J; }
+// TMAP: the raw stages are filled by two tensor-map copies per STAGE (cp.async.bulk.tensor.3d, a box of GROUP
+// steps) instead of two bulk copies per STEP: the TMA unit retires about one request per 128 clocks whatever
+// its size, and two requests per 64-site step put a floor of ~256 clocks under a step that needs 208 of MMAs.
+template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true, TMAP = true; };
+template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = false, A_TMA = false, TMAP = false; };
+template <> struct Tc2Cfg<2> { static constexpr int J = 240, GROUP = 5, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = true, A_TMA = true, TMAP = false; };
+template <> struct Tc2Cfg<3> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = false, TMAP = false; };
+template <> struct Tc2Cfg<4> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true, TMAP = false; };
+constexpr int TC2_CFGS = 5;
+constexpr int tc2_cols(int cfg) { return cfg == 1 ? Tc2Cfg<1>::J : cfg == 2 ? Tc2Cfg<2>::J : cfg == 3 ? Tc2Cfg<3>::J : cfg == 4 ? Tc2Cfg<4>::J : Tc2Cfg<0>::J; }
+constexpr int tc2_group(int cfg) { return cfg == 1 ? Tc2Cfg<1>::GROUP : cfg == 2 ? Tc2Cfg<2>::GROUP : cfg == 3 ? Tc2Cfg<3>::GROUP : cfg == 4 ? Tc2Cfg<4>::GROUP : Tc2Cfg<0>::GROUP; }
+constexpr bool tc2_tmap(int cfg) { return cfg == 0 ? Tc2Cfg<0>::TMAP : false; }
 template <int CFG> struct Tc2Geo {
   using C = Tc2Cfg<CFG>;
   static constexpr int J = C::J, JH = C::J / 2;
@@ -647,9 +660,16 @@ template <int CFG> struct Tc2Geo {
   static constexpr bool A_TMA = C::A_TMA;
   static constexpr int A_PLANE_BYTES = TC2_IH * 32;                         // 4096
   static constexpr int B_STEP_BYTES = JH * 32;                              // the B rows of a step
-  static constexpr int RAW_B_OFF = A_TMA ? A_PLANE_BYTES : 0;               // raw step: [A rows (A_TMA)][B rows]
+  static constexpr bool TMAP = C::TMAP;
+  static constexpr int RAW_B_OFF = A_TMA ? A_PLANE_BYTES : 0;               // bulk copies: a raw step is [A rows (A_TMA)][B rows]
   static constexpr int RAW_STEP_BYTES = RAW_B_OFF + B_STEP_BYTES;
   static constexpr int RAW_STAGE_BYTES = GROUP * RAW_STEP_BYTES;
+  // where the A / B rows of step j of a raw stage are: bulk copies interleave them per step, the two tensor-map
+  // boxes of a stage land as [A rows of GROUP steps][B rows of GROUP steps]
+  static constexpr int RAW_A_STRIDE = TMAP ? A_PLANE_BYTES : RAW_STEP_BYTES;
+  static constexpr int RAW_B_BASE = TMAP ? GROUP * A_PLANE_BYTES : RAW_B_OFF;
+  static constexpr int RAW_B_STRIDE = TMAP ? B_STEP_BYTES : RAW_STEP_BYTES;
+  static_assert(!TMAP || (A_TMA && B_STEP_BYTES % 128 == 0), "tensor-map boxes land on 128-byte boundaries");
   static constexpr int A_PLANES_SMEM = (A_TMA ? 0 : 1) + (AH_TMEM ? 0 : 1);   // A planes the expansion warps write to shared memory
   static constexpr int EXP_A1_OFF = A_TMA ? 0 : A_PLANE_BYTES;              // expanded step: [A plane 0 (!A_TMA)][A plane 1 (!AH_TMEM)][B plane 1]
   static constexpr int EXP_STEP_BYTES = A_PLANES_SMEM * A_PLANE_BYTES + B_STEP_BYTES;
@@ -704,7 +724,7 @@ template <int N> struct RingPos {
 
 template <int MODE, int CFG, bool PROF>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Geo<CFG>::THREADS, 1)
-pair_counts_tc2_kernel(const TcParams P) {
+pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
   using G = Tc2Geo<CFG>;
   constexpr int J = G::J, JH = G::JH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -780,6 +800,17 @@ pair_counts_tc2_kernel(const TcParams P) {
           freed.advance();
         }
         const int kw = min(G::GROUP, n_steps - g * G::GROUP);
+        if (G::TMAP) {
+          // one box of GROUP steps per operand (steps past the end of the stream are zero-filled, steps past
+          // this CTA's range are loaded and not used): the transaction count is always the full boxes
+          const uint32_t dst = raw_a + stage * G::RAW_STAGE_BYTES;
+          const int step0 = static_cast<int>(s_begin) + g * G::GROUP;
+          umma::mbar_expect_tx_a(raw_full_a + stage * 8, G::RAW_STAGE_BYTES);
+          umma::tensor_g2s_3d(dst, &P.tm_a, 0, static_cast<int>(a_row0 >> 3), step0, raw_full_a + stage * 8);
+          umma::tensor_g2s_3d(dst + G::RAW_B_BASE, &P.tm_b, 0, static_cast<int>(b_row0 >> 3), step0, raw_full_a + stage * 8);
+          if (++stage == G::RAW) stage = 0;
+          continue;
+        }
         umma::mbar_expect_tx_a(raw_full_a + stage * 8, kw * G::RAW_STEP_BYTES);
 #pragma unroll
         for (int j = 0; j < G::GROUP; ++j) {
@@ -817,8 +848,9 @@ pair_counts_tc2_kernel(const TcParams P) {
         for (int j = 0; j < G::GROUP; ++j) {
           if (full || j < kw) {
             const uint32_t acc = j > 0 ? 1u : first_acc;
-            const uint32_t ex = e_lo + j * (G::EXP_STEP_BYTES >> 4), rw = r_lo + j * (G::RAW_STEP_BYTES >> 4);
-            umma::mma_mxf4_ss_2cta(tmem + 0 * J, desc_at(G::A_TMA ? rw : ex), desc_at(rw + (G::RAW_B_OFF >> 4)), idesc, acc, tsfa, tsfb);   // XX / TT
+            const uint32_t ex = e_lo + j * (G::EXP_STEP_BYTES >> 4);
+            const uint32_t ra = r_lo + j * (G::RAW_A_STRIDE >> 4), rb = r_lo + ((G::RAW_B_BASE + j * G::RAW_B_STRIDE) >> 4);
+            umma::mma_mxf4_ss_2cta(tmem + 0 * J, desc_at(G::A_TMA ? ra : ex), desc_at(rb), idesc, acc, tsfa, tsfb);   // XX / TT
             const uint64_t b1 = desc_at(ex + ((G::A_PLANES_SMEM * G::A_PLANE_BYTES) >> 4));
             if (G::AH_TMEM) umma::mma_mxf4_ts_2cta(tmem + 1 * J, ta + j * TMEM_A_COLS, b1, idesc, acc, tsfa, tsfb);
             else umma::mma_mxf4_ss_2cta(tmem + 1 * J, desc_at(ex + (G::EXP_A1_OFF >> 4)), b1, idesc, acc, tsfa, tsfb);                   // HH / VV
@@ -909,7 +941,7 @@ pair_counts_tc2_kernel(const TcParams P) {
         for (int j = 0; j < G::GROUP; ++j) {
 #pragma unroll
           for (int q = 0; q < NU; ++q)
-            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_STEP_BYTES + q * 128);
+            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_A_STRIDE + q * 128);
         }
 #pragma unroll
         for (int j = 0; j < G::GROUP; ++j) {
@@ -934,7 +966,7 @@ pair_counts_tc2_kernel(const TcParams P) {
       for (int g = 0; g < n_groups; ++g) {
         stage_begin(g);
         if (g >= G::EXP && G::AH_TMEM) umma::fence_after_thread_sync();   // the MMAs that read these TMEM columns have completed
-        const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+        const int kw = (P.debug & (16 | 512)) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
         if (kw == G::GROUP) derive_stage(true, kw);
         else derive_stage(false, kw);
         stage_end(!G::AH_TMEM, G::AH_TMEM);     // tensor-memory stores need no proxy fence
@@ -1019,7 +1051,7 @@ pair_counts_tc2_kernel(const TcParams P) {
         r = 0;
         kh = 0;
       }
-      const uint32_t raw_row = raw_a + G::RAW_B_OFF + unit_off(r, kh);
+      const uint32_t raw_row = raw_a + G::RAW_B_BASE + unit_off(r, kh);
       const uint32_t exp_row = exp_a + unit_off(r, kh) + G::A_PLANES_SMEM * G::A_PLANE_BYTES;
       auto expand_stage = [&](const bool full, int kw) {
         const uint32_t src0 = raw_row + stage * G::RAW_STAGE_BYTES;
@@ -1029,7 +1061,7 @@ pair_counts_tc2_kernel(const TcParams P) {
         for (int j = 0; j < G::GROUP; ++j) {
 #pragma unroll
           for (int q = 0; q < NU; ++q)
-            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_STEP_BYTES + q * 128);
+            if (full || j < kw) u[j * NU + q] = umma::lds128(src0 + j * G::RAW_B_STRIDE + q * 128);
         }
 #pragma unroll
         for (int j = 0; j < G::GROUP; ++j) {
@@ -1045,7 +1077,7 @@ pair_counts_tc2_kernel(const TcParams P) {
       };
       for (int g = 0; g < n_groups; ++g) {
         stage_begin(g);
-        const int kw = (P.debug & 16) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
+        const int kw = (P.debug & (16 | 1024)) ? 0 : min(G::GROUP, n_steps - g * G::GROUP);
         if (active) {
           if (kw == G::GROUP) expand_stage(true, kw);
           else expand_stage(false, kw);
@@ -1209,6 +1241,23 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
       }
       splits = best_s;
     }
+    if (pair_kernel) {
+      // CTA-pair kernel: every work item pays ~0.19 ms outside its main loop (allocation, two cluster barriers, the
+      // drain of the last stage and 160 K scattered int32 atomics per CTA), as much as ~1,400 pipeline steps, and
+      // 18 splits of 3,000 x 10M spent 14 % of the launch there. Time = waves x (steps per item + that overhead):
+      // take the split count that minimises it (3,000 x 10M: 3 splits = 3.97 waves instead of 18 = 23.8).
+      const double overhead_steps = 1400.0;
+      const double steps = static_cast<double>((n_local + 1) / 2);
+      double best = 1e300;
+      for (int64_t c = 1; c <= 64; ++c) {
+        const double waves = static_cast<double>(pf_ceil_div(c * M.pairs, static_cast<int64_t>(sms)));
+        const double cost = waves * (steps / static_cast<double>(c) + overhead_steps);
+        if (cost < best * 0.999) {
+          best = cost;
+          splits = c;
+        }
+      }
+    }
     const int64_t max_splits = pf_ceil_div(n_local, 64);
     if (splits > max_splits) splits = max_splits;
     const int64_t min_splits = pf_ceil_div(n_local, MAX_WORDS_PER_CTA);   // fp32 accumulators stay exact
@@ -1240,6 +1289,34 @@ cudaError_t tc_launch(const TcParams& P, int64_t grid, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TcEncodeTiledFn tc_encode_fn() {
+  static TcEncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TcEncodeTiledFn>(p);
+  }
+  return fn;
+}
+// the operand stream as [step][row group][256 B], box = `steps` x `row_groups` x 256 B
+bool tc_make_tensor_map(CUtensorMap* tm, const void* stream, int64_t n_tiles_padded, int64_t n_steps, int row_groups, int steps) {
+  TcEncodeTiledFn fn = tc_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {256, static_cast<cuuint64_t>(n_tiles_padded * 8), static_cast<cuuint64_t>(n_steps)};
+  const cuuint64_t strides[2] = {256, static_cast<cuuint64_t>(n_tiles_padded) * CHUNK_BYTES};
+  const cuuint32_t box[3] = {256, static_cast<cuuint32_t>(row_groups), static_cast<cuuint32_t>(steps)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(stream), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int MODE, int CFG>
 cudaError_t tc2_launch_cfg(const TcParams& P, int64_t items, cudaStream_t s) {
   using G = Tc2Geo<CFG>;
@@ -1255,6 +1332,7 @@ cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s) {
     case 1: return tc2_launch_cfg<MODE, 1>(P, items, s);
     case 2: return tc2_launch_cfg<MODE, 2>(P, items, s);
     case 3: return tc2_launch_cfg<MODE, 3>(P, items, s);
+    case 4: return tc2_launch_cfg<MODE, 4>(P, items, s);
     default: return tc2_launch_cfg<MODE, 0>(P, items, s);
   }
 }
@@ -1265,7 +1343,7 @@ cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s) {
 // tiles, default); cfg = pipeline geometry of the pair kernel (0..3). Affects later pf_pair_counts_tc* calls
 // (the workspace layout depends on it: query pf_pair_counts_tc_work_bytes again).
 PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg) {
-  if ((impl != 1 && impl != 2) || cfg < 0 || cfg > 3) return pf_fail("pf_pair_counts_tc_set_impl: bad arguments");
+  if ((impl != 1 && impl != 2) || cfg < 0 || cfg >= TC2_CFGS) return pf_fail("pf_pair_counts_tc_set_impl: bad arguments");
   g_tc_impl = impl;
   g_tc_cfg = cfg;
   return PF_OK;
@@ -1352,6 +1430,12 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     P.words_per_split = static_cast<int>(M.words_per_split);
     const int64_t grid = M.splits * M.pairs;
     if (grid > 0x3fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
+    if (g_tc_impl == 2 && tc2_tmap(g_tc_cfg)) {
+      const int J2 = tc2_cols(g_tc_cfg), G2 = tc2_group(g_tc_cfg);
+      if (!tc_make_tensor_map(&P.tm_a, P.stream, L.n_tiles_padded, L.n_steps, TC2_IH / 8, G2) ||
+          !tc_make_tensor_map(&P.tm_b, P.stream, L.n_tiles_padded, L.n_steps, J2 / 16, G2))
+        return pf_fail_code(PF_ERR_CUDA, "pf_pair_counts_tc: cuTensorMapEncodeTiled failed or is unavailable");
+    }
     if (g_tc_impl == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
     else PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }

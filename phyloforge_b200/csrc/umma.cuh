@@ -179,6 +179,13 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32
       "l"(src), "r"(bytes), "r"(bar)
       : "memory");
 }
+// one box of a 3-D tensor map (global -> this CTA's shared memory), completion counted in bytes on `bar`
+__device__ __forceinline__ void tensor_g2s_3d(uint32_t dst, const void* tensor_map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tensor_map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));

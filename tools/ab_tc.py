@@ -78,11 +78,16 @@ for impl, cfg, dbg in cfgs:
         ts.append(e0.elapsed_time(e1))
     buf = (C.c_longlong * 16)()
     eng.lib.pf_pair_counts_tc_profile(1 | (dbg << 4), None)
+    check(eng.lib.pf_pair_counts_tc_timing(1, None))
     eng.pair_counts(planes, n, nw, counts, variant=3)
     torch.cuda.synchronize()
+    ms2 = (C.c_float * 2)()
+    check(eng.lib.pf_pair_counts_tc_timing(0, ms2))
     eng.lib.pf_pair_counts_tc_profile(0, buf)
     v = list(buf)
     steps = max(v[8], 1)
     print(f"impl={impl} cfg={cfg} dbg={dbg} n={n} m={m}: counts (conversion + GEMM) {min(ts):.2f} ms (all {[round(t, 2) for t in ts]}), same as first={same}; "
           f"per step: MMA thread {v[1] / steps:.0f} clk, waiting {v[0] / steps:.0f}; A warp {v[4] / steps:.0f}, waiting {v[3] / steps:.0f}; "
-          f"B warp {v[11] / steps:.0f}, waiting {v[10] / steps:.0f} (expansion warps of CTA rank {(dbg >> 6) & 1})", flush=True)
+          f"B warp {v[11] / steps:.0f}, waiting {v[10] / steps:.0f} (expansion warps of CTA rank {(dbg >> 6) & 1}); "
+          f"instrumented run: conversion {ms2[0]:.2f} ms, GEMM {ms2[1]:.2f} ms, MMA-thread loop time summed over items / pairs = "
+          f"{v[1] / 74 / 1.965e6:.2f} ms", flush=True)
