@@ -887,12 +887,15 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
     // per instruction: the expansion warps, not the memory system, were what the MMAs waited for) =====
     constexpr int NU = G::NU;
     constexpr int NR = G::GROUP * NU;
-    long long t_wait = 0;
+    long long t_wait = 0, t_fence = 0, t_end = 0;
     const long long t_start = PROF ? clock64() : 0;
     // Stage hand-over inside a CTA goes through hardware named barriers: ONE thread polls the mbarriers (raw
     // data landed, stage slot free) and ONE thread arrives on the leader's exp_full. With every expansion warp
     // polling and arriving on the mbarriers themselves (30 arrivals per stage on one barrier word that the
     // MMA thread polls) an arrive took ~400 clocks.
+    // (Releasing the first three steps of a stage slot early - a second commit per stage, the expansion warps
+    // refilling that half while the rest is still being multiplied - was measured and is slower: 296 vs 264
+    // clocks per step; the extra barrier round costs more than the overlap gains.)
     constexpr int EXP_THREADS = G::EXP_WARPS * 32;
     int stage = 0, e = 0;
     uint32_t raw_phase = 0;
@@ -912,8 +915,14 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
         umma::tmem_wait_st();
         umma::fence_before_thread_sync();
       }
+      const long long tf = PROF ? clock64() : 0;
       if (wrote_smem) umma::fence_proxy_async_smem();    // generic-proxy operand writes -> the tensor cores' async proxy
+      const long long tb = PROF ? clock64() : 0;
       asm volatile("bar.sync 3, %0;" ::"r"(EXP_THREADS) : "memory");
+      if (PROF) {
+        t_fence += tb - tf;
+        t_end += clock64() - tb;
+      }
       if (tid == 0) {
         if (strict) umma::mbar_arrive_cluster(exp_full_leader + e * 8);
         else if (rank == 0) umma::mbar_arrive_a(exp_full_a + e * 8);
@@ -1089,6 +1098,8 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
       const int o = warp == 0 ? 2 : 9;           // [3], [4]: an A-row warp waiting / total; [10], [11]: a B-row warp
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 1]), static_cast<unsigned long long>(t_wait));
       atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[o + 2]), static_cast<unsigned long long>(clock64() - t_start));
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 12 : 14]), static_cast<unsigned long long>(t_fence));   // proxy fence
+      atomicAdd(reinterpret_cast<unsigned long long*>(&g_tc_prof[warp == 0 ? 13 : 15]), static_cast<unsigned long long>(t_end));     // end-of-stage barrier
     }
     const bool uniform = (MODE == 0) && !general;
     if (uniform) {

@@ -89,5 +89,6 @@ for impl, cfg, dbg in cfgs:
     print(f"impl={impl} cfg={cfg} dbg={dbg} n={n} m={m}: counts (conversion + GEMM) {min(ts):.2f} ms (all {[round(t, 2) for t in ts]}), same as first={same}; "
           f"per step: MMA thread {v[1] / steps:.0f} clk, waiting {v[0] / steps:.0f}; A warp {v[4] / steps:.0f}, waiting {v[3] / steps:.0f}; "
           f"B warp {v[11] / steps:.0f}, waiting {v[10] / steps:.0f} (expansion warps of CTA rank {(dbg >> 6) & 1}); "
+          f"proxy fence A {v[12] / steps:.0f} B {v[14] / steps:.0f}, end-of-stage barrier A {v[13] / steps:.0f} B {v[15] / steps:.0f}; "
           f"instrumented run: conversion {ms2[0]:.2f} ms, GEMM {ms2[1]:.2f} ms, MMA-thread loop time summed over items / pairs = "
           f"{v[1] / 74 / 1.965e6:.2f} ms", flush=True)
