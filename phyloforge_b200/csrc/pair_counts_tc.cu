@@ -185,8 +185,11 @@ struct TcParams {
   int64_t hsum_ld;
   const int* flags;       // flags[0] != 0: sample-specific missingness (set by the converter). Mode 0 then leaves
                           // V and VV - TT to the mode-1 launch; mode 1 exits at once when it is 0.
-  int debug;              // timing experiments (results are wrong): 1 = MMAs do not wait for operands,
-                          // 2 = expansion warps do no work, 4 = no MMAs are issued
+  int debug;              // single-CTA kernel, profile build only (results are wrong): 1 = MMAs do not wait for operands,
+                          // 2 = expansion warps do no work, 4 = no MMAs are issued. CTA-pair kernel: 1 = every hand-over
+                          // with a cluster-scope release ("strict", results identical); timing experiments with wrong
+                          // results: 16 = expansion warps do no work, 32 = no A-row loads, 64 = profile the peer CTA,
+                          // 256 = no wait for the raw data
   // CTA-pair kernel with TMAP: the stream as a 3-D tensor [step][row group of 8 samples][256 bytes]; boxes of
   // GROUP steps x 16 (A) / J / 16 (B) row groups, so that ONE request per operand fetches a whole stage
   alignas(64) CUtensorMap tm_a;
@@ -1204,11 +1207,43 @@ cudaEvent_t g_tc_ev[3] = {nullptr, nullptr, nullptr};
 int g_tc_impl = 2;
 int g_tc_cfg = 0;
 
+// CTA pairs of the default pair-kernel geometry the device runs at once (B200: 74, one per TPC); -1 when the
+// query itself fails (no device: plans are still computed), 0 when the device cannot co-schedule the cluster
+int tc2_cluster_slots() {
+  static int cached_dev = -1, cached = -1;
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev == cached_dev) return cached;
+  using G = Tc2Geo<0>;
+  auto kernel = pair_counts_tc2_kernel<0, 0, false>;
+  int n = -1;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM)) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2, 1, 1);
+    cfg.blockDim = dim3(G::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = G::SMEM;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess) n = -1;
+  }
+  cudaGetLastError();   // a failed query must not poison later calls
+  cached_dev = dev;
+  cached = n;
+  return n;
+}
+// the GEMM kernel that will run: the CTA-pair kernel unless it was switched off or the device cannot run clusters of two
+int tc_effective_impl() { return (g_tc_impl == 2 && tc2_cluster_slots() != 0) ? 2 : 1; }
+
 TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   TcPlan L;
   L.n_local = n_local;
   L.n_tiles = pf_ceil_div(n_samples, PF_TILE);
-  const bool pair_kernel = g_tc_impl == 2;
+  const bool pair_kernel = tc_effective_impl() == 2;
   L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, pair_kernel ? TC2_I : TC_I));
   const int widths[2] = {TcCfg<0>::J, TcCfg<1>::J};
   L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
@@ -1217,7 +1252,8 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
     const int64_t rows = static_cast<int64_t>(TC2_I) * L.n_itiles;
     const int J2 = tc2_cols(g_tc_cfg);
     L.n_tiles_padded = pf_ceil_div(rows > n_samples + J2 ? rows : n_samples + J2, PF_TILE);
-    sms /= 2;                                    // work items run on CTA pairs
+    const int slots = tc2_cluster_slots();
+    sms = slots > 0 ? slots : sms / 2;           // work items run on CTA pairs
     if (sms < 1) sms = 1;
   }
   for (int mode = 0; mode < 2; ++mode) {
@@ -1441,13 +1477,13 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     P.words_per_split = static_cast<int>(M.words_per_split);
     const int64_t grid = M.splits * M.pairs;
     if (grid > 0x3fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
-    if (g_tc_impl == 2 && tc2_tmap(g_tc_cfg)) {
+    if (tc_effective_impl() == 2 && tc2_tmap(g_tc_cfg)) {
       const int J2 = tc2_cols(g_tc_cfg), G2 = tc2_group(g_tc_cfg);
       if (!tc_make_tensor_map(&P.tm_a, P.stream, L.n_tiles_padded, L.n_steps, TC2_IH / 8, G2) ||
           !tc_make_tensor_map(&P.tm_b, P.stream, L.n_tiles_padded, L.n_steps, J2 / 16, G2))
         return pf_fail_code(PF_ERR_CUDA, "pf_pair_counts_tc: cuTensorMapEncodeTiled failed or is unavailable");
     }
-    if (g_tc_impl == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
+    if (tc_effective_impl() == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
     else PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }
   if (g_tc_timing) PF_CUDA(cudaEventRecord(g_tc_ev[2], s));
