@@ -273,8 +273,8 @@ def test_host_buffer_path_matches_resident_path(engine):
         assert np.array_equal(got.dist_host, want.dist.cpu().numpy()) and got.d2h_bytes > 0
 
 
-@pytest.fixture(params=[(2, 0, False), (2, 1, False), (2, 2, False), (2, 3, False), (2, 0, True), (1, 0, False)],
-                ids=["pair", "pair-j240-regs", "pair-j240-tma", "pair-j208-regs", "pair-strict", "single-cta"])
+@pytest.fixture(params=[(2, 0, False), (2, 1, False), (2, 2, False), (2, 3, False), (2, 4, False), (2, 0, True), (1, 0, False)],
+                ids=["pair", "pair-j240-regs", "pair-j240-tma", "pair-j208-regs", "pair-bulk-copies", "pair-strict", "single-cta"])
 def tc_impl(engine, request):
     """Every GEMM kernel behind pf_pair_counts_tc: the CTA-pair kernel (default geometry, the alternatives, and
     with cluster-scope release on the hand-over) and the single-CTA kernel."""
@@ -282,6 +282,23 @@ def tc_impl(engine, request):
     engine.set_tc_impl(impl, cfg, strict)
     yield request.param
     engine.set_tc_impl()
+
+
+@pytest.mark.parametrize("n,k", [(32, 64), (208, 256), (240, 1024), (256, 128)])
+def test_cta_pair_mma_instruction_is_exact(engine, n, k):
+    """tcgen05.mma.cta_group::2 kind::mxf4 on one CTA pair (256 x n x k, E2M1 operands, operands written by
+    generic-proxy stores in both CTAs, remote arrive, multicast commit) == integer dot products."""
+    from phyloforge_b200._lib import check
+    rng = np.random.default_rng(n * 1000 + k)
+    vals = np.array([-6, -4, -3, -2, -1, 0, 1, 2, 3, 4, 6], dtype=np.int8) if k <= 128 else np.array([-1, 0, 1], dtype=np.int8)
+    a = rng.choice(vals, size=(256, k))
+    b = rng.choice(vals, size=(n, k))
+    da, db = torch.from_numpy(a).to(engine.device), torch.from_numpy(b).to(engine.device)
+    dc = torch.full((256, n), -7.0, dtype=torch.float32, device=engine.device)
+    check(engine.lib.pf_selftest_umma_fp4_2cta(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k,
+                                               torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(dc.cpu().numpy().astype(np.int64), a.astype(np.int64) @ b.astype(np.int64).T)
 
 
 @pytest.mark.parametrize("n,m", [(2, 40), (130, 5000), (256, 4096), (257, 4100), (300, 70000), (700, 20000)])
