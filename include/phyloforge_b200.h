@@ -210,7 +210,8 @@ PF_API int pf_pair_counts_tc_profile(int enable, long long* h_out16);
 
 /* Diagnostic / A-B switch for pf_pair_counts_tc: impl 1 = the single-CTA GEMM kernel (128 x 192 sample
  * tiles), impl 2 = the CTA-pair kernel (cluster of two CTAs, tcgen05.mma.cta_group::2, 256 x 240 tiles;
- * the default); cfg 0..3 = pipeline geometry of the pair kernel. The workspace layout depends on impl:
+ * the default); cfg 0..4 = tile width / pipeline geometry of the pair kernel (0 = default: 256 x 208 tiles, A rows
+ * by TMA tensor-map copies, one A plane in tensor memory). The workspace layout depends on impl and cfg:
  * query pf_pair_counts_tc_work_bytes again after changing it. Results are identical. */
 PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg);
 

@@ -601,38 +601,42 @@ pair_counts_tc_kernel(const TcParams P) {
 }
 
 // ------------------------------------------------------------------ the CTA-pair GEMM kernel
-// tcgen05.mma.cta_group::2: a cluster of two CTAs (the two SMs of a TPC) works on one 256 x 240 sample tile
-// pair. Each CTA holds 128 A rows and 120 B rows of every step in its own shared memory and accumulates its
-// 128 rows x 240 columns in its own tensor memory; the leader CTA (cluster rank 0) issues the instructions
-// for both. Measured (pf_probe_umma_fp4_2cta_rate): the pair instruction takes 0.5 clocks per B column (120
-// clocks for 256 x 240 x 64) where the single-CTA one takes 147 clocks for any N <= 256, and every SM
-// expands 248 sample rows per 128 x 240 x 64 MACs instead of 320 per 128 x 192 x 64 and reads 7.75 KB
-// instead of 10 KB per step from L2.
-// Per CTA: warps 0-3 = the 128 A rows (stream -> registers, two stages ahead -> both A planes to shared
-// memory), warps 4-7 = the 120 B rows (raw ring -> derived plane to shared memory), warp 8 = TMA producer
-// (its B rows), warp 9 = MMA issuer (leader only).
-// Hand-over. Operands ready: every expansion warp of both CTAs arrives on the LEADER's exp_full barrier after
-// its operand writes and a generic->async proxy fence; the peer's warps use a remote arrive. Stage consumed:
-// ONE multicast commit per stage on a ring of stage_done barriers in both CTAs; the expansion warps (reuse of
-// the expanded stage EXP stages later) and the TMA producer (reuse of the raw stage RAW stages later) wait on
-// the same ring, whose depth max(RAW, EXP) keeps a waiter at most one phase behind. (A commit costs the
-// issuing thread ~200 clocks during which no MMA is issued; the first version had two per stage.)
+// tcgen05.mma.cta_group::2: a cluster of two CTAs (the two SMs of a TPC) works on one 256 x J sample tile pair
+// (default J = 208). Each CTA holds 128 A rows and J / 2 B rows of every 64-site step in its own shared memory and
+// accumulates its 128 rows x J columns (two products) in its own tensor memory; the leader CTA (cluster rank 0)
+// issues the instructions for both. Measured (pf_probe_umma_fp4_2cta_rate): the pair instruction takes 0.5
+// clocks per B column (120 clocks for 256 x 240 x 64, the nominal fp4 rate) where the single-CTA one takes 147
+// clocks for any N <= 256, and every SM fetches and expands only half of the B tile.
+// Default data flow per CTA (the Tc2Cfg flags below select the alternatives that the tests also run):
+//   TMA producer (1 thread): two tensor-map copies per stage - the 128 A rows and the J / 2 B rows of GROUP steps -
+//     into a ring of RAW raw stages. Plane 0 of both operands (x / t) is read by the MMAs straight from there.
+//   A-row warps (2 threads per row): LDS raw -> plane 1 (h / v) -> TENSOR memory (tcgen05.st): no shared-memory
+//     write, no proxy fence, no operand read from shared memory for the A side of the second product.
+//   B-row warps (2 threads per row): LDS raw -> plane 1 -> shared memory (ring of EXP expanded stages).
+//   MMA issuer (leader CTA, 1 thread): per step XX += A_x(raw) B_x(raw), HH += A_h(TMEM) B_h(expanded); one
+//     multicast commit per stage.
+// Hand-over. Inside a CTA through hardware named barriers: thread 0 polls the mbarriers (raw data landed, stage
+// slot free) and releases the expansion warps with bar.sync; after the stage's writes (tcgen05.wait::st +
+// tcgen05.fence / fence.proxy.async) another bar.sync, and thread 0 arrives on the LEADER's exp_full barrier (count
+// 2: one arrival per CTA; the peer's is a remote arrive). Stage consumed: ONE multicast tcgen05.commit per stage on
+// a ring of stage_done barriers in both CTAs; the expansion warps (reuse of the expanded stage EXP stages later)
+// and the TMA producer (reuse of the raw stage RAW stages later) wait on the same ring, whose depth max(RAW, EXP)
+// keeps a waiter at most one phase behind.
 // Memory-model note: the remote arrive is the default `mbarrier.arrive.shared::cluster` (release at CTA
 // scope), as in CUTLASS's ClusterBarrier::arrive. The PTX model would ask for `.release.cluster`; that
-// compiles to MEMBAR.ALL.GPU, which stalls the SM's whole memory pipeline: with it in every expansion warp
-// the kernel runs at 665 instead of ~400 clocks per step. The data in question is shared memory written by
-// STS and made visible to the async proxy by FENCE.VIEW.ASYNC before the arrive leaves the SM, so nothing is
-// in flight that the heavier fence could order; TcParams::debug bit 0 selects the strict form for A/B runs
-// (tests/test_gpu_kernels.py runs both and compares them bit for bit).
-// B tiles of A block ti start at its first row (256 ti + 240 k), so only the first tile of a block straddles
-// the diagonal.
+// compiles to MEMBAR.ALL.GPU, which stalls the SM's whole memory pipeline (563 instead of 263 clocks per step even
+// with one such arrive per CTA and stage). The data in question is shared / tensor memory written by STS /
+// tcgen05.st and completed (FENCE.VIEW.ASYNC, tcgen05.wait::st) before the arrive leaves the SM, so nothing is in
+// flight that the heavier fence could order; TcParams::debug bit 0 selects the strict form
+// (tests/test_gpu_kernels.py runs both and compares them with the oracle bit for bit).
+// B tiles of A block ti start at its first row (256 ti + J k), so only the first tile of a block straddles
+// the diagonal. profiles/r01_mma_probe.md lists the variants that were measured on the way.
 constexpr int TC2_I = 256, TC2_IH = 128;     // rows per pair / per CTA
-// Geometry. J = columns of the pair's tile (each CTA supplies J / 2 B rows). Shared-memory bandwidth is what
-// bounds this kernel (ncu, J = 240 with both A planes in shared memory: LSU wavefronts 46 % + tensor-core
-// operand reads 27 % of the peak, tensor pipe 53 % active at 423 clocks per step), so with AH_TMEM the
-// derived A plane (h / v) goes to TENSOR memory (tcgen05.st, no shared-memory write, no operand read): the
-// 16 accumulator + 16 scale-factor columns leave 512 - 2 J - 16 columns for EXP x GROUP steps of 8 columns,
-// which is what limits J to 208 there.
+// Geometry. J = columns of the pair's tile (each CTA supplies J / 2 B rows). With both A planes in shared memory
+// (J = 240) the shared-memory data pipe was the bound (ncu: LSU wavefronts 46 % + tensor-core operand reads 27 %
+// of the peak, tensor pipe 53 % active at 423 clocks per step), so with AH_TMEM the derived A plane (h / v) goes
+// to TENSOR memory: the 2 J accumulator and 16 scale-factor columns leave 512 - 2 J - 16 columns for EXP x GROUP
+// steps of 8 columns, which is what limits J to 208 there.
 template <int CFG> struct Tc2Cfg;
 // SPLIT: two threads per sample row (one per 32-site half of a step) instead of one: the per-stage latency
 // chain of an expansion warp (wake-up, loads, stores, fences, arrive) is what the MMAs wait for, and it
@@ -642,8 +646,8 @@ template <int CFG> struct Tc2Cfg;
 // global loads in flight across a proxy fence (fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC,
 // and the MEMBAR waits for the register prefetch of the following stages).
 // TMAP: the raw stages are filled by two tensor-map copies per STAGE (cp.async.bulk.tensor.3d, a box of GROUP
-// steps) instead of two bulk copies per STEP: the TMA unit retires about one request per 128 clocks whatever
-// its size, and two requests per 64-site step put a floor of ~256 clocks under a step that needs 208 of MMAs.
+// steps) instead of two bulk copies per STEP (the TMA unit retires about one request per 128 clocks whatever its
+// size, so two requests per step would cap a step at ~256 clocks; at today's 263 the two forms measure the same).
 template <> struct Tc2Cfg<0> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true, TMAP = true; };
 template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = false, A_TMA = false, TMAP = false; };
 template <> struct Tc2Cfg<2> { static constexpr int J = 240, GROUP = 5, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = true, A_TMA = true, TMAP = false; };
