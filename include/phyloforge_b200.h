@@ -161,6 +161,19 @@ PF_API int pf_vcf_sv_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t
 PF_API int pf_chars_to_codes(const uint8_t* d_chars, int64_t ld, int64_t n_sites, int64_t n_samples,
                              uint8_t* d_codes, int64_t ldc, int32_t* d_line_info, void* stream);
 
+/* Character-mismatch counts for the columns that do NOT fit the 2-bit code (more than two alleles, '*'-derived
+ * lower-case characters): what a mismatch model sees on the all_snp.fa the reference hands to `treebest nj`
+ * (treetool/vcftree.py:26-65 writes the characters, treetool/script.py:359-360 runs the tool).
+ * pf_chars_state_codes: for one character state, d_codes[k][i] = 0 where d_chars[rows[k]][i] == state, 2 where it is
+ * another non-missing character, 3 where it is missing ('-', 'N', '.'); d_rows may be NULL (all rows in order).
+ * Feeding these codes through pf_pack_codes_u8 + pf_pair_counts once per state into a zeroed [3][n][ld_state] buffer
+ * gives V summed n_states times and D1 = twice the mismatches; pf_counts_add_mismatch adds V / n_states and D1 / 2
+ * (both exact) to the V and D1 planes of d_counts. D2 is left alone: these columns only enter the p-distance. */
+PF_API int pf_chars_state_codes(const uint8_t* d_chars, int64_t ld, const int64_t* d_rows, int64_t n_rows,
+                                int64_t n_samples, int state, uint8_t* d_codes, int64_t ldc, void* stream);
+PF_API int pf_counts_add_mismatch(const int32_t* d_state_counts, int64_t ld_state, int n_states, int32_t* d_counts,
+                                  int64_t n_samples, int64_t ld, void* stream);
+
 /* Exclusive scan of PF_LINE_COLS over lines -> gather rows. d_rows[c] = source row of matrix
  * column c (SNP: line index; SV: 2*line + which). If require_fit != 0 SNP lines whose
  * FITS2BIT bit is clear are left out (and counted in h_summary[2]).

@@ -161,6 +161,22 @@ def pair_counts_numpy(codes_sm: np.ndarray) -> np.ndarray:
     return out
 
 
+def char_mismatch_counts(chars_sm: np.ndarray) -> np.ndarray:
+    """int64 [2, n, n] (V, D1) of a sample-major CHARACTER matrix, as a mismatch model sees the all_snp.fa
+    that treetool/vcftree.py:159-171 writes and treetool/script.py:359-360 hands to `treebest nj`: a column is
+    valid for a pair when neither character is '-', 'N' or '.', and a valid column is a mismatch when the two
+    characters differ. On columns that fit the 2-bit code this equals V and D1 of pair_counts."""
+    c = np.asarray(chars_sm, dtype=np.uint8)
+    n = c.shape[0]
+    valid = ~np.isin(c, np.frombuffer(b"-N.", dtype=np.uint8))
+    out = np.zeros((2, n, n), dtype=np.int64)
+    for i in range(n):
+        both = valid[i][None, :] & valid
+        out[0, i] = both.sum(1)
+        out[1, i] = (both & (c[i][None, :] != c)).sum(1)
+    return out
+
+
 def normalise(counts: np.ndarray, metric: str = "ibs"):
     """int64 [3, n, n] -> (fp64 [n, n], number of pairs with V == 0 counted over i != j)."""
     counts = np.ascontiguousarray(counts, dtype=np.int64)

@@ -70,7 +70,7 @@ def load_alignment(engine, path: str, non_biallelic: str = "error") -> PackedGen
     summary = (C.c_int64 * 5)()
     check(lib.pf_vcf_select_rows(d_info.data_ptr(), m, 1, 1, d_rows.data_ptr(), m, summary, stream))
     n_fit, n_unfit = int(summary[0]), int(summary[2])
-    if n_unfit and non_biallelic != "skip":
+    if n_unfit and non_biallelic not in ("skip", "mismatch"):
         raise VcfFormatError(
             f"{path}: {n_unfit} column(s) hold more than two alleles (or '*'-derived characters) and do not fit "
             "the 2-bit genotype code (non_biallelic = skip leaves them out of the distance matrix)")
@@ -80,5 +80,10 @@ def load_alignment(engine, path: str, non_biallelic: str = "error") -> PackedGen
         engine.pack_codes(d_codes, n, planes, n_words, rows=d_rows[:n_fit], n_sites=n_fit)
     else:
         planes.fill_(-1)
+    extra = None
+    if n_unfit and non_biallelic == "mismatch":
+        is_unfit = torch.ones(m, dtype=torch.bool, device=dev)
+        is_unfit[d_rows[:n_fit]] = False
+        extra = d_cols.index_select(0, is_unfit.nonzero().flatten())
     return PackedGenotypes(names=names, n_samples=n, n_sites=n_fit, n_words=n_words, planes=planes, chars=mat,
-                           n_columns=m, n_lines=m, n_not_2bit=n_unfit, h2d_bytes=int(mat.nbytes))
+                           n_columns=m, n_lines=m, n_not_2bit=n_unfit, h2d_bytes=int(mat.nbytes), extra_chars=extra)

@@ -63,7 +63,66 @@ chars_to_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, int64_t n_s
   if (lane == 0) line_info[s] = 1 | (fits ? 4 : 0);
 }
 
+// Columns that do not fit the 2-bit code (more than two alleles, '*'-derived lower-case characters) can still be
+// counted as CHARACTER mismatches, which is what a mismatch model sees on all_snp.fa (the
+// p-distance). One pass per character state s: code 0 where the character is s, 2 where it is another
+// non-missing character, 3 where it is missing ('-', 'N', '.'). For such a column pf_pair_counts gives
+// V_s = both non-missing (the same for every s) and D1_s = "exactly one of the two is s"; a column where the
+// two characters differ is counted by exactly two states, an equal one by none: mismatches = sum_s D1_s / 2.
+__global__ void __launch_bounds__(256)
+chars_state_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, const int64_t* __restrict__ rows, int64_t n_rows,
+                         int64_t n_samples, int state, uint8_t* __restrict__ codes, int64_t ldc) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t k = idx / ldc, i = idx % ldc;
+  if (k >= n_rows) return;
+  uint32_t g = 3;
+  if (i < n_samples) {
+    const uint32_t c = chars[(rows ? rows[k] : k) * ld + i];
+    g = (c == static_cast<uint32_t>(state)) ? 0u : ((c == '-' || c == 'N' || c == '.') ? 3u : 2u);
+  }
+  codes[k * ldc + i] = static_cast<uint8_t>(g);
+}
+
+// counts.V += state_counts.V / n_states, counts.D1 += state_counts.D1 / 2 (both divisions are exact, see above)
+__global__ void __launch_bounds__(256)
+counts_add_mismatch_kernel(const int32_t* __restrict__ sc, int32_t* __restrict__ counts, int64_t n, int64_t ld_s, int64_t ld,
+                           int n_states) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const int64_t i = idx / n, j = idx % n;
+  counts[i * ld + j] += sc[i * ld_s + j] / n_states;
+  counts[n * ld + i * ld + j] += sc[n * ld_s + i * ld_s + j] / 2;
+}
+
 }  // namespace
+
+PF_API int pf_chars_state_codes(const uint8_t* d_chars, int64_t ld, const int64_t* d_rows, int64_t n_rows,
+                                int64_t n_samples, int state, uint8_t* d_codes, int64_t ldc, void* stream) {
+  PF_TRY_BEGIN
+  if (n_rows == 0) return PF_OK;
+  if (!d_chars || !d_codes || n_rows < 0 || n_samples <= 0 || ld < n_samples || ldc < n_samples || state <= 0 || state > 255)
+    return pf_fail("pf_chars_state_codes: bad arguments");
+  const int64_t grid = pf_ceil_div(n_rows * ldc, 256);
+  if (grid > 0x7fffffffLL) return pf_fail("pf_chars_state_codes: too many columns");
+  chars_state_codes_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_chars, ld, d_rows, n_rows, n_samples, state, d_codes, ldc);
+  PF_CUDA(cudaGetLastError());
+  return PF_OK;
+  PF_TRY_END
+}
+
+PF_API int pf_counts_add_mismatch(const int32_t* d_state_counts, int64_t ld_state, int n_states, int32_t* d_counts,
+                                  int64_t n_samples, int64_t ld, void* stream) {
+  PF_TRY_BEGIN
+  if (!d_state_counts || !d_counts || n_samples <= 0 || ld < n_samples || ld_state < n_samples || n_states <= 0)
+    return pf_fail("pf_counts_add_mismatch: bad arguments");
+  const int64_t grid = pf_ceil_div(n_samples * n_samples, 256);
+  counts_add_mismatch_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_state_counts, d_counts, n_samples, ld_state, ld, n_states);
+  PF_CUDA(cudaGetLastError());
+  return PF_OK;
+  PF_TRY_END
+}
 
 PF_API int pf_chars_to_codes(const uint8_t* d_chars, int64_t ld, int64_t n_sites, int64_t n_samples,
                              uint8_t* d_codes, int64_t ldc, int32_t* d_line_info, void* stream) {

@@ -291,15 +291,45 @@ class Engine:
         return merge, length
 
     # ------------------------------------------------------------------ composed path
+    def add_char_mismatch_counts(self, chars_rows: torch.Tensor, n_samples: int, counts: torch.Tensor) -> int:
+        """counts[V], counts[D1] += character-mismatch counts of alignment columns that do not fit the 2-bit
+        code (chars_rows: uint8 [k, >= n_samples], one row per column, on the device). One pack + pair-count
+        pass per character state present (include/phyloforge_b200.h: pf_chars_state_codes). D2 is untouched:
+        these columns only enter the p-distance. Returns the number of states."""
+        k = int(chars_rows.shape[0])
+        if k == 0:
+            return 0
+        assert chars_rows.dtype == torch.uint8 and chars_rows.stride(1) == 1 and chars_rows.shape[1] >= n_samples
+        states = [int(c) for c in torch.unique(chars_rows[:, :n_samples]).tolist() if c not in (ord("-"), ord("N"), ord("."))]
+        if not states:
+            return 0
+        ldc = (n_samples + 3) // 4 * 4
+        codes = torch.empty((k, ldc), dtype=torch.uint8, device=self.device)
+        nw = self.n_words(k)
+        planes = self.alloc_planes(n_samples, nw)
+        per_state = torch.zeros_like(counts)
+        for st in states:
+            check(self.lib.pf_chars_state_codes(chars_rows.data_ptr(), chars_rows.stride(0), None, k, n_samples, st,
+                                                codes.data_ptr(), ldc, _stream_ptr()))
+            self.pack_codes(codes, n_samples, planes, nw, n_sites=k)
+            self.pair_counts(planes, n_samples, nw, per_state)
+        check(self.lib.pf_counts_add_mismatch(per_state.data_ptr(), per_state.stride(1), len(states), counts.data_ptr(),
+                                              n_samples, counts.stride(1), _stream_ptr()))
+        return len(states)
+
     def tree_from_planes(self, planes: torch.Tensor, n_samples: int, n_words: int, names,
                          metric="ibs", variant: int = 0, keep: bool = True,
-                         n_sites: int | None = None) -> TreeResult:
+                         n_sites: int | None = None, extra_chars: torch.Tensor | None = None) -> TreeResult:
         """counts -> (allreduce) -> distances -> NJ -> Newick, on the current stream. `n_words` is
         the planes buffer's words per tile; only the words that hold the `n_sites` packed sites are
         counted (a buffer sized for an upper bound has unwritten words behind them)."""
         word_end = n_words if n_sites is None else (n_sites + 31) // 32
         counts = self.alloc_counts(n_samples)
         self.pair_counts(planes, n_samples, n_words, counts, word_end=word_end, variant=variant)
+        if extra_chars is not None:
+            if metric not in ("p", 0):
+                raise PhyloForgeError("columns outside the 2-bit code can only enter the p-distance (distance = p)")
+            self.add_char_mismatch_counts(extra_chars, n_samples, counts)
         self.allreduce_counts(counts)
         return self.tree_from_counts(counts, names, metric=metric, keep=keep)
 

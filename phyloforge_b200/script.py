@@ -86,8 +86,12 @@ class RunCmd:
             print(f"distance: {self.distance} is not recognized (ibs or p), please check it")
             sys.exit()
         self.non_biallelic = str(self.non_biallelic).strip().lower()
-        if self.non_biallelic not in ("error", "skip"):
-            print(f"non_biallelic: {self.non_biallelic} is not recognized (error or skip), please check it")
+        if self.non_biallelic not in ("error", "skip", "mismatch"):
+            print(f"non_biallelic: {self.non_biallelic} is not recognized (error, skip or mismatch), please check it")
+            sys.exit()
+        if self.non_biallelic == "mismatch" and self.distance != "p":
+            print("non_biallelic = mismatch counts sites outside the 2-bit genotype code as character mismatches, "
+                  "which is defined for the p-distance only: set distance = p")
             sys.exit()
         try:
             self.bootstrap = int(self.bootstrap)
@@ -137,6 +141,10 @@ class RunCmd:
             print("At least two samples are needed to build a tree")
             sys.exit(1)
         t0 = time.perf_counter()
+        extra = getattr(packed, "extra_chars", None)
+        if extra is not None and self.bootstrap > 0:
+            print("bootstrap support is computed on the 2-bit sites only; set non_biallelic = skip (or bootstrap = 0)")
+            sys.exit(1)
         if self.bootstrap > 0 and packed.n_samples >= 4:
             # main tree + seeded block-bootstrap support on its internal edges (labels in percent)
             res, support, _ = eng.bootstrap_tree(packed.planes, packed.n_samples, packed.n_words, packed.names,
@@ -146,7 +154,7 @@ class RunCmd:
                                 "bootstrap_mean_support": float(support.mean()) if support.size else None})
         else:
             res = eng.tree_from_planes(packed.planes, packed.n_samples, packed.n_words, packed.names,
-                                       metric=self.distance, n_sites=packed.n_sites)
+                                       metric=self.distance, n_sites=packed.n_sites, extra_chars=extra)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         with open(out_file, "w") as f:

@@ -50,6 +50,8 @@ class PackedGenotypes:
     n_lines: int
     n_not_2bit: int = 0     # kept SNP sites that do not fit the 2-bit code (multi-allelic, '*')
     h2d_bytes: int = 0
+    extra_chars: torch.Tensor | None = None   # uint8 [n_not_2bit, ld] on the device (non_biallelic = mismatch): the
+                                              # characters of those sites, site-major, for Engine.add_char_mismatch_counts
 
 
 def _is_gzip(path: str) -> bool:
@@ -192,7 +194,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 torch.empty((carry_rows + cap * rpl, ld), dtype=torch.uint8, device=dev),
                 torch.empty((cap * rpl, ld), dtype=torch.uint8, device=dev),
                 torch.empty(carry_rows + cap * rpl, dtype=torch.int64, device=dev),
-                torch.empty(cap * rpl, dtype=torch.int64, device=dev) if keep_chars else None)
+                torch.empty(cap * rpl, dtype=torch.int64, device=dev) if (keep_chars or non_biallelic == "mismatch") else None)
 
     d_lines, d_info, d_codes, d_chars, d_rows, d_rows_all = alloc_line_buffers(max_lines)
     n_carry = 0            # leftover sites (< 32) waiting in d_codes[0:n_carry]
@@ -201,6 +203,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     n_unfit_total = 0
     h2d = 0
     char_blocks = []
+    extra_blocks = []
     summary = (C.c_int64 * 5)()
     parse = lib.pf_vcf_snp_parse if kind == "snp" else lib.pf_vcf_sv_parse
     try:
@@ -233,13 +236,14 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 raise VcfFormatError(
                     f"{path}: {n_err} record(s) the reference cannot convert; first at line "
                     f"{n_lines_total + first_line + 1}: {ERR_TEXT.get(first_cls, first_cls)}")
-            if n_unfit and non_biallelic != "skip":
+            if n_unfit and non_biallelic not in ("skip", "mismatch"):
                 raise VcfFormatError(
                     f"{path}: {n_unfit} kept site(s) are not biallelic A/C/G/T and do not fit the 2-bit "
                     "genotype code (set `non_biallelic = skip` in the config to leave them out of the "
-                    "distance matrix; all_snp.fa still contains them)")
+                    "distance matrix, or `non_biallelic = mismatch` with `distance = p` to count them as "
+                    "character mismatches; all_snp.fa contains them either way)")
             n_unfit_total += n_unfit
-            if keep_chars:
+            if keep_chars or (n_unfit and non_biallelic == "mismatch"):
                 if n_unfit:
                     check(lib.pf_vcf_select_rows(d_info.data_ptr(), nl, rpl, 0, d_rows_all.data_ptr(),
                                                  max_lines * rpl, summary, stream))
@@ -248,6 +252,13 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 else:
                     n_all = n_cols
                     rows_all = d_rows[carry_rows:carry_rows + n_cols]
+            if n_unfit and non_biallelic == "mismatch":
+                # the kept rows that are not in the fit list: their characters stay on the device
+                is_unfit = torch.zeros(max_lines * rpl, dtype=torch.bool, device=dev)
+                is_unfit[rows_all] = True
+                is_unfit[d_rows[carry_rows:carry_rows + n_cols]] = False
+                extra_blocks.append(d_chars.index_select(0, is_unfit.nonzero().flatten()))
+            if keep_chars:
                 if n_all:
                     block = engine.transpose_u8(d_chars, n, rows=rows_all, n_rows=n_all)
                     host_block = torch.empty(block.shape, dtype=torch.uint8).pin_memory()
@@ -288,7 +299,8 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
         n_columns = chars.shape[1]
     return PackedGenotypes(names=names, n_samples=n, n_sites=n_sites, n_words=n_words_cap, planes=planes,
                            chars=chars, n_columns=n_columns, n_lines=n_lines_total,
-                           n_not_2bit=n_unfit_total, h2d_bytes=h2d)
+                           n_not_2bit=n_unfit_total, h2d_bytes=h2d,
+                           extra_chars=torch.cat(extra_blocks, dim=0) if extra_blocks else None)
 
 
 def load_snp_vcf(engine, path: str, keep_chars: bool = True, non_biallelic: str = "error",
