@@ -10,7 +10,7 @@ import numpy as np
 sys.path.insert(0, ".")
 sys.path.insert(0, "tests")
 import vcfgen
-from oracle import ref_convert as rc
+from oracle import cpu as oracle, ref_convert as rc
 from phyloforge_b200 import vcf
 from phyloforge_b200.engine import Engine
 
@@ -19,7 +19,7 @@ seed0 = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
 rng = np.random.default_rng(seed0)
 t_end = time.time() + budget
-n_snp = n_sv = 0
+n_snp = n_sv = n_mis = 0
 
 
 def fasta(names, chars):
@@ -44,6 +44,17 @@ with tempfile.TemporaryDirectory() as tmp:
             packed = vcf.load_snp_vcf(eng, path, non_biallelic="skip", chunk_bytes=chunk)
             assert fasta(packed.names, packed.chars) == rc.fasta_text(names, seqs).encode(), ("snp", seed, n, m, chunk)
             n_snp += 1
+            if n >= 2 and packed.n_columns:
+                # every column of the character matrix as mismatch counts (2-bit columns + one pass per character state)
+                packed = vcf.load_snp_vcf(eng, path, non_biallelic="mismatch", chunk_bytes=chunk)
+                counts = eng.alloc_counts(n)
+                eng.pair_counts(packed.planes, n, packed.n_words, counts, word_end=(packed.n_sites + 31) // 32)
+                if packed.extra_chars is not None:
+                    eng.add_char_mismatch_counts(packed.extra_chars, n, counts)
+                want = oracle.char_mismatch_counts(packed.chars)
+                got = counts.cpu().numpy().astype(np.int64)
+                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), ("mismatch", seed, n, m, chunk)
+                n_mis += 1
         text, _ = vcfgen.random_sv_vcf(seed, n, m, miss=float(rng.choice([0, 0.08, 0.6])))
         open(path, "w").write(text)
         chunk = max(chunk, 2 * max(map(len, text.split("\n"))) + 2)
@@ -55,4 +66,4 @@ with tempfile.TemporaryDirectory() as tmp:
             packed = vcf.load_sv_vcf(eng, path, chunk_bytes=chunk)
             assert fasta(packed.names, packed.chars) == rc.fasta_text(names, seqs).encode(), ("sv", seed, n, m, chunk)
             n_sv += 1
-print(f"fuzz ok: {n_snp} SNP VCFs, {n_sv} SV VCFs")
+print(f"fuzz ok: {n_snp} SNP VCFs, {n_sv} SV VCFs, {n_mis} character-mismatch count matrices")
