@@ -161,18 +161,27 @@ PF_API int pf_vcf_sv_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t
 PF_API int pf_chars_to_codes(const uint8_t* d_chars, int64_t ld, int64_t n_sites, int64_t n_samples,
                              uint8_t* d_codes, int64_t ldc, int32_t* d_line_info, void* stream);
 
-/* Character-mismatch counts for the columns that do NOT fit the 2-bit code (more than two alleles, '*'-derived
- * lower-case characters): what a mismatch model sees on the all_snp.fa the reference hands to `treebest nj`
- * (treetool/vcftree.py:26-65 writes the characters, treetool/script.py:359-360 runs the tool).
+/* Counts for the columns that do NOT fit the 2-bit code (more than two alleles, '*'-derived lower-case characters),
+ * from the characters of the all_snp.fa the reference hands to `treebest nj` (treetool/vcftree.py:26-65 writes them -
+ * each stands for one unordered allele pair over {A, C, G, T, *}, BASELINE.md section 5 - treetool/script.py:359-360
+ * runs the tool). For a pair and a column where neither character is missing ('-', 'N', '.'): D1 = the characters
+ * differ (mismatch model, p-distance), D1 + D2 = 2 - alleles shared (allele-sharing / IBS distance; on a biallelic
+ * column |g_i - g_j|), i.e. D2 = no allele shared.
  * pf_chars_state_codes: for one character state, d_codes[k][i] = 0 where d_chars[rows[k]][i] == state, 2 where it is
- * another non-missing character, 3 where it is missing ('-', 'N', '.'); d_rows may be NULL (all rows in order).
- * Feeding these codes through pf_pack_codes_u8 + pf_pair_counts once per state into a zeroed [3][n][ld_state] buffer
- * gives V summed n_states times and D1 = twice the mismatches; pf_counts_add_mismatch adds V / n_states and D1 / 2
- * (both exact) to the V and D1 planes of d_counts. D2 is left alone: these columns only enter the p-distance. */
+ * another non-missing character, 3 where it is missing; d_rows may be NULL (all rows in order).
+ * pf_chars_allele_codes: for one allele (0..4 = A, C, G, T, *), d_codes[k][i] = copies of it in the genotype (0, 1, 2),
+ * 3 where the character is missing or stands for no genotype.
+ * Feeding these codes through pf_pack_codes_u8 + pf_pair_counts, once per state present into one zeroed
+ * [3][n][ld_state] buffer and once per allele into another, gives V summed n_states times, D1 = twice the mismatches
+ * and (allele buffer) D1 + D2 = twice (2 - shared); pf_counts_add_extra adds V / n_states and D1 / 2 to the V and D1
+ * planes of d_counts and, when d_allele_counts is not NULL, (D1 + D2) / 2 - mismatches to its D2 plane (all exact). */
 PF_API int pf_chars_state_codes(const uint8_t* d_chars, int64_t ld, const int64_t* d_rows, int64_t n_rows,
                                 int64_t n_samples, int state, uint8_t* d_codes, int64_t ldc, void* stream);
-PF_API int pf_counts_add_mismatch(const int32_t* d_state_counts, int64_t ld_state, int n_states, int32_t* d_counts,
-                                  int64_t n_samples, int64_t ld, void* stream);
+PF_API int pf_chars_allele_codes(const uint8_t* d_chars, int64_t ld, const int64_t* d_rows, int64_t n_rows,
+                                 int64_t n_samples, int allele, uint8_t* d_codes, int64_t ldc, void* stream);
+PF_API int pf_counts_add_extra(const int32_t* d_state_counts, int64_t ld_state, int n_states,
+                               const int32_t* d_allele_counts, int64_t ld_allele, int32_t* d_counts, int64_t n_samples,
+                               int64_t ld, void* stream);
 
 /* Exclusive scan of PF_LINE_COLS over lines -> gather rows. d_rows[c] = source row of matrix
  * column c (SNP: line index; SV: 2*line + which). If require_fit != 0 SNP lines whose

@@ -161,11 +161,44 @@ def pair_counts_numpy(codes_sm: np.ndarray) -> np.ndarray:
     return out
 
 
+_ALLELE_PAIRS = {"A": (0, 0), "C": (1, 1), "G": (2, 2), "T": (3, 3), "M": (0, 1), "R": (0, 2), "W": (0, 3), "S": (1, 2),
+                 "Y": (1, 3), "K": (2, 3), "a": (0, 4), "c": (1, 4), "g": (2, 4), "t": (3, 4)}
+
+
+def char_pair_counts(chars_sm: np.ndarray) -> np.ndarray:
+    """int64 [3, n, n] (V, D1, D2) of a sample-major CHARACTER matrix as treetool/vcftree.py:159-171 writes it
+    (all_snp.fa, the input of `treebest nj`, treetool/script.py:359-360). Every character stands for one unordered
+    allele pair over {A, C, G, T, *} (vcftree.py:26-65); '-', 'N' and '.' are missing. A column is valid for a pair
+    when neither character is missing; D1 = valid and the characters differ (mismatch model); D2 = valid and the two
+    genotypes share no allele, so that D1 + D2 = 2 - (alleles shared, with multiplicity), the allele-sharing
+    distance. On columns that fit the 2-bit code this equals pair_counts of the codes."""
+    c = np.asarray(chars_sm, dtype=np.uint8)
+    n, m = c.shape
+    missing = np.isin(c, np.frombuffer(b"-N.", dtype=np.uint8))
+    copies = np.zeros((n, m, 5), dtype=np.int64)
+    known = missing.copy()
+    for ch, (a1, a2) in _ALLELE_PAIRS.items():
+        sel = c == ord(ch)
+        copies[sel, a1] += 1
+        copies[sel, a2] += 1
+        known |= sel
+    if not known.all():
+        raise ValueError("a character that stands for no genotype: " + repr(bytes(np.unique(c[~known])).decode()))
+    valid = ~missing
+    out = np.zeros((3, n, n), dtype=np.int64)
+    for i in range(n):
+        both = valid[i][None, :] & valid
+        shared = np.minimum(copies[i][None, :, :], copies).sum(2)
+        differ = c[i][None, :] != c
+        assert np.array_equal(both & differ, both & (shared < 2))      # one character per allele pair
+        out[0, i] = both.sum(1)
+        out[1, i] = (both & differ).sum(1)
+        out[2, i] = (both & (shared == 0)).sum(1)
+    return out
+
+
 def char_mismatch_counts(chars_sm: np.ndarray) -> np.ndarray:
-    """int64 [2, n, n] (V, D1) of a sample-major CHARACTER matrix, as a mismatch model sees the all_snp.fa
-    that treetool/vcftree.py:159-171 writes and treetool/script.py:359-360 hands to `treebest nj`: a column is
-    valid for a pair when neither character is '-', 'N' or '.', and a valid column is a mismatch when the two
-    characters differ. On columns that fit the 2-bit code this equals V and D1 of pair_counts."""
+    """int64 [2, n, n] (V, D1) as above for ANY characters ('-', 'N', '.' missing): the mismatch model alone."""
     c = np.asarray(chars_sm, dtype=np.uint8)
     n = c.shape[0]
     valid = ~np.isin(c, np.frombuffer(b"-N.", dtype=np.uint8))

@@ -50,7 +50,8 @@ PROTOTYPES = {
     "pf_vcf_sv_parse": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp]),
     "pf_chars_to_codes": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _vp]),
     "pf_chars_state_codes": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp]),
-    "pf_counts_add_mismatch": (_i32, [_vp, _i64, _i32, _vp, _i64, _i64, _vp]),
+    "pf_chars_allele_codes": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _i64, _vp]),
+    "pf_counts_add_extra": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _i64, _i64, _vp]),
     "pf_vcf_select_rows": (_i32, [_vp, _i64, _i32, _i32, _vp, _i64, _i64p, _vp]),
     "pf_pair_counts": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _vp]),
     "pf_pair_counts_tc_work_bytes": (_i64, [_i64, _i64]),

@@ -70,7 +70,7 @@ def load_alignment(engine, path: str, non_biallelic: str = "error") -> PackedGen
     summary = (C.c_int64 * 5)()
     check(lib.pf_vcf_select_rows(d_info.data_ptr(), m, 1, 1, d_rows.data_ptr(), m, summary, stream))
     n_fit, n_unfit = int(summary[0]), int(summary[2])
-    if n_unfit and non_biallelic not in ("skip", "mismatch"):
+    if n_unfit and non_biallelic not in ("skip", "include"):
         raise VcfFormatError(
             f"{path}: {n_unfit} column(s) hold more than two alleles (or '*'-derived characters) and do not fit "
             "the 2-bit genotype code (non_biallelic = skip leaves them out of the distance matrix)")
@@ -81,7 +81,7 @@ def load_alignment(engine, path: str, non_biallelic: str = "error") -> PackedGen
     else:
         planes.fill_(-1)
     extra = None
-    if n_unfit and non_biallelic == "mismatch":
+    if n_unfit and non_biallelic == "include":
         is_unfit = torch.ones(m, dtype=torch.bool, device=dev)
         is_unfit[d_rows[:n_fit]] = False
         extra = d_cols.index_select(0, is_unfit.nonzero().flatten())

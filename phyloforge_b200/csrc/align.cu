@@ -63,12 +63,19 @@ chars_to_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, int64_t n_s
   if (lane == 0) line_info[s] = 1 | (fits ? 4 : 0);
 }
 
-// Columns that do not fit the 2-bit code (more than two alleles, '*'-derived lower-case characters) can still be
-// counted as CHARACTER mismatches, which is what a mismatch model sees on all_snp.fa (the
-// p-distance). One pass per character state s: code 0 where the character is s, 2 where it is another
-// non-missing character, 3 where it is missing ('-', 'N', '.'). For such a column pf_pair_counts gives
-// V_s = both non-missing (the same for every s) and D1_s = "exactly one of the two is s"; a column where the
-// two characters differ is counted by exactly two states, an equal one by none: mismatches = sum_s D1_s / 2.
+// Columns that do not fit the 2-bit code (more than two alleles, '*'-derived lower-case characters) are counted
+// from the characters the reference writes to all_snp.fa (treetool/vcftree.py:26-65; BASELINE.md section 5: every
+// character stands for one unordered allele pair over {A, C, G, T, *}). For a pair of samples and a column where
+// neither character is missing ('-', 'N', '.'):
+//   D1 = the characters differ (what a mismatch model sees; SURVEY.md 8(c).3, the p-distance),
+//   D1 + D2 = 2 - (alleles shared, with multiplicity) - the allele-sharing (IBS) distance, which on a biallelic
+//             column is |g_i - g_j| - so D2 = the genotypes share no allele.
+// Both come from the ordinary packer and pair-count kernels fed with pseudo genotype codes:
+//  * one pass per character STATE s (code 0 where the character is s, 2 where it is another non-missing one, 3
+//    where missing): V_s = both non-missing (the same for every s), D1_s = exactly one of the two is s. A column
+//    where the characters differ is counted by exactly two states, an equal one by none: mismatches = sum_s D1_s / 2;
+//  * one pass per ALLELE a (code = copies of a in the genotype: 0, 1, 2; 3 where missing): D1_a + D2_a =
+//    |c_a(i) - c_a(j)|, and sum_a |c_a(i) - c_a(j)| = 4 - 2 shared, so sum_a (D1_a + D2_a) / 2 = 2 - shared.
 __global__ void __launch_bounds__(256)
 chars_state_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, const int64_t* __restrict__ rows, int64_t n_rows,
                          int64_t n_samples, int state, uint8_t* __restrict__ codes, int64_t ldc) {
@@ -83,15 +90,46 @@ chars_state_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, const in
   codes[k * ldc + i] = static_cast<uint8_t>(g);
 }
 
-// counts.V += state_counts.V / n_states, counts.D1 += state_counts.D1 / 2 (both divisions are exact, see above)
+// the allele pair (indices 0..4 = A, C, G, T, *) a character of all_snp.fa stands for; false = missing / not a genotype
+__device__ __forceinline__ bool allele_pair(uint32_t c, int& a1, int& a2) {
+  switch (c) {
+    case 'A': a1 = 0; a2 = 0; return true;  case 'C': a1 = 1; a2 = 1; return true;
+    case 'G': a1 = 2; a2 = 2; return true;  case 'T': a1 = 3; a2 = 3; return true;
+    case 'M': a1 = 0; a2 = 1; return true;  case 'R': a1 = 0; a2 = 2; return true;
+    case 'W': a1 = 0; a2 = 3; return true;  case 'S': a1 = 1; a2 = 2; return true;
+    case 'Y': a1 = 1; a2 = 3; return true;  case 'K': a1 = 2; a2 = 3; return true;
+    case 'a': a1 = 0; a2 = 4; return true;  case 'c': a1 = 1; a2 = 4; return true;
+    case 'g': a1 = 2; a2 = 4; return true;  case 't': a1 = 3; a2 = 4; return true;
+    default: return false;
+  }
+}
+
 __global__ void __launch_bounds__(256)
-counts_add_mismatch_kernel(const int32_t* __restrict__ sc, int32_t* __restrict__ counts, int64_t n, int64_t ld_s, int64_t ld,
-                           int n_states) {
+chars_allele_codes_kernel(const uint8_t* __restrict__ chars, int64_t ld, const int64_t* __restrict__ rows, int64_t n_rows,
+                          int64_t n_samples, int allele, uint8_t* __restrict__ codes, int64_t ldc) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t k = idx / ldc, i = idx % ldc;
+  if (k >= n_rows) return;
+  uint32_t g = 3;
+  if (i < n_samples) {
+    int a1, a2;
+    if (allele_pair(chars[(rows ? rows[k] : k) * ld + i], a1, a2)) g = static_cast<uint32_t>((a1 == allele) + (a2 == allele));
+  }
+  codes[k * ldc + i] = static_cast<uint8_t>(g);
+}
+
+// counts.V += sc.V / n_states, counts.D1 += sc.D1 / 2; with allele counts: counts.D2 += (ac.D1 + ac.D2) / 2 - sc.D1 / 2
+// (all divisions are exact, see above)
+__global__ void __launch_bounds__(256)
+counts_add_extra_kernel(const int32_t* __restrict__ sc, int64_t ld_s, int n_states, const int32_t* __restrict__ ac, int64_t ld_a,
+                        int32_t* __restrict__ counts, int64_t n, int64_t ld) {
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= n * n) return;
   const int64_t i = idx / n, j = idx % n;
+  const int32_t mism = sc[n * ld_s + i * ld_s + j] / 2;
   counts[i * ld + j] += sc[i * ld_s + j] / n_states;
-  counts[n * ld + i * ld + j] += sc[n * ld_s + i * ld_s + j] / 2;
+  counts[n * ld + i * ld + j] += mism;
+  if (ac) counts[2 * n * ld + i * ld + j] += (ac[n * ld_a + i * ld_a + j] + ac[2 * n * ld_a + i * ld_a + j]) / 2 - mism;
 }
 
 }  // namespace
@@ -111,14 +149,30 @@ PF_API int pf_chars_state_codes(const uint8_t* d_chars, int64_t ld, const int64_
   PF_TRY_END
 }
 
-PF_API int pf_counts_add_mismatch(const int32_t* d_state_counts, int64_t ld_state, int n_states, int32_t* d_counts,
-                                  int64_t n_samples, int64_t ld, void* stream) {
+PF_API int pf_chars_allele_codes(const uint8_t* d_chars, int64_t ld, const int64_t* d_rows, int64_t n_rows,
+                                 int64_t n_samples, int allele, uint8_t* d_codes, int64_t ldc, void* stream) {
   PF_TRY_BEGIN
-  if (!d_state_counts || !d_counts || n_samples <= 0 || ld < n_samples || ld_state < n_samples || n_states <= 0)
-    return pf_fail("pf_counts_add_mismatch: bad arguments");
+  if (n_rows == 0) return PF_OK;
+  if (!d_chars || !d_codes || n_rows < 0 || n_samples <= 0 || ld < n_samples || ldc < n_samples || allele < 0 || allele > 4)
+    return pf_fail("pf_chars_allele_codes: bad arguments");
+  const int64_t grid = pf_ceil_div(n_rows * ldc, 256);
+  if (grid > 0x7fffffffLL) return pf_fail("pf_chars_allele_codes: too many columns");
+  chars_allele_codes_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_chars, ld, d_rows, n_rows, n_samples, allele, d_codes, ldc);
+  PF_CUDA(cudaGetLastError());
+  return PF_OK;
+  PF_TRY_END
+}
+
+PF_API int pf_counts_add_extra(const int32_t* d_state_counts, int64_t ld_state, int n_states, const int32_t* d_allele_counts,
+                               int64_t ld_allele, int32_t* d_counts, int64_t n_samples, int64_t ld, void* stream) {
+  PF_TRY_BEGIN
+  if (!d_state_counts || !d_counts || n_samples <= 0 || ld < n_samples || ld_state < n_samples || n_states <= 0 ||
+      (d_allele_counts && ld_allele < n_samples))
+    return pf_fail("pf_counts_add_extra: bad arguments");
   const int64_t grid = pf_ceil_div(n_samples * n_samples, 256);
-  counts_add_mismatch_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_state_counts, d_counts, n_samples, ld_state, ld, n_states);
+  counts_add_extra_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_state_counts, ld_state, n_states, d_allele_counts, ld_allele, d_counts, n_samples, ld);
   PF_CUDA(cudaGetLastError());
   return PF_OK;
   PF_TRY_END

@@ -291,16 +291,24 @@ class Engine:
         return merge, length
 
     # ------------------------------------------------------------------ composed path
-    def add_char_mismatch_counts(self, chars_rows: torch.Tensor, n_samples: int, counts: torch.Tensor) -> int:
-        """counts[V], counts[D1] += character-mismatch counts of alignment columns that do not fit the 2-bit
-        code (chars_rows: uint8 [k, >= n_samples], one row per column, on the device). One pack + pair-count
-        pass per character state present (include/phyloforge_b200.h: pf_chars_state_codes). D2 is untouched:
-        these columns only enter the p-distance. Returns the number of states."""
+    GENOTYPE_CHARS = b"ACGTMRWSYKacgt"      # what treetool/vcftree.py:26-65 writes for a genotype; '-', 'N' (and '.') are missing
+
+    def add_extra_column_counts(self, chars_rows: torch.Tensor, n_samples: int, counts: torch.Tensor,
+                                allele_sharing: bool = True) -> int:
+        """counts += the V / D1 (/ D2) of alignment columns that do not fit the 2-bit code (chars_rows: uint8
+        [k, >= n_samples], one row per column, on the device): D1 = characters differ, D1 + D2 = 2 - alleles shared
+        (include/phyloforge_b200.h: pf_chars_state_codes, pf_chars_allele_codes). One pack + pair-count pass per
+        character state present and, with allele_sharing, per allele (A, C, G, T, *); without it D2 is left
+        alone and the columns only enter the p-distance. Returns the number of states."""
         k = int(chars_rows.shape[0])
         if k == 0:
             return 0
         assert chars_rows.dtype == torch.uint8 and chars_rows.stride(1) == 1 and chars_rows.shape[1] >= n_samples
-        states = [int(c) for c in torch.unique(chars_rows[:, :n_samples]).tolist() if c not in (ord("-"), ord("N"), ord("."))]
+        present = [int(c) for c in torch.unique(chars_rows[:, :n_samples]).tolist()]
+        states = [c for c in present if c not in (ord("-"), ord("N"), ord("."))]
+        if allele_sharing and any(c not in self.GENOTYPE_CHARS for c in states):
+            bad = "".join(chr(c) for c in states if c not in self.GENOTYPE_CHARS)
+            raise PhyloForgeError(f"characters {bad!r} stand for no genotype: such columns can only enter the p-distance")
         if not states:
             return 0
         ldc = (n_samples + 3) // 4 * 4
@@ -313,8 +321,18 @@ class Engine:
                                                 codes.data_ptr(), ldc, _stream_ptr()))
             self.pack_codes(codes, n_samples, planes, nw, n_sites=k)
             self.pair_counts(planes, n_samples, nw, per_state)
-        check(self.lib.pf_counts_add_mismatch(per_state.data_ptr(), per_state.stride(1), len(states), counts.data_ptr(),
-                                              n_samples, counts.stride(1), _stream_ptr()))
+        per_allele = None
+        if allele_sharing:
+            per_allele = torch.zeros_like(counts)
+            for allele in range(5):
+                check(self.lib.pf_chars_allele_codes(chars_rows.data_ptr(), chars_rows.stride(0), None, k, n_samples,
+                                                     allele, codes.data_ptr(), ldc, _stream_ptr()))
+                self.pack_codes(codes, n_samples, planes, nw, n_sites=k)
+                self.pair_counts(planes, n_samples, nw, per_allele)
+        check(self.lib.pf_counts_add_extra(per_state.data_ptr(), per_state.stride(1), len(states),
+                                           per_allele.data_ptr() if per_allele is not None else None,
+                                           per_allele.stride(1) if per_allele is not None else 0,
+                                           counts.data_ptr(), n_samples, counts.stride(1), _stream_ptr()))
         return len(states)
 
     def tree_from_planes(self, planes: torch.Tensor, n_samples: int, n_words: int, names,
@@ -327,9 +345,7 @@ class Engine:
         counts = self.alloc_counts(n_samples)
         self.pair_counts(planes, n_samples, n_words, counts, word_end=word_end, variant=variant)
         if extra_chars is not None:
-            if metric not in ("p", 0):
-                raise PhyloForgeError("columns outside the 2-bit code can only enter the p-distance (distance = p)")
-            self.add_char_mismatch_counts(extra_chars, n_samples, counts)
+            self.add_extra_column_counts(extra_chars, n_samples, counts)
         self.allreduce_counts(counts)
         return self.tree_from_counts(counts, names, metric=metric, keep=keep)
 

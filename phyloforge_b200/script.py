@@ -86,12 +86,8 @@ class RunCmd:
             print(f"distance: {self.distance} is not recognized (ibs or p), please check it")
             sys.exit()
         self.non_biallelic = str(self.non_biallelic).strip().lower()
-        if self.non_biallelic not in ("error", "skip", "mismatch"):
-            print(f"non_biallelic: {self.non_biallelic} is not recognized (error, skip or mismatch), please check it")
-            sys.exit()
-        if self.non_biallelic == "mismatch" and self.distance != "p":
-            print("non_biallelic = mismatch counts sites outside the 2-bit genotype code as character mismatches, "
-                  "which is defined for the p-distance only: set distance = p")
+        if self.non_biallelic not in ("error", "skip", "include"):
+            print(f"non_biallelic: {self.non_biallelic} is not recognized (error, skip or include), please check it")
             sys.exit()
         try:
             self.bootstrap = int(self.bootstrap)

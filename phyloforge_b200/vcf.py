@@ -50,8 +50,8 @@ class PackedGenotypes:
     n_lines: int
     n_not_2bit: int = 0     # kept SNP sites that do not fit the 2-bit code (multi-allelic, '*')
     h2d_bytes: int = 0
-    extra_chars: torch.Tensor | None = None   # uint8 [n_not_2bit, ld] on the device (non_biallelic = mismatch): the
-                                              # characters of those sites, site-major, for Engine.add_char_mismatch_counts
+    extra_chars: torch.Tensor | None = None   # uint8 [n_not_2bit, ld] on the device (non_biallelic = include): the
+                                              # characters of those sites, site-major, for Engine.add_extra_column_counts
 
 
 def _is_gzip(path: str) -> bool:
@@ -194,7 +194,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 torch.empty((carry_rows + cap * rpl, ld), dtype=torch.uint8, device=dev),
                 torch.empty((cap * rpl, ld), dtype=torch.uint8, device=dev),
                 torch.empty(carry_rows + cap * rpl, dtype=torch.int64, device=dev),
-                torch.empty(cap * rpl, dtype=torch.int64, device=dev) if (keep_chars or non_biallelic == "mismatch") else None)
+                torch.empty(cap * rpl, dtype=torch.int64, device=dev) if (keep_chars or non_biallelic == "include") else None)
 
     d_lines, d_info, d_codes, d_chars, d_rows, d_rows_all = alloc_line_buffers(max_lines)
     n_carry = 0            # leftover sites (< 32) waiting in d_codes[0:n_carry]
@@ -236,14 +236,14 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 raise VcfFormatError(
                     f"{path}: {n_err} record(s) the reference cannot convert; first at line "
                     f"{n_lines_total + first_line + 1}: {ERR_TEXT.get(first_cls, first_cls)}")
-            if n_unfit and non_biallelic not in ("skip", "mismatch"):
+            if n_unfit and non_biallelic not in ("skip", "include"):
                 raise VcfFormatError(
                     f"{path}: {n_unfit} kept site(s) are not biallelic A/C/G/T and do not fit the 2-bit "
                     "genotype code (set `non_biallelic = skip` in the config to leave them out of the "
-                    "distance matrix, or `non_biallelic = mismatch` with `distance = p` to count them as "
-                    "character mismatches; all_snp.fa contains them either way)")
+                    "distance matrix, or `non_biallelic = include` to count them from their characters; "
+                    "all_snp.fa contains them either way)")
             n_unfit_total += n_unfit
-            if keep_chars or (n_unfit and non_biallelic == "mismatch"):
+            if keep_chars or (n_unfit and non_biallelic == "include"):
                 if n_unfit:
                     check(lib.pf_vcf_select_rows(d_info.data_ptr(), nl, rpl, 0, d_rows_all.data_ptr(),
                                                  max_lines * rpl, summary, stream))
@@ -252,7 +252,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 else:
                     n_all = n_cols
                     rows_all = d_rows[carry_rows:carry_rows + n_cols]
-            if n_unfit and non_biallelic == "mismatch":
+            if n_unfit and non_biallelic == "include":
                 # the kept rows that are not in the fit list: their characters stay on the device
                 is_unfit = torch.zeros(max_lines * rpl, dtype=torch.bool, device=dev)
                 is_unfit[rows_all] = True

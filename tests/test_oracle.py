@@ -171,16 +171,19 @@ def test_nj_incremental_row_sums_vs_from_scratch(n):
     assert rf == 0 and dl < 1e-11
 
 
-def test_char_mismatch_counts_known_answer_and_agreement_with_genotype_counts():
-    """oracle.char_mismatch_counts: a hand-checked case, and on biallelic characters V / D1 equal those of the
-    genotype-code counts (D1 is the character mismatch on the reference's FASTA)."""
-    chars = np.array([list(b"ACGN-T"), list(b"ACTNGT"), list(b"MC-NGt")], dtype=np.uint8)
-    got = oracle.char_mismatch_counts(chars)
-    assert got[0].tolist() == [[4, 4, 3], [4, 5, 4], [3, 4, 4]]
-    assert got[1].tolist() == [[0, 1, 2], [1, 0, 2], [2, 2, 0]]
+def test_char_pair_counts_known_answer_and_agreement_with_genotype_counts():
+    """oracle.char_pair_counts / char_mismatch_counts: a hand-checked case, and on biallelic characters they equal
+    the genotype-code counts (D1 is the character mismatch on the reference's FASTA, D1 + D2 the
+    allele-sharing distance |g_i - g_j|)."""
+    chars = np.array([list(b"ACGN-Ta"), list(b"ACTNGTc"), list(b"MC-NGtA")], dtype=np.uint8)
+    got = oracle.char_pair_counts(chars)
+    assert got[0].tolist() == [[5, 5, 4], [5, 6, 5], [4, 5, 5]]
+    assert got[1].tolist() == [[0, 2, 3], [2, 0, 3], [3, 3, 0]]      # (0,1): G/T, a/c; (0,2): A/M, T/t, a/A; (1,2): A/M, T/t, c/A
+    assert got[2].tolist() == [[0, 1, 0], [1, 0, 1], [0, 1, 0]]      # no allele shared: G/T; c (C*) / A
+    assert np.array_equal(oracle.char_mismatch_counts(chars), got[:2])
     rng = np.random.default_rng(4)
     codes = rng.integers(0, 4, size=(9, 300)).astype(np.uint8)          # REF = A, ALT = G, het = R, missing = N
     lut = np.frombuffer(b"ARGN", dtype=np.uint8)
-    vd = oracle.char_mismatch_counts(lut[codes])
-    base = oracle.pair_counts(codes)
-    assert np.array_equal(vd[0], base[0]) and np.array_equal(vd[1], base[1])
+    assert np.array_equal(oracle.char_pair_counts(lut[codes]), oracle.pair_counts(codes))
+    with pytest.raises(ValueError):
+        oracle.char_pair_counts(np.array([list(b"AX")], dtype=np.uint8))

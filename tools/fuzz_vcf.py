@@ -46,14 +46,13 @@ with tempfile.TemporaryDirectory() as tmp:
             n_snp += 1
             if n >= 2 and packed.n_columns:
                 # every column of the character matrix as mismatch counts (2-bit columns + one pass per character state)
-                packed = vcf.load_snp_vcf(eng, path, non_biallelic="mismatch", chunk_bytes=chunk)
+                packed = vcf.load_snp_vcf(eng, path, non_biallelic="include", chunk_bytes=chunk)
                 counts = eng.alloc_counts(n)
                 eng.pair_counts(packed.planes, n, packed.n_words, counts, word_end=(packed.n_sites + 31) // 32)
                 if packed.extra_chars is not None:
-                    eng.add_char_mismatch_counts(packed.extra_chars, n, counts)
-                want = oracle.char_mismatch_counts(packed.chars)
-                got = counts.cpu().numpy().astype(np.int64)
-                assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], want[1]), ("mismatch", seed, n, m, chunk)
+                    eng.add_extra_column_counts(packed.extra_chars, n, counts)
+                want = oracle.char_pair_counts(packed.chars)
+                assert np.array_equal(counts.cpu().numpy().astype(np.int64), want), ("include", seed, n, m, chunk)
                 n_mis += 1
         text, _ = vcfgen.random_sv_vcf(seed, n, m, miss=float(rng.choice([0, 0.08, 0.6])))
         open(path, "w").write(text)
@@ -66,4 +65,4 @@ with tempfile.TemporaryDirectory() as tmp:
             packed = vcf.load_sv_vcf(eng, path, chunk_bytes=chunk)
             assert fasta(packed.names, packed.chars) == rc.fasta_text(names, seqs).encode(), ("sv", seed, n, m, chunk)
             n_sv += 1
-print(f"fuzz ok: {n_snp} SNP VCFs, {n_sv} SV VCFs, {n_mis} character-mismatch count matrices")
+print(f"fuzz ok: {n_snp} SNP VCFs, {n_sv} SV VCFs, {n_mis} count matrices over every column (non_biallelic = include)")
