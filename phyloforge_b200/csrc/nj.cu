@@ -236,6 +236,8 @@ __device__ __forceinline__ void nj_scan(const double* __restrict__ D, int64_t ld
 // ===================================================================== fast kernel
 constexpr int NJF_THREADS = 512;
 constexpr int NJF_U = 8;             // 256-column scan items, two in flight per warp
+constexpr int NJF_U_WIDE = 16;       // 512-column items for matrices of NJF_WIDE_FROM nodes or more
+constexpr int NJF_WIDE_FROM = 5000;
 constexpr int NJF_K = 8;             // slots per thread and batch of the update
 constexpr int64_t NJ_FAST_MAX_N = 11000;   // 20 n bytes of shared memory
 constexpr int NJF_SHARDS = 8;        // arrival counters of the exchange, one 128-byte line each
@@ -295,7 +297,11 @@ template <> struct NjFastView<true> {
   __device__ __forceinline__ unsigned long long* recs() const { return w(p.recs); }
 };
 
-template <bool PROF, bool BATCH>
+// U = scan item width in 32-column units. 256-column items (U = 8) are best up to a few thousand nodes; from
+// ~5,000 on, where the scan is bandwidth-bound, 512-column items amortise the per-item overhead better (whole runs
+// at n = 6,000: 87.6 ms with 256 columns, 82.3 ms with 512; n = 3,000: 22.0 vs 23.1). One width per launch: a
+// kernel that switched per iteration held three instantiations of the scan, spilled and was slower everywhere.
+template <bool PROF, bool BATCH, int U = NJF_U>
 __global__ void __launch_bounds__(NJF_THREADS, 1)
 nj_fast_kernel(const NjFastParams P_in) {
   cg::grid_group grid = cg::this_grid();
@@ -346,7 +352,7 @@ nj_fast_kernel(const NjFastParams P_in) {
     const double n2 = static_cast<double>(na - 2);
     double bq = CUDART_INF;
     int ba = NJ_NONE, bb = NJ_NONE;
-    nj_scan<NJF_U, true, true>(D, ld, V.spare(), n, s_phys, s_r, s_du, na, n2, pend, gwarp, nwarps, lane, bq, ba, bb);
+    nj_scan<U, true, true>(D, ld, V.spare(), n, s_phys, s_r, s_du, na, n2, pend, gwarp, nwarps, lane, bq, ba, bb);
     warp_argmin(bq, ba, bb);
     if (lane == 0) s_rec[warp] = NjRec{bq, ba, bb};
     __syncthreads();
@@ -816,7 +822,10 @@ int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
       static_assert(sizeof(NjRecG) * NJ_MAX_BLOCKS <= NJ_XCHG_BYTES, "record area");
       const int64_t blocks = per_mat * batch;
       int rc;
-      if (batch == 1)
+      if (batch == 1 && n >= NJF_WIDE_FROM)
+        rc = g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true, false, NJF_U_WIDE>, NJF_THREADS, smem, blocks, blocks, &P, s)
+                               : nj_launch(nj_fast_kernel<false, false, NJF_U_WIDE>, NJF_THREADS, smem, blocks, blocks, &P, s);
+      else if (batch == 1)
         rc = g_nj_prof_enabled ? nj_launch(nj_fast_kernel<true, false>, NJF_THREADS, smem, blocks, blocks, &P, s)
                                : nj_launch(nj_fast_kernel<false, false>, NJF_THREADS, smem, blocks, blocks, &P, s);
       else
