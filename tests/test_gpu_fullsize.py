@@ -110,6 +110,19 @@ def test_config5_10000x5M_missing_row_subset(engine):
     assert torch.equal(a, b)
     del a, b, planes, codes
     names = [f"s{i}" for i in range(n)]
+    # N = 10,000 is beyond what the CPU oracle joins in test time: the two GPU NJ kernels (the fast one with
+    # 512-column scan items at this size, and the general one: other item width, two grid barriers per iteration,
+    # row sums in global memory) must give the same join list and branch lengths bit for bit
+    from phyloforge_b200._lib import check
+    dist, _ = engine.normalise(counts, "ibs")
+    fast = engine.nj(dist)
+    check(engine.lib.pf_nj_profile(2, None))
+    try:
+        general = engine.nj(dist)
+    finally:
+        check(engine.lib.pf_nj_profile(0, None))
+    assert torch.equal(fast[0], general[0]) and torch.equal(fast[1], general[1])
+    del dist, fast, general
     res = engine.tree_from_counts(counts, names, keep=False)
     tree = treecmp.parse_newick(res.newick)
     assert sorted(treecmp.leaves(tree)) == sorted(names)
