@@ -617,8 +617,9 @@ pair_counts_tc_kernel(const TcParams P) {
 //     multicast commit per stage.
 // Hand-over. Inside a CTA through hardware named barriers: thread 0 polls the mbarriers (raw data landed, stage
 // slot free) and releases the expansion warps with bar.sync; after the stage's writes (tcgen05.wait::st +
-// tcgen05.fence / fence.proxy.async) another bar.sync, and thread 0 arrives on the LEADER's exp_full barrier (count
-// 2: one arrival per CTA; the peer's is a remote arrive). Stage consumed: ONE multicast tcgen05.commit per stage on
+// tcgen05.fence / fence.proxy.async) every warp bumps a shared-memory counter (acq_rel at CTA scope) and the warp that
+// finishes the slot last arrives on the LEADER's exp_full barrier (count 2: one arrival per CTA; the peer's is a
+// remote arrive). Stage consumed: ONE multicast tcgen05.commit per stage on
 // a ring of stage_done barriers in both CTAs; the expansion warps (reuse of the expanded stage EXP stages later)
 // and the TMA producer (reuse of the raw stage RAW stages later) wait on the same ring, whose depth max(RAW, EXP)
 // keeps a waiter at most one phase behind.
@@ -740,6 +741,7 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
   __shared__ uint32_t s_tmem;
   __shared__ int s_hcount[TC2_IH + J];
   __shared__ int s_valid_sites;
+  __shared__ int s_stage_warps[8];      // per expanded slot: expansion warps that have finished writing it
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool general = __ldg(P.flags) != 0;
@@ -777,6 +779,7 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
     umma::fence_mbar_init();
   }
   if (tid == 0) s_valid_sites = 0;
+  if (tid < 8) s_stage_warps[tid] = 0;
   umma::fence_before_thread_sync();
   umma::cluster_sync();                          // barriers of both CTAs exist before any remote arrival
   umma::fence_after_thread_sync();
@@ -925,15 +928,22 @@ pair_counts_tc2_kernel(const __grid_constant__ TcParams P) {
       const long long tf = PROF ? clock64() : 0;
       if (wrote_smem) umma::fence_proxy_async_smem();    // generic-proxy operand writes -> the tensor cores' async proxy
       const long long tb = PROF ? clock64() : 0;
-      asm volatile("bar.sync 3, %0;" ::"r"(EXP_THREADS) : "memory");
+      // the warp that finishes the slot last hands it over (no second barrier round: a counter in shared memory,
+      // acquire-release at CTA scope, orders the other warps' fenced writes before the arrive)
+      __syncwarp();
+      if (lane == 0) {
+        int done;
+        asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(done) : "r"(umma::smem_addr(&s_stage_warps[e])) : "memory");
+        if (done == G::EXP_WARPS - 1) {
+          s_stage_warps[e] = 0;             // next used EXP stages later, after a named-barrier round of all warps
+          if (strict) umma::mbar_arrive_cluster(exp_full_leader + e * 8);
+          else if (rank == 0) umma::mbar_arrive_a(exp_full_a + e * 8);
+          else umma::mbar_arrive_remote(exp_full_leader + e * 8);
+        }
+      }
       if (PROF) {
         t_fence += tb - tf;
         t_end += clock64() - tb;
-      }
-      if (tid == 0) {
-        if (strict) umma::mbar_arrive_cluster(exp_full_leader + e * 8);
-        else if (rank == 0) umma::mbar_arrive_a(exp_full_a + e * 8);
-        else umma::mbar_arrive_remote(exp_full_leader + e * 8);
       }
       if (++stage == G::RAW) {
         stage = 0;
