@@ -253,3 +253,49 @@ def test_tensor_path_workspace_size_of_degenerate_ranges():
     sizes = [lib.pf_pair_counts_tc_work_bytes(300, w) for w in (1, 2, 15, 16, 17, 63, 64, 65, 1000)]
     assert all(b > 0 for b in sizes) and sizes == sorted(sizes)
     assert lib.pf_pair_counts_tc_work_bytes(10000, 156250) > 2 * 25_000_000_000 // 2      # two operand streams at C5
+
+
+def test_bgzf_reader_inflates_blocks_in_order(tmp_path):
+    """phyloforge_b200.vcf._BgzfReader (parallel inflate of bgzip blocks) returns the original bytes for any read
+    size, recognises BGZF by its 'BC' subfield (a plain gzip file is left to the gzip module), and reports damage."""
+    import gzip
+    import numpy as np
+    import vcfgen
+    from phyloforge_b200 import vcf
+    rng = np.random.default_rng(3)
+    data = bytes(rng.integers(32, 127, size=700_001, dtype=np.uint8)) + b"\n"
+    path = tmp_path / "x.vcf.gz"
+    vcfgen.write_bgzf(path, data, block=40_000, seed=1)
+    assert gzip.open(path, "rb").read() == data                      # a valid multi-member gzip file
+    assert isinstance(vcf._open_stream(str(path)), vcf._BgzfReader)
+    for size in (1, 4096, 65536 * 3 + 17, len(data) + 5):
+        out = bytearray()
+        with vcf._BgzfReader(str(path), threads=3) as r:
+            buf = bytearray(size)
+            while True:
+                k = r.readinto(buf)
+                if not k:
+                    break
+                out += buf[:k]
+                if len(out) > len(data):
+                    break
+        assert bytes(out) == data, size
+    plain = tmp_path / "p.vcf.gz"
+    with gzip.open(plain, "wb") as f:
+        f.write(data)
+    assert not isinstance(vcf._open_stream(str(plain)), vcf._BgzfReader)
+    raw = bytearray(path.read_bytes())
+    broken = tmp_path / "b.vcf.gz"
+    broken.write_bytes(bytes(raw[:len(raw) // 2]))                  # cut in the middle of a block
+    with pytest.raises(vcf.VcfFormatError):
+        with vcf._BgzfReader(str(broken)) as r:
+            buf = bytearray(1 << 20)
+            while r.readinto(buf):
+                pass
+    raw[300] ^= 0x55                                                 # flip bits inside the first block's deflate stream
+    broken.write_bytes(bytes(raw))
+    with pytest.raises(vcf.VcfFormatError):
+        with vcf._BgzfReader(str(broken)) as r:
+            buf = bytearray(1 << 20)
+            while r.readinto(buf):
+                pass

@@ -175,3 +175,28 @@ def bad_sv_lines():
         ("allele index 2", "chr1\t5\t.\tN\t<DEL>\t.\t.\tSVTYPE=DEL\tGT\t2/2\t0/0\n"),
         ("haploid GT", "chr1\t5\t.\tN\t<DEL>\t.\t.\tSVTYPE=DEL\tGT\t1\t0/0\n"),
     ]
+
+
+def write_bgzf(path, data: bytes, block=0xff00, seed=0):
+    """bgzip-style file: independent gzip members with the 'BC' extra subfield (SAM specification 4.1), blocks of
+    varying uncompressed size, terminated by the 28-byte empty EOF block."""
+    import random
+    import struct
+    import zlib
+    rng = random.Random(seed)
+
+    def member(chunk: bytes) -> bytes:
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        cdata = co.compress(chunk) + co.flush()
+        bsize = 12 + 6 + len(cdata) + 8
+        assert bsize <= 65536
+        return (b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\0\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+                + cdata + struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+
+    with open(path, "wb") as f:
+        pos = 0
+        while pos < len(data):
+            k = rng.randint(1, block)
+            f.write(member(data[pos:pos + k]))
+            pos += k
+        f.write(member(b""))
