@@ -4,12 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (config.workload): BASELINE.json configs[3], "3,000 samples x 10M SNPs", the shape the
-north-star target is quoted on; it fits one B200 (30 GB of site-major byte genotypes + 7.5 GB of
-bit planes), so the same total work is used at every N and the site axis is sharded over the
-ranks. Default "scaling": "weak" — every GPU holds the named configuration's 10M sites (the global
-matrix has N x 10M sites; N = 1 is exactly the named configuration); `--scaling strong` splits the 10M
-sites over the GPUs instead (round-1 measurements of both are in profiles/).
+Workload (config.workload): BASELINE.json configs[3], "3,000 samples x 10M SNPs, sites sharded over 2/4/8
+B200", the shape the north-star target is quoted on. It fits one B200 (30 GB of site-major byte genotypes +
+7.5 GB of bit planes). Default "scaling": "strong" — the named configuration's 10M sites are split over the N
+ranks, as BASELINE.json words it, so every N measures the SAME job; `--scaling weak` gives every GPU the full 10M
+sites instead. The default run also prints two bounded sub-records under "extra": "weak" (N > 1) and "c5"
+(BASELINE configs[4], 10,000 x 5M with 10 % missing genotypes, which BASELINE names for 8 GPUs).
 
 A step = one pass of the hot path over the whole batch:
     pack (byte genotypes -> bit planes) -> all-pairs counts -> [NCCL allreduce of the
@@ -20,12 +20,19 @@ A step = one pass of the hot path over the whole batch:
           memory (2-bit site-major rows by default, --e2e-format u8 for one byte per genotype),
           host->device copies (chunked, overlapped with pack + counts) and the device->host read
           of the result (distance matrix, join list -> Newick) are timed.
-  roofline      the pair-count kernel against the integer-pipe peak measured live by
-                pf_microbench_int_pipe (MEASURED_PEAKS.json has no integer peaks).
+  roofline      the pair-count kernel: tensor-core kernel against 4 x MEASURED_PEAKS bf16 and against the fp4
+                rate measured in this run by the probes library; popcount kernel against the integer-pipe
+                peak measured in this run.
+  roofline_nj   the NJ kernel against measured HBM (4 n^2 bytes of live upper triangle per iteration).
   cpu_baseline  the CPU oracle (oracle/pf_oracle.c, all host threads) on a bounded sample,
                 rank 0 at N=1 only.
 `--impl reference` times that CPU port alone (the reference's own engine for distance + NJ is
 the absent external `treebest`; oracle/__init__.py).
+
+`--workload c1-vcf | c2-vcf`: BASELINE configs[0] / configs[1] as real VCF TEXT through the reference-facing
+entry point (`phyloforge -s/-S cfg`): file -> character matrix -> packed genotypes -> distances -> NJ -> tree
+files; the CPU leg beside it is the reference's own converter (the unmodified one when /root/reference is
+present, else its restatement oracle/ref_convert.py), which is all of this path the reference runs itself.
 """
 from __future__ import annotations
 
@@ -48,9 +55,16 @@ WORKLOADS = {
     "c4": (3000, 10_000_000, 0, "3,000 samples x 10M SNPs (BASELINE configs[3])"),
     "c5": (10000, 5_000_000, 100_000, "10,000 samples x 5M SNPs, 10% missing (BASELINE configs[4])"),
 }
+VCF_WORKLOADS = {
+    # name: (kind, samples, records, miss_ppm, description)
+    "c1-vcf": ("snp", 50, 100_000, 0, "VCF text, 50 samples x 100k biallelic SNPs through `phyloforge -s` (BASELINE configs[0])"),
+    "c2-vcf": ("sv", 500, 100_000, 50_000, "SV VCF text, 500 samples x 100k SVs, 5% missing, through `phyloforge -S` (BASELINE configs[1])"),
+}
 METRIC = "sample_pair_sites_per_s"
 UNIT = "pair-sites/s"
 SEED = 42
+DTYPE = ("e2m1 x e2m1 -> f32 tensor-core indicator products (exact: integers < 2^24 per CTA) -> int32 counts; "
+         "f64 distances + NJ; u32 bit planes")
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
 NCU_TRAFFIC_BYTES_TC = 54_051_894_000  # r01: 52.15 GB read + 1.90 GB written per launch of pair_counts_tc2_kernel (profiles/r01_ncu_pair_counts_tc2_raw_subset.csv), N=1
@@ -59,6 +73,30 @@ NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (prof
 
 def pair_sites(n, m):
     return n * (n - 1) // 2 * m
+
+
+def workload_config(name: str, world: int, scaling: str) -> dict:
+    """The `config` object of the JSON line. Both arms (ours / --impl reference) print exactly this dict."""
+    if name in VCF_WORKLOADS:
+        kind, n, m, miss, desc = VCF_WORKLOADS[name]
+        return {"workload": desc, "samples": n, "sites": m, "miss_ppm": miss, "gpus": world, "scaling": scaling,
+                "parallelism": "one GPU (the VCF text workloads run through the single-process entry point)",
+                "l2": "every step re-reads the VCF file (page cache) and re-parses it; inputs exceed L2 except c1-vcf (23 MB), "
+                      "whose step writes > 126 MB of intermediate buffers between passes",
+                "seed": SEED}
+    n, m, miss, desc = WORKLOADS[name]
+    m_total = m * world if scaling == "weak" else m
+    ld = (n + 3) // 4 * 4
+    per_gpu = m if scaling == "weak" else -(-m // world)
+    return {"workload": desc + ("" if world == 1 or scaling == "strong" else
+                                f" per GPU: {m_total} sites over {world} GPUs (weak scaling)"),
+            "samples": n, "sites": m_total, "miss_ppm": miss, "gpus": world, "scaling": scaling,
+            "parallelism": f"sites sharded over {world} GPU(s), int32 counts allreduce (NCCL), NJ replicated",
+            "l2": ("inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (per_gpu * ld / 1e9)
+                   if per_gpu * ld > 256e6 else
+                   "inputs (%.0f MB/GPU) are smaller than L2 and not flushed: a parity-size workload, not a bench line"
+                   % (per_gpu * ld / 1e6)),
+            "seed": SEED}
 
 
 # ---------------------------------------------------------------------- clocks
@@ -117,12 +155,23 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------- CPU arm
+def cpu_threads_all() -> int:
+    """Use every host core for the CPU arm, whatever OMP_NUM_THREADS says: torch.distributed.run exports
+    OMP_NUM_THREADS=1 to its workers, which made the round-1 reference arm 16x slower under torchrun."""
+    from oracle import cpu as oracle
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    return oracle.set_num_threads(cores)
+
+
 def cpu_port_run(n, m, miss_ppm, sample_sites, with_nj=True):
     """The CPU oracle on `sample_sites` sites of the workload (all host threads) + NJ at the
     full sample count. Returns timings and the extrapolated whole-path throughput."""
     import numpy as np
     from oracle import cpu as oracle
-    sample_sites = min(sample_sites, m)
+    sample_sites = max(64, min(sample_sites, m))
     t0 = time.perf_counter()
     codes = oracle.synth_codes(n, 0, sample_sites, seed=SEED, miss_ppm=miss_ppm)      # site-major (untimed input)
     t_gen = time.perf_counter() - t0
@@ -149,15 +198,31 @@ def cpu_port_run(n, m, miss_ppm, sample_sites, with_nj=True):
             "counts_only_value": pair_sites(n, sample_sites) / t_counts}
 
 
+CPU_PORT_NOTE = ("The reference's own engine for counts + NJ (treebest) is absent: this is the restated oracle "
+                 "(oracle/pf_oracle.c, gcc -O3 -fopenmp), whose counts loop is an unblocked row-pair popcount - a soft "
+                 "baseline, stated, never the target")
+
+
 def run_reference_arm(args):
-    """`--impl reference`: the CPU port of the path, all host threads, bounded sample per step."""
+    """`--impl reference`: the CPU port of the path, all host threads, bounded sample per step.
+    The sample per step is sized from a short calibration pass so that the whole run (W + K steps + one full NJ)
+    stays near --cpu-arm-seconds whatever K and W the driver passes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if args.workload in VCF_WORKLOADS:
+        return run_reference_arm_vcf(args)
+    threads = cpu_threads_all()
     n, m, miss, desc = WORKLOADS[args.workload]
     if args.scaling == "weak":
         m = m * max(1, args.gpus)          # same global configuration as our arm at this N
+    t_start = time.perf_counter()
     sample = args.cpu_sample_sites
+    if sample <= 0:
+        probe = cpu_port_run(n, m, miss, 1 << 14, with_nj=False)
+        per_site = (probe["gen_s"] + probe["pack_s"] + probe["counts_s"]) / probe["sample_sites"]
+        budget = max(5.0, args.cpu_arm_seconds * 0.8) / max(1, args.warmup + args.steps)
+        sample = int(min(1 << 18, max(1 << 12, budget / per_site)) // 64 * 64)
     runs = []
     for i in range(args.warmup + args.steps):
         r = cpu_port_run(n, m, miss, sample, with_nj=(i == args.warmup))   # NJ (independent of M) once
@@ -172,43 +237,32 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": statistics.mean(r["pack_s"] + r["counts_s"] + r["normalise_s"] for r in runs) * 1e3,
-        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u32 bit-planes / int64 counts / f64",
-        "data": "synthetic", "config": {"workload": desc, "samples": n, "sites": m, "miss_ppm": miss},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": runs[0]["threads"], "kind": "port",
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "u64 bit planes + popcount -> int64 counts; f64 distances + NJ",
+        "data": "synthetic", "config": workload_config(args.workload, max(1, args.gpus), args.scaling),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": (f"{runs[0]['sample_sites']} of {m} sites x all {n} samples per step "
                                     f"(pack + counts, scaled linearly in sites) + normalise + one full NJ at N={n} "
-                                    f"({nj_s:.2f} s); whole-path time extrapolated to {full_s:.1f} s. The reference's "
-                                    "own engine for this step (treebest) is absent: this is the restated oracle"),
+                                    f"({nj_s:.2f} s); whole-path time extrapolated to {full_s:.1f} s. " + CPU_PORT_NOTE),
                          "nj_seconds": nj_s},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t_start,
     }
     print(json.dumps(line), file=args.out, flush=True)
     return 0
 
 
 # ---------------------------------------------------------------------- GPU arm
-def run_ours(args):
+def _measure(eng, args, n, m, miss, scaling, steps, warmup, world, rank, with_e2e, with_split):
+    """Time `steps` passes of the hot path (after `warmup` untimed ones) on this rank's site shard of an
+    n x m workload; returns a dict of measurements (times are max over ranks where noted)."""
     import torch
     import torch.distributed as dist
-    from phyloforge_b200.engine import Engine
     from phyloforge_b200 import sharding
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = Engine(local_rank)
     dev = eng.device
-
-    n, m, miss, desc = WORKLOADS[args.workload]
     names = [f"S{i:05d}" for i in range(n)]
-    if args.scaling == "weak":
+    if scaling == "weak":
         # every rank holds one full copy's worth of sites of the named configuration: the global
         # matrix has world x m sites (rank r owns sites [r m, (r + 1) m)); N = 1 is the named config
         m_total = m * world
@@ -260,34 +314,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(False)
     barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     time.sleep(0.25)
+    launches0 = int(eng.lib.pf_launch_count())
     t_wall0 = time.perf_counter()
     start = torch.cuda.Event(enable_timing=True)
     stop = torch.cuda.Event(enable_timing=True)
     start.record()
-    for _ in range(args.steps):
-        merge, length = step(True)
+    for _ in range(steps):
+        step(True)
     stop.record()
     barrier()
+    launches = int(eng.lib.pf_launch_count()) - launches0
     t_wall1 = time.perf_counter()
     clocks = sampler.stop(t_wall0, t_wall1)
     elapsed_ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    ms_per_step = float(elapsed_ms.item()) / args.steps
-    value = pair_sites(n, m_total) / (ms_per_step * 1e-3)
+    ms_per_step = float(elapsed_ms.item()) / steps
     stages_ms = {k: statistics.mean(a.elapsed_time(b) for a, b in v) for k, v in stage_ev.items()}
-    counts_ms = stages_ms["counts"]
     del codes
+    out = {"n": n, "m_total": m_total, "my_sites": my_sites, "my_words": my_words, "ld": ld, "ms_per_step": ms_per_step,
+           "value": pair_sites(n, m_total) / (ms_per_step * 1e-3), "stages_ms": stages_ms, "clocks": clocks,
+           "variant": ran_variant[0], "gpu_launches": launches, "tc_split": None, "e2e": None,
+           "tc_launches": getattr(eng, "tc_launches", 1) if ran_variant[0] == 3 else 0}
     # split of the counts stage into its two kernels (untimed extra passes, CUDA events on the launching stream
     # recorded inside pf_pair_counts_tc): operand-stream conversion and the tensor-core GEMM launch(es)
-    tc_split = None
-    if ran_variant[0] == 3:
+    if with_split and ran_variant[0] == 3:
         import ctypes as C
         from phyloforge_b200._lib import check
         check(eng.lib.pf_pair_counts_tc_timing(1, None))
@@ -300,42 +357,131 @@ def run_ours(args):
             conv.append(float(ms2[0]))
             gemm.append(float(ms2[1]))
         check(eng.lib.pf_pair_counts_tc_timing(0, None))
-        tc_split = {"conversion_ms": statistics.mean(conv), "gemm_ms": statistics.mean(gemm)}
+        out["tc_split"] = {"conversion_ms": statistics.mean(conv), "gemm_ms": statistics.mean(gemm)}
+    del planes, counts
 
     # ---- end to end from pinned host memory through the public host-buffer API
-    e2e = None
-    if not args.no_e2e:
+    if with_e2e:
         chunk_sites = args.e2e_chunk_sites
         packed2 = args.e2e_format == "2bit"
         ld_host = ((n + 15) // 16 * 4) if packed2 else ld
-        host = torch.empty((my_sites, ld_host), dtype=torch.uint8).pin_memory()
+        host = eng.pinned_host_buffer((my_sites, ld_host))
         for c0 in range(0, my_sites, chunk_sites):                 # fill the host buffer (untimed)
             c1 = min(my_sites, c0 + chunk_sites)
             tmp = eng.synth_codes(n, site0 + c0, c1 - c0, seed=SEED, miss_ppm=miss)
             host[c0:c1].copy_(eng.to_2bit_rows(tmp, n) if packed2 else tmp)
             del tmp
         torch.cuda.synchronize()
-        e2e_steps = max(1, min(args.steps, args.e2e_steps))
-        res = None
-        for _ in range(1):
-            res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant,
-                                           packed2=packed2)
+        e2e_steps = max(1, min(steps, args.e2e_steps))
+        res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant,
+                                       packed2=packed2)
         barrier()
         t0 = time.perf_counter()
+        h2d_ms = []
         for _ in range(e2e_steps):
             res = eng.tree_from_host_codes(host, n, names, metric="ibs", chunk_sites=chunk_sites, variant=args.variant,
                                            packed2=packed2)
+            h2d_ms.append(res.timings_ms.get("h2d", 0.0))
         barrier()
         t_e2e = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        h2d_bytes = int(my_sites) * ld_host
+        my_rate = torch.tensor([h2d_bytes / max(1e-9, statistics.mean(h2d_ms) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        rates = [my_rate.clone() for _ in range(world)]
         if world > 1:
             dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": pair_sites(n, m_total) / float(t_e2e.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(my_sites) * ld_host, "d2h_bytes_per_step": int(res.d2h_bytes),
-               "host_format": ("site-major 2-bit genotypes, 4 samples per byte" if packed2 else "site-major u8 genotype codes"),
-               "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps,
-               "api": "Engine.tree_from_host_codes (pinned host genotype rows -> Newick + distance matrix)",
-               "timing": "host wall clock between barriers + cuda synchronize (includes H2D, D2H, host Newick assembly)"}
+            dist.all_gather(rates, my_rate)
+        out["e2e"] = {"value": pair_sites(n, m_total) / float(t_e2e.item()), "unit": UNIT,
+                      "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(res.d2h_bytes),
+                      "host_format": ("site-major 2-bit genotypes, 4 samples per byte" if packed2 else "site-major u8 genotype codes"),
+                      "ms_per_step": float(t_e2e.item()) * 1e3, "steps": e2e_steps,
+                      "h2d_gbps_per_rank": [round(float(r.item()), 2) for r in rates],
+                      "h2d_note": "bytes of this rank's rows / time from its first to its last host->device copy "
+                                  "(copy-stream events); the copies overlap pack + counts of the previous chunk",
+                      "api": "Engine.tree_from_host_codes (pinned host genotype rows -> Newick + distance matrix)",
+                      "timing": "host wall clock between barriers + cuda synchronize (includes H2D, D2H, host Newick assembly)"}
         del host
+    eng.release_scratch()
+    torch.cuda.empty_cache()
+    return out
+
+
+def _roofline_nj(n, nj_ms, hbm_peak, peak_src):
+    """NJ: the scan of the live upper triangle is the only part that scales - 4 na^2 bytes per iteration
+    (DESIGN.md §4); the rest is a chain of dependent round trips, reported as microseconds per iteration."""
+    scan_bytes = sum(4 * na * na for na in range(4, n + 1))
+    ach = scan_bytes / (nj_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+            "kernel": "nj_fast_kernel" if n <= 11000 else "nj_kernel", "kernel_ms": nj_ms,
+            "us_per_iteration": nj_ms * 1e3 / max(1, n - 3), "iterations": n - 3, "algorithmic_bytes": scan_bytes,
+            "peak_source": peak_src,
+            "note": "algorithmic bytes = sum over iterations of 4 na^2 (fp64 upper triangle of the live matrix), ~4 n^3 / 3; "
+                    "the matrix (8 n^2 bytes) is L2-resident below ~3,900 nodes, so DRAM traffic is far lower than this "
+                    "and the kernel is bound by the per-iteration latency chain (one grid-wide exchange + update), "
+                    "not by HBM: us_per_iteration is the number to read"}
+
+
+def _fp4_peak(eng):
+    """Sustained rate of tcgen05.mma.cta_group::2 kind::mxf4 on every CTA pair of the device at once, timed with
+    CUDA events around a ~0.4 s launch (probes library; operands resident in shared memory)."""
+    import ctypes as C
+    import torch
+    from phyloforge_b200 import _lib
+    try:
+        probes = _lib.load_probes()
+        tops, ms = C.c_double(), C.c_double()
+        out = {}
+        for n_cols in (208, 240):
+            _lib.check_probe(probes.pf_probe_umma_fp4_2cta_peak(n_cols, 200_000, 4, C.byref(tops), C.byref(ms),
+                                                               torch.cuda.current_stream().cuda_stream))
+            reps = int(max(200_000, 200_000 * 400.0 / max(1e-3, ms.value)))
+            _lib.check_probe(probes.pf_probe_umma_fp4_2cta_peak(n_cols, reps, 4, C.byref(tops), C.byref(ms),
+                                                               torch.cuda.current_stream().cuda_stream))
+            out[n_cols] = {"tops": tops.value, "ms": ms.value}
+        return out
+    except Exception as e:  # noqa: BLE001 - a missing probe must not lose the bench line
+        return {"error": str(e)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from phyloforge_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if args.workload in VCF_WORKLOADS:
+        rc = run_ours_vcf(args, world, rank, local_rank)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return rc
+    eng = Engine(local_rank)
+
+    n, m, miss, desc = WORKLOADS[args.workload]
+    main = _measure(eng, args, n, m, miss, args.scaling, args.steps, args.warmup, world, rank,
+                    with_e2e=not args.no_e2e, with_split=True)
+    extra = {}
+    if not args.no_extra:
+        xs, xw = max(1, min(args.steps, args.extra_steps)), 2
+        if world > 1 and args.scaling == "strong":
+            w = _measure(eng, args, n, m, miss, "weak", xs, xw, world, rank, with_e2e=not args.no_e2e, with_split=False)
+            extra["weak"] = {"config": workload_config(args.workload, world, "weak"), "value": w["value"], "unit": UNIT,
+                             "ms_per_step": w["ms_per_step"], "steps": xs, "warmup": xw, "stages_ms": w["stages_ms"],
+                             "e2e": w["e2e"], "scaling": "weak"}
+        if args.workload == "c4":
+            n5, m5, miss5, _ = WORKLOADS["c5"]
+            c5 = _measure(eng, args, n5, m5, miss5, "strong", xs, 1, world, rank, with_e2e=False, with_split=False)
+            extra["c5"] = {"config": workload_config("c5", world, "strong"), "value": c5["value"], "unit": UNIT,
+                           "ms_per_step": c5["ms_per_step"], "steps": xs, "warmup": 1, "stages_ms": c5["stages_ms"],
+                           "nj_seconds": c5["stages_ms"]["nj"] * 1e-3, "gemm_launches": c5["tc_launches"],
+                           "scaling": "strong", "pair_counts_variant": c5["variant"]}
 
     if rank != 0:
         if world > 1:
@@ -343,46 +489,47 @@ def run_ours(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (pair counts), against the live integer-pipe peak
-    popc_ops, _ = eng.microbench_int_pipe(0, 1500)
-    lop3_ops, _ = eng.microbench_int_pipe(1, 1500)
-    pair_words = n * (n - 1) // 2 * my_words       # algorithmic: unordered pairs x words of this rank
-    # Instructions the kernel needs per unordered pair per 32-site word (DESIGN.md "Kernels";
-    # counted in the SASS of pair_counts_kernel):
-    #   plain popcount (variant 1): 2 LOP3 + 2 POPC without missing data, 4.5 LOP3 + 3 POPC with
-    #   carry-save (variant 0/2)  : 4 LOP3 + 1 POPC (+1 IMAD) without missing data; chunks that hold
-    #                               missing genotypes run the plain body
+    my_sites, my_words, ld = main["my_sites"], main["my_words"], main["ld"]
+    stages_ms, counts_ms, tc_split = main["stages_ms"], main["stages_ms"]["counts"], main["tc_split"]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"
+    pair_words = n * (n - 1) // 2 * my_words       # algorithmic: unordered pairs x words of this rank
     achieved_pw = pair_words / (counts_ms * 1e-3)
-    plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
-    variant_ran = ran_variant[0]
+    variant_ran = main["variant"]
     if variant_ran == 3:
         # tensor-core indicator GEMMs on 4-bit (E2M1) operands: 2 multiply-accumulates per unordered pair
         # per site (4 with sample-specific missingness)
         bf16 = peaks.get("bf16_tflops", 1590.0)
         peak_tops = 4.0 * bf16                      # dense fp4 = 4 x dense bf16 on the same tensor cores (9 vs 2.25 PFLOP/s nominal)
-        launches = getattr(eng, "tc_launches", 1)    # 2 = the missing-data launch (TT, VV) ran too
+        launches = main["tc_launches"]              # 2 = the missing-data launch (TT, VV) ran too
         macs_per = 4.0 if launches == 2 else 2.0
         macs = macs_per * pair_sites(n, my_sites)
         gemm_ms = tc_split["gemm_ms"] if tc_split else counts_ms
         achieved_tops = 2.0 * macs / (gemm_ms * 1e-3) / 1e12
         stage_tops = 2.0 * macs / (counts_ms * 1e-3) / 1e12
+        fp4 = _fp4_peak(eng)
+        fp4_tops = fp4.get(208, {}).get("tops") if isinstance(fp4, dict) else None
         roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": peak_tops, "unit": "TOP/s (fp4)",
                     "frac": achieved_tops / peak_tops, "traffic": NCU_TRAFFIC_BYTES_TC,
                     "kernel": "pair_counts_tc2_kernel (tcgen05.mma.cta_group::2 kind::mxf4 on CTA pairs, E2M1 operands)",
                     "kernel_ms": gemm_ms, "stream_conversion_ms": tc_split["conversion_ms"] if tc_split else None,
                     "counts_stage_ms": counts_ms, "frac_of_counts_stage": stage_tops / peak_tops,
+                    "peak_fp4_measured": fp4_tops,
+                    "frac_of_fp4_measured": (achieved_tops / fp4_tops) if fp4_tops else None,
+                    "frac_of_counts_stage_vs_fp4_measured": (stage_tops / fp4_tops) if fp4_tops else None,
+                    "fp4_probe": fp4,
                     "ops_per_pair_site": {"fp4_mac": macs_per}, "gemm_launches": launches,
-                    "frac_of_popcount_kernel_roofline": achieved_pw / (min(lop3_ops / 4.0, popc_ops / 1.0) if miss == 0
-                                                                       else plain_popc_peak_pw),
-                    "frac_of_plain_popcount_roofline": achieved_pw / plain_popc_peak_pw,
                     "frac_of_int8_tensor_peak": achieved_tops / (2.0 * bf16),
-                    "peak_source": "4 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no fp4 entry; nominal dense "
-                                   "fp4 is 9000 TOP/s, 4 x the 2250 of bf16)" % ("of measured" if peaks else "of fallback 1590"),
+                    "peak_source": "peak = 4 x MEASURED_PEAKS.json bf16_tflops (%s; the file has no fp4 entry; nominal dense "
+                                   "fp4 is 9000 TOP/s, 4 x the 2250 of bf16). peak_fp4_measured = the same instruction "
+                                   "(256 x 208 x 64 kind::mxf4 on CTA pairs) issued back to back on resident operands by every "
+                                   "pair of the device for ~0.4 s, CUDA events around the launch, in this run (probes "
+                                   "library): the harsher denominator" % ("of measured" if peaks else "of fallback 1590"),
                     "note": "algorithmic work = unordered sample pairs x sites x 2 MAC (x.x' and h.h'; 4 MAC with "
                             "sample-specific missingness: + t.t', v.v'); the kernel also computes ~16% redundant "
                             "pairs in the 256 x 208 tiles that straddle the diagonal. frac = the GEMM kernel alone "
@@ -390,6 +537,20 @@ def run_ours(args):
                             "frac_of_counts_stage also charges the planes -> 4-bit operand stream conversion "
                             "(planes_to_e2m1_kernel, stream_conversion_ms) to it, as the timed step does"}
     else:
+        import ctypes as C
+        from phyloforge_b200 import _lib
+        probes = _lib.load_probes()
+
+        def int_pipe(kind):
+            a, b = C.c_double(), C.c_double()
+            _lib.check_probe(probes.pf_microbench_int_pipe(kind, 1500, C.byref(a), C.byref(b),
+                                                           torch.cuda.current_stream().cuda_stream))
+            return a.value
+        popc_ops, lop3_ops = int_pipe(0), int_pipe(1)
+        plain_popc_peak_pw = popc_ops / (2.0 if miss == 0 else 3.0)
+        # Instructions the kernel needs per unordered pair per 32-site word (DESIGN.md "Kernels"; counted in the SASS of
+        # pair_counts_kernel): plain popcount (variant 1) 2 LOP3 + 2 POPC without missing data, 4.5 LOP3 + 3 POPC with;
+        # carry-save (variant 0/2) 4 LOP3 + 1 POPC (+1 IMAD) without missing data; chunks with missing genotypes run the plain body
         csa = variant_ran != 1
         if miss == 0:
             lop_per_pw, popc_per_pw = (4.0, 1.0) if csa else (2.0, 2.0)
@@ -410,40 +571,245 @@ def run_ours(args):
                     "note": "algorithmic pair-words = unordered sample pairs x 32-site words of this rank; "
                             "frac_of_plain_popcount_roofline is against SURVEY 8(d)'s POPC-only bound "
                             "(POPC rate / 2 or 3 per pair-word), which the carry-save kernel may exceed"}
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
     pack_bytes = my_sites * ld + my_words * ((n + 63) // 64) * 64 * 8
     roofline_pack = {"bound": "hbm", "achieved": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": None, "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"],
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s"}
+                     "traffic": None, "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"], "peak_source": hbm_src}
+    roofline_nj = _roofline_nj(n, stages_ms["nj"], hbm_peak, hbm_src)
+    if "c5" in extra:
+        extra["c5"]["roofline_nj"] = _roofline_nj(WORKLOADS["c5"][0], extra["c5"]["stages_ms"]["nj"], hbm_peak, hbm_src)
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_port_run(n, m, miss, args.cpu_sample_sites, with_nj=True)
-        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+        threads = cpu_threads_all()
+        sample = args.cpu_sample_sites if args.cpu_sample_sites > 0 else 1 << 18
+        r = cpu_port_run(n, m, miss, sample, with_nj=True)
+        cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": (f"{r['sample_sites']} of {m} sites x all {n} samples (pack {r['pack_s']:.2f} s + "
                                    f"counts {r['counts_s']:.2f} s, scaled linearly in sites) + normalise + full NJ at "
-                                   f"N={n} ({r['nj_s']:.2f} s): whole path extrapolated to {r['extrapolated_full_s']:.1f} s"),
+                                   f"N={n} ({r['nj_s']:.2f} s): whole path extrapolated to {r['extrapolated_full_s']:.1f} s. "
+                                   + CPU_PORT_NOTE),
                         "counts_only_value": r["counts_only_value"], "nj_seconds": r["nj_s"]}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": "u32 bit-planes / int32 counts / f64 distances+NJ", "data": "synthetic",
-        "config": {"workload": desc + ("" if world == 1 or args.scaling == "strong" else
-                                       f" per GPU: {m_total} sites over {world} GPUs (weak scaling)"),
-                   "samples": n, "sites": m_total, "miss_ppm": miss, "sites_per_gpu": my_sites,
-                   "parallelism": f"sites sharded over {world} GPU(s), int32 counts allreduce (NCCL), NJ replicated",
-                   "l2": "inputs (%.1f GB/GPU of byte genotypes) exceed L2; no flush needed" % (my_sites * ld / 1e9),
-                   "pair_counts_variant": ran_variant[0], "pair_counts_variant_requested": args.variant, "seed": SEED},
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": DTYPE, "data": "synthetic", "config": workload_config(args.workload, world, args.scaling),
+        "detail": {"sites_per_gpu": my_sites, "pair_counts_variant": variant_ran,
+                   "pair_counts_variant_requested": args.variant},
         "nj_seconds": stages_ms["nj"] * 1e-3, "stages_ms": stages_ms,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": (7 if ran_variant[0] == 3 else 4) * args.steps,   # pack, (2 stream conversions, 2 GEMM launches | popcount), normalise, NJ
-        "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu_baseline,
+        "clocks": main["clocks"], "e2e": main["e2e"], "gpu_launches": main["gpu_launches"],
+        "gpu_launches_note": "pf_launch_count() after - before the timed region on rank 0: every kernel launch of "
+                             "libphyloforge_b200.so (pack, operand-stream conversions, tensor-core GEMM launches, normalise, NJ)",
+        "roofline": roofline, "roofline_pack": roofline_pack, "roofline_nj": roofline_nj, "cpu_baseline": cpu_baseline,
+        "extra": extra,
     }
     print(json.dumps(line), file=args.out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+# ---------------------------------------------------------------------- VCF text workloads
+def _make_vcf(eng, name, path):
+    """Synthetic VCF text of a VCF workload (genotype codes from the device generator, rendered by
+    phyloforge_b200/synth.py), written to `path`. Returns (bytes, n, m)."""
+    from phyloforge_b200 import synth
+    kind, n, m, miss, _ = VCF_WORKLOADS[name]
+    names = [f"S{i:04d}" for i in range(n)]
+    codes = eng.synth_codes(n, 0, m, seed=SEED, miss_ppm=miss)[:, :n].cpu().numpy()
+    text = synth.snp_vcf_bytes(codes, names)[0] if kind == "snp" else synth.sv_vcf_bytes(codes, names)[0]
+    with open(path, "wb") as f:
+        f.write(text)
+    return len(text), n, m
+
+
+def _vcf_paths(name):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else ROOT + "/gpurun_out"
+    d = os.path.join(base, f"pf_bench_{name}_{os.getpid()}")
+    os.makedirs(d, exist_ok=True)
+    return d, os.path.join(d, "in.vcf"), os.path.join(d, "run.cfg"), os.path.join(d, "out")
+
+
+def run_ours_vcf(args, world, rank, local_rank):
+    import contextlib
+    import io
+    import shutil
+    import torch
+    from phyloforge_b200 import run as pf_run
+    from phyloforge_b200 import vcf as pf_vcf
+    from phyloforge_b200.engine import Engine
+    if rank != 0:
+        return 0                      # the text entry point is one process; other ranks have nothing to do
+    eng = Engine(local_rank)
+    kind, n, m, miss, desc = VCF_WORKLOADS[args.workload]
+    d, vcf_path, cfg_path, out_dir = _vcf_paths(args.workload)
+    try:
+        nbytes, _, _ = _make_vcf(eng, args.workload, vcf_path)
+        section, flag, tool = ("snp_opt", "-s", "treebest") if kind == "snp" else ("sv_opt", "-S", "nj")
+        with open(cfg_path, "w") as f:
+            f.write(f"[{section}]\nvcf_file = {vcf_path}\nout_path = {out_dir}\ntree_software = {tool}\nthread = 8\n"
+                    "distance = ibs\n")
+        load = pf_vcf.load_snp_vcf if kind == "snp" else pf_vcf.load_sv_vcf
+
+        def dev_step():
+            # device-timed leg: text (page cache -> pinned -> HBM) -> parse -> pack -> counts -> distances -> NJ
+            p = load(eng, vcf_path, keep_chars=False)
+            return p, eng.tree_from_planes(p.planes, p.n_samples, p.n_words, [str(i) for i in range(p.n_samples)],
+                                           metric="ibs", n_sites=p.n_sites)
+
+        def e2e_step():
+            with contextlib.redirect_stdout(io.StringIO()):
+                pf_run.main([flag, cfg_path])
+
+        for _ in range(args.warmup):
+            dev_step()
+        torch.cuda.synchronize()
+        launches0 = int(eng.lib.pf_launch_count())
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        t_wall0 = time.perf_counter()
+        t_parse = []
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            p, res = dev_step()
+            torch.cuda.synchronize()
+            t_parse.append(time.perf_counter() - t0)
+        t_wall1 = time.perf_counter()
+        launches = int(eng.lib.pf_launch_count()) - launches0
+        clocks = sampler.stop(t_wall0, t_wall1)
+        columns = p.n_sites
+        # conversion alone (file -> packed planes), for the parser's roofline
+        t_conv = []
+        for _ in range(max(3, args.steps)):
+            t0 = time.perf_counter()
+            load(eng, vcf_path, keep_chars=False)
+            torch.cuda.synchronize()
+            t_conv.append(time.perf_counter() - t0)
+        for _ in range(2):
+            e2e_step()
+        e2e_steps = max(1, min(args.steps, args.e2e_steps))
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        t_e2e = (time.perf_counter() - t0) / e2e_steps
+        out_bytes = sum(os.path.getsize(os.path.join(out_dir, f)) for f in os.listdir(out_dir)
+                        if os.path.isfile(os.path.join(out_dir, f)))
+        ms_per_step = statistics.mean(t_parse) * 1e3
+        work = pair_sites(n, columns)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        conv_s = min(t_conv)
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu = _cpu_convert(args.workload, vcf_path, d)
+            cpu["gpu_convert_seconds"] = conv_s
+            cpu["speedup_conversion"] = cpu["seconds_full"] / conv_s
+        line = {
+            "metric": METRIC, "value": work / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "text bytes -> u8 codes -> 2-bit planes; " + DTYPE, "data": "synthetic",
+            "config": workload_config(args.workload, world, args.scaling),
+            "detail": {"vcf_bytes": nbytes, "matrix_columns": columns, "records": m,
+                       "value_is": "VCF file in the page cache -> GPU parse -> packed planes -> counts -> distances -> NJ join list "
+                                   "(vcf.load_*_vcf + Engine.tree_from_planes), host wall clock with device synchronise"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": work / t_e2e, "unit": UNIT, "ms_per_step": t_e2e * 1e3, "steps": e2e_steps,
+                    "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": out_bytes,
+                    "api": f"phyloforge {flag} run.cfg (phyloforge_b200.run.main): VCF file -> all_snp.fa / SV.matrix, "
+                           "distance matrix file, tree file on disk",
+                    "d2h_note": "bytes of the artefacts written (character matrix, distance matrix, tree)"},
+            "roofline_parse": {"bound": "hbm", "achieved": nbytes / conv_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                               "frac": nbytes / conv_s / 1e9 / hbm_peak, "traffic": None,
+                               "kernel": "pf_line_index + %s_parse_kernel + select + pack" % kind, "kernel_ms": conv_s * 1e3,
+                               "genotypes_per_s": n * m / conv_s,
+                               "note": "whole conversion from the file (page cache -> pinned buffer -> H2D -> kernels), best of "
+                                       "%d; bounded by the host read + PCIe copy, not by the kernels" % len(t_conv)},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), file=args.out, flush=True)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return 0
+
+
+def _cpu_convert(name, vcf_path, work_dir):
+    """The reference's CPU half of the VCF workloads: its converter. The UNMODIFIED reference when /root/reference
+    is present (kind "reference", oracle/run_reference.py in its own process), else the restatement
+    oracle/ref_convert.py (kind "port", single Python process). Bounded: the SV converter is quadratic in the
+    reference (766 s at full size) and the port takes minutes too, so both run on a prefix of the records and the
+    full-size figure is extrapolated linearly (a lower bound for the reference's super-linear SV converter)."""
+    from oracle import run_reference
+    kind, n, m, miss, _ = VCF_WORKLOADS[name]
+    cores = os.cpu_count() or 1
+    use_ref = run_reference.available()
+    sample = m if (kind == "snp" and use_ref) else (20_000 if kind == "snp" else 4_000)
+    sample = min(sample, m)
+    sub = os.path.join(work_dir, "cpu_sample.vcf")
+    with open(vcf_path, "rb") as f, open(sub, "wb") as g:
+        k = 0
+        for line in f:
+            g.write(line)
+            if not line.startswith(b"#"):
+                k += 1
+                if k >= sample:
+                    break
+    t0 = time.perf_counter()
+    if use_ref:
+        cmd = [sys.executable, os.path.join(ROOT, "oracle", "run_reference.py"), kind, sub, os.path.join(work_dir, "ref_out")]
+        if kind == "snp":
+            cmd += [str(cores), "treebest"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        info = json.loads(r.stdout.strip().splitlines()[-1]) if r.stdout.strip() else {"error": r.stderr[-300:]}
+        seconds = float(info.get("total_s", time.perf_counter() - t0))
+        used = cores if kind == "snp" else 1
+        kind_s = "reference"
+    else:
+        from oracle import ref_convert
+        text = open(sub, encoding="utf-8").read()
+        t0 = time.perf_counter()
+        (ref_convert.snp_convert if kind == "snp" else ref_convert.sv_convert)(text)
+        seconds = time.perf_counter() - t0
+        used, kind_s = 1, "port"
+    full = seconds * m / sample
+    return {"value": n * m / full, "unit": "genotypes/s (conversion only: the reference runs nothing else of this path itself)",
+            "cores": used, "kind": kind_s, "seconds_sample": seconds, "seconds_full": full,
+            "sample": f"first {sample} of {m} records x all {n} samples through "
+                      + ("the unmodified reference converter (oracle/run_reference.py)" if use_ref else
+                         "oracle/ref_convert.py (restated converter, one Python process)")
+                      + (", scaled linearly to the full file" if sample < m else "")}
+
+
+def run_reference_arm_vcf(args):
+    import shutil
+    kind, n, m, miss, desc = VCF_WORKLOADS[args.workload]
+    d, vcf_path, cfg_path, out_dir = _vcf_paths(args.workload)
+    try:
+        # input text from the CPU generator (same counter-based codes as the device generator)
+        from oracle import cpu as oracle
+        from phyloforge_b200 import synth
+        names = [f"S{i:04d}" for i in range(n)]
+        codes = oracle.synth_codes(n, 0, m, seed=SEED, miss_ppm=miss)
+        text = synth.snp_vcf_bytes(codes, names)[0] if kind == "snp" else synth.sv_vcf_bytes(codes, names)[0]
+        with open(vcf_path, "wb") as f:
+            f.write(text)
+        cpu = _cpu_convert(args.workload, vcf_path, d)
+        line = {"impl": "reference", "metric": "genotypes_per_s", "value": cpu["value"], "unit": "genotypes/s",
+                "n_gpus": args.gpus, "steps": 1, "warmup": 0, "ms_per_step": cpu["seconds_sample"] * 1e3,
+                "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "text",
+                "data": "synthetic", "config": workload_config(args.workload, max(1, args.gpus), args.scaling),
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "genotypes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "conversion only (VCF -> character matrix): the reference delegates distance + NJ to the absent treebest / iqtree"}
+        print(json.dumps(line), file=args.out, flush=True)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
     return 0
 
 
@@ -463,18 +829,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: every GPU gets the named configuration's site count (default); "
-                         "strong: the named configuration is split over the GPUs")
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + sorted(VCF_WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="strong (default): the named configuration's sites are split over the GPUs, as BASELINE.json "
+                         "words configs[3]; weak: every GPU gets the named configuration's site count")
     ap.add_argument("--variant", type=int, default=0, help="pair-count kernel: 0 auto, 1 plain popcount, 2 carry-save popcount, 3 tcgen05 4-bit (E2M1) GEMMs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bounded sub-records (weak scaling at N > 1, BASELINE configs[4])")
+    ap.add_argument("--extra-steps", type=int, default=3)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-format", default="2bit", choices=["2bit", "u8"],
                     help="host genotype format of the end-to-end path: 2 bits (4 samples per byte) or one byte per genotype")
     ap.add_argument("--e2e-chunk-sites", type=int, default=1 << 19)
-    ap.add_argument("--cpu-sample-sites", type=int, default=1 << 18)
+    ap.add_argument("--cpu-sample-sites", type=int, default=0,
+                    help="sites per CPU-arm step; 0 = sized from a calibration pass so that the arm takes ~--cpu-arm-seconds")
+    ap.add_argument("--cpu-arm-seconds", type=float, default=60.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: timing rules ask for >= 3 warm-up steps", file=sys.stderr)

@@ -42,6 +42,12 @@ def num_threads() -> int:
     return int(lib().pfo_num_threads())
 
 
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (torchrun exports OMP_NUM_THREADS=1 to its workers). Returns the count in use."""
+    lib().pfo_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 # ------------------------------------------------------------------ synthetic genotypes
 def synth_codes(n_samples: int, site0: int, n_sites: int, seed: int = 42, n_pops: int | None = None,
                 miss_ppm: int = 0) -> np.ndarray:

@@ -212,6 +212,15 @@ PFO_API void pfo_pair_counts_bits(const uint64_t* lo, const uint64_t* hi, int64_
   }
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm of bench.py sets the count explicitly */
+PFO_API void pfo_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 PFO_API int pfo_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -12,6 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libphyloforge_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
+PROBES_LIB_PATH = Path(__file__).resolve().parent / "libphyloforge_b200_probes.so"
 
 
 class PhyloForgeError(RuntimeError):
@@ -34,10 +35,6 @@ PROTOTYPES = {
     "pf_version": (C.c_char_p, []),
     "pf_tile": (_i32, []),
     "pf_device_info": (_i32, [_ip, _ip, _ip, _i64p, _ip]),
-    "pf_microbench_int_pipe": (_i32, [_i32, _i32, _dp, _dp, _vp]),
-    "pf_microbench_mma": (_i32, [_i32, _i32, _dp, _vp]),
-    "pf_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
-    "pf_probe_umma_rate": (_i32, [_i32, _i32, _i32, _i32, _dp, _vp]),
     "pf_planes_len": (_i64, [_i64, _i64]),
     "pf_synth_codes": (_i32, [_vp, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _vp]),
     "pf_pack_codes_u8": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
@@ -64,15 +61,27 @@ PROTOTYPES = {
     "pf_bootstrap_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "pf_nj_work_bytes": (_i64, [_i64]),
     "pf_nj_profile": (_i32, [_i32, _vp]),
+    "pf_pair_counts_tc_set_impl": (_i32, [_i32, _i32]),
+    "pf_pair_counts_tc_timing": (_i32, [_i32, _vp]),
+    "pf_nj_batch": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
+    "pf_nj": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pf_launch_count": (_i64, []),
+}
+
+# libphyloforge_b200_probes.so (include/phyloforge_b200_probes.h): measurement and self-test entry points,
+# not part of the drop-in boundary; nothing in the product calls them
+PROBE_PROTOTYPES = {
+    "pf_last_error": (C.c_char_p, []),
+    "pf_microbench_int_pipe": (_i32, [_i32, _i32, _dp, _dp, _vp]),
+    "pf_microbench_mma": (_i32, [_i32, _i32, _dp, _vp]),
+    "pf_selftest_umma": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "pf_probe_umma_rate": (_i32, [_i32, _i32, _i32, _i32, _dp, _vp]),
     "pf_probe_latency": (_i32, [_i32, _i32, _i32, _dp, _vp]),
     "pf_selftest_umma_fp4": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pf_probe_umma_fp4_rate": (_i32, [_i32, _i32, _i32, _i32, _i32, _i32, _dp, _vp]),
-    "pf_pair_counts_tc_set_impl": (_i32, [_i32, _i32]),
-    "pf_pair_counts_tc_timing": (_i32, [_i32, _vp]),
     "pf_selftest_umma_fp4_2cta": (_i32, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "pf_probe_umma_fp4_2cta_rate": (_i32, [_i32, _i32, _i32, _dp, _vp, _vp]),
-    "pf_nj_batch": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),
-    "pf_nj": (_i32, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "pf_probe_umma_fp4_2cta_peak": (_i32, [_i32, _i32, _i32, _dp, _dp, _vp]),
 }
 
 _lib = None
@@ -99,6 +108,33 @@ def load(path: os.PathLike | None = None) -> C.CDLL:
     if path is None:
         _lib = lib
     return lib
+
+
+_probes = None
+
+
+def load_probes() -> C.CDLL:
+    """The probes / self-test library (bench.py, tests, tools). Raises if it is missing."""
+    global _probes
+    if _probes is None:
+        if not PROBES_LIB_PATH.exists():
+            raise PhyloForgeError(f"{PROBES_LIB_PATH} not found: build it with `python -m phyloforge_b200.build`")
+        lib = C.CDLL(str(PROBES_LIB_PATH))
+        for name, (res, args) in PROBE_PROTOTYPES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise PhyloForgeError(f"{PROBES_LIB_PATH} does not export {name}") from e
+            fn.restype = res
+            fn.argtypes = args
+        _probes = lib
+    return _probes
+
+
+def check_probe(status: int) -> None:
+    if status != 0:
+        msg = load_probes().pf_last_error().decode("utf-8", "replace")
+        raise PhyloForgeError(f"status {status}: {msg}")
 
 
 def check(status: int) -> None:

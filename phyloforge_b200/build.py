@@ -1,4 +1,6 @@
-"""Build libphyloforge_b200.so in-tree with nvcc for sm_100a (and nothing else).
+"""Build libphyloforge_b200.so (the product: the path's kernels + the C ABI of include/phyloforge_b200.h)
+and libphyloforge_b200_probes.so (microbenchmarks / instruction self-tests, include/phyloforge_b200_probes.h;
+used by bench.py's roofline denominators, tests and tools, never by the product) in-tree with nvcc for sm_100a.
 
 Called by ``__graft_entry__.build()`` and usable as ``python -m phyloforge_b200.build``.
 The library is the product; there is no CPU fallback and no JIT cache: the built
@@ -16,6 +18,8 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libphyloforge_b200.so"
+PROBES_LIB_PATH = PKG_DIR / "libphyloforge_b200_probes.so"
+PROBE_SOURCES = {"latency_probe.cu", "microbench.cu", "umma_selftest.cu", "umma_fp4_probe.cu", "umma_fp4_2cta_probe.cu"}
 STAMP = PKG_DIR / "csrc" / ".build_stamp"
 
 NVCC_FLAGS = [
@@ -36,13 +40,19 @@ def _nvcc() -> str:
 
 
 def sources() -> list[Path]:
-    return sorted(CSRC.glob("*.cu"))
+    """Sources of the product library."""
+    return sorted(p for p in CSRC.glob("*.cu") if p.name not in PROBE_SOURCES)
+
+
+def probe_sources() -> list[Path]:
+    return sorted(p for p in CSRC.glob("*.cu") if p.name in PROBE_SOURCES)
 
 
 def _digest() -> str:
     h = hashlib.sha256()
     for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) +
-                    [PKG_DIR.parent / "include" / "phyloforge_b200.h"]):
+                    [PKG_DIR.parent / "include" / "phyloforge_b200.h",
+                     PKG_DIR.parent / "include" / "phyloforge_b200_probes.h"]):
         if p.exists():
             h.update(p.name.encode())
             h.update(p.read_bytes())
@@ -53,18 +63,22 @@ def _digest() -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ into one shared library. Returns its path."""
     digest = _digest()
-    if not force and LIB_PATH.exists() and STAMP.exists() and STAMP.read_text().strip() == digest:
+    if (not force and LIB_PATH.exists() and PROBES_LIB_PATH.exists() and STAMP.exists()
+            and STAMP.read_text().strip() == digest):
         return LIB_PATH
     objdir = PKG_DIR / "csrc" / "build"
     objdir.mkdir(exist_ok=True)
     nvcc = _nvcc()
     inc = ["-I", str(CSRC), "-I", str(PKG_DIR.parent / "include")]
     procs = []
-    objs = []
-    for src in sources():
-        obj = objdir / (src.stem + ".o")
-        objs.append(str(obj))
-        cmd = [nvcc, *NVCC_FLAGS, *inc, "-c", str(src), "-o", str(obj)]
+    objs, probe_objs = [], []
+    jobs = [(src, objdir / (src.stem + ".o"), [], objs) for src in sources()]
+    jobs += [(src, objdir / (src.stem + ".o"), [], probe_objs) for src in probe_sources()]
+    # the probes library carries its own copy of the error plumbing (api.cu without the product's exports)
+    jobs.append((CSRC / "api.cu", objdir / "api_probes.o", ["-DPF_PROBES_LIB"], probe_objs))
+    for src, obj, extra, into in jobs:
+        into.append(str(obj))
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *inc, "-c", str(src), "-o", str(obj)]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     logs = []
     failed = False
@@ -78,8 +92,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         sys.stderr.write("\n".join(logs) + "\n")
     if failed:
         raise RuntimeError("nvcc failed; see log above")
-    link = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *objs]
-    subprocess.run(link, check=True)
+    for lib, lib_objs in ((LIB_PATH, objs), (PROBES_LIB_PATH, probe_objs)):
+        subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *lib_objs],
+                       check=True)
     STAMP.write_text(digest)
     return LIB_PATH
 

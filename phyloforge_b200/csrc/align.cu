@@ -142,6 +142,7 @@ PF_API int pf_chars_state_codes(const uint8_t* d_chars, int64_t ld, const int64_
     return pf_fail("pf_chars_state_codes: bad arguments");
   const int64_t grid = pf_ceil_div(n_rows * ldc, 256);
   if (grid > 0x7fffffffLL) return pf_fail("pf_chars_state_codes: too many columns");
+  pf_count_launch();
   chars_state_codes_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_chars, ld, d_rows, n_rows, n_samples, state, d_codes, ldc);
   PF_CUDA(cudaGetLastError());
@@ -157,6 +158,7 @@ PF_API int pf_chars_allele_codes(const uint8_t* d_chars, int64_t ld, const int64
     return pf_fail("pf_chars_allele_codes: bad arguments");
   const int64_t grid = pf_ceil_div(n_rows * ldc, 256);
   if (grid > 0x7fffffffLL) return pf_fail("pf_chars_allele_codes: too many columns");
+  pf_count_launch();
   chars_allele_codes_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_chars, ld, d_rows, n_rows, n_samples, allele, d_codes, ldc);
   PF_CUDA(cudaGetLastError());
@@ -171,6 +173,7 @@ PF_API int pf_counts_add_extra(const int32_t* d_state_counts, int64_t ld_state, 
       (d_allele_counts && ld_allele < n_samples))
     return pf_fail("pf_counts_add_extra: bad arguments");
   const int64_t grid = pf_ceil_div(n_samples * n_samples, 256);
+  pf_count_launch();
   counts_add_extra_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_state_counts, ld_state, n_states, d_allele_counts, ld_allele, d_counts, n_samples, ld);
   PF_CUDA(cudaGetLastError());
@@ -186,6 +189,7 @@ PF_API int pf_chars_to_codes(const uint8_t* d_chars, int64_t ld, int64_t n_sites
     return pf_fail("pf_chars_to_codes: bad arguments");
   const int64_t grid = pf_ceil_div(n_sites, 8);
   if (grid > 0x7fffffffLL) return pf_fail("pf_chars_to_codes: too many sites");
+  pf_count_launch();
   chars_to_codes_kernel<<<static_cast<unsigned>(grid), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_chars, ld, n_sites, n_samples, d_codes, ldc, d_line_info);
   PF_CUDA(cudaGetLastError());

@@ -1,6 +1,7 @@
 // Error plumbing and device queries of the C ABI (include/phyloforge_b200.h).
 #include "pf_common.cuh"
 
+#include <atomic>
 #include <cstring>
 
 namespace {
@@ -10,7 +11,10 @@ int vfail(int code, const char* fmt, va_list ap) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   return code;
 }
+std::atomic<long long> g_launches{0};
 }  // namespace
+
+void pf_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int pf_fail(const char* fmt, ...) {
   va_list ap;
@@ -29,6 +33,9 @@ int pf_fail_code(int code, const char* fmt, ...) {
 }
 
 PF_API const char* pf_last_error(void) { return g_err; }
+
+#ifndef PF_PROBES_LIB
+PF_API int64_t pf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 PF_API const char* pf_version(void) { return "phyloforge_b200 0.1.0 (sm_100a)"; }
 
@@ -49,3 +56,4 @@ PF_API int pf_device_info(int* sm_count, int* cc_major, int* cc_minor, int64_t* 
   return PF_OK;
   PF_TRY_END
 }
+#endif  // PF_PROBES_LIB

@@ -69,6 +69,7 @@ cudaError_t bs_launch(const int32_t* blocks, int n_blocks, int64_t vec, const in
   const size_t smem = static_cast<size_t>(R) * n_blocks * sizeof(int32_t);
   cudaError_t e = cudaFuncSetAttribute(bootstrap_counts_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return e;
+  pf_count_launch();
   bootstrap_counts_kernel<R><<<static_cast<unsigned>(pf_ceil_div(vec, static_cast<int64_t>(256))), 256, smem, s>>>(
       reinterpret_cast<const int4*>(blocks), n_blocks, vec, w, reinterpret_cast<int4*>(out));
   return cudaGetLastError();
@@ -84,6 +85,7 @@ PF_API int pf_bootstrap_weights(uint64_t seed, int64_t replicate0, int n_reps, i
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t total = static_cast<int64_t>(n_reps) * n_blocks;
   PF_CUDA(cudaMemsetAsync(d_weights, 0, static_cast<size_t>(total) * sizeof(int32_t), s));
+  pf_count_launch();
   bootstrap_weights_kernel<<<static_cast<unsigned>(pf_ceil_div(total, static_cast<int64_t>(256))), 256, 0, s>>>(
       seed, replicate0, n_reps, n_blocks, d_weights);
   PF_CUDA(cudaGetLastError());

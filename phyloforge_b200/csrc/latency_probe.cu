@@ -2,6 +2,7 @@
 // trip, one gpu-scope fence, one CTA barrier, one tagged-word exchange between CTAs and one cooperative
 // grid barrier cost on this GPU. Diagnostic only (tools/probe_latency.py).
 #include "pf_common.cuh"
+#include "phyloforge_b200_probes.h"
 #include "umma.cuh"
 
 #include <cooperative_groups.h>

@@ -11,6 +11,7 @@
 // Reported: thread-level ops/s from CUDA events, and ops/clk/SM from clock64().
 
 #include "pf_common.cuh"
+#include "phyloforge_b200_probes.h"
 
 namespace {
 

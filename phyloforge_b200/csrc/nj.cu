@@ -761,6 +761,7 @@ int nj_launch(K kernel, int threads, size_t smem, int64_t want_blocks, int64_t m
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   void* args[] = {params};
+  pf_count_launch();
   PF_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3(static_cast<unsigned>(blocks)),
                                       dim3(threads), args, smem, s));
   return PF_OK;

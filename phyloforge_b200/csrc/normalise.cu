@@ -41,6 +41,7 @@ PF_API int pf_normalise(const int32_t* d_counts, int64_t n_samples, int64_t ld, 
   if (metric != 0 && metric != 1) return pf_fail("pf_normalise: metric must be 0 (p) or 1 (ibs)");
   if (n_samples > 65535) return pf_fail("pf_normalise: n_samples > 65535 not supported");
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_samples, 256)), static_cast<unsigned>(n_samples));
+  pf_count_launch();
   normalise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_counts, n_samples, ld, metric,
                                                                          d_dist, ld_dist, d_n_zero_valid);
   PF_CUDA(cudaGetLastError());

@@ -240,6 +240,7 @@ PF_API int pf_pack_codes_u8(const uint8_t* d_codes, int64_t ld, const int64_t* d
             static_cast<unsigned>(pf_ceil_div(n_groups, gx)));
   const bool aligned = (ld % 4 == 0) && (reinterpret_cast<uintptr_t>(d_codes) % 4 == 0);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  pf_count_launch();
   if (aligned)
     pack_kernel<true><<<grid, block, 0, s>>>(d_codes, ld, d_rows, n_samples, n_sites, d_planes,
                                              n_words, word0, n_groups);
@@ -262,6 +263,7 @@ PF_API int pf_unpack_codes_u8(const uint32_t* d_planes, int64_t n_words, int64_t
   if (n_sites == 0) return PF_OK;
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_local_words, 32)),
             static_cast<unsigned>(pf_ceil_div(n_samples, PF_TILE)));
+  pf_count_launch();
   unpack_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_planes, n_words, word0, n_samples,
                                                                       n_sites, d_out, ld_out);
   PF_CUDA(cudaGetLastError());
@@ -278,6 +280,7 @@ PF_API int pf_transpose_u8(const uint8_t* d_in, int64_t ld_in, const int64_t* d_
   const int64_t gy = pf_ceil_div(n_cols, 64);
   if (gy > 65535) return pf_fail("pf_transpose_u8: n_cols too large");
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_rows, 64)), static_cast<unsigned>(gy));
+  pf_count_launch();
   transpose_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, ld_in, d_rows, n_rows, n_cols,
                                                                          d_out, ld_out);
   PF_CUDA(cudaGetLastError());
@@ -301,6 +304,7 @@ PF_API int pf_pack_codes_2bit(const uint8_t* d_codes2, int64_t ld2, int64_t n_sa
   const int gy = 128 / gx;
   dim3 block(gx, gy);
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_local_words, gy)), static_cast<unsigned>(pf_ceil_div(n_groups, gx)));
+  pf_count_launch();
   pack2_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_codes2, ld2, n_samples, n_sites, d_planes,
                                                                        n_words, word0, n_groups, plink);
   PF_CUDA(cudaGetLastError());

@@ -365,6 +365,7 @@ PF_API int pf_pair_counts(const uint32_t* d_planes, int64_t n_samples, int64_t n
   const size_t smem_bytes = static_cast<size_t>(STAGES) * 2 * SIDE_WORDS * sizeof(uint32_t);
   auto kernel = (variant == 1) ? pair_counts_kernel<false> : pair_counts_kernel<true>;
   PF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes)));
+  pf_count_launch();
   kernel<<<static_cast<unsigned>(grid), THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(P);
   PF_CUDA(cudaGetLastError());
   return PF_OK;

@@ -1346,6 +1346,7 @@ cudaError_t tc_launch(const TcParams& P, int64_t grid, cudaStream_t s) {
   auto kernel = g_tc_prof_enabled ? pair_counts_tc_kernel<MODE, true> : pair_counts_tc_kernel<MODE, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM));
   if (e != cudaSuccess) return e;
+  pf_count_launch();
   kernel<<<static_cast<unsigned>(grid), G::THREADS, G::SMEM, s>>>(P);
   return cudaGetLastError();
 }
@@ -1384,6 +1385,7 @@ cudaError_t tc2_launch_cfg(const TcParams& P, int64_t items, cudaStream_t s) {
   auto kernel = g_tc_prof_enabled ? pair_counts_tc2_kernel<MODE, CFG, true> : pair_counts_tc2_kernel<MODE, CFG, false>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(G::SMEM));
   if (e != cudaSuccess) return e;
+  pf_count_launch();
   kernel<<<static_cast<unsigned>(2 * items), G::THREADS, G::SMEM, s>>>(P);   // __cluster_dims__(2): one pair per item
   return cudaGetLastError();
 }
@@ -1446,12 +1448,14 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   {
     const int64_t n_runs = pf_ceil_div(n_local, HSUM_RUN);
     const int64_t threads = L.n_tiles_padded * n_runs * 64;
+    pf_count_launch();
     planes_to_e2m1_kernel<0><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
         d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded, nib4, ref_v, flags, hsum,
         L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
     if (allow_general) {
       // returns at once unless the first pass found sample-specific missingness
+      pf_count_launch();
       planes_to_e2m1_kernel<1><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
           d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded,
           reinterpret_cast<uint4*>(w + L.stream1_off), ref_v, flags, hsum, L.m[0].words_per_split, L.hsum_ld);

@@ -27,6 +27,7 @@
 #define PF_ERR_INPUT 3
 #define PF_ERR_INTERNAL 4
 
+void pf_count_launch(int n = 1);                  // bumps the counter behind pf_launch_count()
 int pf_fail(const char* fmt, ...);                 // records message, returns PF_ERR_ARG
 int pf_fail_code(int code, const char* fmt, ...);  // records message, returns code
 

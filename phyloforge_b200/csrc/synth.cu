@@ -56,6 +56,7 @@ PF_API int pf_synth_codes(uint8_t* d_codes, int64_t n_samples, int64_t ld, int64
   if (n_sites == 0) return PF_OK;
   dim3 grid(static_cast<unsigned>(pf_ceil_div(n_samples, 256)),
             static_cast<unsigned>(n_sites < 65535 ? n_sites : 65535));
+  pf_count_launch();
   synth_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_codes, n_samples, ld, site0,
                                                                      n_sites, seed, n_pops, miss_ppm);
   PF_CUDA(cudaGetLastError());

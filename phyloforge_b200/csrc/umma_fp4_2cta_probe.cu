@@ -7,6 +7,7 @@
 // cluster-scope release, multicast commit); pf_probe_umma_fp4_2cta_rate measures clocks per instruction.
 // Diagnostic only.
 #include "pf_common.cuh"
+#include "phyloforge_b200_probes.h"
 #include "umma.cuh"
 
 namespace {
@@ -195,6 +196,44 @@ PF_API int pf_probe_umma_fp4_2cta_rate(int n, int reps, int n_bufs, double* tick
   for (int i = 0; i < pairs; ++i) mean += double(h[i]);
   *ticks_per_mma = mean / pairs / (2.0 * reps);
   if (h_pairs) *h_pairs = pairs;
+  return PF_OK;
+  PF_TRY_END
+}
+
+// the same kernel timed with CUDA events around the launch: the sustained device-wide rate in TOP/s
+PF_API int pf_probe_umma_fp4_2cta_peak(int n, int reps, int n_bufs, double* h_tops, double* h_ms, void* stream) {
+  PF_TRY_BEGIN
+  if (n < 32 || n > 240 || n % 16 != 0 || reps <= 0 || n_bufs < 1 || n_bufs > 16 || !h_tops)
+    return pf_fail("pf_probe_umma_fp4_2cta_peak: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int pairs = sms / 2;
+  long long* d = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PF_CUDA(cudaMalloc(&d, sizeof(long long) * pairs));
+  const size_t smem = static_cast<size_t>(128 * 2 + (n / 2) * n_bufs) * 32;
+  float ms = 0.f;
+  cudaError_t e = cudaFuncSetAttribute(umma_fp4_2cta_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) {
+    umma_fp4_2cta_rate_kernel<<<2 * pairs, 128, smem, s>>>(n, 64, n_bufs, d);   // warm-up
+    cudaEventRecord(e0, s);
+    umma_fp4_2cta_rate_kernel<<<2 * pairs, 128, smem, s>>>(n, reps, n_bufs, d);
+    cudaEventRecord(e1, s);
+    e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(d);
+  PF_CUDA(e);
+  const double ops = 2.0 * 256.0 * n * 64.0 * 2.0 * reps * pairs;
+  *h_tops = ops / (ms * 1e-3) / 1e12;
+  if (h_ms) *h_ms = ms;
   return PF_OK;
   PF_TRY_END
 }

@@ -5,6 +5,7 @@
 // pf_selftest_umma_fp4 checks exactness against integer dot products; pf_probe_umma_fp4_rate
 // measures clocks per instruction. Diagnostic only.
 #include "pf_common.cuh"
+#include "phyloforge_b200_probes.h"
 #include "umma.cuh"
 
 namespace {

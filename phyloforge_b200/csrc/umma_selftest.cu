@@ -2,6 +2,7 @@
 // signed 8-bit operands and 32-bit accumulation, one CTA, operands staged into the canonical
 // K-major no-swizzle layout by ordinary stores. tests/test_gpu_umma.py checks it against numpy.
 #include "pf_common.cuh"
+#include "phyloforge_b200_probes.h"
 #include "umma.cuh"
 
 namespace {

@@ -13,6 +13,8 @@
 // (PF_LINE_ERR_*) instead of being emulated; the host raises.
 #include "pf_common.cuh"
 
+#include <mutex>
+
 namespace {
 
 constexpr int LINES_PER_CTA = 8;  // 256 threads
@@ -545,8 +547,10 @@ PF_API int pf_line_index(const uint8_t* d_text, int64_t n_bytes, int64_t* d_line
   if (n_blocks > 0x7fffffffLL) return pf_fail("pf_line_index: text too large");
   int64_t* counts = static_cast<int64_t*>(d_work);
   int64_t* total = counts + n_blocks;
+  pf_count_launch();
   li_count_kernel<<<static_cast<unsigned>(n_blocks), LI_THREADS, 0, s>>>(d_text, n_bytes, counts);
   PF_CUDA(cudaGetLastError());
+  pf_count_launch();
   scan_i64_kernel<<<1, 1024, 0, s>>>(counts, n_blocks, total);
   PF_CUDA(cudaGetLastError());
   int64_t h_total = 0;
@@ -556,6 +560,7 @@ PF_API int pf_line_index(const uint8_t* d_text, int64_t n_bytes, int64_t* d_line
   if (n_lines > capacity)
     return pf_fail_code(PF_ERR_INPUT, "pf_line_index: %lld lines exceed capacity %lld", (long long)n_lines,
                         (long long)capacity);
+  pf_count_launch();
   li_write_kernel<<<static_cast<unsigned>(n_blocks), LI_THREADS, 0, s>>>(d_text, n_bytes, counts, d_line_start,
                                                                          capacity);
   PF_CUDA(cudaGetLastError());
@@ -578,6 +583,7 @@ PF_API int pf_vcf_snp_parse(const uint8_t* d_text, int64_t n_bytes, const int64_
     return pf_fail("pf_vcf_snp_parse: bad arguments");
   const int64_t grid = pf_ceil_div(n_lines, LINES_PER_CTA);
   if (grid > 0x7fffffffLL) return pf_fail("pf_vcf_snp_parse: too many lines");
+  pf_count_launch();
   snp_parse_kernel<<<static_cast<unsigned>(grid), 32 * LINES_PER_CTA, 0, static_cast<cudaStream_t>(stream)>>>(
       d_text, n_bytes, d_line_start, n_lines, n_samples, d_chars, d_codes, ld, d_line_info);
   PF_CUDA(cudaGetLastError());
@@ -594,6 +600,7 @@ PF_API int pf_vcf_sv_parse(const uint8_t* d_text, int64_t n_bytes, const int64_t
     return pf_fail("pf_vcf_sv_parse: bad arguments");
   const int64_t grid = pf_ceil_div(n_lines, LINES_PER_CTA);
   if (grid > 0x7fffffffLL) return pf_fail("pf_vcf_sv_parse: too many lines");
+  pf_count_launch();
   sv_parse_kernel<<<static_cast<unsigned>(grid), 32 * LINES_PER_CTA, 0, static_cast<cudaStream_t>(stream)>>>(
       d_text, n_bytes, d_line_start, n_lines, n_samples, d_chars, d_codes, ld, d_line_info);
   PF_CUDA(cudaGetLastError());
@@ -612,14 +619,22 @@ PF_API int pf_vcf_select_rows(const int32_t* d_line_info, int64_t n_lines, int r
   if (!d_line_info || !d_rows || n_lines < 0 || capacity < 0 || (rows_per_line != 1 && rows_per_line != 2))
     return pf_fail("pf_vcf_select_rows: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  SelSummary* d_sum = nullptr;
-  PF_CUDA(cudaMalloc(&d_sum, sizeof(SelSummary)));
+  // the 40-byte device summary is allocated once per device and kept for the life of the process (a cudaMalloc /
+  // cudaFree pair per chunk synchronised the whole device every call); calls on one device are serialised by the lock
+  static std::mutex mu;
+  static SelSummary* d_sum_of[64] = {nullptr};
+  int dev = 0;
+  PF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return pf_fail("pf_vcf_select_rows: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(mu);
+  if (!d_sum_of[dev]) PF_CUDA(cudaMalloc(&d_sum_of[dev], sizeof(SelSummary)));
+  SelSummary* d_sum = d_sum_of[dev];
+  pf_count_launch();
   select_rows_kernel<<<1, 1024, 0, s>>>(d_line_info, n_lines, rows_per_line, require_fit, d_rows, capacity, d_sum);
   cudaError_t e = cudaGetLastError();
   SelSummary h{};
   if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d_sum, sizeof(h), cudaMemcpyDeviceToHost, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  cudaFree(d_sum);
   PF_CUDA(e);
   h_summary[0] = h.total_cols;
   h_summary[1] = h.n_err;

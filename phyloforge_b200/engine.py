@@ -139,6 +139,10 @@ class Engine:
     # samples only); 0 = auto: 3 when the sample count fills a 128 x 192 tensor-core tile reasonably,
     # else 2.
     TC_MIN_SAMPLES = 192
+    # the tensor-core variant's scratch (two 4-bit operand streams over padded tiles) is ~4x the planes of
+    # the word range it is given: longer ranges are walked in pieces of at most this many bytes of scratch,
+    # accumulating into the same count matrices (integer adds: the result does not depend on the cut)
+    TC_WORK_BUDGET = 56 << 30
 
     def pair_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, counts: torch.Tensor,
                     word_begin: int = 0, word_end: int | None = None, variant: int = 0,
@@ -152,6 +156,20 @@ class Engine:
         assert counts.dtype == torch.int32 and counts.is_contiguous() and counts.shape[0] == 3
         if variant == 0:
             variant = 3 if n_samples >= self.TC_MIN_SAMPLES else 2
+        if variant == 3 and word_end - word_begin > 1024:
+            budget = min(self.TC_WORK_BUDGET, max(1 << 30, self.total_mem // 3))
+            need = int(self.lib.pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin))
+            if need > budget:
+                pieces = -(-need // budget)
+                step = max(1024, -(-(word_end - word_begin) // pieces + 63) // 64 * 64)
+                ran, general = 3, False
+                for wb in range(word_begin, word_end, step):
+                    ran = self.pair_counts(planes, n_samples, n_words, counts, wb, min(word_end, wb + step), variant,
+                                           tc_general)
+                    general = general or (ran == 3 and self.tc_launches == 2)
+                self._tc_general_any = general
+                return ran
+        self._tc_general_any = None
         if variant == 3:
             need = int(self.lib.pf_pair_counts_tc_work_bytes(n_samples, word_end - word_begin))
             work = getattr(self, "_tc_work", None)
@@ -182,6 +200,8 @@ class Engine:
     def tc_launches(self) -> int:
         """GEMM launches that did work in the last variant-3 call: 2 when it met genotypes missing in
         some samples only, else 1 (0: the call declined). Synchronises the current stream."""
+        if getattr(self, "_tc_general_any", None) is not None:      # a call that was walked in pieces
+            return 2 if self._tc_general_any else 1
         last = getattr(self, "_tc_last", None)
         if last is None or last[1] <= 0:
             return 0 if last is None else 1
@@ -197,7 +217,12 @@ class Engine:
         from .sharding import shard_words
         if word_end is None:
             word_end = n_words
-        blocks = torch.zeros((n_blocks, 3, n_samples, n_samples), dtype=torch.int32, device=self.device)
+        # pf_bootstrap_counts works on groups of four elements: the per-block stride is rounded up once here,
+        # so that no call ever has to pad (and copy) the whole block tensor
+        elems = 3 * n_samples * n_samples
+        stride = (elems + 3) // 4 * 4
+        store = torch.zeros((n_blocks, stride), dtype=torch.int32, device=self.device)
+        blocks = store[:, :elems].view(n_blocks, 3, n_samples, n_samples)
         for b in range(n_blocks):
             wb, we = shard_words(word_end, n_blocks, b)
             if we > wb:
@@ -210,18 +235,22 @@ class Engine:
         return w
 
     def bootstrap_counts(self, blocks: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
-        """blocks [B, 3, n, n] int32, weights [R <= 8, B] int32 -> [R, 3, n, n] int32 weighted sums."""
-        n_blocks = blocks.shape[0]
+        """blocks [B, 3, n, n] int32, weights [R <= 8, B] int32 -> [R, 3, n, n] int32 weighted sums. Blocks that
+        come from block_counts are used in place (their stride is a multiple of four elements); any other
+        layout costs one padded copy."""
+        n_blocks, shape = blocks.shape[0], tuple(blocks.shape[1:])
         elems = blocks[0].numel()
-        assert blocks.is_contiguous() and weights.is_contiguous() and weights.shape[1] == n_blocks
-        pad = (-elems) % 4                     # the kernel works on groups of four elements
-        src = blocks.reshape(n_blocks, elems)
-        if pad:
-            src = torch.nn.functional.pad(src, (0, pad)).contiguous()
-        out = torch.empty((weights.shape[0], elems + pad), dtype=torch.int32, device=self.device)
-        check(self.lib.pf_bootstrap_counts(src.data_ptr(), n_blocks, elems + pad, weights.data_ptr(), weights.shape[0],
+        stride = blocks.stride(0) if n_blocks > 1 else (elems + 3) // 4 * 4
+        assert weights.is_contiguous() and weights.shape[1] == n_blocks
+        if not (blocks[0].is_contiguous() and stride % 4 == 0 and stride >= elems and blocks.data_ptr() % 16 == 0
+                and (n_blocks > 1 or elems % 4 == 0)):
+            src = torch.zeros((n_blocks, (elems + 3) // 4 * 4), dtype=torch.int32, device=self.device)
+            src[:, :elems] = blocks.reshape(n_blocks, elems)
+            blocks, stride = src, src.stride(0)
+        out = torch.empty((weights.shape[0], stride), dtype=torch.int32, device=self.device)
+        check(self.lib.pf_bootstrap_counts(blocks.data_ptr(), n_blocks, stride, weights.data_ptr(), weights.shape[0],
                                            out.data_ptr(), _stream_ptr()))
-        return out[:, :elems].reshape((weights.shape[0],) + tuple(blocks.shape[1:]))
+        return out[:, :elems].view((weights.shape[0],) + shape)
 
     def bootstrap_tree(self, planes: torch.Tensor, n_samples: int, n_words: int, names, replicates: int = 100,
                        seed: int = 1, n_blocks: int = 256, metric="ibs", variant: int = 0,
@@ -408,14 +437,18 @@ class Engine:
         counts = self.alloc_counts(n_samples)
         nw_chunk = chunk_sites // 32
         done = [None, None]
+        h2d_first = h2d_last = None
         for k, c0 in enumerate(range(0, m, chunk_sites)):
             c1 = min(m, c0 + chunk_sites)
             buf = bufs["codes"][k & 1]
             with torch.cuda.stream(copy):
                 if done[k & 1] is not None:
                     copy.wait_event(done[k & 1])          # the kernels that read this buffer are finished
+                if h2d_first is None:
+                    h2d_first = torch.cuda.Event(enable_timing=True)
+                    h2d_first.record(copy)
                 buf[:c1 - c0].copy_(host_codes[c0:c1], non_blocking=True)
-                arrived = torch.cuda.Event()
+                arrived = h2d_last = torch.cuda.Event(enable_timing=True)
                 arrived.record(copy)
             compute.wait_event(arrived)
             if packed2:
@@ -430,7 +463,49 @@ class Engine:
         self.allreduce_counts(counts)
         res = self.tree_from_counts(counts, names, metric=metric, keep=True, fetch_dist=True)
         res.d2h_bytes = int(res.dist_host.nbytes + res.merge.nbytes + res.length.nbytes)
+        if h2d_first is not None:
+            res.timings_ms["h2d"] = h2d_first.elapsed_time(h2d_last)     # first copy issued -> last copy landed
         return res
+
+    # ------------------------------------------------------------------ host memory
+    def numa_node(self) -> int:
+        """NUMA node of this GPU's PCIe device from sysfs, or -1 when the platform does not say."""
+        try:
+            bus = torch.cuda.get_device_properties(self.device).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.device).pci_domain_id
+            dev_id = torch.cuda.get_device_properties(self.device).pci_device_id
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+            with open(path) as f:
+                return int(f.read().strip())
+        except (OSError, ValueError, AttributeError):
+            return -1
+
+    def pinned_host_buffer(self, shape, dtype=torch.uint8) -> torch.Tensor:
+        """Page-locked host staging buffer for tree_from_host_codes, placed on the NUMA node of this GPU where the
+        platform reports one (set_mempolicy(MPOL_PREFERRED) around the allocation: with one process per GPU,
+        eight ranks pulling from one node's memory was what capped the 8-GPU end-to-end path in round 1)."""
+        node = self.numa_node()
+        libc = None
+        if node >= 0:
+            try:
+                libc = C.CDLL(None, use_errno=True)
+                mask = C.c_ulong(1 << node)
+                if libc.syscall(C.c_long(238), C.c_long(1), C.byref(mask), C.c_ulong(8 * C.sizeof(C.c_ulong))) != 0:   # set_mempolicy(MPOL_PREFERRED)
+                    libc = None
+            except (OSError, AttributeError):
+                libc = None
+        try:
+            buf = torch.empty(shape, dtype=dtype).pin_memory()
+        finally:
+            if libc is not None:
+                libc.syscall(C.c_long(238), C.c_long(0), None, C.c_ulong(0))                                            # MPOL_DEFAULT
+        return buf
+
+    def release_scratch(self) -> None:
+        """Drop the cached scratch buffers (tensor-core operand streams, host-path staging, pinned result)."""
+        for name in ("_tc_work", "_hp", "_hp_key", "_dist_pinned", "_tc_last"):
+            if hasattr(self, name):
+                setattr(self, name, None)
 
     def _copy_stream(self):
         if getattr(self, "_copy", None) is None:
@@ -445,9 +520,3 @@ class Engine:
                         "planes": self.alloc_planes(n_samples, chunk_sites // 32)}
             self._hp_key = key
         return self._hp
-
-    # ------------------------------------------------------------------ microbenchmarks
-    def microbench_int_pipe(self, kind: int, iters: int = 2000):
-        a, b = C.c_double(), C.c_double()
-        check(self.lib.pf_microbench_int_pipe(kind, iters, C.byref(a), C.byref(b), _stream_ptr()))
-        return a.value, b.value

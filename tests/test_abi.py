@@ -11,6 +11,7 @@ from phyloforge_b200 import _lib, build
 
 ROOT = Path(__file__).resolve().parents[1]
 HEADER = ROOT / "include" / "phyloforge_b200.h"
+PROBES_HEADER = ROOT / "include" / "phyloforge_b200_probes.h"
 
 
 @pytest.fixture(scope="module")
@@ -18,8 +19,8 @@ def lib_path():
     return build.build()
 
 
-def _declared():
-    text = HEADER.read_text()
+def _declared(header=HEADER):
+    text = header.read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return set(re.findall(r"PF_API\s+[\w\s\*]+?\b(pf_\w+)\s*\(", text))
 
@@ -39,6 +40,19 @@ def test_library_exports_every_declared_symbol(lib_path):
     assert not extra, f"exported but not declared in the header: {extra}"
 
 
+def test_probes_are_a_separate_library(lib_path):
+    """Microbenchmarks / self-tests live in libphyloforge_b200_probes.so with their own header: the product
+    ABI exports no pf_probe_* / pf_selftest_* / pf_microbench_* symbol."""
+    declared = _declared(PROBES_HEADER)
+    assert declared == set(_lib.PROBE_PROTOTYPES), (declared ^ set(_lib.PROBE_PROTOTYPES))
+    out = subprocess.run(["nm", "-D", "--defined-only", str(build.PROBES_LIB_PATH)], capture_output=True, text=True,
+                         check=True)
+    exported = {ln.split()[-1] for ln in out.stdout.splitlines() if " T " in ln and ln.split()[-1].startswith("pf_")}
+    assert exported == declared, exported ^ declared
+    assert not [s for s in _declared() if s.startswith(("pf_probe_", "pf_selftest_", "pf_microbench_"))]
+    _lib.load_probes()
+
+
 def test_library_loads_and_answers_without_a_gpu(lib_path):
     lib = _lib.load()
     assert b"sm_100a" in lib.pf_version()
@@ -46,6 +60,7 @@ def test_library_loads_and_answers_without_a_gpu(lib_path):
     assert lib.pf_planes_len(65, 10) == 2 * 10 * 2 * 64
     assert lib.pf_nj_work_bytes(1000) > 12 * 1000
     assert lib.pf_line_index_work_bytes(1 << 20) >= 8 * 64
+    assert lib.pf_launch_count() == 0
 
 
 def test_sass_is_sm_100a_with_tma_bulk_copies(lib_path):

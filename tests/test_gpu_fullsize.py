@@ -110,9 +110,8 @@ def test_config5_10000x5M_missing_row_subset(engine):
     assert torch.equal(a, b)
     del a, b, planes, codes
     names = [f"s{i}" for i in range(n)]
-    # N = 10,000 is beyond what the CPU oracle joins in test time: the two GPU NJ kernels (the fast one with
-    # 512-column scan items at this size, and the general one: other item width, two grid barriers per iteration,
-    # row sums in global memory) must give the same join list and branch lengths bit for bit
+    # NJ at N = 10,000 against the oracle: tests/test_gpu_nj_pinned.py. Here: the general kernel (other scan item
+    # width, two grid barriers per iteration, row sums in global memory) agrees with the fast one bit for bit
     from phyloforge_b200._lib import check
     dist, _ = engine.normalise(counts, "ibs")
     fast = engine.nj(dist)

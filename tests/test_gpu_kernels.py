@@ -6,6 +6,7 @@ import torch
 
 from oracle import cpu as oracle, treecmp
 from phyloforge_b200.newick import merges_to_newick
+from phyloforge_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -295,7 +296,7 @@ def test_cta_pair_mma_instruction_is_exact(engine, n, k):
     b = rng.choice(vals, size=(n, k))
     da, db = torch.from_numpy(a).to(engine.device), torch.from_numpy(b).to(engine.device)
     dc = torch.full((256, n), -7.0, dtype=torch.float32, device=engine.device)
-    check(engine.lib.pf_selftest_umma_fp4_2cta(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k,
+    _lib.check_probe(_lib.load_probes().pf_selftest_umma_fp4_2cta(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k,
                                                torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     assert np.array_equal(dc.cpu().numpy().astype(np.int64), a.astype(np.int64) @ b.astype(np.int64).T)

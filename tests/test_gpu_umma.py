@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from phyloforge_b200._lib import check
+from phyloforge_b200 import _lib
 
 pytestmark = pytest.mark.gpu
 
@@ -16,7 +17,7 @@ def test_umma_i8_matches_numpy(engine, k, a_in_tmem):
     b = rng.integers(-2, 3, size=(256, k), dtype=np.int8)
     da, db = torch.from_numpy(a).to(engine.device), torch.from_numpy(b).to(engine.device)
     dc = torch.full((128, 256), -7, dtype=torch.int32, device=engine.device)
-    check(engine.lib.pf_selftest_umma(da.data_ptr(), db.data_ptr(), dc.data_ptr(), k, a_in_tmem,
+    _lib.check_probe(_lib.load_probes().pf_selftest_umma(da.data_ptr(), db.data_ptr(), dc.data_ptr(), k, a_in_tmem,
                                       torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     want = a.astype(np.int32) @ b.astype(np.int32).T

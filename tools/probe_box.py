@@ -27,7 +27,7 @@ def main():
         "cpu": sh("lscpu | grep -E 'Model name|Socket|Thread|Core'"),
         "ulimit_l": sh("ulimit -l"),
     }
-    lib = C.CDLL(str(ROOT / "phyloforge_b200" / "libphyloforge_b200.so"))
+    lib = C.CDLL(str(ROOT / "phyloforge_b200" / "libphyloforge_b200_probes.so"))
     lib.pf_microbench_int_pipe.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
     lib.pf_last_error.restype = C.c_char_p
     names = ["popc", "lop3", "add_s32(2 per IADD3)", "imad", "popc:lop3 1:6", "popc:imad 1:6", "lop3:imad 1:1",

@@ -7,6 +7,7 @@ import torch
 
 sys.path.insert(0, ".")
 from phyloforge_b200._lib import check
+from phyloforge_b200 import _lib
 from phyloforge_b200.engine import Engine
 
 eng = Engine(0)
@@ -20,7 +21,7 @@ for n, k, vals in ((128, 64, (-1, 0, 1)), (192, 256, (-1, 0, 1)), (128, 1024, (-
     want = a.astype(np.int64) @ b.astype(np.int64).T
     for ts in (0, 1):
         dc = torch.zeros((128, n), dtype=torch.float32, device="cuda")
-        check(eng.lib.pf_selftest_umma_fp4(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k, ts, st))
+        _lib.check_probe(_lib.load_probes().pf_selftest_umma_fp4(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k, ts, st))
         torch.cuda.synchronize()
         got = dc.cpu().numpy()
         ok = np.array_equal(got.astype(np.int64), want) and np.array_equal(got, np.rint(got))
@@ -32,6 +33,6 @@ for n, acc, ts, bufs, noise in ((128, 1, 0, 2, 0), (192, 2, 0, 8, 0), (192, 2, 1
                                 (192, 2, 1, 8, 400), (192, 2, 1, 8, 200), (192, 2, 1, 8, 100), (192, 2, 1, 8, 50), (192, 2, 1, 8, 25),
                                 (192, 2, 0, 8, 100), (192, 2, 0, 8, 50)):
     v = C.c_double()
-    check(eng.lib.pf_probe_umma_fp4_rate(n, 4000, acc, ts, bufs, noise, C.byref(v), st))
+    _lib.check_probe(_lib.load_probes().pf_probe_umma_fp4_rate(n, 4000, acc, ts, bufs, noise, C.byref(v), st))
     extra = f", LDS+STS noise {3 * 1024 / noise:.0f} B/clk" if noise else ""
     print(f"mxf4 128x{n}x64 A-in-{'TMEM' if ts else 'smem'}, {acc} accumulators, {bufs} B tiles{extra}: {v.value:.1f} clocks per MMA", flush=True)

@@ -7,6 +7,7 @@ import torch
 
 sys.path.insert(0, ".")
 from phyloforge_b200._lib import check
+from phyloforge_b200 import _lib
 from phyloforge_b200.engine import Engine
 
 eng = Engine(0)
@@ -19,7 +20,7 @@ for n, k, vals in ((128, 64, (-1, 0, 1)), (240, 64, (-1, 0, 1)), (240, 1024, (-1
     da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     want = a.astype(np.int64) @ b.astype(np.int64).T
     dc = torch.full((256, n), -7.0, dtype=torch.float32, device="cuda")
-    check(eng.lib.pf_selftest_umma_fp4_2cta(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k, st))
+    _lib.check_probe(_lib.load_probes().pf_selftest_umma_fp4_2cta(da.data_ptr(), db.data_ptr(), dc.data_ptr(), n, k, st))
     torch.cuda.synchronize()
     got = dc.cpu().numpy()
     ok = np.array_equal(got.astype(np.int64), want) and np.array_equal(got, np.rint(got))
@@ -30,5 +31,5 @@ for n, k, vals in ((128, 64, (-1, 0, 1)), (240, 64, (-1, 0, 1)), (240, 1024, (-1
 for n, bufs in ((128, 8), (192, 8), (224, 8), (240, 8), (240, 2)):
     v = C.c_double()
     pairs = C.c_int()
-    check(eng.lib.pf_probe_umma_fp4_2cta_rate(n, 4000, bufs, C.byref(v), C.byref(pairs), st))
+    _lib.check_probe(_lib.load_probes().pf_probe_umma_fp4_2cta_rate(n, 4000, bufs, C.byref(v), C.byref(pairs), st))
     print(f"mxf4 cta_group::2 256x{n}x64, 2 accumulators, {bufs} B tiles, {pairs.value} CTA pairs: {v.value:.1f} clocks per MMA", flush=True)

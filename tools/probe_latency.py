@@ -6,6 +6,7 @@ import torch
 
 sys.path.insert(0, ".")
 from phyloforge_b200._lib import check
+from phyloforge_b200 import _lib
 from phyloforge_b200.engine import Engine
 
 eng = Engine(0)
@@ -20,5 +21,5 @@ for kind, name in enumerate(KINDS):
         continue
     for n_ctas in ((2, 32, 148) if kind in (3, 4) else (2,)):
         out = C.c_double(0)
-        check(eng.lib.pf_probe_latency(kind, 2000, n_ctas, C.byref(out), st))
+        _lib.check_probe(_lib.load_probes().pf_probe_latency(kind, 2000, n_ctas, C.byref(out), st))
         print(f"{name:42s} ctas={n_ctas:4d}: {out.value:8.1f} ns/step", flush=True)
