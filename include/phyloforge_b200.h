@@ -72,6 +72,15 @@ PF_API int pf_pack_codes_2bit(const uint8_t* d_codes2, int64_t ld2, int64_t n_sa
                               uint32_t* d_planes, int64_t n_words, int64_t word0, int plink,
                               void* stream);
 
+/* d_dst = d_src moved by `shift` (0..31) sites towards higher site indices: site s of the source is site
+ * s + shift of the destination; sites [0, shift) and everything behind n_sites + shift are code 3. Used when the
+ * site axis of ONE file is parsed by several GPUs (treetool/vcftree.py:77-93 cuts it over worker processes): a rank
+ * packs its own columns from site 0 and, once the column counts of the ranks before it are known, moves them onto
+ * the global 32-site word grid, so that word ranges (bootstrap blocks) mean the same sites for any number of GPUs.
+ * The buffers must not overlap; d_dst needs ceil((n_sites + shift) / 32) <= n_words_dst words per tile. */
+PF_API int pf_planes_shift(const uint32_t* d_src, int64_t n_words_src, uint32_t* d_dst, int64_t n_words_dst,
+                           int64_t n_samples, int64_t n_sites, int shift, void* stream);
+
 /* planes -> sample-major u8 codes d_out[i * ld_out + s] for s in [0, n_sites) taken from
  * words [word0, ...). Used to emit the reference's on-disk artefacts and by parity tests. */
 PF_API int pf_unpack_codes_u8(const uint32_t* d_planes, int64_t n_words, int64_t word0,

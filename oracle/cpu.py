@@ -115,6 +115,22 @@ def pack_planes(codes_sm: np.ndarray, n_words: int | None = None) -> np.ndarray:
     return out
 
 
+def shift_planes(planes: np.ndarray, n_samples: int, n_sites: int, shift: int) -> np.ndarray:
+    """Restatement of pf_planes_shift on the tiled layout: site s of the source becomes site s + shift; the vacated
+    low bits and everything behind the last site are code 3 (all ones). planes: pack_planes(...) of n_sites sites."""
+    n_tiles = (n_samples + TILE - 1) // TILE
+    nw_src = (n_sites + 31) // 32
+    nw_dst = (n_sites + shift + 31) // 32
+    src = np.asarray(planes, dtype=np.uint32).reshape(n_tiles, nw_src, 2 * TILE)
+    bits = np.unpackbits(src.view(np.uint8).reshape(n_tiles, nw_src, 2 * TILE, 4), axis=-1, bitorder="little")
+    bits = bits.reshape(n_tiles, nw_src, 2 * TILE, 32).transpose(0, 2, 1, 3).reshape(n_tiles, 2 * TILE, nw_src * 32)
+    out = np.ones((n_tiles, 2 * TILE, nw_dst * 32), dtype=np.uint8)
+    out[:, :, shift:shift + n_sites] = bits[:, :, :n_sites]
+    out = out.reshape(n_tiles, 2 * TILE, nw_dst, 32).transpose(0, 2, 1, 3)
+    words = np.packbits(out, axis=-1, bitorder="little").reshape(n_tiles, nw_dst, 2 * TILE, 4)
+    return np.ascontiguousarray(words).view(np.uint32).reshape(-1)
+
+
 # ------------------------------------------------------------------ counts / distance
 def pair_counts(codes_sm: np.ndarray, method: str = "auto") -> np.ndarray:
     """Sample-major codes [n, m] -> int64 [3, n, n] (V, D1, D2)."""

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "pf_synth_codes": (_i32, [_vp, _i64, _i64, _i64, _i64, _u64, _i32, _u32, _vp]),
     "pf_pack_codes_u8": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "pf_pack_codes_2bit": (_i32, [_vp, _i64, _i64, _i64, _vp, _i64, _i64, _i32, _vp]),
+    "pf_planes_shift": (_i32, [_vp, _i64, _vp, _i64, _i64, _i64, _i32, _vp]),
     "pf_unpack_codes_u8": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "pf_transpose_u8": (_i32, [_vp, _i64, _vp, _i64, _i64, _vp, _i64, _vp]),
     "pf_line_index_work_bytes": (_i64, [_i64]),

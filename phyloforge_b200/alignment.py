@@ -53,7 +53,7 @@ def read_alignment(path: str):
     return names, mat
 
 
-def load_alignment(engine, path: str, non_biallelic: str = "error") -> PackedGenotypes:
+def load_alignment(engine, path: str, non_biallelic: str = "include") -> PackedGenotypes:
     names, mat = read_alignment(path)
     n, m = mat.shape
     dev = engine.device

@@ -213,6 +213,33 @@ transpose_kernel(const uint8_t* __restrict__ in, int64_t ld_in, const int64_t* _
   }
 }
 
+// Shift a packed matrix by `shift` sites (0..31) towards higher site indices: site s of the source becomes site
+// s + shift of the destination; the vacated low bits of word 0 and everything behind site n_sites + shift is
+// code 3 (L = H = 1: missing). One thread per (tile, destination word, plane, lane) entry.
+__global__ void __launch_bounds__(256)
+planes_shift_kernel(const uint32_t* __restrict__ src, int64_t n_words_src, uint32_t* __restrict__ dst,
+                    int64_t n_words_dst, int64_t n_tiles, int64_t n_sites, int shift, int64_t words_out) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t per_tile = words_out * 2 * PF_TILE;
+  if (idx >= n_tiles * per_tile) return;
+  const int64_t T = idx / per_tile;
+  const int64_t rem = idx - T * per_tile;
+  const int64_t w = rem / (2 * PF_TILE);
+  const int pl = static_cast<int>(rem - w * 2 * PF_TILE);          // plane * 64 + lane
+  const int64_t src_words = (n_sites + 31) / 32;
+  auto load = [&](int64_t ws) -> uint32_t {                        // source word with the padding behind n_sites forced to 1
+    if (ws < 0 || ws >= src_words) return 0xffffffffu;
+    uint32_t v = src[(T * n_words_src + ws) * 2 * PF_TILE + pl];
+    const int64_t left = n_sites - ws * 32;
+    if (left < 32) v |= ~((1u << left) - 1u);
+    return v;
+  };
+  const uint32_t hi = load(w), lo = load(w - 1);
+  const uint32_t v = shift ? ((hi << shift) | (lo >> (32 - shift))) : hi;
+  dst[(T * n_words_dst + w) * 2 * PF_TILE + pl] = v;
+}
+
+
 }  // namespace
 
 PF_API int64_t pf_planes_len(int64_t n_samples, int64_t n_words) {
@@ -307,6 +334,25 @@ PF_API int pf_pack_codes_2bit(const uint8_t* d_codes2, int64_t ld2, int64_t n_sa
   pf_count_launch();
   pack2_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(d_codes2, ld2, n_samples, n_sites, d_planes,
                                                                        n_words, word0, n_groups, plink);
+  PF_CUDA(cudaGetLastError());
+  return PF_OK;
+  PF_TRY_END
+}
+
+PF_API int pf_planes_shift(const uint32_t* d_src, int64_t n_words_src, uint32_t* d_dst, int64_t n_words_dst,
+                           int64_t n_samples, int64_t n_sites, int shift, void* stream) {
+  PF_TRY_BEGIN
+  if (!d_src || !d_dst || d_src == d_dst || n_samples <= 0 || n_sites < 0 || shift < 0 || shift > 31)
+    return pf_fail("pf_planes_shift: bad arguments");
+  const int64_t words_out = pf_ceil_div(n_sites + shift, 32);
+  if (pf_ceil_div(n_sites, 32) > n_words_src || words_out > n_words_dst)
+    return pf_fail("pf_planes_shift: word range exceeds a buffer");
+  if (words_out == 0) return PF_OK;
+  const int64_t n_tiles = pf_ceil_div(n_samples, PF_TILE);
+  const int64_t total = n_tiles * words_out * 2 * PF_TILE;
+  pf_count_launch();
+  planes_shift_kernel<<<static_cast<unsigned>(pf_ceil_div(total, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_src, n_words_src, d_dst, n_words_dst, n_tiles, n_sites, shift, words_out);
   PF_CUDA(cudaGetLastError());
   return PF_OK;
   PF_TRY_END

@@ -212,19 +212,26 @@ class Engine:
 
     # ------------------------------------------------------------------ bootstrap support
     def block_counts(self, planes: torch.Tensor, n_samples: int, n_words: int, n_blocks: int,
-                     word_end: int | None = None, variant: int = 0) -> torch.Tensor:
-        """Count matrices of n_blocks contiguous word ranges: int32 [n_blocks, 3, n, n]."""
+                     word_end: int | None = None, variant: int = 0, word0: int = 0, total_words: int | None = None,
+                     n_extra_blocks: int = 0) -> torch.Tensor:
+        """Count matrices of n_blocks contiguous word ranges: int32 [n_blocks + n_extra_blocks, 3, n, n] (the extra
+        blocks are left zero for the caller). The ranges are cut on the GLOBAL word axis [0, total_words); this
+        buffer holds global words [word0, word0 + word_end), so a worker that owns a part of the site axis fills the
+        part of every block that lies in its words (the workers' tensors are then summed)."""
         from .sharding import shard_words
         if word_end is None:
             word_end = n_words
+        if total_words is None:
+            total_words = word0 + word_end
         # pf_bootstrap_counts works on groups of four elements: the per-block stride is rounded up once here,
         # so that no call ever has to pad (and copy) the whole block tensor
         elems = 3 * n_samples * n_samples
         stride = (elems + 3) // 4 * 4
-        store = torch.zeros((n_blocks, stride), dtype=torch.int32, device=self.device)
-        blocks = store[:, :elems].view(n_blocks, 3, n_samples, n_samples)
+        store = torch.zeros((n_blocks + n_extra_blocks, stride), dtype=torch.int32, device=self.device)
+        blocks = store[:, :elems].view(n_blocks + n_extra_blocks, 3, n_samples, n_samples)
         for b in range(n_blocks):
-            wb, we = shard_words(word_end, n_blocks, b)
+            gb, ge = shard_words(total_words, n_blocks, b)
+            wb, we = max(gb, word0) - word0, min(ge, word0 + word_end) - word0
             if we > wb:
                 self.pair_counts(planes, n_samples, n_words, blocks[b], word_begin=wb, word_end=we, variant=variant)
         return blocks
@@ -252,31 +259,81 @@ class Engine:
                                            out.data_ptr(), _stream_ptr()))
         return out[:, :elems].view((weights.shape[0],) + shape)
 
+    @staticmethod
+    def bootstrap_block_plan(n_blocks: int, total_words: int, total_extra: int, total_cols: int, per_block_bytes: int,
+                             max_block_bytes: int):
+        """(blocks over the 2-bit words, blocks over the columns outside the 2-bit code): at most n_blocks in all and
+        at most max_block_bytes of block matrices; the extra columns get their share of the blocks by column count.
+        A function of the WHOLE matrix only, so every worker of a multi-GPU run - and a one-GPU run of the same file
+        - cuts the same blocks."""
+        cap = int(max(1, min(n_blocks, max_block_bytes // max(1, per_block_bytes))))
+        bx = 0
+        if total_extra > 0:
+            bx = int(max(1, min(total_extra, cap - 1 if total_words > 0 and cap > 1 else cap,
+                                round(cap * total_extra / max(1, total_cols + total_extra)))))
+        b2 = int(max(1, min(cap - bx, total_words))) if total_words > 0 else 0
+        return b2, bx
+
     def bootstrap_tree(self, planes: torch.Tensor, n_samples: int, n_words: int, names, replicates: int = 100,
                        seed: int = 1, n_blocks: int = 256, metric="ibs", variant: int = 0,
-                       n_sites: int | None = None, max_block_bytes: int = 48 << 30):
+                       n_sites: int | None = None, max_block_bytes: int = 48 << 30,
+                       extra_chars: torch.Tensor | None = None, word0: int = 0, total_cols: int | None = None,
+                       extra0: int = 0, total_extra: int | None = None):
         """NJ tree of all sites with block-bootstrap support on its internal edges.
         Returns (TreeResult of the main tree with support labels in .newick, support [n-3] in percent,
-        replicate join lists [replicates, n-2, 3] int32)."""
+        replicate join lists [replicates, n-2, 3] int32).
+
+        Blocks: contiguous ranges of the global 32-site word axis, plus (extra_chars: the columns that do not fit
+        the 2-bit code, site-major characters) contiguous ranges of those columns, in proportion to their number.
+        Several workers (torch.distributed initialised; word0 / total_cols / extra0 / total_extra place this worker's
+        words and extra columns in the whole matrix, phyloforge_b200/multigpu.py): every worker fills its part of
+        the block matrices, one allreduce sums them, the replicates are dealt out to the workers in batches of 8
+        and their join lists gathered - the draws are a function of (seed, replicate), so the support values do
+        not depend on the number of workers."""
+        import torch.distributed as dist
         from .bootstrap import split_support
+        from .sharding import allreduce_counts, shard_words
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        rank, world = (dist.get_rank(), dist.get_world_size()) if multi else (0, 1)
         word_end = n_words if n_sites is None else (n_sites + 31) // 32
-        per_block = 12 * n_samples * n_samples
-        n_blocks = int(max(1, min(n_blocks, word_end, max_block_bytes // max(1, per_block))))
-        blocks = self.block_counts(planes, n_samples, n_words, n_blocks, word_end=word_end, variant=variant)
-        ones = torch.ones((1, n_blocks), dtype=torch.int32, device=self.device)
+        local_cols = word_end * 32 if n_sites is None else n_sites
+        if total_cols is None:
+            total_cols = word0 * 32 + local_cols
+        total_words = (total_cols + 31) // 32
+        n_extra = 0 if extra_chars is None else int(extra_chars.shape[0])
+        if total_extra is None:
+            total_extra = extra0 + n_extra
+        b2, bx = self.bootstrap_block_plan(n_blocks, total_words, total_extra, total_cols, 12 * n_samples * n_samples,
+                                           max_block_bytes)
+        blocks = self.block_counts(planes, n_samples, n_words, b2, word_end=word_end, variant=variant, word0=word0,
+                                   total_words=total_words, n_extra_blocks=bx)
+        for e in range(bx):
+            gb, ge = shard_words(total_extra, bx, e)            # the same contiguous cut, on the extra-column axis
+            lo, hi = max(gb, extra0) - extra0, min(ge, extra0 + n_extra) - extra0
+            if hi > lo:
+                self.add_extra_column_counts(extra_chars[lo:hi], n_samples, blocks[b2 + e])
+        n_all = b2 + bx
+        if multi:
+            allreduce_counts(blocks if blocks.is_contiguous() else blocks.as_strided(
+                (n_all, blocks.stride(0)), (blocks.stride(0), 1)))
+        ones = torch.ones((1, n_all), dtype=torch.int32, device=self.device)
         total = self.bootstrap_counts(blocks, ones)[0].contiguous()
         main = self.tree_from_counts(total, names, metric=metric, keep=True)
         if n_samples < 4 or replicates <= 0:
             return main, np.zeros((0,)), np.zeros((0, max(0, n_samples - 2), 3), dtype=np.int32)
-        merges = []
-        for r0 in range(0, replicates, 8):
+        rep_merges = torch.zeros((replicates, n_samples - 2, 3), dtype=torch.int32, device=self.device)
+        for i, r0 in enumerate(range(0, replicates, 8)):
+            if i % world != rank:
+                continue
             k = min(8, replicates - r0)
-            w = self.bootstrap_weights(seed, r0, k, n_blocks)
+            w = self.bootstrap_weights(seed, r0, k, n_all)
             rep = self.bootstrap_counts(blocks, w)
-            dists = torch.stack([self.normalise(rep[j].contiguous(), metric)[0] for j in range(k)])
+            dists = torch.stack([self.normalise(rep[j], metric)[0] for j in range(k)])
             merge, _ = self.nj_batch(dists)          # the replicates of a batch are joined concurrently
-            merges.append(merge)
-        rep_merges = torch.cat(merges).cpu().numpy()
+            rep_merges[r0:r0 + k] = merge
+        if multi:
+            allreduce_counts(rep_merges)             # every replicate was written by exactly one worker
+        rep_merges = rep_merges.cpu().numpy()
         support = split_support(main.merge, rep_merges, n_samples)
         main.newick = merges_to_newick_native(self.lib, main.merge, main.length, list(names), support=support)
         return main, support, rep_merges
@@ -372,7 +429,8 @@ class Engine:
         counted (a buffer sized for an upper bound has unwritten words behind them)."""
         word_end = n_words if n_sites is None else (n_sites + 31) // 32
         counts = self.alloc_counts(n_samples)
-        self.pair_counts(planes, n_samples, n_words, counts, word_end=word_end, variant=variant)
+        if word_end > 0:
+            self.pair_counts(planes, n_samples, n_words, counts, word_end=word_end, variant=variant)
         if extra_chars is not None:
             self.add_extra_column_counts(extra_chars, n_samples, counts)
         self.allreduce_counts(counts)

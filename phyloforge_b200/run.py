@@ -88,15 +88,31 @@ def get_parser(argv=None):
 
 def main(argv=None):
     cfg, tree = get_parser(argv)
-    if tree == "snp":
-        from . import vcftree
-        vcftree.VcfTree(cfg).snp_tree()
-    elif tree == "sv":
-        from . import svtree
-        svtree.SvTree(cfg).sv_tree()
-    else:
-        print(f"The {tree} workflow is not part of phyloforge_b200 (only -s and -S are); use PhyloForge itself.")
-        sys.exit(2)
+    try:
+        if tree == "snp":
+            from . import vcftree
+            vcftree.VcfTree(cfg).snp_tree()
+        elif tree == "sv":
+            from . import svtree
+            svtree.SvTree(cfg).sv_tree()
+        else:
+            print(f"The {tree} workflow is not part of phyloforge_b200 (only -s and -S are); use PhyloForge itself.")
+            sys.exit(2)
+    finally:
+        _leave_process_group()
+
+
+def _leave_process_group():
+    """A worker of a `gpus = N` run (phyloforge_b200/multigpu.py) leaves the workers' process group on its way out."""
+    if "torch" not in sys.modules:
+        return
+    import torch.distributed as dist
+    from . import multigpu
+    if multigpu.worker_env()[1] > 1 and dist.is_available() and dist.is_initialized():
+        try:
+            dist.destroy_process_group()
+        except Exception:  # noqa: BLE001 - the run's own exit status matters, not the teardown's
+            pass
 
 
 if __name__ == "__main__":

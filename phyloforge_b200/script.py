@@ -40,10 +40,16 @@ class RunCmd:
         self.seq = "cds"
         self.thread = 10                        # script.py:25
         self.out_path = os.getcwd()
-        self.distance = "ibs"                   # new optional key
-        self.non_biallelic = "error"            # new optional key
-        self.bootstrap = 0                      # new optional key: block-bootstrap replicates (the reference asks
-        self.bootstrap_seed = 1                 # treebest for -b 1000, script.py:360); 0 = no support values
+        # new optional keys; the defaults keep a configuration written for PhyloForge running unchanged
+        self.distance = "p"                     # p = mismatches / valid columns: what a mismatch model sees on
+                                                # all_snp.fa, the metric of the treebest slot; or ibs
+        self.non_biallelic = "include"          # the reference keeps multi-allelic / '*' sites (vcftree.py:109,
+                                                # 126-127, 56-63): they are counted from their characters; or skip / error
+        self.bootstrap = 0                      # block-bootstrap replicates (the reference asks treebest for
+        self.bootstrap_seed = 1                 # -b 1000, script.py:360); 0 = no support values
+        self.gpus = 1                           # worker processes / GPUs the site axis of the VCF is cut over
+        from . import multigpu
+        self.rank, self.world = multigpu.worker_env()
         self._engine = None
         self._packed = None
         self.report = {}
@@ -97,6 +103,16 @@ class RunCmd:
         except ValueError:
             print(f"bootstrap: {self.bootstrap} / bootstrap_seed: {self.bootstrap_seed} must be non-negative integers")
             sys.exit()
+        try:
+            if str(self.gpus).strip().lower() in ("all", "auto"):
+                import torch
+                self.gpus = max(1, torch.cuda.device_count())
+            self.gpus = int(self.gpus)
+            if self.gpus < 1:
+                raise ValueError
+        except ValueError:
+            print(f"gpus: {self.gpus} must be a positive integer (or all)")
+            sys.exit()
 
     # ------------------------------------------------------------------ config
     def get_config(self, opt_cfg, opt):
@@ -114,8 +130,23 @@ class RunCmd:
         """The GPU engine, created on first use. Raises if the CUDA library or a GPU is missing."""
         if self._engine is None:
             from .engine import Engine
-            self._engine = Engine()
+            device = None
+            if self.world > 1:
+                from . import multigpu
+                device = multigpu.init_worker(self.rank, self.world)
+            self._engine = Engine(device)
         return self._engine
+
+    def spawn_if_multi_gpu(self, flag: str):
+        """``gpus = N`` (N > 1) in the parent process: run the same command as N worker processes, one per GPU
+        (phyloforge_b200/multigpu.py), and return their exit status; None when this process should do the work."""
+        if self.gpus <= 1 or self.world > 1:
+            return None
+        from . import multigpu
+        status = multigpu.spawn_workers([flag, self.cfg_path], self.gpus)
+        if status != 0:
+            sys.exit(status)
+        return status
 
     # ------------------------------------------------------------------ shell
     def run_command(self, command):
@@ -129,7 +160,9 @@ class RunCmd:
     # ------------------------------------------------------------------ tree
     def gpu_tree(self, packed, out_file: str, basename: str) -> int:
         """Distance matrix + NJ on the GPU from packed genotypes; writes the tree to
-        `out_file`, the distance matrix to ``{out}/{basename}.dist`` and a timing record."""
+        `out_file`, the distance matrix to ``{out}/{basename}.dist`` and a timing record. With several workers
+        (gpus = N) every worker counts its own columns, the count matrices are summed over the workers inside
+        the engine, and rank 0 writes the files."""
         import torch
         from .phylip import write_distance_matrix
         eng = self.engine()
@@ -138,14 +171,15 @@ class RunCmd:
             sys.exit(1)
         t0 = time.perf_counter()
         extra = getattr(packed, "extra_chars", None)
-        if extra is not None and self.bootstrap > 0:
-            print("bootstrap support is computed on the 2-bit sites only; set non_biallelic = skip (or bootstrap = 0)")
-            sys.exit(1)
         if self.bootstrap > 0 and packed.n_samples >= 4:
             # main tree + seeded block-bootstrap support on its internal edges (labels in percent)
             res, support, _ = eng.bootstrap_tree(packed.planes, packed.n_samples, packed.n_words, packed.names,
                                                  replicates=self.bootstrap, seed=self.bootstrap_seed,
-                                                 metric=self.distance, n_sites=packed.n_sites)
+                                                 metric=self.distance, n_sites=packed.n_sites, extra_chars=extra,
+                                                 word0=getattr(packed, "word0", 0),
+                                                 total_cols=getattr(packed, "total_cols", None),
+                                                 extra0=getattr(packed, "extra0", 0),
+                                                 total_extra=getattr(packed, "total_extra", None))
             self.report.update({"bootstrap_replicates": self.bootstrap, "bootstrap_seed": self.bootstrap_seed,
                                 "bootstrap_mean_support": float(support.mean()) if support.size else None})
         else:
@@ -153,6 +187,8 @@ class RunCmd:
                                        metric=self.distance, n_sites=packed.n_sites, extra_chars=extra)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
+        if self.rank != 0:
+            return 0
         with open(out_file, "w") as f:
             f.write(res.newick + "\n")
         out_dir = os.path.dirname(out_file)
@@ -160,8 +196,9 @@ class RunCmd:
         if res.n_zero_valid:
             print(f"[{stamp()}] Warning: {res.n_zero_valid // 2} sample pairs share no genotyped site; "
                   "their distance was set to 1.0")
-        self.report.update({"samples": packed.n_samples, "sites": packed.n_sites, "distance": self.distance,
-                            "tree_seconds": t1 - t0, "tree_file": out_file})
+        self.report.update({"samples": packed.n_samples, "sites": getattr(packed, "total_cols", packed.n_sites),
+                            "distance": self.distance, "gpus": self.world, "tree_seconds": t1 - t0,
+                            "tree_file": out_file})
         with open(os.path.join(out_dir, f"{basename}.phyloforge_b200.json"), "w") as f:
             json.dump(self.report, f, indent=1)
         return 0
@@ -186,6 +223,8 @@ class RunCmd:
                     sys.exit(1)
             out = f"{outpath}/{basename}_treebest.NHX" if tool == "treebest" else f"{outpath}/{basename}.treefile"
             return self.gpu_tree(self._packed, out, basename)
+        if self.rank != 0:
+            return 0                            # the external tool runs once, on the files rank 0 wrote
         if tool == "iqtree":
             cmd = f"{self.iqtree} -s {infile} -pre {outpath}/{basename} -nt {thread} -m MFP --quiet -B 1000 -redo"
         elif tool == "fasttree":

@@ -28,5 +28,11 @@ def allreduce_counts(counts):
     bit-identical for any number of ranks. No-op without an initialised process group."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        if counts.is_cuda and dist.get_backend() != "nccl":
+            # workers that share a GPU (more workers than devices: testing) sum through host copies
+            host = counts.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM)
+            counts.copy_(host)
+        else:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts

@@ -32,6 +32,10 @@ ERR_TEXT = {
 }
 
 DEFAULT_CHUNK_BYTES = 256 << 20
+# first guess of the text size of a gzip / bgzip file (ratio x compressed size + slack): its planes start at that
+# size (at most 256 MB) and double whenever the packed columns outgrow them
+GZ_TEXT_RATIO_GUESS = 16
+GZ_TEXT_SLACK = 1 << 20
 
 
 class VcfFormatError(PhyloForgeError):
@@ -189,16 +193,18 @@ def _open_stream(path: str):
     return _open_bytes(path)
 
 
-def read_header(path: str):
+def read_header(path: str, with_body_offset: bool = False):
     """Sample names from the first line that starts with ``#CHROM`` (vcftree.py:69-73,
-    99-100). Returns (names, size bound in bytes of the text)."""
+    99-100). Returns (names, size in bytes of the text; None for gzip input, whose text size is not known
+    up front) and, with_body_offset, the byte offset just behind the ``#CHROM`` line."""
     size = os.path.getsize(path)
     if _is_gzip(path):
-        # uncompressed size is unknown up front: bound it generously (VCF text rarely beats 40:1)
-        size = size * 64 + (1 << 20)
+        size = None
     names = None
+    body = 0
     with _open_bytes(path) as f:
         for raw in f:
+            body += len(raw)
             if raw.startswith(b"#CHROM"):
                 names = raw.decode("utf-8", "replace").strip().split()[9:]
                 break
@@ -208,7 +214,43 @@ def read_header(path: str):
         raise VcfFormatError(f"{path}: no #CHROM header line before the first record")
     if not names:
         raise VcfFormatError(f"{path}: the #CHROM header names no samples")
+    if with_body_offset:
+        return names, size, body
     return names, size
+
+
+def line_start_at_or_after(f, pos: int, size: int) -> int:
+    """Offset of the first line that starts at byte `pos` or later (a line starts at 0 or just behind a newline)."""
+    if pos <= 0:
+        return 0
+    if pos >= size:
+        return size
+    f.seek(pos - 1)
+    at = pos - 1
+    while at < size:
+        block = f.read(1 << 16)
+        if not block:
+            break
+        k = block.find(b"\n")
+        if k >= 0:
+            return at + k + 1
+        at += len(block)
+    return size
+
+
+def byte_range_of_rank(path: str, body_offset: int, rank: int, world: int):
+    """The contiguous run of whole lines of the VCF body that worker `rank` of `world` converts: the body bytes are
+    cut evenly and every cut is moved forward to the next line start - the axis the reference cuts over its worker
+    processes (contiguous line ranges in file order, treetool/vcftree.py:77-93). Returns (begin, end) byte offsets;
+    the ranges of ranks 0..world-1 tile [body_offset, file size) exactly."""
+    size = os.path.getsize(path)
+    span = max(0, size - body_offset)
+    with open(path, "rb", buffering=0) as f:
+        cut = [line_start_at_or_after(f, body_offset + span * r // world, size) if r else body_offset
+               for r in (rank, rank + 1)]
+    if rank + 1 == world:
+        cut[1] = size
+    return max(cut[0], body_offset), max(cut[1], cut[0], body_offset)
 
 
 class _ChunkReader:
@@ -216,9 +258,14 @@ class _ChunkReader:
     after a newline; the partial line behind it is carried to the front of the next buffer. The
     read (page cache -> pinned memory) of chunk k+1 overlaps the GPU work on chunk k."""
 
-    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2):
+    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2, byte_range=None):
         self.path, self.size, self.buf_bytes = path, size, buf_bytes
-        self.bufs = [torch.empty(buf_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_bufs)]
+        self.byte_range = byte_range          # (begin, end) of a plain-text file, cut at line starts
+        # page-locked staging buffers (plain ones only where no CUDA driver exists: the reader's line cutting is
+        # exercised by the CPU tests; the loader itself needs the GPU)
+        pin = torch.cuda.is_available()
+        self.bufs = [torch.empty(buf_bytes, dtype=torch.uint8).pin_memory() if pin else
+                     torch.empty(buf_bytes, dtype=torch.uint8) for _ in range(n_bufs)]
         self.free = queue.Queue()
         self.full = queue.Queue()
         for i in range(n_bufs):
@@ -232,6 +279,11 @@ class _ChunkReader:
             done = 0
             eof = False
             with _open_stream(self.path) as f:
+                left = None
+                if self.byte_range is not None:
+                    f.seek(self.byte_range[0])
+                    left = self.byte_range[1] - self.byte_range[0]
+                    eof = left <= 0
                 while not eof or carry:
                     i = self.free.get()
                     if i is None:
@@ -245,12 +297,16 @@ class _ChunkReader:
                     filled = k
                     mv = memoryview(arr)
                     while filled < self.buf_bytes and not eof:
-                        got = f.readinto(mv[filled:])
+                        want = mv[filled:] if left is None else mv[filled:filled + min(left, self.buf_bytes - filled)]
+                        got = f.readinto(want)
                         if not got:
                             eof = True
                             break
                         filled += got
                         done += got
+                        if left is not None:
+                            left -= got
+                            eof = left <= 0
                     if eof:
                         cut = filled                       # last chunk: take everything
                     else:
@@ -285,26 +341,53 @@ class _ChunkReader:
         self.free.put(None)
 
 
-def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, chunk_bytes: int):
+def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, chunk_bytes: int,
+          rank: int = 0, world: int = 1):
     lib, dev = engine.lib, engine.device
-    names, size = read_header(path)
+    names, size, body = read_header(path, with_body_offset=True)
     n = len(names)
     rpl = 1 if kind == "snp" else 2          # matrix rows a line can yield
     ld = (n + 3) // 4 * 4
     stream = torch.cuda.current_stream().cuda_stream
     if size == 0:
         raise VcfFormatError(f"{path}: empty file")
+    byte_range = None
+    if world > 1:
+        if size is None:
+            raise VcfFormatError(f"{path}: a compressed VCF cannot be cut into byte ranges; use gpus = 1 (or unpack it)")
+        byte_range = byte_range_of_rank(path, body, rank, world)
+        size = byte_range[1] - byte_range[0]
 
     # A record that yields a matrix column has 9 fixed fields and n sample fields of >= 1 byte, each
-    # followed by a separator: at least 2n + 18 bytes. That bounds the columns of the whole file and
-    # (for well-formed input) the lines of a chunk; blank-line-heavy chunks fall back to counting.
+    # followed by a separator: at least 2n + 18 bytes. That bounds the columns of a plain-text file and
+    # (for well-formed input) the lines of a chunk; blank-line-heavy chunks fall back to counting. The text
+    # size of a gzip file is not known up front: its planes start small and grow geometrically.
     min_line = 2 * n + 18
-    buf_bytes = int(min(max(chunk_bytes, 4096), size + 1))
-    n_words_cap = max(1, ((size // min_line + 2) * rpl + 31) // 32)
+    known = size is not None
+    buf_bytes = int(min(max(chunk_bytes, 4096), size + 1)) if known else int(max(chunk_bytes, 4096))
+    text_bound = size if known else GZ_TEXT_RATIO_GUESS * os.path.getsize(path) + GZ_TEXT_SLACK
+    n_words_cap = max(1, ((text_bound // min_line + 2) * rpl + 31) // 32)
+    if not known:
+        n_words_cap = max(1, min(n_words_cap, (1 << 28) // max(1, 512 * ((n + 63) // 64))))   # <= 256 MB to begin with
     planes = engine.alloc_planes(n, n_words_cap)
     max_lines = buf_bytes // min_line + 2
 
-    reader = _ChunkReader(path, size, buf_bytes)
+    def grow_planes(need_words):
+        """Planes of a larger capacity holding the words packed so far (tiles keep their [word][plane][lane] order)."""
+        nonlocal planes, n_words_cap
+        new_cap = max(need_words, 2 * n_words_cap)
+        bigger = engine.alloc_planes(n, new_cap)
+        n_tiles = (n + 63) // 64
+        bigger.view(n_tiles, new_cap, 128)[:, :words_done] = planes.view(n_tiles, n_words_cap, 128)[:, :words_done]
+        planes, n_words_cap = bigger, new_cap
+
+    if known and size <= 0:
+        # a worker whose byte range holds no line: an empty shard (all of its one word is code 3)
+        planes.fill_(-1)
+        return PackedGenotypes(names=names, n_samples=n, n_sites=0, n_words=n_words_cap, planes=planes,
+                               chars=np.zeros((n, 0), dtype=np.uint8) if keep_chars else None, n_columns=0, n_lines=0)
+
+    reader = _ChunkReader(path, size, buf_bytes, byte_range=byte_range)
     d_text = torch.empty(buf_bytes, dtype=torch.uint8, device=dev)
     d_work = torch.empty(int(lib.pf_line_index_work_bytes(buf_bytes)), dtype=torch.uint8, device=dev)
     carry_rows = 32     # rows [0, 32) of the code buffer carry the sites left over from the previous chunk
@@ -393,7 +476,9 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
             avail = n_carry + n_cols
             full = (avail // 32) * 32
             if words_done + (avail + 31) // 32 > n_words_cap:
-                raise VcfFormatError(f"{path}: more matrix columns than the file size allows")
+                if known:
+                    raise VcfFormatError(f"{path}: more matrix columns than the file size allows")
+                grow_planes(words_done + (avail + 31) // 32)
             if full:
                 engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done,
                                   rows=d_rows[first:first + full], n_sites=full)
@@ -424,16 +509,17 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                            extra_chars=torch.cat(extra_blocks, dim=0) if extra_blocks else None)
 
 
-def load_snp_vcf(engine, path: str, keep_chars: bool = True, non_biallelic: str = "error",
-                 chunk_bytes: int = DEFAULT_CHUNK_BYTES) -> PackedGenotypes:
-    """SNP VCF -> planes of the biallelic sites + the IUPAC character matrix of every kept site."""
-    return _load(engine, path, "snp", keep_chars, non_biallelic, chunk_bytes)
+def load_snp_vcf(engine, path: str, keep_chars: bool = True, non_biallelic: str = "include",
+                 chunk_bytes: int = DEFAULT_CHUNK_BYTES, rank: int = 0, world: int = 1) -> PackedGenotypes:
+    """SNP VCF -> planes of the biallelic sites + the IUPAC character matrix of every kept site.
+    world > 1: only the lines of worker `rank`'s byte range (byte_range_of_rank) are converted."""
+    return _load(engine, path, "snp", keep_chars, non_biallelic, chunk_bytes, rank, world)
 
 
 def load_sv_vcf(engine, path: str, keep_chars: bool = True,
-                chunk_bytes: int = DEFAULT_CHUNK_BYTES) -> PackedGenotypes:
+                chunk_bytes: int = DEFAULT_CHUNK_BYTES, rank: int = 0, world: int = 1) -> PackedGenotypes:
     """SV VCF -> planes and the 0/1/. matrix (one or two columns per DEL/INS record)."""
-    return _load(engine, path, "sv", keep_chars, "error", chunk_bytes)
+    return _load(engine, path, "sv", keep_chars, "error", chunk_bytes, rank, world)
 
 
 def write_fasta(path: str, names, chars: np.ndarray):

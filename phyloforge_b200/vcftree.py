@@ -29,9 +29,10 @@ class VcfTree(RunCmd):
     def __init__(self, cfg: str | None = None, tree: str | None = "snp"):
         super().__init__(cfg, tree if cfg is not None else None)
         wd = f"{self.out_path}/working_dir"      # vcftree.py:16-24: always start from an empty dir
-        if os.path.isdir(wd):
-            shutil.rmtree(wd)
-        os.makedirs(wd)
+        if self.rank == 0 and not (self.gpus > 1 and self.world == 1):   # (the workers' rank 0 does it, not their parent)
+            if os.path.isdir(wd):
+                shutil.rmtree(wd)
+            os.makedirs(wd)
         self.working_dir = os.path.abspath(wd)
 
     # ------------------------------------------------------------------ helpers
@@ -112,33 +113,71 @@ class VcfTree(RunCmd):
 
     # ------------------------------------------------------------------ workflow
     def snp_tree(self):
-        print(f"[{stamp()}] Converting a VCF file to a base sequence...")
+        status = self.spawn_if_multi_gpu("-s")          # gpus = N: N worker processes run this method, one per GPU
+        if status is not None:
+            return status
+        from . import multigpu
+        chief = self.rank == 0
+        if chief:
+            print(f"[{stamp()}] Converting a VCF file to a base sequence...")
         basename = "SNP"
         t0 = time.perf_counter()
+        packed, failure = None, None
         try:
-            packed = vcf.load_snp_vcf(self.engine(), self.vcf_file, keep_chars=True,
-                                      non_biallelic=self.non_biallelic)
+            eng = self.engine()
+            multigpu.barrier()                           # rank 0 has emptied working_dir before anybody writes there
+            packed = vcf.load_snp_vcf(eng, self.vcf_file, keep_chars=True, non_biallelic=self.non_biallelic,
+                                      rank=self.rank, world=self.world)
         except vcf.VcfFormatError as e:
-            print(f"[{stamp()}] Failed to Convert VCF file to base sequence, please check the input file!")
-            print(e)
+            failure = e
+        if not multigpu.agree_ok(failure is None):
+            if chief:
+                print(f"[{stamp()}] Failed to Convert VCF file to base sequence, please check the input file!")
+            if failure is not None:
+                print(failure if self.world == 1 else f"worker {self.rank} (lines are counted from its first line): {failure}")
             sys.exit(1)
         self._packed = packed
-        if self.tree_software.upper() in ("TREEBEST", "FASTTREE"):      # vcftree.py:229-235
-            infile = f"{self.out_path}/all_snp.fa"
-            vcf.write_fasta(infile, packed.names, packed.chars)
+        use_fasta = self.tree_software.upper() in ("TREEBEST", "FASTTREE")      # vcftree.py:229-235
+        if self.world == 1:
+            if use_fasta:
+                infile = f"{self.out_path}/all_snp.fa"
+                vcf.write_fasta(infile, packed.names, packed.chars)
+            else:
+                infile = f"{self.out_path}/all_snp.phy"
+                vcf.write_phylip(infile, packed.names, packed.chars)
+                print(infile)
         else:
-            infile = f"{self.out_path}/all_snp.phy"
-            vcf.write_phylip(infile, packed.names, packed.chars)
-            print(infile)
+            # the reference's own layout: one chunk FASTA per worker in working_dir, concatenated in chunk order
+            # (convert_vcf_to_seq -> merge_seq, vcftree.py:139-171)
+            stem = os.path.splitext(os.path.basename(self.vcf_file))[0]
+            chunk = [os.path.join(self.working_dir, f"{stem}{r}.fa") for r in range(self.world)]
+            vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
+            multigpu.barrier()
+            infile = f"{self.out_path}/all_snp" + (".fa" if use_fasta else ".phy")
+            if chief:
+                multigpu.merge_chunk_fastas(chunk, f"{self.out_path}/all_snp", "fa" if use_fasta else "phylip")
+                if not use_fasta:
+                    print(infile)
+            multigpu.globalise(eng, packed, self.rank, self.world)
         t1 = time.perf_counter()
-        print(f"[{stamp()}] Finish Converting a VCF file to a base sequence.")
-        self.report.update({"vcf_file": self.vcf_file, "convert_seconds": t1 - t0, "lines": packed.n_lines,
-                            "alignment_columns": packed.n_columns, "sites_not_2bit": packed.n_not_2bit,
-                            "alignment_file": infile})
-        print(f"[{stamp()}] Constructing tree...")
+        n_unfit = getattr(packed, "total_not_2bit", packed.n_not_2bit)
+        if chief:
+            print(f"[{stamp()}] Finish Converting a VCF file to a base sequence.")
+            if n_unfit and self.tree_software in ("treebest", "nj"):
+                how = {"include": "counted from their characters", "skip": "left out of the distance matrix"}
+                print(f"[{stamp()}] {n_unfit} site(s) are not biallelic A/C/G/T (more than two alleles, or '*'): "
+                      f"{how.get(self.non_biallelic, self.non_biallelic)} (non_biallelic = {self.non_biallelic})")
+        self.report.update({"vcf_file": self.vcf_file, "convert_seconds": t1 - t0,
+                            "lines": getattr(packed, "total_lines", packed.n_lines),
+                            "alignment_columns": getattr(packed, "total_columns", packed.n_columns),
+                            "sites_not_2bit": n_unfit, "alignment_file": infile})
+        if chief:
+            print(f"[{stamp()}] Constructing tree...")
+        multigpu.barrier()
         status = self.built_tree(infile, f"{self.out_path}", basename, 1)
-        if status == 0:
-            print(f"[{stamp()}] Finish constructing the SNP tree.")
-        else:
-            print(f"[{stamp()}] SNP tree failed to construct.")
+        if chief:
+            if status == 0:
+                print(f"[{stamp()}] Finish constructing the SNP tree.")
+            else:
+                print(f"[{stamp()}] SNP tree failed to construct.")
         return status

@@ -152,7 +152,7 @@ def test_config1_50x100k_vcf_through_the_entry_point(engine, tmp_path):
     assert [h[1:].decode() for h in fa[0:-1:2]] == names
     assert b"".join(fa[1::2]) == want_chars.tobytes()
     counts = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
-    dist, _ = oracle.normalise(counts, "ibs")
+    dist, _ = oracle.normalise(counts, "p")                       # the entry point's default metric
     merge, length = oracle.nj(dist)
     rf, dl = treecmp.compare((out / "SNP_treebest.NHX").read_text(), merges_to_newick(merge, length, names))
     assert rf == 0 and dl <= 1e-9

@@ -97,7 +97,10 @@ def test_runcmd_reads_reference_keys(tmp_path):
     assert r.vcf_file == "/data/in.vcf" and r.tree_software == "treebest"      # '*software*' values lower-cased
     assert r.thread == 2                                                       # clamped to >= 2 (script.py:69-71)
     assert r.out_path == os.path.abspath(out) and os.path.isdir(out)
-    assert r.distance == "ibs" and r.non_biallelic == "error"                  # new keys default
+    # new optional keys default to what keeps a PhyloForge config running unchanged: the treebest slot's metric,
+    # multi-allelic sites kept (the reference converts them), one GPU, no bootstrap
+    assert r.distance == "p" and r.non_biallelic == "include" and r.gpus == 1 and r.bootstrap == 0
+    assert (r.rank, r.world) == (0, 1)
     assert r.treebest == "treebest" and r.iqtree == "iqtree"                   # software.ini
 
 
@@ -106,7 +109,8 @@ def test_runcmd_defaults_and_validation(tmp_path):
     assert RunCmd(cfg, "sv").tree_software == "iqtree"                         # script.py:50-52
     cfg = _cfg(tmp_path, "snp_opt", f"vcf_file = x.vcf\nout_path = {tmp_path}/o\nthread = 8\n")
     assert RunCmd(cfg, "snp").tree_software == "raxml"                         # script.py:23
-    for body in ("thread = ten\n", "thread = 4\ntree_software = mrbayes\n", "thread = 4\ndistance = jc69\n"):
+    for body in ("thread = ten\n", "thread = 4\ntree_software = mrbayes\n", "thread = 4\ndistance = jc69\n",
+                 "thread = 4\ngpus = 0\n", "thread = 4\ngpus = two\n", "thread = 4\nnon_biallelic = maybe\n"):
         cfg = _cfg(tmp_path, "snp_opt", f"vcf_file = x.vcf\nout_path = {tmp_path}/o\n" + body)
         with pytest.raises(SystemExit):
             RunCmd(cfg, "snp")
