@@ -193,6 +193,9 @@ def _open_stream(path: str):
     return _open_bytes(path)
 
 
+_HEADER_LINES: dict = {}     # path -> lines up to and including #CHROM (set by read_header)
+
+
 def read_header(path: str, with_body_offset: bool = False):
     """Sample names from the first line that starts with ``#CHROM`` (vcftree.py:69-73,
     99-100). Returns (names, size in bytes of the text; None for gzip input, whose text size is not known
@@ -201,10 +204,12 @@ def read_header(path: str, with_body_offset: bool = False):
     if _is_gzip(path):
         size = None
     names = None
-    body = 0
+    body = n_header = 0
     with _open_bytes(path) as f:
         for raw in f:
             body += len(raw)
+            n_header += 1
+            _HEADER_LINES[path] = n_header
             if raw.startswith(b"#CHROM"):
                 names = raw.decode("utf-8", "replace").strip().split()[9:]
                 break
@@ -403,7 +408,9 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     d_lines, d_info, d_codes, d_chars, d_rows, d_rows_all = alloc_line_buffers(max_lines)
     n_carry = 0            # leftover sites (< 32) waiting in d_codes[0:n_carry]
     words_done = 0
-    n_lines_total = 0
+    # lines before this worker's first line: the header for the first of several workers (so that its line
+    # numbers are the file's and the workers' line counts add up to the file's), nothing otherwise
+    n_lines_total = _HEADER_LINES.get(path, 0) if (world > 1 and rank == 0) else 0
     n_unfit_total = 0
     h2d = 0
     char_blocks = []
