@@ -92,6 +92,31 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> bit 0 of
   return x;
 }
 
+// 16 bits -> 8 nibbles that each hold one bit PAIR (nibble k = bits 2k, 2k + 1): the selectors of two PRMTs
+__device__ __forceinline__ uint32_t pairs16(uint32_t x16) {
+  uint32_t t = (x16 | (x16 << 8)) & 0x00ff00ffu;
+  t = (t | (t << 4)) & 0x0f0f0f0fu;
+  t = (t | (t << 2)) & 0x33333333u;
+  return t;
+}
+
+// 32 sign-plane bits S and 32 magnitude-plane bits M -> 32 nibbles (S << 3 | M << 1), without shared memory:
+// a bit pair selects one byte (two nibbles) of a 4-entry table held in a register, so one PRMT (__byte_perm)
+// expands 8 bits; the two tables are the two source registers of the same PRMT (selector 0-3: sign, 4-7:
+// magnitude). ~46 ALU instructions per word against 8 shared-memory lookups (whose bank conflicts made the
+// LUT form of this kernel LSU-bound at 0.57 of the HBM rate).
+__device__ __forceinline__ uint4 expand_e2m1(uint32_t S, uint32_t M) {
+  constexpr uint32_t TS = 0x88800800u, TM = 0x22200200u;
+  const uint32_t s0 = pairs16(S & 0xffffu), s1 = pairs16(S >> 16);
+  const uint32_t m0 = pairs16(M & 0xffffu) | 0x44444444u, m1 = pairs16(M >> 16) | 0x44444444u;
+  uint4 o;
+  o.x = __byte_perm(TS, TM, s0) | __byte_perm(TS, TM, m0);
+  o.y = __byte_perm(TS, TM, s0 >> 16) | __byte_perm(TS, TM, m0 >> 16);
+  o.z = __byte_perm(TS, TM, s1) | __byte_perm(TS, TM, m1);
+  o.w = __byte_perm(TS, TM, s1 >> 16) | __byte_perm(TS, TM, m1 >> 16);
+  return o;
+}
+
 // stream[((s * n_tiles_padded + T) * 128 + (l >> 3) * 16 + kh * 8 + (l & 7))] (uint4) = the 32 sites of word
 // 2 s + kh of sample 64 T + l, nibble j of 32-bit word q = site 8 q + j: bit 3 = "hom-REF or missing",
 // bit 1 = "homozygous" (see the file header; stream 1: bit 3 = "missing", bit 1 = "heterozygous"). A second
@@ -100,7 +125,7 @@ __device__ __forceinline__ uint32_t spread8(uint32_t b) {  // 8 bits -> bit 0 of
 // it, i.e. when some site is genotyped in some samples and missing in others.
 // hsum[split][sample] = homozygous genotypes of the sample in the split's word range (|h_i|).
 // One thread = one sample x a run of HSUM_RUN consecutive words (runs never straddle a split).
-template <int STREAM>
+template <int STREAM, bool LUT>
 __global__ void __launch_bounds__(256)
 planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int64_t word_begin, int64_t n_local,
                       int64_t n_samples, int64_t n_tiles, int64_t n_tiles_padded, uint4* __restrict__ stream,
@@ -109,14 +134,14 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
   // 8 plane bits -> 8 nibbles through two 256-entry tables (bit 3 for the sign plane, bit 1 for the
   // homozygous plane): 20 instructions per word instead of ~110 of shift-and-mask spreading, which made
   // this kernel ALU-bound
-  __shared__ uint32_t s_lut_s[256], s_lut_m[256];
+  __shared__ uint32_t s_lut_s[LUT ? 256 : 1], s_lut_m[LUT ? 256 : 1];
   if (STREAM == 1 && __ldg(flags) == 0) return;   // stream 1 is needed only with sample-specific missingness
-  {
+  if (LUT) {
     const uint32_t sp = spread8(threadIdx.x);
     s_lut_s[threadIdx.x] = sp << 3;
     s_lut_m[threadIdx.x] = sp << 1;
+    __syncthreads();
   }
-  __syncthreads();
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int l = static_cast<int>(idx & 63);
   const int64_t tr = idx >> 6;
@@ -130,6 +155,7 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
   const int unit = (l >> 3) * 16 + (l & 7);
   int hom = 0;
   bool mixed = false;
+#pragma unroll(LUT ? 1 : 4)
   for (int64_t w = w0; w < w1; ++w) {
     uint32_t L = 0xffffffffu, H = 0xffffffffu;
     if (t < n_tiles) {
@@ -141,10 +167,14 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
     // stream 1: code 3 -> sign bit; code 1 -> bit 1       (t =  0 / +1 /  0 / -0)
     const uint32_t S = STREAM == 0 ? ~(L ^ H) : (L & H), M = STREAM == 0 ? ~L : (L & ~H);
     uint4 out;
-    out.x = s_lut_s[S & 0xffu] | s_lut_m[M & 0xffu];
-    out.y = s_lut_s[(S >> 8) & 0xffu] | s_lut_m[(M >> 8) & 0xffu];
-    out.z = s_lut_s[(S >> 16) & 0xffu] | s_lut_m[(M >> 16) & 0xffu];
-    out.w = s_lut_s[S >> 24] | s_lut_m[M >> 24];
+    if (LUT) {
+      out.x = s_lut_s[S & 0xffu] | s_lut_m[M & 0xffu];
+      out.y = s_lut_s[(S >> 8) & 0xffu] | s_lut_m[(M >> 8) & 0xffu];
+      out.z = s_lut_s[(S >> 16) & 0xffu] | s_lut_m[(M >> 16) & 0xffu];
+      out.w = s_lut_s[S >> 24] | s_lut_m[M >> 24];
+    } else {
+      out = expand_e2m1(S, M);
+    }
     stream[((w >> 1) * n_tiles_padded + t) * 128 + (w & 1) * 8 + unit] = out;
     if (w == n_local - 1 && (w & 1) == 0)
       stream[((w >> 1) * n_tiles_padded + t) * 128 + 8 + unit] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
@@ -159,6 +189,103 @@ planes_to_e2m1_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int6
   if (STREAM == 0 && real) {
     if (mixed) atomicOr(flags, 1);
     if (hom) atomicAdd(hsum + (w0 / words_per_split) * hsum_ld + t * PF_TILE + l, hom);
+  }
+}
+
+// The same conversion with more work per thread: one thread = FOUR samples of a tile (lanes j, j + 16, j + 32,
+// j + 48) x a run of HSUM_RUN words, walked one 64-site step (two words) at a time; the 8 expansions of a step are
+// register-only (expand_e2m1). With that interleaving every load and every store instruction of the 16 threads of
+// a tile touches whole 32-byte sectors (lanes j = 0..7 -> 8 consecutive 16-byte units of the chunk), and a thread
+// keeps 16 independent loads in flight per step instead of 2 per word. (Four CONSECUTIVE samples per thread with
+// 16-byte loads was measured first: its store instructions wrote 16 bytes per lane into 32 different sectors and
+// the kernel took 16.3 ms on 3,000 x 10M against 6.3 ms for the one-sample-per-thread kernel above.)
+// Same outputs bit for bit (stream, ref_v, flags, hsum).
+template <int STREAM>
+__global__ void __launch_bounds__(256)
+planes_to_e2m1_x4_kernel(const uint32_t* __restrict__ planes, int64_t n_words, int64_t word_begin, int64_t n_local,
+                         int64_t n_samples, int64_t n_tiles, int64_t n_tiles_padded, uint4* __restrict__ stream,
+                         uint32_t* __restrict__ ref_v, int* __restrict__ flags, int* __restrict__ hsum,
+                         int64_t words_per_split, int64_t hsum_ld) {
+  static_assert(HSUM_RUN % 2 == 0, "runs are whole steps");
+  if (STREAM == 1 && __ldg(flags) == 0) return;   // stream 1 is needed only with sample-specific missingness
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int j = static_cast<int>(idx & 15);        // lanes j + 16 k of the tile, k = 0..3
+  const int64_t tr = idx >> 4;
+  const int64_t n_runs = (n_local + HSUM_RUN - 1) / HSUM_RUN;
+  // tile fastest: the CTAs that run at the same time then write ONE contiguous window of the step-major stream
+  // (all tiles of a few runs of steps) instead of one 2 KB chunk out of every 96 KB over gigabytes
+  const int64_t t = tr % n_tiles_padded;
+  const int64_t run = tr / n_tiles_padded;
+  if (run >= n_runs) return;
+  const int64_t w0 = run * HSUM_RUN;
+  const int64_t w1 = min(n_local, w0 + HSUM_RUN);
+  const int unit0 = (j >> 3) * 16 + (j & 7);       // unit of lane j; lane j + 16 k is 32 k units further
+  const bool tile_real = t < n_tiles;
+  bool real[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) real[k] = (t * PF_TILE + j + 16 * k) < n_samples;
+  int hom[4] = {0, 0, 0, 0};
+  bool mixed = false;
+#pragma unroll 2
+  for (int64_t w = w0; w < w1; w += 2) {
+    const bool has2 = (w + 1) < w1;
+    uint32_t L[2][4], H[2][4];
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) L[kh][k] = H[kh][k] = 0xffffffffu;
+    if (tile_real) {
+      const uint32_t* p = planes + ((t * n_words + word_begin + w) * 2) * PF_TILE + j;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        L[0][k] = p[16 * k];
+        H[0][k] = p[PF_TILE + 16 * k];
+      }
+      if (has2) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          L[1][k] = p[2 * PF_TILE + 16 * k];
+          H[1][k] = p[3 * PF_TILE + 16 * k];
+        }
+      }
+    }
+    uint4* chunk = stream + ((w >> 1) * n_tiles_padded + t) * 128 + unit0;
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+      if (kh == 1 && !has2) {
+        // a second half-step past the last word is all missing
+        if (w == n_local - 1) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) chunk[8 + 32 * k] = make_uint4(0x88888888u, 0x88888888u, 0x88888888u, 0x88888888u);
+        }
+        break;
+      }
+      uint32_t ref = 0;
+      if (STREAM == 0) {
+        const uint32_t* p0 = planes + ((word_begin + w + kh) * 2) * PF_TILE;   // sample 0: tile 0, lane 0
+        ref = ~(__ldg(p0) & __ldg(p0 + PF_TILE));
+        if (t == 0 && j == 0) ref_v[w + kh] = ref;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // stream 0: code 0 / 3 -> sign bit; code 0 / 2 -> bit 1 (x = -1 / +0 / +1 / -0 for codes 0 / 1 / 2 / 3)
+        // stream 1: code 3 -> sign bit; code 1 -> bit 1       (t =  0 / +1 /  0 / -0)
+        const uint32_t lw = L[kh][k], hw = H[kh][k];
+        const uint32_t S = STREAM == 0 ? ~(lw ^ hw) : (lw & hw);
+        const uint32_t M = STREAM == 0 ? ~lw : (lw & ~hw);
+        chunk[kh * 8 + 32 * k] = expand_e2m1(S, M);
+        if (STREAM == 0) {
+          mixed |= real[k] && (~(lw & hw) != ref);
+          hom[k] += __popc(M);          // homozygous <=> low code bit 0 (missing has it set)
+        }
+      }
+    }
+  }
+  if (STREAM == 0) {
+    if (mixed) atomicOr(flags, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (real[k] && hom[k]) atomicAdd(hsum + (w0 / words_per_split) * hsum_ld + t * PF_TILE + j + 16 * k, hom[k]);
   }
 }
 
@@ -1447,16 +1574,21 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
   PF_CUDA(cudaMemsetAsync(hsum, 0, static_cast<size_t>(L.m[0].splits * L.hsum_ld) * 4, s));
   {
     const int64_t n_runs = pf_ceil_div(n_local, HSUM_RUN);
-    const int64_t threads = L.n_tiles_padded * n_runs * 64;
     pf_count_launch();
-    planes_to_e2m1_kernel<0><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
+    // A/B switches: debug bit 2048 = the one-sample-per-thread kernel, bit 4096 = that kernel with the PRMT expansion
+    // (default: four samples per thread, PRMT expansion)
+    const bool narrow = (g_tc_debug & (2048 | 4096)) != 0, lut = (g_tc_debug & 4096) == 0;
+    auto conv0 = !narrow ? planes_to_e2m1_x4_kernel<0> : lut ? planes_to_e2m1_kernel<0, true> : planes_to_e2m1_kernel<0, false>;
+    auto conv1 = !narrow ? planes_to_e2m1_x4_kernel<1> : lut ? planes_to_e2m1_kernel<1, true> : planes_to_e2m1_kernel<1, false>;
+    const int64_t threads = L.n_tiles_padded * n_runs * (narrow ? 64 : 16);
+    conv0<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
         d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded, nib4, ref_v, flags, hsum,
         L.m[0].words_per_split, L.hsum_ld);
     PF_CUDA(cudaGetLastError());
     if (allow_general) {
       // returns at once unless the first pass found sample-specific missingness
       pf_count_launch();
-      planes_to_e2m1_kernel<1><<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
+      conv1<<<static_cast<unsigned>(pf_ceil_div(threads, 256)), 256, 0, s>>>(
           d_planes, n_words, word_begin, n_local, n_samples, L.n_tiles, L.n_tiles_padded,
           reinterpret_cast<uint4*>(w + L.stream1_off), ref_v, flags, hsum, L.m[0].words_per_split, L.hsum_ld);
       PF_CUDA(cudaGetLastError());
