@@ -288,6 +288,9 @@ PF_API int pf_bootstrap_counts(const int32_t* d_blocks, int n_blocks, int64_t el
  * [3] update; general kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update,
  * [3] grid barrier 2. Reading resets the counters. */
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
+/* Diagnostic: phase accounting of the bounded-scan NJ kernel (csrc/nj_lazy.cu), 16 counters in nanoseconds (see the
+ * definition); enable != 0 switches the instrumented kernel on for the following pf_nj calls. */
+PF_API int pf_nj_lazy_profile(int enable, unsigned long long* h_out16);
 
 /* Number of kernels this library has launched in the calling process since it was loaded (every
  * <<< >>> / cudaLaunch* site of the product kernels bumps one counter). bench.py reports the difference

@@ -62,6 +62,7 @@ PROTOTYPES = {
     "pf_bootstrap_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "pf_nj_work_bytes": (_i64, [_i64]),
     "pf_nj_profile": (_i32, [_i32, _vp]),
+    "pf_nj_lazy_profile": (_i32, [_i32, _vp]),
     "pf_pair_counts_tc_set_impl": (_i32, [_i32, _i32]),
     "pf_pair_counts_tc_timing": (_i32, [_i32, _vp]),
     "pf_nj_batch": (_i32, [_vp, _i64, _i64, _i32, _i64, _vp, _vp, _vp, _vp]),

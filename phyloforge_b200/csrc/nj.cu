@@ -29,48 +29,20 @@
 //     visible with the NEXT exchange; the scan in between takes the affected entries from s_du /
 //     the last slot's column instead ("pending" update).
 // nj_kernel (any n): row sums in global memory when they do not fit, two grid barriers per iteration.
-#include "pf_common.cuh"
+#include "nj_common.cuh"
 
 #include <cooperative_groups.h>
-#include <math_constants.h>
 
 namespace cg = cooperative_groups;
 
 namespace {
 
+using njc::NJ_NONE;
+using njc::NjRec;
+using njc::rec_less;
+using njc::warp_argmin;
+
 constexpr int NJ_MAX_BLOCKS = 1024;
-constexpr int NJ_NONE = 0x7fffffff;
-
-struct NjRec {
-  double q;
-  int a;
-  int b;
-};
-
-__device__ __forceinline__ bool rec_less(double q1, int a1, int b1, double q2, int a2, int b2) {
-  return (q1 < q2) || (q1 == q2 && (a1 < a2 || (a1 == a2 && b1 < b2)));
-}
-
-// lexicographic (q, a, b) minimum over the warp with four integer REDUX steps: q through its
-// order-preserving 64-bit key (high word, then low word among the lanes that hold the minimal high
-// word), then a among the lanes that hold the minimal q, then b. q is never NaN here (a NaN candidate
-// never replaces a thread's best); -0.0 is folded into +0.0 so that key equality is double equality.
-__device__ __forceinline__ void warp_argmin(double& q, int& a, int& b) {
-  const unsigned full = 0xffffffffu;
-  const long long bits = __double_as_longlong(__dadd_rn(q, 0.0));
-  const unsigned long long key = static_cast<unsigned long long>(bits) ^ ((bits < 0) ? 0xffffffffffffffffull : 0x8000000000000000ull);
-  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
-  const unsigned mhi = __reduce_min_sync(full, hi);
-  const unsigned mlo = __reduce_min_sync(full, hi == mhi ? lo : 0xffffffffu);
-  const bool is_min = hi == mhi && lo == mlo;
-  const unsigned ma = __reduce_min_sync(full, is_min ? static_cast<unsigned>(a) : 0xffffffffu);
-  const unsigned mb = __reduce_min_sync(full, (is_min && static_cast<unsigned>(a) == ma) ? static_cast<unsigned>(b) : 0xffffffffu);
-  const unsigned long long mkey = (static_cast<unsigned long long>(mhi) << 32) | mlo;
-  const unsigned long long mbits = (mkey & 0x8000000000000000ull) ? (mkey ^ 0x8000000000000000ull) : ~mkey;
-  q = __longlong_as_double(static_cast<long long>(mbits));
-  a = static_cast<int>(ma);
-  b = static_cast<int>(mb);
-}
 
 // optional phase accounting (pf_nj_profile): nanoseconds of CTA 0 per phase, summed over iterations
 __device__ unsigned long long g_nj_prof[8];
@@ -91,12 +63,7 @@ __device__ __forceinline__ unsigned long long nj_now() {
 __device__ __forceinline__ void nj_initial_row_sums(const double* __restrict__ D, int64_t ld, int n, int gwarp,
                                                     int nwarps, int lane, double* r_out) {
   for (int row = gwarp; row < n; row += nwarps) {
-    const double* rp = D + static_cast<int64_t>(row) * ld;
-    double acc = 0.0;
-#pragma unroll 8
-    for (int k = lane; k < n; k += 32) acc = __dadd_rn(acc, __ldcg(rp + k));
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, off));
+    const double acc = njc::nj_row_sum32(D + static_cast<int64_t>(row) * ld, n, lane);
     if (lane == 0) r_out[row] = acc;
   }
 }
@@ -259,6 +226,7 @@ struct NjFastParams {
   int n_mat, ctas_per_mat;
   int64_t mat_stride;         // doubles between distance matrices
   int64_t work_stride;        // bytes between the workspaces (r0, spare, arrive, recs)
+  const int* status;          // per matrix, may be null: 0 = already joined by the bounded-scan kernel (nj_lazy.cu), skip it
 };
 
 struct NjWinner {
@@ -329,6 +297,10 @@ nj_fast_kernel(const NjFastParams P_in) {
   const int gthread = cta * NJF_THREADS + tid;
   const int nthreads = n_cta * NJF_THREADS;
 
+  if (P_in.status && P_in.status[mat] == 0) {   // nothing to do for this matrix (every CTA still meets the grid barrier)
+    grid.sync();
+    return;
+  }
   for (int k = gthread; k < NJF_SHARDS * 32; k += nthreads) V.arrive()[k] = 0u;
   nj_initial_row_sums(D, ld, n, gwarp, nwarps, lane, V.r0());
   grid.sync();
@@ -513,43 +485,8 @@ nj_fast_kernel(const NjFastParams P_in) {
     d12 = vread(1, 2);
   }
   __syncthreads();   // the log written by thread 0 is visible to the CTA; s_r / s_du / s_phys are free
-  const int n_iter = t;
-  int2* s_log = reinterpret_cast<int2*>(nj_dyn);   // 8 bytes per iteration over s_r
-  int* s_node = s_phys;
-  for (int i = tid; i < n_iter; i += NJF_THREADS) {
-    s_log[i] = make_int2(__ldcg(V.merge() + 3 * i), __ldcg(V.merge() + 3 * i + 1));
-    const double rra = __ldcg(V.len() + 3 * i), rrb = __ldcg(V.len() + 3 * i + 1), dab = __ldcg(V.len() + 3 * i + 2);
-    const double n2 = static_cast<double>(n - i - 2);
-    double tt = __dsub_rn(rra, rrb);
-    tt = __ddiv_rn(tt, __dmul_rn(2.0, n2));
-    double la = __dmul_rn(0.5, dab);
-    la = __dadd_rn(la, tt);
-    V.len()[3 * i + 0] = la;
-    V.len()[3 * i + 1] = __dsub_rn(dab, la);
-    V.len()[3 * i + 2] = 0.0;
-    V.merge()[3 * i + 2] = 0;
-  }
-  for (int k = tid; k < n; k += NJF_THREADS) s_node[k] = k;
-  __syncthreads();
-  if (tid == 0) {
-    for (int i = 0; i < n_iter; ++i) {
-      const int2 ab = s_log[i];
-      const int last = n - i - 1;
-      V.merge()[3 * i + 0] = s_node[ab.x];
-      V.merge()[3 * i + 1] = s_node[ab.y];
-      if (ab.y != last) s_node[ab.y] = s_node[last];
-      s_node[ab.x] = n + i;
-    }
-    double l0 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d02), d12));
-    double l1 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d01, d12), d02));
-    double l2 = __dmul_rn(0.5, __dsub_rn(__dadd_rn(d02, d12), d01));
-    V.merge()[3 * n_iter + 0] = s_node[0];
-    V.merge()[3 * n_iter + 1] = s_node[1];
-    V.merge()[3 * n_iter + 2] = s_node[2];
-    V.len()[3 * n_iter + 0] = l0;
-    V.len()[3 * n_iter + 1] = l1;
-    V.len()[3 * n_iter + 2] = l2;
-  }
+  njc::nj_finish_from_log(V.merge(), V.len(), n, t, d01, d02, d12, reinterpret_cast<int2*>(nj_dyn), s_phys, tid,
+                          NJF_THREADS);   // the log (8 bytes per iteration) over s_r, the node map over s_phys
 }
 
 // ===================================================================== general kernel
@@ -745,6 +682,11 @@ nj_kernel(const NjParams P) {
 constexpr int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t NJ_MAX_SMEM_R = 200 * 1024;
 int g_nj_force_general = 0;
+int g_nj_no_lazy = 0;        // diagnostic: full-scan kernels only
+
+// per-matrix workspace: the full-scan kernels' part, the bounded-scan kernel's part, one status line
+int64_t nj_classic_bytes(int64_t n) { return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES; }
+constexpr int64_t NJ_STATUS_BYTES = 256;
 
 template <typename K>
 int nj_launch(K kernel, int threads, size_t smem, int64_t want_blocks, int64_t max_blocks, void* params,
@@ -771,7 +713,7 @@ int nj_launch(K kernel, int threads, size_t smem, int64_t want_blocks, int64_t m
 
 PF_API int64_t pf_nj_work_bytes(int64_t n) {
   if (n < 0) return 0;
-  return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES;
+  return nj_classic_bytes(n) + nj_lazy_work_bytes(n) + NJ_STATUS_BYTES;
 }
 
 namespace {
@@ -785,8 +727,21 @@ int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
   PF_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   PF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   if (!coop) return pf_fail_code(PF_ERR_CUDA, "pf_nj: device does not support cooperative launch");
-  const int64_t work_stride = 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES;
+  // workspace of n_mat matrices: [n_mat x full-scan part][n_mat x bounded-scan part][n_mat x status line]
+  const int64_t work_stride = nj_classic_bytes(n);
   const int64_t out3 = 3 * (n - 2);
+  char* const w_lazy = static_cast<char*>(d_work) + n_mat * work_stride;
+  int* const d_status = reinterpret_cast<int*>(w_lazy + n_mat * nj_lazy_work_bytes(n));
+
+  // bounded scan on one cluster per matrix first; it reports per matrix whether a full-scan kernel has to run
+  const bool lazy = n <= NJ_FAST_MAX_N && n <= nj_lazy_max_n() && nj_lazy_work_bytes(n) > 0 && !g_nj_force_general &&
+                    !g_nj_no_lazy && !g_nj_prof_enabled;
+  if (lazy) {
+    unsigned long long* d_stats = nullptr;
+    PF_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&d_stats), g_nj_prof));
+    const int rc = nj_lazy_run(d_dist, n, ld, n_mat, mat_stride, d_merge, d_len, w_lazy, d_status, d_stats + 4, s);
+    if (rc != PF_OK) return rc;
+  }
 
   if (n <= NJ_FAST_MAX_N && !g_nj_force_general) {
     int done = 0;
@@ -810,6 +765,7 @@ int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
       P.n_mat = batch;
       P.mat_stride = mat_stride;
       P.work_stride = work_stride;
+      P.status = lazy ? d_status + done : nullptr;
       const int64_t n_pad = (n + 1) & ~int64_t(1);
       const size_t smem = static_cast<size_t>(16 * n_pad + 4 * n_pad);
       // about four 256-column scan items per warp; fewer CTAs make the exchange cheaper for small matrices
@@ -887,7 +843,10 @@ PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t
 // summed over iterations. Fast kernel: [0] scan, [1] CTA reduction + publish, [2] waiting for the arrivals,
 // [3] reading the records + winner, [4] update.
 // General kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update, [3] grid barrier 2.
-// enable: bit 0 = instrumented kernels, bit 1 = force the general kernel. Reading resets the counters.
+// [4..7]: counters of the bounded-scan kernel (nj_lazy.cu): row rescans, list evaluations, iterations, matrices
+// joined by it (0 when a full-scan kernel did the work).
+// enable: bit 0 = instrumented kernels (full-scan), bit 1 = force the general kernel, bit 2 = full-scan kernels
+// only (no bounded scan). Reading resets the counters.
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {
   PF_TRY_BEGIN
   if (h_out8) PF_CUDA(cudaMemcpyFromSymbol(h_out8, g_nj_prof, sizeof(unsigned long long) * 8));
@@ -895,6 +854,7 @@ PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {
   PF_CUDA(cudaMemcpyToSymbol(g_nj_prof, zero, sizeof(zero)));
   g_nj_prof_enabled = (enable & 1) != 0;
   g_nj_force_general = (enable & 2) != 0;
+  g_nj_no_lazy = (enable & 4) != 0;
   return PF_OK;
   PF_TRY_END
 }
