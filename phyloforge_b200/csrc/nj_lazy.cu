@@ -41,9 +41,10 @@ using njc::warp_argmin;
 
 constexpr int NJL_THREADS = 256;                     // few warps: the iteration is a latency chain, and every warp pays its fixed parts
 constexpr int NJL_WARPS = NJL_THREADS / 32;
+constexpr int NJL_MAX_RPT = 3;                       // rows of a CTA per thread (template parameter RPT): ceil((NJL_MAX_N + 1) / 16 / NJL_THREADS)
 constexpr int NJL_MAX_CLUSTER = 16;
 constexpr int NJL_EPOCH = 8;                         // iterations between snapshots
-constexpr int NJL_MAX_G = 32;
+constexpr int NJL_MAX_G = 64;
 constexpr unsigned short NJL_EMPTY = 0xffffu;
 constexpr int64_t NJL_MAX_N = 11000;                 // slots and rows are 16-bit, row indices of a CTA 15-bit
 constexpr int NJL_SMEM_LIMIT = 227 * 1024;
@@ -62,22 +63,19 @@ struct NjLazyParams {
 
 // dynamic shared memory carve-up (host and device agree through this struct)
 struct NjLazySmem {
-  int r, snap, s2p, R1, R2, duo, ld, lc, slot, champ, q_resc, q_reev, team, total;
+  int r, snap, s2p, R1, R2, ld, lc, slot, champ, q_resc, total;
   __host__ __device__ NjLazySmem(int n, int G, int rc) {
     const int n_pad = (n + 3) & ~3, rc_pad = (rc + 3) & ~3;
     int o = 0;
-    r = o; o += 8 * n_pad;
+    r = o; o += 8 * (n_pad + 2);   // + a scratch element for masked writes
     R1 = o; o += 8 * rc_pad;
     R2 = o; o += 8 * rc_pad;
-    duo = o; o += 8 * rc_pad;
     ld = o; o += 8 * G * rc;
-    team = o; o += NJL_WARPS * G * 32;   // rescan: per warp and group v, d, b2 (8 B each) + column (4 B, padded)
     snap = o; o += 4 * n_pad;
     s2p = o; o += 2 * n_pad;
     lc = o; o += (2 * G * rc + 7) & ~7;
     slot = o; o += 2 * rc_pad;
     q_resc = o; o += 2 * rc_pad;
-    q_reev = o; o += 2 * rc_pad;
     champ = o; o += rc_pad;
     total = (o + 15) & ~15;
   }
@@ -120,15 +118,41 @@ __device__ __forceinline__ double fpq(double n2, const double* s_r, int i, int j
   return q;
 }
 
+// warp-wide min / max of doubles through their order-preserving 64-bit keys: two integer REDUX steps (high word,
+// then the low word among the lanes that hold the extreme high word). No NaN among the inputs (callers filter them);
+// -0.0 and +0.0 are distinct keys, which is harmless for bounds.
+__device__ __forceinline__ unsigned long long f64_key(double x) {
+  const long long bits = __double_as_longlong(x);
+  return static_cast<unsigned long long>(bits) ^ ((bits < 0) ? 0xffffffffffffffffull : 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unkey(unsigned long long key) {
+  const unsigned long long bits = (key & 0x8000000000000000ull) ? (key ^ 0x8000000000000000ull) : ~key;
+  return __longlong_as_double(static_cast<long long>(bits));
+}
 __device__ __forceinline__ double warp_min_f64(double x) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) x = fmin(x, __shfl_xor_sync(0xffffffffu, x, off));
-  return x;
+  const unsigned long long key = f64_key(x);
+  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  return f64_unkey((static_cast<unsigned long long>(mhi) << 32) | mlo);
 }
 __device__ __forceinline__ double warp_max_f64(double x) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, off));
-  return x;
+  const unsigned long long key = f64_key(x);
+  const unsigned hi = static_cast<unsigned>(key >> 32), lo = static_cast<unsigned>(key);
+  const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+  return f64_unkey((static_cast<unsigned long long>(mhi) << 32) | mlo);
+}
+// min / max of the NJL_WARPS per-warp values in shared memory (every thread, balanced tree)
+__device__ __forceinline__ double smem_min_warps(const double* s) {
+  static_assert(NJL_WARPS == 8, "tree of eight");
+  const double a = fmin(s[0], s[1]), b = fmin(s[2], s[3]), c = fmin(s[4], s[5]), d = fmin(s[6], s[7]);
+  return fmin(fmin(a, b), fmin(c, d));
+}
+__device__ __forceinline__ double smem_max_warps(const double* s) {
+  static_assert(NJL_WARPS == 8, "tree of eight");
+  const double a = fmax(s[0], s[1]), b = fmax(s[2], s[3]), c = fmax(s[4], s[5]), d = fmax(s[6], s[7]);
+  return fmax(fmax(a, b), fmax(c, d));
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -161,7 +185,6 @@ struct RowCtx {   // per-CTA shared-memory views
   unsigned short* s_s2p;
   double* s_R1;
   double* s_R2;
-  double* s_duo;
   double* s_ld;
   unsigned short* s_lc;
   short* s_slot;
@@ -170,141 +193,184 @@ struct RowCtx {   // per-CTA shared-memory views
 };
 
 // exact evaluation of the list of own row lr (slot k) by one warp: every entry is a candidate, the best becomes the
-// champion, R1 bounds the others. Lane g holds entry g (col, d); returns the row's best in (q, lo, hi) on all lanes.
-__device__ __forceinline__ void list_evaluate(const RowCtx& C, int lr, int k, int col, double d, double n2, int lane,
-                                              Cand& out) {
-  const bool valid = lane < C.G && col != NJL_EMPTY;
-  double q = CUDART_INF;
-  int lo = NJ_NONE, hi = NJ_NONE;
-  if (valid) {
-    q = fpq(n2, C.s_r, k, col, d, lo, hi);
-    if (!(q < CUDART_INF)) { lo = NJ_NONE; hi = NJ_NONE; q = CUDART_INF; }   // NaN / +inf never win
+// champion, R1 bounds the others. Lane l holds the entries l, l + 32, ...; returns the row's best on all lanes.
+template <int G>
+__device__ __forceinline__ void list_evaluate(const RowCtx& C, int lr, int k, double n2, int lane, Cand& out) {
+  constexpr int EPL = (G + 31) / 32;
+  double ve[EPL];
+  int elo[EPL], ehi[EPL];
+  Cand me{CUDART_INF, NJ_NONE, NJ_NONE};
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int g = lane + 32 * e;
+    const int col = (g < G) ? C.s_lc[g * C.rc + lr] : NJL_EMPTY;
+    elo[e] = NJ_NONE;
+    ehi[e] = NJ_NONE;
+    ve[e] = CUDART_INF;
+    if (col != NJL_EMPTY) {
+      const double d = C.s_ld[g * C.rc + lr];
+      int lo, hi;
+      const double q = fpq(n2, C.s_r, k, col, d, lo, hi);
+      const double v = d - static_cast<double>(C.s_snap[col]);
+      ve[e] = (v == v) ? v : CUDART_INF;   // NaN: a distance that can never win (the oracle's q is NaN too)
+      if (q < CUDART_INF) {                // NaN / +inf never win
+        elo[e] = lo;
+        ehi[e] = hi;
+        cand_take(me, q, lo, hi);
+      }
+    }
   }
-  double bq = q;
-  int ba = lo, bb = hi;
-  warp_argmin(bq, ba, bb);
-  const bool is_champ = valid && ba != NJ_NONE && lo == ba && hi == bb;
-  const unsigned champ_mask = __ballot_sync(0xffffffffu, is_champ);
-  const double ve = (valid && !is_champ) ? d - static_cast<double>(C.s_snap[col]) : CUDART_INF;
-  const double r1 = warp_min_f64(ve == ve ? ve : CUDART_INF);   // NaN: a distance that can never win (the oracle's q is NaN too)
+  warp_argmin(me.q, me.lo, me.hi);
+  int gch = -1;
+  double r1 = CUDART_INF;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const bool is_champ = me.lo != NJ_NONE && elo[e] == me.lo && ehi[e] == me.hi;   // the pair identifies the entry
+    if (is_champ) gch = lane + 32 * e;
+    else r1 = fmin(r1, ve[e]);
+  }
+  const unsigned champ_mask = __ballot_sync(0xffffffffu, gch >= 0);
+  r1 = warp_min_f64(r1);
+  const int gsel = champ_mask ? __shfl_sync(0xffffffffu, gch, __ffs(champ_mask) - 1) : -1;
   if (lane == 0) {
-    C.s_champ[lr] = champ_mask ? static_cast<signed char>(__ffs(champ_mask) - 1) : static_cast<signed char>(-1);
+    C.s_champ[lr] = static_cast<signed char>(gsel);
     C.s_R1[lr] = r1;
   }
-  out.q = bq;
-  out.lo = ba;
-  out.hi = bb;
+  out = me;
   __syncwarp();   // the row's owner is a lane of this warp
 }
 
-// two partial results of the same group: the smaller (v, column) stays, the other one is covered by the bound.
-// Symmetric in its arguments, so both lanes of a shuffle pair arrive at the same result.
+// two partial results of the same group (v = ve of the tracked candidate, b2 = bound of the others): the smaller
+// (v, column) stays, the other one is covered by the bound. Symmetric in its arguments, so both lanes of a shuffle
+// pair arrive at the same result.
 __device__ __forceinline__ void group_merge(double& v, int& col, double& d, double& b2, double v2, int col2, double d2,
-                                            double b22, const float* s_snap) {
+                                            double b22) {
   const bool other = (v2 < v) || (v2 == v && col2 < col);
-  const int lcol = other ? col : col2;
-  const double ldist = other ? d : d2;
-  double b = fmin(b2, b22);
-  if (lcol != NJL_EMPTY) {
-    const double ve = ldist - static_cast<double>(s_snap[lcol]);
-    if (ve < b) b = ve;
-  }
+  const double lv = other ? v : v2;   // ve of the loser (+inf when it is empty)
+  b2 = fmin(fmin(b2, b22), lv);
   v = other ? v2 : v;
   col = other ? col2 : col;
   d = other ? d2 : d;
-  b2 = b;
 }
 
-// rescan of own row lr by the CTA: per group the column with the smallest v becomes the list entry, everything
-// else goes into R2; then the list is evaluated (warp 0). Returns the row's best candidate on all lanes of warp 0
-// (other warps: +inf). Contains two CTA barriers.
-template <int G>
+// rescan of own row lr by the CTA: per group the column with the smallest ve = d - snap becomes the list entry,
+// everything else goes into R2; the list is evaluated by the owner's warp in the next iteration (no champion, R1 =
+// -inf). The row's candidate of this iteration does not depend on the list: every column whose q is not PROVEN worse
+// than the CTA's threshold T (the same bound and margin as bound_clears, per column) is evaluated with the oracle's
+// operations, so ties and near-ties beyond the list's capacity are decided as the oracle decides them.
+// The NJL_THREADS / G threads of a group are neighbouring lanes of one warp (a warp reads 32 / TPG consecutive
+// columns per 32-column period: full sectors), so a group is finished with shuffles; only R2 and the candidate cross
+// the warps (buffers `buf`, alternating between consecutive calls: one CTA barrier per call).
+// Returns the row's best candidate on all lanes of warp 0 (other warps: +inf).
+template <int G, bool PROF>
 __device__ __forceinline__ void rescan_row(const RowCtx& C, const double* __restrict__ rowp, int lr, int na, double n2,
-                                           double inv, int tid, unsigned char* s_team, Cand& out) {
+                                           double inv, double M, double T, int tid, NjRec* s_rrec, double* s_rb2,
+                                           Cand& out, int rank) {
+  constexpr int TPG = NJL_THREADS / G;   // threads per group: 4 ... 32
+  constexpr int GPW = 32 / TPG;          // groups per warp
+  unsigned long long t_prev = PROF ? njl_now() : 0;
+  if (PROF && rank == 0 && tid == 0) {   // one dependent load from the row: the round trip as this kernel sees it
+    const double x = __ldcg(rowp + 1);
+    if (x == 123.456) g_njl_prof[15] += 1;
+    NJL_MARK(13)
+  }
   const int k = C.s_slot[lr];
   const int lane = tid & 31, warp = tid >> 5;
+  const int sub = lane % TPG, g = warp * GPW + lane / TPG;
   double bv = CUDART_INF, bd = 0.0, b2 = CUDART_INF;
   int bcol = NJL_EMPTY;
+  const double rk = C.s_r[k];
+  // column j is skipped when n2 ((ve_j - M) - s_k) - margin > T, i.e. ve_j - 1e-9 |ve_j| > theta
+  const double sk = rk * inv, Tn = T * inv;
+  const double theta = ((Tn + M) + sk) + 1e-9 * ((fabs(M) + fabs(sk)) + fabs(Tn)) + 1e-290;
+  Cand ex{CUDART_INF, NJ_NONE, NJ_NONE};
   constexpr int U = 8;
-  for (int j0 = tid; j0 < na; j0 += NJL_THREADS * U) {
+  for (int j0 = g + G * sub; j0 < na; j0 += NJL_THREADS * U) {
     double dv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = j0 + u * NJL_THREADS;
-      dv[u] = (j < na) ? __ldcg(rowp + j) : CUDART_NAN;
+      dv[u] = (j < na) ? __ldcg(rowp + j) : 0.0;
     }
+    double ve[U];
+    bool any_pass = false;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = j0 + u * NJL_THREADS;
-      if (j >= na || j == k) continue;
-      const double d = dv[u];
-      const double v = d - C.s_r[j] * inv;
-      const double ve = d - static_cast<double>(C.s_snap[j]);
-      if (v < bv) {
-        if (bcol != NJL_EMPTY) {
-          const double veo = bd - static_cast<double>(C.s_snap[bcol]);
-          if (veo < b2) b2 = veo;
+      const bool valid = j < na && j != k;
+      const double x = dv[u] - static_cast<double>(C.s_snap[min(j, na - 1)]);
+      ve[u] = valid ? x : CUDART_INF;
+      any_pass |= valid && !(__fma_rn(-1e-9, fabs(x), x) > theta);   // not proven worse than T (NaN: not proven)
+    }
+    if (any_pass) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = j0 + u * NJL_THREADS;
+        if (j < na && j != k && !(__fma_rn(-1e-9, fabs(ve[u]), ve[u]) > theta)) {
+          const double rj = C.s_r[j];
+          const bool jlo = j < k;
+          double q = __dmul_rn(n2, dv[u]);
+          q = __dsub_rn(q, jlo ? rj : rk);
+          q = __dsub_rn(q, jlo ? rk : rj);
+          if (q < CUDART_INF) cand_take(ex, q, jlo ? j : k, jlo ? k : j);
         }
-        bv = v;
-        bcol = j;
-        bd = d;
-      } else if (ve < b2) {
-        b2 = ve;
       }
     }
-  }
-  // lanes l, l + G, ... of a warp share a group (NJL_THREADS is a multiple of G, so a thread stays in one group)
 #pragma unroll
-  for (int off = 16; off >= G; off >>= 1) {
+    for (int u = 0; u < U; ++u) {
+      // the smaller ve stays, the other one (the old best, or this column) is covered by the bound
+      const bool lt = ve[u] < bv;
+      b2 = fmin(b2, lt ? bv : ve[u]);
+      bv = lt ? ve[u] : bv;
+      bcol = lt ? j0 + u * NJL_THREADS : bcol;
+      bd = lt ? dv[u] : bd;
+    }
+  }
+  NJL_MARK(9)   // rescan: loads + scan
+#pragma unroll
+  for (int off = TPG / 2; off >= 1; off >>= 1) {
     const double v2 = __shfl_xor_sync(0xffffffffu, bv, off);
     const int c2 = __shfl_xor_sync(0xffffffffu, bcol, off);
     const double d2 = __shfl_xor_sync(0xffffffffu, bd, off);
     const double b22 = __shfl_xor_sync(0xffffffffu, b2, off);
-    group_merge(bv, bcol, bd, b2, v2, c2, d2, b22, C.s_snap);
+    group_merge(bv, bcol, bd, b2, v2, c2, d2, b22);
   }
-  // across the warps through shared memory: [warp][group] records of 32 bytes
-  double* tb = reinterpret_cast<double*>(s_team);
-  if (lane < G) {
-    double* rec = tb + (warp * G + lane) * 4;
-    rec[0] = bv;
-    rec[1] = bd;
-    rec[2] = b2;
-    reinterpret_cast<int*>(rec + 3)[0] = bcol;
+  if (sub == 0) {
+    C.s_lc[g * C.rc + lr] = static_cast<unsigned short>(bcol);
+    C.s_ld[g * C.rc + lr] = bd;
+  }
+  b2 = warp_min_f64(b2);
+  warp_argmin(ex.q, ex.lo, ex.hi);
+  if (lane == 0) {
+    s_rrec[warp] = NjRec{ex.q, ex.lo, ex.hi};
+    s_rb2[warp] = b2;
   }
   __syncthreads();
+  NJL_MARK(10)   // rescan: group and warp reductions, barrier
   out.q = CUDART_INF;
   out.lo = NJ_NONE;
   out.hi = NJ_NONE;
   if (warp == 0) {
-    double v = CUDART_INF, d = 0.0, b = CUDART_INF;
-    int c = NJL_EMPTY;
-    if (lane < G) {
-#pragma unroll
-      for (int w = 0; w < NJL_WARPS; ++w) {
-        const double* rec = tb + (w * G + lane) * 4;
-        const double v2 = rec[0], d2 = rec[1], b22 = rec[2];
-        const int c2 = reinterpret_cast<const int*>(rec + 3)[0];
-        if (w == 0) { v = v2; d = d2; b = b22; c = c2; }
-        else group_merge(v, c, d, b, v2, c2, d2, b22, C.s_snap);
-      }
-      C.s_lc[lane * C.rc + lr] = static_cast<unsigned short>(c);
-      C.s_ld[lane * C.rc + lr] = d;
+    const double r2 = smem_min_warps(s_rb2);
+    if (lane == 0) {
+      C.s_R2[lr] = r2;
+      C.s_champ[lr] = -1;
+      C.s_R1[lr] = -CUDART_INF;   // the owner's warp evaluates the list in the next iteration
     }
-    const double r2 = warp_min_f64(b);
-    if (lane == 0) C.s_R2[lr] = r2;
-    list_evaluate(C, lr, k, c, d, n2, lane, out);
+    if (lane < NJL_WARPS) cand_take(out, s_rrec[lane].q, s_rrec[lane].a, s_rrec[lane].b);
+    warp_argmin(out.q, out.lo, out.hi);
   }
-  __syncthreads();   // the buffer is free again, the row's new state is visible to its owner
+  NJL_MARK(11)   // rescan: tail of warp 0
+  if (PROF && rank == 0 && tid == 0) g_njl_prof[12] += 1;
 }
 
 // maintenance of the list of own row lr (slot k, distance du to the merged node) after the join of (wa, wb):
 // the joined columns leave, column `last` becomes column wb, the merged node enters as column wa.
 __device__ __forceinline__ void row_update(const RowCtx& C, int lr, int k, double du, int wa, int wb, int last, bool move,
-                                           double inv_new, double su, double sue) {
+                                           double sue) {
   const int G = C.G, rc = C.rc;
   int champ = C.s_champ[lr];
   double R1 = C.s_R1[lr], R2 = C.s_R2[lr];
-  auto v_of = [&](int col, double d) { return d - C.s_r[col] * inv_new; };
   auto ve_of = [&](int col, double d) { return d - static_cast<double>(C.s_snap[col]); };
   auto fold = [&](double& R, double ve) { if (!(ve >= R)) R = (ve == ve) ? ve : R; };   // NaN bounds nothing away: ignored like the oracle ignores NaN q
   // (1) the joined columns disappear
@@ -339,7 +405,7 @@ __device__ __forceinline__ void row_update(const RowCtx& C, int lr, int k, doubl
           // two tracked columns in one group: the better one stays, R2 covers the other. (s_r / s_snap of slot
           // wb already hold the moved node's values.)
           const double od = C.s_ld[gb * rc + lr];
-          if (v_of(wb, dl) < v_of(oc, od)) {
+          if (ve_of(wb, dl) < ve_of(oc, od)) {
             fold(R2, ve_of(oc, od));
             if (champ == gb) { champ = -1; R1 = -CUDART_INF; }
             C.s_lc[gb * rc + lr] = static_cast<unsigned short>(wb);
@@ -356,14 +422,14 @@ __device__ __forceinline__ void row_update(const RowCtx& C, int lr, int k, doubl
   // (3) the merged node is a new column (slot wa)
   {
     const int g = wa % G;
-    const double ve_new = du - sue, v_new = du - su;
+    const double ve_new = du - sue;
     const int oc = C.s_lc[g * rc + lr];
     bool placed = false;
     if (oc == NJL_EMPTY) {
       placed = true;
     } else {
       const double od = C.s_ld[g * rc + lr];
-      if (v_new < v_of(oc, od)) {
+      if (ve_new < ve_of(oc, od)) {
         fold(R2, ve_of(oc, od));
         if (champ == g) champ = -1;
         placed = true;
@@ -379,7 +445,7 @@ __device__ __forceinline__ void row_update(const RowCtx& C, int lr, int k, doubl
       } else {
         const int cc = C.s_lc[champ * rc + lr];
         const double cd = C.s_ld[champ * rc + lr];
-        if (v_new < v_of(cc, cd)) {
+        if (ve_new < ve_of(cc, cd)) {
           fold(R1, ve_of(cc, cd));
           champ = g;
         } else {
@@ -393,12 +459,14 @@ __device__ __forceinline__ void row_update(const RowCtx& C, int lr, int k, doubl
   C.s_R2[lr] = R2;
 }
 
-template <int G, bool PROF>
+template <int G, int RPT, bool PROF>
 __global__ void __launch_bounds__(NJL_THREADS, 1)
 nj_lazy_kernel(const NjLazyParams P) {
   extern __shared__ __align__(16) unsigned char nl_dyn[];
   __shared__ double s_wq[NJL_WARPS];          // per-warp best champion q (threshold of the CTA)
   __shared__ NjRec s_wrec[NJL_WARPS];          // per-warp best candidate after the list evaluations
+  __shared__ NjRec s_rrec[2][NJL_WARPS];       // rescans: per-warp best exact candidate (alternating buffers)
+  __shared__ double s_rb2[2][NJL_WARPS];       // rescans: per-warp bound of the untracked columns
   __shared__ double s_red[3][NJL_WARPS];
   __shared__ __align__(16) unsigned long long s_x[2][NJL_MAX_CLUSTER][4];   // exchange records {q, lo | hi << 16 | flags << 32, r_lo, r_hi}
   __shared__ int s_cnt;                                                     // rows queued for a rescan
@@ -415,7 +483,6 @@ nj_lazy_kernel(const NjLazyParams P) {
   C.s_s2p = reinterpret_cast<unsigned short*>(nl_dyn + L.s2p);
   C.s_R1 = reinterpret_cast<double*>(nl_dyn + L.R1);
   C.s_R2 = reinterpret_cast<double*>(nl_dyn + L.R2);
-  C.s_duo = reinterpret_cast<double*>(nl_dyn + L.duo);
   C.s_ld = reinterpret_cast<double*>(nl_dyn + L.ld);
   C.s_lc = reinterpret_cast<unsigned short*>(nl_dyn + L.lc);
   C.s_slot = reinterpret_cast<short*>(nl_dyn + L.slot);
@@ -423,7 +490,6 @@ nj_lazy_kernel(const NjLazyParams P) {
   C.rc = rc;
   C.G = G;
   unsigned short* q_resc = reinterpret_cast<unsigned short*>(nl_dyn + L.q_resc);
-  unsigned char* s_team = nl_dyn + L.team;
 
   double* __restrict__ W = P.W + mat * P.w_stride;
   const int64_t ldw = P.ldw;
@@ -462,10 +528,13 @@ nj_lazy_kernel(const NjLazyParams P) {
     // rows of this CTA: physical rows rank, rank + ncta, ... < n (the spare row n is not live)
     if (tid == 0) s_cnt = (n - rank + ncta - 1) >> shift;
     __syncthreads();
-    M = warp_max_f64(lane < NJL_WARPS ? s_red[0][lane] : -CUDART_INF);
+    M = smem_max_warps(s_red[0]);
   }
   cluster_sync_all();   // every CTA of the cluster is running
 
+  double* own_row[RPT];   // the matrix rows of this thread's list rows
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) own_row[i] = W + static_cast<int64_t>(((tid + i * NJL_THREADS) << shift) + rank) * ldw;
   unsigned long long n_rescan = 0, n_reeval = 0;   // warp 0 counts for the CTA
   unsigned long long t_prev = PROF ? njl_now() : 0;
   int spare = n;
@@ -474,13 +543,29 @@ nj_lazy_kernel(const NjLazyParams P) {
 
   while (na > 3) {
     const double n2 = static_cast<double>(na - 2);
-    const double inv_new = (na > 3) ? 1.0 / static_cast<double>(na - 3) : 0.0;   // (for the update: off the critical path here)
     Cand best{CUDART_INF, NJ_NONE, NJ_NONE};
+    double T = CUDART_INF;   // the CTA's threshold: its best champion (first iteration: none yet)
     if (!first) {
-      // ---- A: champions of the own rows, exactly -> the CTA's threshold T
-      for (int lr = tid; lr < rc; lr += NJL_THREADS) {
-        const int k = C.s_slot[lr];
-        const int ch = C.s_champ[lr];
+      // ---- A: champions of the own rows, exactly -> the CTA's threshold T. Lists without a champion that ask for it
+      // (R1 = -inf: after a rescan, or when the champion was joined) are evaluated here, by the warp of the owner.
+      unsigned fresh = 0;   // bit i: row tid + i * NJL_THREADS was evaluated in this phase
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int lr = tid + i * NJL_THREADS;
+        const int k = (lr < rc) ? static_cast<int>(C.s_slot[lr]) : -1;
+        const int ch = (k >= 0) ? static_cast<int>(C.s_champ[lr]) : -1;
+        const bool need = k >= 0 && ch < 0 && C.s_R1[lr] == -CUDART_INF;
+        unsigned mev = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) n_reeval += __popc(mev);
+        while (mev) {
+          const int src = __ffs(mev) - 1;
+          mev &= mev - 1;
+          const int lr_s = __shfl_sync(0xffffffffu, lr, src), k_s = __shfl_sync(0xffffffffu, k, src);
+          Cand c;
+          list_evaluate<G>(C, lr_s, k_s, n2, lane, c);
+          cand_take(best, c.q, c.lo, c.hi);
+        }
+        if (need) fresh |= 1u << i;
         if (k < 0 || ch < 0) continue;
         int lo, hi;
         const double q = fpq(n2, C.s_r, k, C.s_lc[ch * rc + lr], C.s_ld[ch * rc + lr], lo, hi);
@@ -491,22 +576,21 @@ nj_lazy_kernel(const NjLazyParams P) {
         if (lane == 0) s_wq[warp] = wq;
       }
       __syncthreads();
-      double T = s_wq[0];
-#pragma unroll
-      for (int w = 1; w < NJL_WARPS; ++w) T = fmin(T, s_wq[w]);
+      T = smem_min_warps(s_wq);
       NJL_MARK(1)   // A
       // ---- B: bounds that do not clear T. Lists are evaluated on the spot by the warp of the row's owner;
       // rows whose rest-of-row bound fails are queued for a rescan by the whole CTA.
-      for (int base = 0; base < rc; base += NJL_THREADS) {
-        const int lr = base + tid;
-        const int k = (lr < rc) ? C.s_slot[lr] : -1;
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int lr = tid + i * NJL_THREADS;
+        const int k = (lr < rc) ? static_cast<int>(C.s_slot[lr]) : -1;
         bool ev = false;
         if (k >= 0) {
           const double si = C.s_r[k] * inv;
           const double R2 = C.s_R2[lr], R1 = C.s_R1[lr];
           if (!(R2 == CUDART_INF) && !bound_clears(R2, M, si, n2, T)) {
             q_resc[atomicAdd(&s_cnt, 1)] = static_cast<unsigned short>(lr);
-          } else if (!(R1 == CUDART_INF) && !bound_clears(R1, M, si, n2, T)) {
+          } else if (!((fresh >> i) & 1u) && !(R1 == CUDART_INF) && !bound_clears(R1, M, si, n2, T)) {
             ev = true;
           }
         }
@@ -516,10 +600,8 @@ nj_lazy_kernel(const NjLazyParams P) {
           const int src = __ffs(mev) - 1;
           mev &= mev - 1;
           const int lr_s = __shfl_sync(0xffffffffu, lr, src), k_s = __shfl_sync(0xffffffffu, k, src);
-          const int col = (lane < G) ? C.s_lc[lane * rc + lr_s] : NJL_EMPTY;
-          const double d = (lane < G) ? C.s_ld[lane * rc + lr_s] : 0.0;
           Cand c;
-          list_evaluate(C, lr_s, k_s, col, d, n2, lane, c);
+          list_evaluate<G>(C, lr_s, k_s, n2, lane, c);
           cand_take(best, c.q, c.lo, c.hi);
         }
       }
@@ -535,7 +617,7 @@ nj_lazy_kernel(const NjLazyParams P) {
       const int lr = q_resc[qi];
       const int p = (lr << shift) + rank;
       Cand c;
-      rescan_row<G>(C, W + static_cast<int64_t>(p) * ldw, lr, na, n2, inv, tid, s_team, c);
+      rescan_row<G, PROF>(C, W + static_cast<int64_t>(p) * ldw, lr, na, n2, inv, M, T, tid, s_rrec[qi & 1], s_rb2[qi & 1], c, rank);
       cand_take(bres, c.q, c.lo, c.hi);
     }
     // ---- D: exchange over the cluster. Warp 0 assembles the CTA's candidate and writes it to every CTA
@@ -561,8 +643,13 @@ nj_lazy_kernel(const NjLazyParams P) {
     }
     first = false;
     NJL_MARK(3)   // C + publish
+    const double inv_new = (na > 3) ? 1.0 / static_cast<double>(na - 3) : 0.0;   // (before the barrier: off the critical path)
     cluster_sync_all();
     NJL_MARK(4)   // cluster barrier (includes waiting for the slowest CTA)
+    if (PROF) {
+      cluster_sync_all();
+      NJL_MARK(8)   // the barrier alone (nobody is late, nothing to publish)
+    }
     int wa, wb;
     double rra, rrb;
     {
@@ -613,77 +700,61 @@ nj_lazy_kernel(const NjLazyParams P) {
     const bool own_u = (spare & (ncta - 1)) == rank;
     const double dab = __ldcg(row_a + wb);
     const bool resnap = ((t + 1) % NJL_EPOCH) == 0;
+    // the rows of this CTA: their distances to a and b (and the entry that moves into column b) are requested now and
+    // used after the replicated part
+    int ok_[RPT];
+    double oa_[RPT], ob_[RPT], om_[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int lr = tid + i * NJL_THREADS;
+      int k = (lr < rc) ? static_cast<int>(C.s_slot[lr]) : -1;
+      if (k == wa || k == wb) k = -1;
+      ok_[i] = k;
+      oa_[i] = (k >= 0) ? __ldcg(row_a + k) : 0.0;
+      ob_[i] = (k >= 0) ? __ldcg(row_b + k) : 0.0;
+      om_[i] = (k >= 0 && move && k != last) ? __ldcg(own_row[i] + last) : 0.0;
+    }
     NJL_MARK(5)   // winner
-    double mx = -CUDART_INF, mx2 = -CUDART_INF, mn2 = CUDART_INF;
+    // replicated: r_k <- ((r_k - d_ak) - d_bk) + d_uk for every untouched node, the maximal drift against the snapshot
+    double mx = -CUDART_INF;
+    const int r_dummy = (n + 3) & ~3;   // the scratch element after the row sums
     constexpr int UK = 8;
     for (int k0 = tid; k0 < na; k0 += NJL_THREADS * UK) {
-      double dak[UK], dbk[UK], mv[UK];
-      int pk[UK];
+      double dak[UK], dbk[UK];
+#pragma unroll
+      for (int u = 0; u < UK; ++u) {
+        const int k = k0 + u * NJL_THREADS;
+        dak[u] = (k < na) ? __ldcg(row_a + k) : 0.0;
+        dbk[u] = (k < na) ? __ldcg(row_b + k) : 0.0;
+      }
 #pragma unroll
       for (int u = 0; u < UK; ++u) {
         const int k = k0 + u * NJL_THREADS;
         const bool live = k < na && k != wa && k != wb;
-        dak[u] = live ? __ldcg(row_a + k) : 0.0;
-        dbk[u] = live ? __ldcg(row_b + k) : 0.0;
-        pk[u] = live ? static_cast<int>(C.s_s2p[k]) : -1;
-        const bool own = live && (pk[u] & (ncta - 1)) == rank;
-        if (!own) pk[u] = -1;
-        mv[u] = (own && move && k != last) ? __ldcg(W + static_cast<int64_t>(pk[u]) * ldw + last) : 0.0;
-      }
-#pragma unroll
-      for (int u = 0; u < UK; ++u) {
-        const int k = k0 + u * NJL_THREADS;
-        if (k >= na || k == wb) continue;
-        if (k == wa) {
-          if (own_u) row_u[wa] = 0.0;
-          continue;
-        }
+        const int kc = min(k, na - 1);
         double d = __dadd_rn(dak[u], dbk[u]);
         d = __dsub_rn(d, dab);
         d = __dmul_rn(0.5, d);
-        double rk = __dsub_rn(C.s_r[k], dak[u]);
+        double rk = __dsub_rn(C.s_r[kc], dak[u]);
         rk = __dsub_rn(rk, dbk[u]);
         rk = __dadd_rn(rk, d);
-        const bool is_last = move && k == last;
-        const int slot = is_last ? wb : k;   // the last live slot moves into slot b
-        const double s_new = rk * inv_new;
-        const float sn_old = C.s_snap[k];
-        mx = fmax(mx, s_new - static_cast<double>(sn_old));
-        C.s_r[slot] = rk;
-        if (resnap) {
-          const float sn = static_cast<float>(s_new);
-          const double df = s_new - static_cast<double>(sn);
-          mx2 = fmax(mx2, df);
-          mn2 = fmin(mn2, df);
-          C.s_snap[slot] = sn;
-        } else if (is_last) {
-          C.s_snap[wb] = sn_old;
-        }
-        if (pk[u] >= 0) {
-          C.s_duo[pk[u] >> shift] = d;
-          double* rk_p = W + static_cast<int64_t>(pk[u]) * ldw;
-          rk_p[wa] = d;                               // column a of this node's row
-          if (move && k != last) rk_p[wb] = mv[u];    // column b <- column last
-        }
-        if (own_u) row_u[slot] = d;   // row of the merged node, in the spare physical row
+        const int slot = (move && k == last) ? wb : kc;   // the last live slot moves into slot b
+        const double drift = rk * inv_new - static_cast<double>(C.s_snap[kc]);
+        mx = live ? fmax(mx, drift) : mx;
+        C.s_r[live ? slot : r_dummy] = rk;                // (a scratch element takes the writes of the joined slots)
+        if (own_u && live) row_u[slot] = d;               // row of the merged node, in the spare physical row
       }
     }
+    if (tid == 0 && move) C.s_snap[wb] = C.s_snap[last];  // (nobody else touches these two elements in this phase)
     // r of the merged node: every thread computes it (same bits), one writes it
     double ru = __dadd_rn(rra, rrb);
     ru = __dsub_rn(ru, __dmul_rn(static_cast<double>(na), dab));
     ru = __dmul_rn(0.5, ru);
     mx = warp_max_f64(mx);
-    if (resnap) {
-      mx2 = warp_max_f64(mx2);
-      mn2 = warp_min_f64(mn2);
-    }
-    if (lane == 0) {
-      s_red[0][warp] = mx;
-      s_red[1][warp] = mx2;
-      s_red[2][warp] = mn2;
-    }
+    if (lane == 0) s_red[0][warp] = mx;
     if (tid == 0) {
       C.s_r[wa] = ru;
+      if (own_u) row_u[wa] = 0.0;
       if (rank == 0) {   // log of the join; node ids and branch lengths are derived after the last iteration
         merge[3 * t + 0] = wa;
         merge[3 * t + 1] = wb;
@@ -692,15 +763,47 @@ nj_lazy_kernel(const NjLazyParams P) {
         len[3 * t + 2] = dab;
       }
     }
+    // the rows of this CTA in the matrix: column a <- distance to the merged node, column b <- column last
+    double odu_[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      double d = __dadd_rn(oa_[i], ob_[i]);
+      d = __dsub_rn(d, dab);
+      d = __dmul_rn(0.5, d);
+      odu_[i] = d;
+      if (ok_[i] >= 0) {
+        double* rk_p = own_row[i];
+        rk_p[wa] = d;
+        if (move && ok_[i] != last) rk_p[wb] = om_[i];
+      }
+    }
     __syncthreads();
     NJL_MARK(6)   // E: update of the row sums and the matrix
-    const double M_old_frame = warp_max_f64(lane < NJL_WARPS ? s_red[0][lane] : -CUDART_INF);   // max_j s_j(t + 1) - snap_j, untouched nodes
+    const double M_old_frame = smem_max_warps(s_red[0]);   // max_j s_j(t + 1) - snap_j, untouched nodes
     double radj = 0.0;   // added to every stored bound (new snapshot only)
     double Mn = M_old_frame;
     if (resnap) {
-      const double Mx2 = warp_max_f64(lane < NJL_WARPS ? s_red[1][lane] : -CUDART_INF);
-      const double Mn2 = warp_min_f64(lane < NJL_WARPS ? s_red[2][lane] : CUDART_INF);
-      // bounds move from "d - snap_old >= R" to the new snapshot: d - snap' = (d - s) + (s - snap') >= (R - M_old) + min (s - snap')
+      // new snapshot of every untouched node (the merged node's follows below); the stored bounds move from
+      // "d - snap_old >= R" to the new frame: d - snap' = (d - s) + (s - snap') >= (R - M_old) + min_j (s_j - snap'_j)
+      double mx2 = -CUDART_INF, mn2 = CUDART_INF;
+      for (int j = tid; j < na - 1; j += NJL_THREADS) {
+        if (j == wa) continue;
+        const double sj = C.s_r[j] * inv_new;
+        const float sn = static_cast<float>(sj);
+        const double df = sj - static_cast<double>(sn);
+        C.s_snap[j] = sn;
+        mx2 = fmax(mx2, df);
+        mn2 = fmin(mn2, df);
+      }
+      mx2 = warp_max_f64(mx2);
+      mn2 = warp_min_f64(mn2);
+      if (lane == 0) {
+        s_red[1][warp] = mx2;
+        s_red[2][warp] = mn2;
+      }
+      __syncthreads();
+      const double Mx2 = smem_max_warps(s_red[1]);
+      const double Mn2 = smem_min_warps(s_red[2]);
       radj = Mn2 - M_old_frame;
       Mn = Mx2;
     }
@@ -718,9 +821,11 @@ nj_lazy_kernel(const NjLazyParams P) {
     }
 
     // ---- F: the rows of this CTA (a thread per row): slot relabelling, list maintenance
-    for (int lr = tid; lr < rc; lr += NJL_THREADS) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      const int lr = tid + i * NJL_THREADS;
+      if (lr >= rc) continue;
       const int p = (lr << shift) + rank;
-      int k = C.s_slot[lr];
       if (p == spare) {
         // this physical row now holds the merged node: nothing tracked yet (the other rows cover its pairs)
         C.s_slot[lr] = static_cast<short>(wa);
@@ -730,9 +835,9 @@ nj_lazy_kernel(const NjLazyParams P) {
         for (int g = 0; g < G; ++g) C.s_lc[g * rc + lr] = NJL_EMPTY;
         continue;
       }
-      if (k < 0) continue;
-      if (k == wa || k == wb) {   // joined: the row of a becomes the spare row, the row of b is dead
-        C.s_slot[lr] = -1;
+      int k = ok_[i];
+      if (k < 0) {   // dead already, or joined now: the row of a becomes the spare row, the row of b is dead
+        if (C.s_slot[lr] >= 0) C.s_slot[lr] = -1;
         continue;
       }
       if (move && k == last) {
@@ -744,7 +849,7 @@ nj_lazy_kernel(const NjLazyParams P) {
         if (!(R1 == CUDART_INF) && !(R1 == -CUDART_INF)) C.s_R1[lr] = R1 + radj;
         if (!(R2 == CUDART_INF)) C.s_R2[lr] = R2 + radj;
       }
-      row_update(C, lr, k, C.s_duo[lr], wa, wb, last, move, inv_new, su, sue);
+      row_update(C, lr, k, odu_[i], wa, wb, last, move, sue);
     }
     spare = pwa;   // free from the next iteration on: everybody has read it by the next cluster barrier
     --na;
@@ -847,6 +952,7 @@ __global__ void nj_lazy_status_kernel(int* status, int n_mat, int value) {
 
 struct LazyPlan {
   int ncta, shift, G, rc, smem;
+  int rpt() const { return (rc + NJL_THREADS - 1) / NJL_THREADS; }
 };
 
 // cluster size, list width and shared memory for n nodes; ncta = 0 when the matrix does not fit
@@ -859,7 +965,7 @@ LazyPlan lazy_plan(int64_t n, int ncta) {
   rc |= 1;   // odd: lists are stored [group][row]
   for (int G = NJL_MAX_G; G >= 8; G >>= 1) {
     const NjLazySmem L(static_cast<int>(n), G, rc);
-    if (L.total <= NJL_SMEM_LIMIT - 4096 && 2 * G * rc >= n) {   // (static shared memory: ~3 KB; s_node fits over the lists)
+    if (L.total <= NJL_SMEM_LIMIT - 4096 && 2 * G * rc >= n && rc <= NJL_MAX_RPT * NJL_THREADS) {   // (static shared memory: ~3 KB; s_node fits over the lists)
       pl = LazyPlan{ncta, shift, G, rc, L.total};
       return pl;
     }
@@ -867,13 +973,13 @@ LazyPlan lazy_plan(int64_t n, int ncta) {
   return pl;
 }
 
-template <int G, bool PROF>
+template <int G, int RPT, bool PROF>
 int lazy_cluster_slots(int ncta, int smem) {
-  if (cudaFuncSetAttribute(nj_lazy_kernel<G, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(nj_lazy_kernel<G, RPT, PROF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
-  if (ncta > 8 && cudaFuncSetAttribute(nj_lazy_kernel<G, PROF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+  if (ncta > 8 && cudaFuncSetAttribute(nj_lazy_kernel<G, RPT, PROF>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
@@ -889,24 +995,38 @@ int lazy_cluster_slots(int ncta, int smem) {
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
   int slots = 0;
-  if (cudaOccupancyMaxActiveClusters(&slots, nj_lazy_kernel<G, PROF>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&slots, nj_lazy_kernel<G, RPT, PROF>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   return slots;
 }
 
+// (G, RPT, PROF) -> instantiation
+#define NJL_DISPATCH_RPT(G_, CALL)                                   \
+  switch (pl.rpt()) {                                                \
+    case 1: CALL(G_, 1); break;                                      \
+    case 2: CALL(G_, 2); break;                                      \
+    default: CALL(G_, 3); break;                                     \
+  }
+#define NJL_DISPATCH(CALL)                                           \
+  switch (pl.G) {                                                    \
+    case 64: NJL_DISPATCH_RPT(64, CALL) break;                       \
+    case 32: NJL_DISPATCH_RPT(32, CALL) break;                       \
+    case 16: NJL_DISPATCH_RPT(16, CALL) break;                       \
+    default: NJL_DISPATCH_RPT(8, CALL) break;                        \
+  }
+
 int lazy_slots(const LazyPlan& pl) {
   const bool pr = g_njl_prof_enabled;
-  switch (pl.G) {
-    case 32: return pr ? lazy_cluster_slots<32, true>(pl.ncta, pl.smem) : lazy_cluster_slots<32, false>(pl.ncta, pl.smem);
-    case 16: return pr ? lazy_cluster_slots<16, true>(pl.ncta, pl.smem) : lazy_cluster_slots<16, false>(pl.ncta, pl.smem);
-    case 8: return pr ? lazy_cluster_slots<8, true>(pl.ncta, pl.smem) : lazy_cluster_slots<8, false>(pl.ncta, pl.smem);
-  }
-  return 0;
+  int slots = 0;
+#define NJL_CALL_SLOTS(G_, R_) slots = pr ? lazy_cluster_slots<G_, R_, true>(pl.ncta, pl.smem) : lazy_cluster_slots<G_, R_, false>(pl.ncta, pl.smem)
+  NJL_DISPATCH(NJL_CALL_SLOTS)
+#undef NJL_CALL_SLOTS
+  return slots;
 }
 
-template <int G, bool PROF>
+template <int G, int RPT, bool PROF>
 cudaError_t lazy_launch(const LazyPlan& pl, int n_mat, const NjLazyParams& P, cudaStream_t s) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(pl.ncta * n_mat));
@@ -920,7 +1040,7 @@ cudaError_t lazy_launch(const LazyPlan& pl, int n_mat, const NjLazyParams& P, cu
   attr.val.clusterDim.z = 1;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, nj_lazy_kernel<G, PROF>, P);
+  return cudaLaunchKernelEx(&cfg, nj_lazy_kernel<G, RPT, PROF>, P);
 }
 
 int64_t align256(int64_t x) { return (x + 255) / 256 * 256; }
@@ -998,11 +1118,9 @@ int nj_lazy_run(const double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t 
   pf_count_launch();
   cudaError_t e;
   const bool pr = g_njl_prof_enabled;
-  switch (pl.G) {
-    case 32: e = pr ? lazy_launch<32, true>(pl, n_mat, P, s) : lazy_launch<32, false>(pl, n_mat, P, s); break;
-    case 16: e = pr ? lazy_launch<16, true>(pl, n_mat, P, s) : lazy_launch<16, false>(pl, n_mat, P, s); break;
-    default: e = pr ? lazy_launch<8, true>(pl, n_mat, P, s) : lazy_launch<8, false>(pl, n_mat, P, s); break;
-  }
+#define NJL_CALL_LAUNCH(G_, R_) e = pr ? lazy_launch<G_, R_, true>(pl, n_mat, P, s) : lazy_launch<G_, R_, false>(pl, n_mat, P, s)
+  NJL_DISPATCH(NJL_CALL_LAUNCH)
+#undef NJL_CALL_LAUNCH
   if (e != cudaSuccess) {
     // the cluster could not be launched: every matrix goes to the full-scan kernel
     cudaGetLastError();

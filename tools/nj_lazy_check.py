@@ -66,6 +66,9 @@ def run(name, d, with_oracle=True):
     check(eng.lib.pf_nj_lazy_profile(0, ph))
     names = ["-", "A champions+T", "B checks+list evals", "C rescans+publish", "D cluster barrier", "D winner", "E update", "F rows", "barrier alone"]
     rec["phases_us_per_iter"] = {nm: round(ph[i] / 1e3 / n, 3) for i, nm in enumerate(names)}
+    if ph[12]:
+        rec["rank0_rescan_us"] = {"n": int(ph[12]), "loads+scan": round(ph[9] / 1e3 / ph[12], 3),
+                                  "reduce+barrier": round(ph[10] / 1e3 / ph[12], 3), "merge+list+barrier": round(ph[11] / 1e3 / ph[12], 3), "one_load_round_trip": round(ph[13] / 1e3 / ph[12], 3)}
     if with_oracle and n <= 3000:
         wm, wl = oracle.nj(d.cpu().numpy())
         rec["same_as_oracle"] = bool(np.array_equal(wm, m1.cpu().numpy()) and np.array_equal(wl, l1.cpu().numpy()))
