@@ -242,18 +242,25 @@ PF_API int pf_normalise(const int32_t* d_counts, int64_t n_samples, int64_t ld, 
  * (the stand-in for the absent `treebest nj`, script.py:359-360): fp64, no FMA
  * contraction, row sums in the fixed 32-lane strided + butterfly order, Q argmin ties ->
  * lowest slot i then lowest slot j, merged node replaces slot i, last slot moves into j.
- * d_dist (n x ld, symmetric, zero diagonal) is destroyed. Outputs (device):
+ * d_dist (n x ld, symmetric, zero diagonal) may be destroyed. Outputs (device):
  *   d_merge[3*t+0..2] for t < n-3: node ids (a, b) joined at step t and 0;
  *   d_merge[3*(n-3)+0..2]: the three node ids of the final trifurcation;
  *   d_len likewise: branch lengths of those children.
  * Node ids: leaves 0..n-1; the node created at step t is n + t. n >= 3.
- * d_work must hold pf_nj_work_bytes(n) bytes. One cooperative persistent launch. */
+ * d_work must hold pf_nj_work_bytes(n) bytes (for n <= 11,000 this includes a private copy of the matrix,
+ * 8 (n + 1) n bytes rounded up).
+ * Two implementations with identical results (join order, branch lengths, ties): from 3,500 to 11,000 nodes (in
+ * batches: from 1,536) the bounded-scan kernel (csrc/nj_lazy.cu: one thread-block cluster per matrix, per-row candidate lists with lower
+ * bounds, the matrix read only where a bound does not exclude the minimum) runs first; it hands a matrix over to
+ * the full-scan kernels (csrc/nj.cu: cooperative persistent launch over all SMs) when the input is not symmetric or
+ * its bounds do not prune (degenerate inputs: everything ties, NaN). Larger matrices go to the full-scan kernel. */
 PF_API int64_t pf_nj_work_bytes(int64_t n);
 PF_API int pf_nj(double* d_dist, int64_t n, int64_t ld, int32_t* d_merge, double* d_len,
                  void* d_work, void* stream);
 /* n_mat matrices of the same size in one call (bootstrap replicates): matrix m at d_dist + m * mat_stride
  * doubles, outputs at d_merge / d_len + m * 3 (n - 2), workspace n_mat * pf_nj_work_bytes(n) bytes. The
- * matrices are joined concurrently, each by its own group of CTAs of one cooperative launch. */
+ * matrices are joined concurrently: by one cluster each (bounded scan, from 1,536 nodes on) or each by its own
+ * group of CTAs of one cooperative launch (full scan). */
 PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
                        int32_t* d_merge, double* d_len, void* d_work, void* stream);
 
@@ -286,7 +293,9 @@ PF_API int pf_bootstrap_counts(const int32_t* d_blocks, int n_blocks, int64_t el
  * pf_nj calls, bit 1 = use the general kernel (two grid barriers per iteration) also for matrices the
  * fast kernel would take. h_out8, fast kernel: [0] scan, [1] CTA reduction + publish, [2] exchange,
  * [3] update; general kernel: [0] scan + CTA reduction, [1] grid barrier 1, [2] winner + update,
- * [3] grid barrier 2. Reading resets the counters. */
+ * [3] grid barrier 2; [4..7] counters of the bounded-scan kernel: row rescans, list evaluations, iterations, matrices
+ * it joined. Further bits of enable: bit 2 = full-scan kernels only, bit 3 = bounded scan at every size it can
+ * take (8 ... 11,000 nodes). Reading resets the counters. */
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8);
 /* Diagnostic: phase accounting of the bounded-scan NJ kernel (csrc/nj_lazy.cu), 16 counters in nanoseconds (see the
  * definition); enable != 0 switches the instrumented kernel on for the following pf_nj calls. */

@@ -683,6 +683,9 @@ constexpr int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 constexpr int64_t NJ_MAX_SMEM_R = 200 * 1024;
 int g_nj_force_general = 0;
 int g_nj_no_lazy = 0;        // diagnostic: full-scan kernels only
+int g_nj_lazy_always = 0;    // diagnostic: bounded scan at every size it can take
+constexpr int64_t NJ_LAZY_FROM = 3500;         // single matrix
+constexpr int64_t NJ_LAZY_BATCH_FROM = 1536;   // matrices of a batch
 
 // per-matrix workspace: the full-scan kernels' part, the bounded-scan kernel's part, one status line
 int64_t nj_classic_bytes(int64_t n) { return 2 * align_up(8 * n, 256) + align_up(4 * n, 256) + NJ_XCHG_BYTES; }
@@ -734,8 +737,15 @@ int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
   int* const d_status = reinterpret_cast<int*>(w_lazy + n_mat * nj_lazy_work_bytes(n));
 
   // bounded scan on one cluster per matrix first; it reports per matrix whether a full-scan kernel has to run
+  // Measured on B200 (profiles/r02_nj_bounded_scan.md). One matrix: up to ~3,000 nodes the two kernels are within
+  // +-7 % of each other, the sign depending on the data (genotype distances of a star-like population sample are the
+  // hard case for the bounds: 20.4 vs 21.9 ms with p-distances at 3,000 x 10M, 23.5 vs 21.9 ms with IBS); from there
+  // on the bounded scan pulls away (47 vs 80 ms at 6,000, 134-165 vs 316 ms at 10,000). Batches: a cluster per
+  // matrix beats the shared cooperative launch from ~1,500 nodes on (4.7 vs 10.2 ms per tree at 9 x 3,000), below
+  // that the full-scan batch is ~25 % faster.
   const bool lazy = n <= NJ_FAST_MAX_N && n <= nj_lazy_max_n() && nj_lazy_work_bytes(n) > 0 && !g_nj_force_general &&
-                    !g_nj_no_lazy && !g_nj_prof_enabled;
+                    !g_nj_no_lazy && !g_nj_prof_enabled &&
+                    (g_nj_lazy_always || (n_mat == 1 ? n >= NJ_LAZY_FROM : n >= NJ_LAZY_BATCH_FROM));
   if (lazy) {
     unsigned long long* d_stats = nullptr;
     PF_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&d_stats), g_nj_prof));
@@ -846,7 +856,7 @@ PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t
 // [4..7]: counters of the bounded-scan kernel (nj_lazy.cu): row rescans, list evaluations, iterations, matrices
 // joined by it (0 when a full-scan kernel did the work).
 // enable: bit 0 = instrumented kernels (full-scan), bit 1 = force the general kernel, bit 2 = full-scan kernels
-// only (no bounded scan). Reading resets the counters.
+// only (no bounded scan), bit 3 = bounded scan also for batches of small matrices. Reading resets the counters.
 PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {
   PF_TRY_BEGIN
   if (h_out8) PF_CUDA(cudaMemcpyFromSymbol(h_out8, g_nj_prof, sizeof(unsigned long long) * 8));
@@ -855,6 +865,7 @@ PF_API int pf_nj_profile(int enable, unsigned long long* h_out8) {
   g_nj_prof_enabled = (enable & 1) != 0;
   g_nj_force_general = (enable & 2) != 0;
   g_nj_no_lazy = (enable & 4) != 0;
+  g_nj_lazy_always = (enable & 8) != 0;
   return PF_OK;
   PF_TRY_END
 }

@@ -112,14 +112,25 @@ def test_normalise_bit_exact(engine, metric):
     assert int(nz.item()) == want_nz and want_nz > 0
 
 
-def _check_nj(engine, dist, ld=None):
-    """Both NJ kernels (the fast one and, forced through the diagnostic switch, the general one)."""
+def _nj_counters(engine):
+    """[rescans, list evaluations, iterations, matrices joined] of the bounded-scan kernel since the last reading."""
+    import ctypes as C
+    from phyloforge_b200._lib import check
+    out = (C.c_ulonglong * 8)()
+    check(engine.lib.pf_nj_profile(0, out))
+    return list(out)[4:8]
+
+
+def _check_nj(engine, dist, ld=None, expect_bounded=None):
+    """All three NJ kernels through the diagnostic switch: the bounded scan (8: at every size it can take; by default
+    it runs from 3,500 nodes on), the fast full-scan kernel (4) and the general one (2). expect_bounded: whether the
+    bounded-scan kernel must have joined the matrix itself (True), must have handed it over (False), or either."""
     from phyloforge_b200._lib import check
     n = dist.shape[0]
     want_m, want_l = oracle.nj(dist)
     names = [f"t{i}" for i in range(n)]
     want_nw = merges_to_newick(want_m, want_l, names)
-    for force_general in (0, 2):
+    for force_general in (8, 4, 2):
         check(engine.lib.pf_nj_profile(force_general, None))
         try:
             if ld is None:
@@ -131,10 +142,14 @@ def _check_nj(engine, dist, ld=None):
             merge, length = engine.nj(d)
             torch.cuda.synchronize()
         finally:
-            check(engine.lib.pf_nj_profile(0, None))
+            joined = _nj_counters(engine)[3]
+        if force_general == 8 and expect_bounded is not None and n >= 8:
+            assert joined == (1 if expect_bounded else 0), "bounded-scan kernel: joined %d" % joined
+        if force_general != 8:
+            assert joined == 0
         got_nw = merges_to_newick(merge.cpu().numpy(), length.cpu().numpy(), names)
         rf, dl = treecmp.compare(got_nw, want_nw)
-        which = "general kernel" if force_general else "fast kernel"
+        which = {8: "bounded scan", 4: "fast kernel", 2: "general kernel"}[force_general]
         assert rf == 0, which                                        # Robinson-Foulds distance 0
         assert dl <= 1e-9, which                                     # branch lengths within 1e-9
         assert np.array_equal(merge.cpu().numpy(), want_m), which    # in fact the same join order
@@ -147,14 +162,17 @@ def test_nj_random_distances(engine, n):
     a = rng.random((n, n))
     dist = (a + a.T) / 2
     np.fill_diagonal(dist, 0.0)
-    _check_nj(engine, dist)
+    _check_nj(engine, dist, expect_bounded=True)
     if n in (5, 257):
         _check_nj(engine, dist, ld=n + 3)
 
 
-@pytest.mark.parametrize("k,n", [(1, 30), (5, 100), (20, 40), (3, 700)])
-def test_nj_batch_matches_oracle_tree_by_tree(engine, k, n):
-    """pf_nj_batch: several matrices joined concurrently by groups of CTAs of one launch."""
+@pytest.mark.parametrize("k,n,mode", [(1, 30, 0), (5, 100, 0), (20, 40, 0), (3, 700, 0), (5, 100, 8), (11, 300, 8),
+                                      (3, 1600, 0)])
+def test_nj_batch_matches_oracle_tree_by_tree(engine, k, n, mode):
+    """pf_nj_batch: several matrices joined concurrently - by groups of CTAs of one cooperative launch (full scan) or
+    by one cluster each (bounded scan: from 1,536 nodes on, or forced for small ones with mode 8)."""
+    from phyloforge_b200._lib import check
     rng = np.random.default_rng(k * 1000 + n)
     mats = []
     for _ in range(k):
@@ -162,8 +180,13 @@ def test_nj_batch_matches_oracle_tree_by_tree(engine, k, n):
         d = (a + a.T) / 2
         np.fill_diagonal(d, 0.0)
         mats.append(d)
-    merge, length = engine.nj_batch(torch.from_numpy(np.stack(mats)).to(engine.device))
-    torch.cuda.synchronize()
+    check(engine.lib.pf_nj_profile(mode, None))
+    try:
+        merge, length = engine.nj_batch(torch.from_numpy(np.stack(mats)).to(engine.device))
+        torch.cuda.synchronize()
+    finally:
+        joined = _nj_counters(engine)[3]
+    assert joined == (k if (mode == 8 or (n >= 1536 and k > 1) or n >= 3500) and n >= 8 else 0)
     for j in range(k):
         want_m, want_l = oracle.nj(mats[j])
         assert np.array_equal(merge[j].cpu().numpy(), want_m), j
@@ -179,7 +202,8 @@ def test_nj_many_exact_ties(engine):
         dist = dist + dist.T
         _check_nj(engine, dist)
     _check_nj(engine, np.ones((50, 50)) - np.eye(50))            # star: everything ties
-    _check_nj(engine, np.ones((1030, 1030)) - np.eye(1030))      # ... across scan segments and CTAs
+    # ... across scan segments and CTAs; no bound can prune here: the bounded scan gives up and hands over
+    _check_nj(engine, np.ones((1030, 1030)) - np.eye(1030), expect_bounded=False)
 
 
 def test_nj_ultrametric_and_caterpillar_trees(engine):
@@ -217,7 +241,44 @@ def test_nj_from_genotypes(engine):
     codes = oracle.synth_codes(n, 0, m, seed=1, miss_ppm=50000)
     counts = oracle.pair_counts(np.ascontiguousarray(codes.T), method="bits")
     dist, _ = oracle.normalise(counts, "ibs")
-    _check_nj(engine, dist)
+    _check_nj(engine, dist, expect_bounded=True)
+
+
+def test_nj_bounded_scan_hands_over_what_it_cannot_join(engine):
+    """The bounded-scan kernel reads a distance from the row of either node, so it takes symmetric matrices only; an
+    asymmetric input goes to the full-scan kernel (which reads the oracle's triangle) - same result either way."""
+    rng = np.random.default_rng(5)
+    n = 200
+    a = rng.random((n, n))
+    np.fill_diagonal(a, 0.0)
+    _check_nj(engine, a, expect_bounded=False)                      # asymmetric
+    sym = (a + a.T) / 2
+    dup = sym.copy()
+    dup[:, 50] = dup[:, 51]                                           # two identical samples ...
+    dup[50, :] = dup[51, :]
+    dup[50, 51] = dup[51, 50] = 0.0                                   # ... at distance 0
+    dup[50, 50] = 0.0
+    _check_nj(engine, dup)
+
+
+def test_nj_bounded_scan_every_list_width(engine):
+    """The list width (64, 32, 16 or 8 tracked columns per row) follows from shared memory; n = 3,600 and 6,500 take
+    the narrower ones (the widest runs in every other test). Checked against the full-scan kernel."""
+    from phyloforge_b200._lib import check
+    for n in (3600, 6500):
+        a = torch.rand((n, n), dtype=torch.float64, device=engine.device)
+        d = (a + a.T) / 2
+        d.fill_diagonal_(0)
+        m0, l0 = engine.nj(d)
+        torch.cuda.synchronize()
+        assert _nj_counters(engine)[3] == 1
+        check(engine.lib.pf_nj_profile(4, None))
+        try:
+            m1, l1 = engine.nj(d)
+            torch.cuda.synchronize()
+        finally:
+            check(engine.lib.pf_nj_profile(0, None))
+        assert torch.equal(m0, m1) and torch.equal(l0, l1), n
 
 
 def test_synth_generator_matches_oracle_and_is_shard_invariant(engine):

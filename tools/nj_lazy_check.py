@@ -50,7 +50,7 @@ def timed_nj(d, mode, reps=3):
 
 def run(name, d, with_oracle=True):
     n = d.shape[0]
-    m1, l1, t1, st1 = timed_nj(d, 0)
+    m1, l1, t1, st1 = timed_nj(d, 8)
     m0, l0, t0, _ = timed_nj(d, 4)
     same = bool(torch.equal(m0, m1) and torch.equal(l0, l1))
     calls = 4
@@ -76,9 +76,38 @@ def run(name, d, with_oracle=True):
     return rec
 
 
+def run_batch(k, n):
+    """k matrices of n nodes joined by one pf_nj_batch call: bounded scan (one cluster per matrix) vs full scan."""
+    a = torch.rand((k, n, n), dtype=torch.float64, device=eng.device)
+    d = (a + a.transpose(1, 2)) / 2
+    d.diagonal(dim1=1, dim2=2).zero_()
+    res = {}
+    for mode in (8, 4):
+        check(eng.lib.pf_nj_profile(mode, None))
+        m, l = eng.nj_batch(d.clone())
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            dd = d.clone()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            m, l = eng.nj_batch(dd)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        res[mode] = (m, l, best)
+    check(eng.lib.pf_nj_profile(0, None))
+    print(json.dumps({"case": f"batch {k} x {n}", "lazy_ms": round(res[8][2], 3), "full_scan_ms": round(res[4][2], 3),
+                      "ms_per_tree_lazy": round(res[8][2] / k, 3), "ms_per_tree_full_scan": round(res[4][2] / k, 3),
+                      "same": bool(torch.equal(res[8][0], res[4][0]) and torch.equal(res[8][1], res[4][1]))}), flush=True)
+
+
 cases = sys.argv[1:] or ["u:64", "u:700", "u:1500", "g:1000:1000000", "g:3000:1000000", "u:3000"]
 for c in cases:
     parts = c.split(":")
+    if parts[0] == "b":
+        run_batch(int(parts[1]), int(parts[2]))
+        continue
     if parts[0] == "u":
         n = int(parts[1])
         a = torch.rand((n, n), dtype=torch.float64, device=eng.device)
@@ -88,4 +117,5 @@ for c in cases:
     else:
         n, m = int(parts[1]), int(parts[2])
         miss = int(parts[3]) if len(parts) > 3 else 0
-        run(c, genotype_dist(n, m, miss))
+        metric = parts[4] if len(parts) > 4 else "p"
+        run(c, genotype_dist(n, m, miss, metric))
