@@ -249,8 +249,8 @@ PF_API int pf_normalise(const int32_t* d_counts, int64_t n_samples, int64_t ld, 
  * Node ids: leaves 0..n-1; the node created at step t is n + t. n >= 3.
  * d_work must hold pf_nj_work_bytes(n) bytes (for n <= 11,000 this includes a private copy of the matrix,
  * 8 (n + 1) n bytes rounded up).
- * Two implementations with identical results (join order, branch lengths, ties): from 3,500 to 11,000 nodes (in
- * batches: from 1,536) the bounded-scan kernel (csrc/nj_lazy.cu: one thread-block cluster per matrix, per-row candidate lists with lower
+ * Two implementations with identical results (join order, branch lengths, ties): from 1,536 to 11,000 nodes the
+ * bounded-scan kernel (csrc/nj_lazy.cu: one thread-block cluster per matrix, per-row candidate lists with lower
  * bounds, the matrix read only where a bound does not exclude the minimum) runs first; it hands a matrix over to
  * the full-scan kernels (csrc/nj.cu: cooperative persistent launch over all SMs) when the input is not symmetric or
  * its bounds do not prune (degenerate inputs: everything ties, NaN). Larger matrices go to the full-scan kernel. */

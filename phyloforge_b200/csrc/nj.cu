@@ -684,7 +684,7 @@ constexpr int64_t NJ_MAX_SMEM_R = 200 * 1024;
 int g_nj_force_general = 0;
 int g_nj_no_lazy = 0;        // diagnostic: full-scan kernels only
 int g_nj_lazy_always = 0;    // diagnostic: bounded scan at every size it can take
-constexpr int64_t NJ_LAZY_FROM = 3500;         // single matrix
+constexpr int64_t NJ_LAZY_FROM = 1536;         // single matrix
 constexpr int64_t NJ_LAZY_BATCH_FROM = 1536;   // matrices of a batch
 
 // per-matrix workspace: the full-scan kernels' part, the bounded-scan kernel's part, one status line
@@ -737,12 +737,11 @@ int nj_run(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t mat_stride,
   int* const d_status = reinterpret_cast<int*>(w_lazy + n_mat * nj_lazy_work_bytes(n));
 
   // bounded scan on one cluster per matrix first; it reports per matrix whether a full-scan kernel has to run
-  // Measured on B200 (profiles/r02_nj_bounded_scan.md). One matrix: up to ~3,000 nodes the two kernels are within
-  // +-7 % of each other, the sign depending on the data (genotype distances of a star-like population sample are the
-  // hard case for the bounds: 20.4 vs 21.9 ms with p-distances at 3,000 x 10M, 23.5 vs 21.9 ms with IBS); from there
-  // on the bounded scan pulls away (47 vs 80 ms at 6,000, 134-165 vs 316 ms at 10,000). Batches: a cluster per
-  // matrix beats the shared cooperative launch from ~1,500 nodes on (4.7 vs 10.2 ms per tree at 9 x 3,000), below
-  // that the full-scan batch is ~25 % faster.
+  // Measured on B200 (profiles/r02_nj_bounded_scan.md): from ~1,000 nodes on the bounded scan is at least as fast as
+  // the full scan on every input tried (genotype distances of a star-like population sample are the hard case for the
+  // bounds: 19.0 vs 21.9 ms with p-distances at 3,000 x 10M, 20.8 vs 22.0 ms with IBS), and pulls away with n (47 vs
+  // 80 ms at 6,000, 134-165 vs 316 ms at 10,000; in batches 4.3 vs 10.2 ms per tree at 9 x 3,000). Below that the
+  // cooperative kernel, which shares the SMs among the matrices of a batch, is up to 25 % faster.
   const bool lazy = n <= NJ_FAST_MAX_N && n <= nj_lazy_max_n() && nj_lazy_work_bytes(n) > 0 && !g_nj_force_general &&
                     !g_nj_no_lazy && !g_nj_prof_enabled &&
                     (g_nj_lazy_always || (n_mat == 1 ? n >= NJ_LAZY_FROM : n >= NJ_LAZY_BATCH_FROM));

@@ -13,7 +13,8 @@
 //   * R1 <= v of every other list entry and R2 <= v of every column that is not in the list,
 // R1 / R2 in the frame of a SNAPSHOT of s (snap_j, float): d_ij - s_j(t) >= R - M(t) with
 // M(t) = max_j (s_j(t) - snap_j), one number per iteration computed where the row sums are updated. Per
-// iteration a CTA evaluates the champions of its rows exactly (T = its best), re-evaluates (exactly, from shared
+// iteration a CTA evaluates the champions of its rows exactly (T = its best, or the runner-up of the previous
+// exchange re-evaluated in the new frame if that is better: any exact q of a live pair is a valid threshold), re-evaluates (exactly, from shared
 // memory) the lists whose R1 bound does not clear T, and rescans from the matrix only rows whose R2 bound does
 // not clear T. Whatever is skipped is provably worse than T by a margin far above the rounding of the bound, and
 // everything that is not skipped is evaluated with the oracle's operations, so the winner and the ties are the
@@ -539,6 +540,7 @@ nj_lazy_kernel(const NjLazyParams P) {
   unsigned long long t_prev = PROF ? njl_now() : 0;
   int spare = n;
   bool first = true, bailed = false;
+  double T0 = CUDART_INF;   // exact q of the previous exchange's runner-up in the current frame (a valid threshold)
   double inv = 1.0 / static_cast<double>(na - 2);
 
   while (na > 3) {
@@ -576,7 +578,7 @@ nj_lazy_kernel(const NjLazyParams P) {
         if (lane == 0) s_wq[warp] = wq;
       }
       __syncthreads();
-      T = smem_min_warps(s_wq);
+      T = fmin(smem_min_warps(s_wq), T0);
       NJL_MARK(1)   // A
       // ---- B: bounds that do not clear T. Lists are evaluated on the spot by the warp of the row's owner;
       // rows whose rest-of-row bound fails are queued for a rescan by the whole CTA.
@@ -652,6 +654,7 @@ nj_lazy_kernel(const NjLazyParams P) {
     }
     int wa, wb;
     double rra, rrb;
+    int ru_a = NJ_NONE, ru_b = NJ_NONE;   // the runner-up of this exchange: best published pair that survives the join
     {
       double q = CUDART_INF;
       int a = NJ_NONE, b = NJ_NONE;
@@ -671,6 +674,7 @@ nj_lazy_kernel(const NjLazyParams P) {
         }
       }
       const int a0 = a, b0 = b;
+      const double q0 = q;
       warp_argmin(q, a, b);
       if (__any_sync(0xffffffffu, flags != 0)) { bailed = true; break; }
       if (a == NJ_NONE) {
@@ -687,6 +691,13 @@ nj_lazy_kernel(const NjLazyParams P) {
         wb = b;
         rra = __shfl_sync(0xffffffffu, xa, sl);
         rrb = __shfl_sync(0xffffffffu, xb, sl);
+        // the best record whose nodes are not joined now: after the update its exact q is a threshold every CTA can
+        // use before it has seen anybody else's candidates (the CTA-local best is weaker: more rescans)
+        const bool alive = a0 != NJ_NONE && a0 != wa && a0 != wb && b0 != wa && b0 != wb;
+        double q2 = alive ? q0 : CUDART_INF;
+        ru_a = alive ? a0 : NJ_NONE;
+        ru_b = alive ? b0 : NJ_NONE;
+        warp_argmin(q2, ru_a, ru_b);
       }
     }
 
@@ -699,6 +710,7 @@ nj_lazy_kernel(const NjLazyParams P) {
     double* row_u = W + static_cast<int64_t>(spare) * ldw;
     const bool own_u = (spare & (ncta - 1)) == rank;
     const double dab = __ldcg(row_a + wb);
+    const double ru_d = (ru_a != NJ_NONE) ? __ldcg(W + static_cast<int64_t>(C.s_s2p[ru_a]) * ldw + ru_b) : 0.0;
     const bool resnap = ((t + 1) % NJL_EPOCH) == 0;
     // the rows of this CTA: their distances to a and b (and the entry that moves into column b) are requested now and
     // used after the replicated part
@@ -806,6 +818,16 @@ nj_lazy_kernel(const NjLazyParams P) {
       const double Mn2 = smem_min_warps(s_red[2]);
       radj = Mn2 - M_old_frame;
       Mn = Mx2;
+    }
+    // the runner-up in the frame of the next iteration (its nodes were not touched, only relabelled and their row sums
+    // updated): the exact q of a live pair, hence a valid threshold
+    T0 = CUDART_INF;
+    if (ru_a != NJ_NONE && na > 4) {
+      if (move && ru_a == last) ru_a = wb;
+      if (move && ru_b == last) ru_b = wb;
+      int lo, hi;
+      const double qn = fpq(static_cast<double>(na - 3), C.s_r, ru_a, ru_b, ru_d, lo, hi);
+      if (qn < CUDART_INF) T0 = qn;
     }
     // the merged node's column starts at the current maximal drift, so that it does not raise M
     const double su = ru * inv_new;

@@ -123,7 +123,7 @@ def _nj_counters(engine):
 
 def _check_nj(engine, dist, ld=None, expect_bounded=None):
     """All three NJ kernels through the diagnostic switch: the bounded scan (8: at every size it can take; by default
-    it runs from 3,500 nodes on), the fast full-scan kernel (4) and the general one (2). expect_bounded: whether the
+    it runs from 1,536 nodes on), the fast full-scan kernel (4) and the general one (2). expect_bounded: whether the
     bounded-scan kernel must have joined the matrix itself (True), must have handed it over (False), or either."""
     from phyloforge_b200._lib import check
     n = dist.shape[0]
@@ -186,7 +186,7 @@ def test_nj_batch_matches_oracle_tree_by_tree(engine, k, n, mode):
         torch.cuda.synchronize()
     finally:
         joined = _nj_counters(engine)[3]
-    assert joined == (k if (mode == 8 or (n >= 1536 and k > 1) or n >= 3500) and n >= 8 else 0)
+    assert joined == (k if (mode == 8 or n >= 1536) and n >= 8 else 0)
     for j in range(k):
         want_m, want_l = oracle.nj(mats[j])
         assert np.array_equal(merge[j].cpu().numpy(), want_m), j

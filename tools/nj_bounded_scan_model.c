@@ -100,6 +100,7 @@ int main(int argc, char** argv) {
   int64_t t = 0, bad = 0, iters_resc = 0, max_resc = 0;
   double* du = malloc(n * 8);
   Best* cb = malloc(NC * sizeof(Best)); Best* cb2 = malloc(NC * sizeof(Best));
+  double T0 = INFINITY;   /* exact q of the previous exchange's runner-up in the current frame: a threshold for every CTA */
   while (na > 3) {
     const double n2 = (double)(na - 2), inv = 1.0 / n2;
     /* champions -> the threshold of each CTA */
@@ -113,7 +114,7 @@ int main(int argc, char** argv) {
     memcpy(cb2, cb, NC * sizeof(Best));
     /* bounds that do not clear the threshold: rescan the row, or evaluate its list */
     for (int64_t i = 0; i < na; ++i) {
-      Row* R = &rows[i]; const double T = cb[owner[i]].q, si = r[i] * inv;
+      Row* R = &rows[i]; const double T = fmin(cb[owner[i]].q, T0), si = r[i] * inv;
       if (!(R->R2 == INFINITY) && !bound_clears(R->R2, si, n2, T)) rescan(i, n2, &cb2[owner[i]]);
       else if (!(R->R1 == INFINITY) && !bound_clears(R->R1, si, n2, T)) list_evaluate(i, n2, &cb2[owner[i]]);
     }
@@ -123,6 +124,14 @@ int main(int argc, char** argv) {
     if (n_rescan > resc0) { ++iters_resc; if (n_rescan - resc0 > max_resc) max_resc = n_rescan - resc0; }
     int64_t ba = W.a, bb = W.b;
     if (ba == INT64_MAX) { ba = 0; bb = 1; }
+    /* the runner-up: the best published record whose nodes are not joined now */
+    Best RU = {INFINITY, INT64_MAX, INT64_MAX};
+    for (int c = 0; c < NC; ++c) {
+      const Best x = cb2[c];
+      if (x.a == INT64_MAX || x.a == ba || x.a == bb || x.b == ba || x.b == bb) continue;
+      if (x.q < RU.q || (x.q == RU.q && (x.a < RU.a || (x.a == RU.a && x.b < RU.b)))) RU = x;
+    }
+    const double ru_d = (RU.a != INT64_MAX) ? D[RU.a * ld + RU.b] : 0.0;
     if (node[ba] != mref[3 * t] || node[bb] != mref[3 * t + 1]) {
       if (bad < 5) fprintf(stderr, "MISMATCH t=%lld: (%d,%d) vs oracle (%d,%d)\n", (long long)t, node[ba], node[bb], mref[3 * t], mref[3 * t + 1]);
       ++bad;
@@ -212,6 +221,14 @@ int main(int argc, char** argv) {
     { Row* R = &rows[ba]; for (int g = 0; g < G; ++g) R->col[g] = -1; R->champ = -1; R->R1 = INFINITY; R->R2 = INFINITY; }
     node[ba] = (int32_t)(n + t);
     --na; ++t;
+    T0 = INFINITY;
+    if (RU.a != INT64_MAX && na > 3) {   /* relabelled, in the frame of the next iteration */
+      if (move && RU.a == last) RU.a = bb;
+      if (move && RU.b == last) RU.b = bb;
+      Best x = {INFINITY, INT64_MAX, INT64_MAX};
+      consider(&x, (double)(na - 2), RU.a, RU.b, ru_d);
+      if (x.q < INFINITY) T0 = x.q;
+    }
   }
   printf("n=%lld G=%d ctas=%d epoch=%d perm=%d: mismatches %lld; rescans %.3f / iteration (iterations with one: %lld of %lld, max %lld); "
          "list evaluations %.2f / iteration\n", (long long)n, G, NC, E, perm, (long long)bad, (double)n_rescan / t,
