@@ -26,6 +26,22 @@ import sys
 import time
 
 ENV_RANK, ENV_WORLD, ENV_PORT = "PHYLOFORGE_B200_RANK", "PHYLOFORGE_B200_WORLD", "PHYLOFORGE_B200_PORT"
+ENV_TRACE = "PHYLOFORGE_B200_TRACE"
+
+
+def trace(label: str):
+    """With PHYLOFORGE_B200_TRACE=1: seconds since this process was created, per worker, on stderr."""
+    if not os.environ.get(ENV_TRACE):
+        return
+    try:
+        import psutil
+        t0 = psutil.Process().create_time()
+    except Exception:
+        t0 = _T_IMPORT
+    print(f"[trace rank {os.environ.get(ENV_RANK, '0')}] +{time.time() - t0:7.3f} s  {label}", file=sys.stderr, flush=True)
+
+
+_T_IMPORT = time.time()
 
 
 def worker_env():
@@ -102,8 +118,10 @@ def init_worker(rank: int, world: int) -> int:
             print(f"gpus = {world} but {n_dev} GPU(s) visible: workers share devices and the count matrices are "
                   "summed through gloo on host copies (testing only)")
         kw = {} if shared else {"device_id": torch.device("cuda", device)}
+        trace("cuda device set, joining the process group")
         dist.init_process_group("gloo" if shared else "nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
                                 world_size=world, **kw)
+        trace("process group up")
     return device
 
 

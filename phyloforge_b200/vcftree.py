@@ -124,10 +124,14 @@ class VcfTree(RunCmd):
         t0 = time.perf_counter()
         packed, failure = None, None
         try:
+            multigpu.trace("snp_tree entered")
             eng = self.engine()
+            multigpu.trace("engine ready")
             multigpu.barrier()                           # rank 0 has emptied working_dir before anybody writes there
+            multigpu.trace("first barrier passed")
             packed = vcf.load_snp_vcf(eng, self.vcf_file, keep_chars=True, non_biallelic=self.non_biallelic,
                                       rank=self.rank, world=self.world)
+            multigpu.trace("byte range converted")
         except vcf.VcfFormatError as e:
             failure = e
         if not multigpu.agree_ok(failure is None):
@@ -152,13 +156,16 @@ class VcfTree(RunCmd):
             stem = os.path.splitext(os.path.basename(self.vcf_file))[0]
             chunk = [os.path.join(self.working_dir, f"{stem}{r}.fa") for r in range(self.world)]
             vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
+            multigpu.trace("chunk FASTA written")
             multigpu.barrier()
             infile = f"{self.out_path}/all_snp" + (".fa" if use_fasta else ".phy")
             if chief:
                 multigpu.merge_chunk_fastas(chunk, f"{self.out_path}/all_snp", "fa" if use_fasta else "phylip")
                 if not use_fasta:
                     print(infile)
+            multigpu.trace("chunks merged (rank 0)")
             multigpu.globalise(eng, packed, self.rank, self.world)
+            multigpu.trace("globalised")
         t1 = time.perf_counter()
         n_unfit = getattr(packed, "total_not_2bit", packed.n_not_2bit)
         if chief:
@@ -175,6 +182,7 @@ class VcfTree(RunCmd):
             print(f"[{stamp()}] Constructing tree...")
         multigpu.barrier()
         status = self.built_tree(infile, f"{self.out_path}", basename, 1)
+        multigpu.trace("tree built")
         if chief:
             if status == 0:
                 print(f"[{stamp()}] Finish constructing the SNP tree.")
