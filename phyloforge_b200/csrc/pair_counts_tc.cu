@@ -1351,7 +1351,7 @@ int g_tc_cfg = 0;
 // CTA pairs of the default pair-kernel geometry the device runs at once (B200: 74, one per TPC); -1 when the
 // query itself fails (no device: plans are still computed), 0 when the device cannot co-schedule the cluster
 int tc2_cluster_slots() {
-  static int cached_dev = -1, cached = -1;
+  thread_local int cached_dev = -1, cached = -1;   // per host thread: worker threads of one process drive one device each
   int dev = -1;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
   if (dev == cached_dev) return cached;
@@ -1483,15 +1483,13 @@ typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 TcEncodeTiledFn tc_encode_fn() {
-  static TcEncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const TcEncodeTiledFn fn = [] {   // (initialised once, also when several host threads arrive together)
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<TcEncodeTiledFn>(p);
-  }
+      return reinterpret_cast<TcEncodeTiledFn>(p);
+    return static_cast<TcEncodeTiledFn>(nullptr);
+  }();
   return fn;
 }
 // the operand stream as [step][row group][256 B], box = `steps` x `row_groups` x 256 B

@@ -620,13 +620,13 @@ PF_API int pf_vcf_select_rows(const int32_t* d_line_info, int64_t n_lines, int r
     return pf_fail("pf_vcf_select_rows: bad arguments");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // the 40-byte device summary is allocated once per device and kept for the life of the process (a cudaMalloc /
-  // cudaFree pair per chunk synchronised the whole device every call); calls on one device are serialised by the lock
-  static std::mutex mu;
+  // cudaFree pair per chunk synchronised the whole device every call); calls on one device are serialised by its lock
+  static std::mutex mu[64];   // one per device: worker threads on different devices do not wait for each other
   static SelSummary* d_sum_of[64] = {nullptr};
   int dev = 0;
   PF_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return pf_fail("pf_vcf_select_rows: device index %d out of range", dev);
-  std::lock_guard<std::mutex> lock(mu);
+  std::lock_guard<std::mutex> lock(mu[dev]);
   if (!d_sum_of[dev]) PF_CUDA(cudaMalloc(&d_sum_of[dev], sizeof(SelSummary)));
   SelSummary* d_sum = d_sum_of[dev];
   pf_count_launch();

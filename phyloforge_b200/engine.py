@@ -285,16 +285,16 @@ class Engine:
 
         Blocks: contiguous ranges of the global 32-site word axis, plus (extra_chars: the columns that do not fit
         the 2-bit code, site-major characters) contiguous ranges of those columns, in proportion to their number.
-        Several workers (torch.distributed initialised; word0 / total_cols / extra0 / total_extra place this worker's
+        Several workers (worker threads or a torch.distributed group; word0 / total_cols / extra0 / total_extra place this worker's
         words and extra columns in the whole matrix, phyloforge_b200/multigpu.py): every worker fills its part of
         the block matrices, one allreduce sums them, the replicates are dealt out to the workers in batches of 8
         and their join lists gathered - the draws are a function of (seed, replicate), so the support values do
         not depend on the number of workers."""
-        import torch.distributed as dist
         from .bootstrap import split_support
+        from .multigpu import comm_rank_world
         from .sharding import allreduce_counts, shard_words
-        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        rank, world = (dist.get_rank(), dist.get_world_size()) if multi else (0, 1)
+        rank, world = comm_rank_world()
+        multi = world > 1
         word_end = n_words if n_sites is None else (n_sites + 31) // 32
         local_cols = word_end * 32 if n_sites is None else n_sites
         if total_cols is None:

@@ -12,10 +12,23 @@ So that word ranges of the packed matrix (bootstrap blocks) mean the same sites 
 worker moves its packed columns onto the global 32-site word grid once the column counts of the ranks before it
 are known (``pf_planes_shift``).
 
-Workers are separate processes of the same command line (``python -m phyloforge_b200.run -s cfg``) told their
-rank through the environment; the parent only starts them, relays rank 0's output and exit status, and stops the
-rest if one fails. When there are more workers than visible GPUs (testing on a one-GPU box) the workers share
-devices and the allreduce goes through gloo on host copies — correct, slow, and said so on stdout.
+Two worker models behind the same code (every worker runs ``snp_tree`` / ``sv_tree`` itself and meets the others
+in ``barrier`` / ``agree_ok`` / ``gather_ints`` / ``allreduce_sum`` below):
+
+* ``gpu_workers = threads`` (default): one THREAD per GPU inside this process (``run_threads``). Each thread has
+  its own engine, CUDA stream and pinned staging buffers on its device (the C ABI works on the calling thread's
+  current device; ctypes calls, file reads and kernel launches release the interpreter lock). The count matrices
+  are summed by one in-process NCCL allreduce over all devices (``torch.cuda.nccl``; the communicators are created
+  by a helper thread while the workers convert their byte ranges), or - when workers share a device, or with
+  ``PHYLOFORGE_B200_THREAD_REDUCE=p2p`` - by peer copies over NVLink: device r sums slice r of every peer's matrix
+  and every device then fetches the finished slices. Nothing is started but threads, so `gpus = 8` costs the eight
+  CUDA contexts and nothing else (the process model below spends ~14 s starting eight interpreters and their
+  communicator before the first byte is converted, profiles/r02_vcf_mg8.json).
+* ``gpu_workers = processes``: separate processes of the same command line (``python -m phyloforge_b200.run -s
+  cfg``) told their rank through the environment, joined in a torch.distributed process group (NCCL); the parent
+  only starts them, relays rank 0's output and exit status, and stops the rest if one fails. When there are more
+  workers than visible GPUs (testing on a one-GPU box) the workers share devices and the allreduce goes through
+  gloo on host copies - correct, slow, and said so on stdout.
 """
 from __future__ import annotations
 
@@ -23,10 +36,13 @@ import os
 import socket
 import subprocess
 import sys
+import threading
 import time
+import traceback
 
 ENV_RANK, ENV_WORLD, ENV_PORT = "PHYLOFORGE_B200_RANK", "PHYLOFORGE_B200_WORLD", "PHYLOFORGE_B200_PORT"
 ENV_TRACE = "PHYLOFORGE_B200_TRACE"
+ENV_THREAD_REDUCE = "PHYLOFORGE_B200_THREAD_REDUCE"     # nccl (default) | p2p: how worker THREADS sum their counts
 
 
 def trace(label: str):
@@ -38,14 +54,102 @@ def trace(label: str):
         t0 = psutil.Process().create_time()
     except Exception:
         t0 = _T_IMPORT
-    print(f"[trace rank {os.environ.get(ENV_RANK, '0')}] +{time.time() - t0:7.3f} s  {label}", file=sys.stderr, flush=True)
+    print(f"[trace rank {worker_env()[0]}] +{time.time() - t0:7.3f} s  {label}", file=sys.stderr, flush=True)
 
 
 _T_IMPORT = time.time()
 
 
+class WorkerAborted(RuntimeError):
+    """Another worker thread of the group failed: this one leaves at its next meeting point."""
+
+
+class ThreadGroup:
+    """Meeting points of the worker threads of one `gpus = N` run (gpu_workers = threads)."""
+
+    def __init__(self, world: int):
+        self.world = world
+        self._barrier = threading.Barrier(world)
+        self.slots = [None] * world
+        self.status = [None] * world
+        self.reduce_mode = None           # "nccl" | "p2p", decided by rank 0 at the first allreduce
+        self.reduce_note = ""
+        self._warm = None                 # helper thread creating the NCCL communicators
+        self._warm_error = None
+
+    def barrier(self):
+        try:
+            self._barrier.wait()
+        except threading.BrokenBarrierError:
+            raise WorkerAborted() from None
+
+    def abort(self):
+        self._barrier.abort()
+
+    def exchange(self, rank: int, value):
+        """Every worker's value, in rank order, on every worker."""
+        self.slots[rank] = value
+        self.barrier()
+        out = list(self.slots)
+        self.barrier()                    # nobody overwrites a slot somebody still reads
+        return out
+
+    # -- in-process NCCL: communicators over devices 0..world-1, created while the workers convert
+    def start_nccl_warmup(self):
+        import torch
+        want = os.environ.get(ENV_THREAD_REDUCE, "nccl").strip().lower()
+        if want not in ("nccl", "p2p"):
+            want = "nccl"
+        if want == "p2p":
+            self.reduce_note = f"{ENV_THREAD_REDUCE}=p2p"
+            return
+        if not torch.cuda.is_available() or torch.cuda.device_count() < self.world:
+            self.reduce_note = "workers share devices"
+            return
+
+        def warm():
+            try:
+                import torch.cuda.nccl as nccl
+                ts = [torch.zeros(32, dtype=torch.int32, device=torch.device("cuda", d)) for d in range(self.world)]
+                nccl.all_reduce(ts)
+                for d in range(self.world):
+                    torch.cuda.synchronize(d)
+                trace("in-process NCCL communicators ready")
+            except BaseException as e:  # noqa: BLE001 - reported by rank 0, which then sums through peer copies
+                self._warm_error = e
+
+        self._warm = threading.Thread(target=warm, name="phyloforge-nccl-init", daemon=True)
+        self._warm.start()
+
+    def decide_reduce_mode(self):
+        """Rank 0, once: NCCL when its communicators came up, else peer copies (and why)."""
+        if self.reduce_mode is not None:
+            return
+        if self._warm is None:
+            self.reduce_mode = "p2p"
+            return
+        self._warm.join()
+        if self._warm_error is not None:
+            self.reduce_mode = "p2p"
+            self.reduce_note = f"in-process NCCL failed ({self._warm_error})"
+            print(f"gpus = {self.world}: {self.reduce_note}; the count matrices are summed through peer copies")
+        else:
+            self.reduce_mode = "nccl"
+
+
+_TLS = threading.local()
+
+
+def _thread_ctx():
+    return getattr(_TLS, "ctx", None)       # (rank, ThreadGroup) of a worker thread
+
+
 def worker_env():
-    """(rank, world) of this process: (0, 1) unless it was started by spawn_workers."""
+    """(rank, world) of this worker: a worker thread's (run_threads), else the environment's (spawn_workers),
+    else (0, 1)."""
+    ctx = _thread_ctx()
+    if ctx is not None:
+        return ctx[0], ctx[1].world
     try:
         rank, world = int(os.environ.get(ENV_RANK, "0")), int(os.environ.get(ENV_WORLD, "1"))
     except ValueError:
@@ -101,8 +205,52 @@ def spawn_workers(argv, world: int, poll_s: float = 0.05) -> int:
     return status
 
 
+def _status_of_exit(e: SystemExit) -> int:
+    if e.code is None:
+        return 0
+    return e.code if isinstance(e.code, int) else 1
+
+
+def _thread_main(group: ThreadGroup, rank: int, work):
+    _TLS.ctx = (rank, group)
+    status = 1
+    try:
+        rc = work()
+        status = rc if isinstance(rc, int) else 0
+    except SystemExit as e:                       # the workflow's own exits (bad record, failed child, ...)
+        status = _status_of_exit(e)
+    except WorkerAborted:
+        status = None                             # somebody else failed and said why: that worker's status counts
+    except BaseException:  # noqa: BLE001 - a worker thread must not die silently: the others would wait for it
+        traceback.print_exc()
+        status = 1
+    finally:
+        group.status[rank] = status
+        if status != 0:
+            group.abort()                         # (aborting a broken barrier again is harmless)
+        _TLS.ctx = None
+
+
+def run_threads(work, world: int) -> int:
+    """Run `work()` as `world` worker threads of this process, one per GPU (rank and world reach the workflow
+    through worker_env); returns the exit status: 0 only if every worker returned 0, else the first failure's."""
+    group = ThreadGroup(world)
+    group.start_nccl_warmup()
+    threads = [threading.Thread(target=_thread_main, args=(group, r, work), name=f"phyloforge-worker-{r}")
+               for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for st in group.status:                       # the first worker (in rank order) that failed by itself
+        if st not in (0, None):
+            return st
+    return 0 if all(st == 0 for st in group.status) else 1
+
+
 def init_worker(rank: int, world: int) -> int:
-    """Join the workers' process group; returns the CUDA device index of this worker."""
+    """Bind this worker to its GPU (and, for worker processes, join their process group); returns the CUDA device
+    index of this worker."""
     import torch
     import torch.distributed as dist
     n_dev = torch.cuda.device_count()
@@ -111,6 +259,11 @@ def init_worker(rank: int, world: int) -> int:
         raise PhyloForgeError("no CUDA device: phyloforge_b200 has no CPU fallback")
     device = rank % n_dev
     torch.cuda.set_device(device)
+    if _thread_ctx() is not None:                 # a worker thread: the current device is per thread, nothing to join
+        if world > n_dev and rank == 0:
+            print(f"gpus = {world} but {n_dev} GPU(s) visible: workers share devices (testing only)")
+        trace("cuda device set")
+        return device
     if not dist.is_initialized():
         port = os.environ.get(ENV_PORT, "29541")
         shared = world > n_dev
@@ -128,6 +281,9 @@ def init_worker(rank: int, world: int) -> int:
 def agree_ok(ok: bool) -> bool:
     """True iff every worker says ok (one small allreduce); lets all workers leave together when one of them
     met a record the reference cannot convert."""
+    ctx = _thread_ctx()
+    if ctx is not None:
+        return all(ctx[1].exchange(ctx[0], bool(ok)))
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
@@ -141,6 +297,9 @@ def agree_ok(ok: bool) -> bool:
 
 def gather_ints(values):
     """values (list of ints of this worker) -> [world][len(values)] on every worker."""
+    ctx = _thread_ctx()
+    if ctx is not None:
+        return [list(v) for v in ctx[1].exchange(ctx[0], [int(x) for x in values])]
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
@@ -153,10 +312,84 @@ def gather_ints(values):
     return [[int(x) for x in o.tolist()] for o in out]
 
 
+def gather_local(obj):
+    """Worker threads: every worker's `obj` in rank order (the objects themselves: the workers share an address
+    space). Worker processes: None - they exchange through the files in working_dir, as the reference's do."""
+    ctx = _thread_ctx()
+    if ctx is None:
+        return None
+    return ctx[1].exchange(ctx[0], obj)
+
+
 def barrier():
+    ctx = _thread_ctx()
+    if ctx is not None:
+        ctx[1].barrier()
+        return
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         dist.barrier()
+
+
+def comm_rank_world():
+    """(rank, world) of the group this worker exchanges with: worker threads, a torch.distributed process group
+    (worker processes, torchrun), or (0, 1)."""
+    ctx = _thread_ctx()
+    if ctx is not None:
+        return ctx[0], ctx[1].world
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _sync(t):
+    if t.is_cuda:
+        import torch
+        torch.cuda.current_stream(t.device).synchronize()
+
+
+def thread_allreduce_sum(t):
+    """Sum `t` (int32 counts, same shape on every worker thread, each on its worker's device) over the worker
+    threads, in place. NCCL (one in-process call over all devices) when the workers sit on different GPUs; else -
+    or for a tensor with padded rows - peer copies: worker r sums slice r of every peer's tensor, then every worker
+    fetches the finished slices (a reduce-scatter and an all-gather written as device-to-device copies, over
+    NVLink / NVSwitch between GPUs). Integer sums: the result does not depend on the route."""
+    import torch
+    from .sharding import shard_words
+    rank, group = _thread_ctx()
+    world = group.world
+    _sync(t)                                       # this worker's tensor is complete before anybody reads it
+    peers = group.exchange(rank, t)
+    if rank == 0:
+        group.decide_reduce_mode()
+    group.barrier()
+    if group.reduce_mode == "nccl" and t.is_cuda and all(p.is_contiguous() for p in peers):
+        if rank == 0:
+            import torch.cuda.nccl as nccl
+            nccl.all_reduce(list(peers))           # in place on every device
+            for p in peers:
+                torch.cuda.synchronize(p.device)
+        group.barrier()
+        return t
+    views = [p.view(-1) if p.is_contiguous() else p for p in peers]      # padded rows: cut along the first axis
+    mine = views[rank]
+    n = mine.shape[0]
+    b, e = shard_words(n, world, rank)
+    if e > b:
+        acc = mine[b:e]
+        for p in range(world):
+            if p != rank:
+                acc += views[p][b:e].to(acc.device, non_blocking=True)
+    _sync(t)
+    group.barrier()                                # every slice is finished in its owner's tensor
+    for p in range(world):
+        pb, pe = shard_words(n, world, p)
+        if p != rank and pe > pb:
+            mine[pb:pe].copy_(views[p][pb:pe], non_blocking=True)
+    _sync(t)
+    group.barrier()                                # nobody's tensor changes while a peer still reads it
+    return t
 
 
 def globalise(engine, packed, rank: int, world: int):

@@ -47,7 +47,8 @@ class RunCmd:
                                                 # 126-127, 56-63): they are counted from their characters; or skip / error
         self.bootstrap = 0                      # block-bootstrap replicates (the reference asks treebest for
         self.bootstrap_seed = 1                 # -b 1000, script.py:360); 0 = no support values
-        self.gpus = 1                           # worker processes / GPUs the site axis of the VCF is cut over
+        self.gpus = 1                           # workers / GPUs the site axis of the VCF is cut over
+        self.gpu_workers = "threads"            # one worker thread per GPU in this process; or processes
         from . import multigpu
         self.rank, self.world = multigpu.worker_env()
         self._engine = None
@@ -113,6 +114,10 @@ class RunCmd:
         except ValueError:
             print(f"gpus: {self.gpus} must be a positive integer (or all)")
             sys.exit()
+        self.gpu_workers = str(self.gpu_workers).strip().lower()
+        if self.gpu_workers not in ("threads", "processes"):
+            print(f"gpu_workers: {self.gpu_workers} is not recognized (threads or processes), please check it")
+            sys.exit()
 
     # ------------------------------------------------------------------ config
     def get_config(self, opt_cfg, opt):
@@ -138,12 +143,18 @@ class RunCmd:
         return self._engine
 
     def spawn_if_multi_gpu(self, flag: str):
-        """``gpus = N`` (N > 1) in the parent process: run the same command as N worker processes, one per GPU
-        (phyloforge_b200/multigpu.py), and return their exit status; None when this process should do the work."""
+        """``gpus = N`` (N > 1) in the parent: run this workflow as N workers, one per GPU - threads of this process
+        (default) or processes of the same command line (``gpu_workers = processes``), phyloforge_b200/multigpu.py -
+        and return their exit status; None when the caller is a worker itself and should do the work."""
         if self.gpus <= 1 or self.world > 1:
             return None
         from . import multigpu
-        status = multigpu.spawn_workers([flag, self.cfg_path], self.gpus)
+        if self.gpu_workers == "threads":
+            cls, cfg, kind = type(self), self.cfg_path, self.tree_kind
+            method = {"-s": "snp_tree", "-S": "sv_tree"}[flag]
+            status = multigpu.run_threads(lambda: getattr(cls(cfg, kind), method)(), self.gpus)
+        else:
+            status = multigpu.spawn_workers([flag, self.cfg_path], self.gpus)
         if status != 0:
             sys.exit(status)
         return status

@@ -25,7 +25,11 @@ def shard_sites(n_sites: int, world: int, rank: int):
 def allreduce_counts(counts):
     """Sum the site shards' count matrices over all ranks, in place (NCCL over NVLink on the
     GPUs; gloo in the CPU tests). Integer addition is associative, so the totals are
-    bit-identical for any number of ranks. No-op without an initialised process group."""
+    bit-identical for any number of ranks. Worker threads of one process (gpus = N behind the entry point,
+    multigpu.run_threads) sum through multigpu.thread_allreduce_sum. No-op without a group."""
+    from . import multigpu
+    if multigpu._thread_ctx() is not None:
+        return multigpu.thread_allreduce_sum(counts)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         if counts.is_cuda and dist.get_backend() != "nccl":

@@ -56,9 +56,13 @@ class SvTree(RunCmd):
             os.makedirs(wd, exist_ok=True)
             chunk = [os.path.join(wd, f"SV{r}.matrix") for r in range(self.world)]
             vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
+            shards = multigpu.gather_local(packed.chars)   # worker threads: the shards themselves; processes: None
             multigpu.barrier()
             if chief:
-                os.replace(multigpu.merge_chunk_fastas(chunk, os.path.join(wd, "SV_all"), "fa"), infile)
+                if shards is None:
+                    os.replace(multigpu.merge_chunk_fastas(chunk, os.path.join(wd, "SV_all"), "fa"), infile)
+                else:
+                    vcf.write_fasta(infile, packed.names, shards)
             multigpu.globalise(eng, packed, self.rank, self.world)
         t1 = time.perf_counter()
         if chief:

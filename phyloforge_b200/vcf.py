@@ -10,9 +10,11 @@ packing all run in libphyloforge_b200.so (csrc/vcf_parse.cu, csrc/pack.cu).
 from __future__ import annotations
 
 import ctypes as C
+import io
 import os
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -258,14 +260,36 @@ def byte_range_of_rank(path: str, body_offset: int, rank: int, world: int):
     return max(cut[0], body_offset), max(cut[1], cut[0], body_offset)
 
 
+def _pread_full(fd: int, out, offset: int) -> int:
+    """Positional read of len(out) bytes at `offset` into `out` (fewer only at the end of the file)."""
+    total = 0
+    n = len(out)
+    while total < n:
+        got = os.preadv(fd, [out[total:]], offset + total)
+        if got <= 0:
+            break
+        total += got
+    return total
+
+
 class _ChunkReader:
     """Background reader: fills pinned host buffers with whole lines of the file. A chunk ends just
     after a newline; the partial line behind it is carried to the front of the next buffer. The
     read (page cache -> pinned memory) of chunk k+1 overlaps the GPU work on chunk k."""
 
-    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2, byte_range=None):
+    # plain-text files: a buffer is filled by several positional reads at once (os.preadv releases the interpreter
+    # lock; one thread copies page cache -> pinned memory at ~5 GB/s, which was what the whole conversion waited for)
+    READ_PIECE = 8 << 20
+    READ_THREADS = 8
+
+    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2, byte_range=None, read_threads=None):
         self.path, self.size, self.buf_bytes = path, size, buf_bytes
         self.byte_range = byte_range          # (begin, end) of a plain-text file, cut at line starts
+        if read_threads is None:
+            from . import multigpu
+            world = max(1, multigpu.worker_env()[1])      # worker threads / processes of one box share its cores
+            read_threads = max(1, min(self.READ_THREADS, (os.cpu_count() or 1) // world))
+        self.read_threads = read_threads
         # page-locked staging buffers (plain ones only where no CUDA driver exists: the reader's line cutting is
         # exercised by the CPU tests; the loader itself needs the GPU)
         pin = torch.cuda.is_available()
@@ -279,6 +303,7 @@ class _ChunkReader:
         self.thread.start()
 
     def _run(self):
+        pool = None
         try:
             carry = b""
             done = 0
@@ -289,6 +314,12 @@ class _ChunkReader:
                     f.seek(self.byte_range[0])
                     left = self.byte_range[1] - self.byte_range[0]
                     eof = left <= 0
+                if self.read_threads > 1 and isinstance(f, io.FileIO) and hasattr(os, "preadv"):
+                    pool = ThreadPoolExecutor(self.read_threads, thread_name_prefix="phyloforge-read")
+                    pos = f.tell()
+                    if left is None:
+                        left = max(0, os.fstat(f.fileno()).st_size - pos)
+                        eof = left <= 0
                 while not eof or carry:
                     i = self.free.get()
                     if i is None:
@@ -301,7 +332,25 @@ class _ChunkReader:
                         arr[:k] = np.frombuffer(carry, dtype=np.uint8)
                     filled = k
                     mv = memoryview(arr)
-                    while filled < self.buf_bytes and not eof:
+                    if pool is not None and not eof:
+                        # cut [pos, pos + want) into pieces, one positional read each, all in flight together
+                        want = min(left, self.buf_bytes - filled)
+                        cuts = list(range(0, want, self.READ_PIECE)) + [want]
+                        jobs = [pool.submit(_pread_full, f.fileno(), mv[filled + a:filled + b], pos + a)
+                                for a, b in zip(cuts, cuts[1:])]
+                        got = 0
+                        short = False
+                        for (a, b), job in zip(zip(cuts, cuts[1:]), jobs):
+                            k_got = job.result()
+                            if not short:
+                                got += k_got
+                            short = short or k_got < b - a          # the file ended inside this piece (it shrank)
+                        filled += got
+                        done += got
+                        pos += got
+                        left -= got
+                        eof = left <= 0 or short
+                    while pool is None and filled < self.buf_bytes and not eof:
                         want = mv[filled:] if left is None else mv[filled:filled + min(left, self.buf_bytes - filled)]
                         got = f.readinto(want)
                         if not got:
@@ -329,6 +378,9 @@ class _ChunkReader:
             self.full.put(None)
         except BaseException as e:  # noqa: BLE001 - hand the failure to the consumer
             self.full.put(e)
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=False, cancel_futures=True)
 
     def chunks(self):
         while True:
@@ -529,20 +581,38 @@ def load_sv_vcf(engine, path: str, keep_chars: bool = True,
     return _load(engine, path, "sv", keep_chars, "error", chunk_bytes, rank, world)
 
 
-def write_fasta(path: str, names, chars: np.ndarray):
-    """``>id\\nseq\\n`` per sample (vcftree.py:168-171, svtree.py:122-125)."""
-    with open(path, "wb") as f:
-        for name, row in zip(names, chars):
+def _row_writer(chars):
+    """chars: one [n, m] character matrix, or a list of them (column blocks of the same samples, in order: the
+    workers' shards). Returns (total columns, write(f, i)) where write puts row i of every block into f."""
+    parts = list(chars) if isinstance(chars, (list, tuple)) else [chars]
+    parts = [np.ascontiguousarray(p) for p in parts]
+    total = sum(int(p.shape[1]) for p in parts)
+
+    def write(f, i):
+        for p in parts:
+            if p.shape[1]:
+                f.write(memoryview(p[i]))
+
+    return total, write
+
+
+def write_fasta(path: str, names, chars):
+    """``>id\\nseq\\n`` per sample (vcftree.py:168-171, svtree.py:122-125). chars: a matrix or a list of column
+    blocks (concatenated per sample, what merge_seq does with the chunk files, vcftree.py:145-157)."""
+    _, write = _row_writer(chars)
+    with open(path, "wb", buffering=1 << 20) as f:
+        for i, name in enumerate(names):
             f.write(b">" + name.encode() + b"\n")
-            f.write(row.tobytes())
+            write(f, i)
             f.write(b"\n")
 
 
-def write_phylip(path: str, names, chars: np.ndarray):
+def write_phylip(path: str, names, chars):
     """``N L`` then ``id  seq`` per sample (vcftree.py:159-166)."""
-    with open(path, "wb") as f:
-        f.write(f"{len(names)} {chars.shape[1]}\n".encode())
-        for name, row in zip(names, chars):
+    total, write = _row_writer(chars)
+    with open(path, "wb", buffering=1 << 20) as f:
+        f.write(f"{len(names)} {total}\n".encode())
+        for i, name in enumerate(names):
             f.write(name.encode() + b"  ")
-            f.write(row.tobytes())
+            write(f, i)
             f.write(b"\n")

@@ -157,10 +157,14 @@ class VcfTree(RunCmd):
             chunk = [os.path.join(self.working_dir, f"{stem}{r}.fa") for r in range(self.world)]
             vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
             multigpu.trace("chunk FASTA written")
+            shards = multigpu.gather_local(packed.chars)   # worker threads: the shards themselves; processes: None
             multigpu.barrier()
             infile = f"{self.out_path}/all_snp" + (".fa" if use_fasta else ".phy")
             if chief:
-                multigpu.merge_chunk_fastas(chunk, f"{self.out_path}/all_snp", "fa" if use_fasta else "phylip")
+                if shards is None:
+                    multigpu.merge_chunk_fastas(chunk, f"{self.out_path}/all_snp", "fa" if use_fasta else "phylip")
+                else:                                      # the same concatenation, without reading the chunks back
+                    (vcf.write_fasta if use_fasta else vcf.write_phylip)(infile, packed.names, shards)
                 if not use_fasta:
                     print(infile)
             multigpu.trace("chunks merged (rank 0)")

@@ -1,8 +1,9 @@
-"""`gpus = N` through the entry point: N worker processes, each converting its byte range of the VCF on its GPU,
-count matrices summed over the workers, rank 0 writing the artefacts - the outputs must equal the one-GPU run
-byte for byte (character matrix, distance matrix, tree with bootstrap support). On a box with fewer GPUs than
-workers the workers share a device and sum through gloo (multigpu.init_worker), which exercises everything but
-NCCL itself; with `gpurun --gpus 2` the same tests run over NCCL."""
+"""`gpus = N` through the entry point: N workers (threads of this process by default, processes with
+`gpu_workers = processes`), each converting its byte range of the VCF on its GPU, count matrices summed over the
+workers, rank 0 writing the artefacts - the outputs must equal the one-GPU run byte for byte (character matrix,
+distance matrix, tree with bootstrap support). On a box with fewer GPUs than workers the workers share a device
+(threads sum through device-to-device copies, processes through gloo), which exercises everything but NCCL itself;
+with `gpurun --gpus 2` the same tests run over NCCL (in-process for threads, a process group for processes)."""
 import json
 import os
 
@@ -49,15 +50,16 @@ def _run(tmp_path, tag, section, flag, src, tool, extra):
     return out
 
 
-@pytest.mark.parametrize("gpus", [2, 3])
-def test_snp_entry_point_with_several_workers_equals_one_gpu(engine, tmp_path, gpus):
+@pytest.mark.parametrize("gpus,workers", [(2, "threads"), (3, "threads"), (8, "threads"), (2, "processes")])
+def test_snp_entry_point_with_several_workers_equals_one_gpu(engine, tmp_path, gpus, workers):
     """multi-allelic / '*' sites included, both metrics' ingredients, seeded bootstrap: every artefact identical."""
     text, _ = vcfgen.random_snp_vcf(17, 41, 2600, miss=0.04, multi_p=0.15, star_p=0.04)
     src = tmp_path / "in.vcf"
     src.write_text(text)
     extra = "distance = ibs\nbootstrap = 24\nbootstrap_seed = 5\n"
     one = _run(tmp_path, "1", "snp_opt", "-s", src, "treebest", extra)
-    many = _run(tmp_path, str(gpus), "snp_opt", "-s", src, "treebest", extra + f"gpus = {gpus}\n")
+    many = _run(tmp_path, str(gpus), "snp_opt", "-s", src, "treebest",
+                extra + f"gpus = {gpus}\ngpu_workers = {workers}\n")
     for name in ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX"):
         assert (one / name).read_bytes() == (many / name).read_bytes(), name
     rep1 = json.loads((one / "SNP.phyloforge_b200.json").read_text())
@@ -80,10 +82,11 @@ def test_snp_phylip_for_external_tools_with_two_workers(engine, golden_dir, tmp_
     assert (out / "all_snp.phy").read_bytes() == open(os.path.join(golden_dir, "snp_rand_a.all_snp.phy"), "rb").read()
 
 
-def test_sv_entry_point_with_two_workers_equals_one_gpu(engine, golden_dir, tmp_path):
+@pytest.mark.parametrize("workers", ["threads", "processes"])
+def test_sv_entry_point_with_two_workers_equals_one_gpu(engine, golden_dir, tmp_path, workers):
     src = os.path.join(golden_dir, "sv_rand_b.vcf")
     one = _run(tmp_path, "1", "sv_opt", "-S", src, "nj", "bootstrap = 8\n")
-    two = _run(tmp_path, "2", "sv_opt", "-S", src, "nj", "bootstrap = 8\ngpus = 2\n")
+    two = _run(tmp_path, "2", "sv_opt", "-S", src, "nj", f"bootstrap = 8\ngpus = 2\ngpu_workers = {workers}\n")
     assert (two / "SV.matrix").read_bytes() == open(os.path.join(golden_dir, "sv_rand_b.SV.matrix"), "rb").read()
     for name in ("SV.matrix", "SV.dist", "SV.treefile"):
         assert (one / name).read_bytes() == (two / name).read_bytes(), name
@@ -96,10 +99,14 @@ def test_a_bad_record_in_one_workers_range_fails_the_whole_run(engine, tmp_path,
     src = tmp_path / "bad.vcf"
     src.write_text("\n".join(lines) + "\n")
     cfg = tmp_path / "run.cfg"
-    _cfg(cfg, "snp_opt", src, tmp_path / "out", "treebest", "gpus = 2\n")
-    with pytest.raises(SystemExit) as ei:
-        run.main(["-s", str(cfg)])
-    assert ei.value.code == 1
+    for workers in ("threads", "processes"):
+        _cfg(cfg, "snp_opt", src, tmp_path / "out", "treebest", f"gpus = 2\ngpu_workers = {workers}\n")
+        with pytest.raises(SystemExit) as ei:
+            run.main(["-s", str(cfg)])
+        assert ei.value.code == 1
+        out = capsys.readouterr().out
+        if workers == "threads":                   # (worker processes print to the terminal, not through capsys)
+            assert "allele index out of range" in out and "worker 1" in out
 
 
 def test_more_workers_than_lines(engine, tmp_path):
@@ -110,3 +117,18 @@ def test_more_workers_than_lines(engine, tmp_path):
     four = _run(tmp_path, "4", "snp_opt", "-s", src, "treebest", "gpus = 4\n")
     for name in ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX"):
         assert (one / name).read_bytes() == (four / name).read_bytes(), name
+
+
+def test_worker_threads_leave_the_caller_single(engine, tmp_path):
+    """After a `gpus = N` run on worker threads the calling thread is an ordinary one-GPU caller again, and the
+    engine the test session holds still works on its device."""
+    from phyloforge_b200 import multigpu
+    text, _ = vcfgen.random_snp_vcf(23, 200, 900, miss=0.02, multi_p=0.0, star_p=0.0)
+    src = tmp_path / "in.vcf"
+    src.write_text(text)
+    a = _run(tmp_path, "a", "snp_opt", "-s", src, "treebest", "gpus = 2\n")
+    assert multigpu.worker_env() == (0, 1) and multigpu.comm_rank_world() == (0, 1)
+    b = _run(tmp_path, "b", "snp_opt", "-s", src, "treebest", "")
+    for name in ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX"):
+        assert (a / name).read_bytes() == (b / name).read_bytes(), name
+    assert torch.cuda.current_device() == engine.device.index

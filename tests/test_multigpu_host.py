@@ -98,6 +98,11 @@ def test_merge_chunk_fastas_is_merge_seq(tmp_path):
     out = multigpu.merge_chunk_fastas(paths, str(tmp_path / "all_snp"), "phylip")
     vcf.write_phylip(str(tmp_path / "want.phy"), names, whole)
     assert open(out, "rb").read() == open(tmp_path / "want.phy", "rb").read()
+    # worker threads hand the shards themselves to the writers (no chunk file is read back): the same bytes
+    vcf.write_fasta(str(tmp_path / "parts.fa"), names, blocks)
+    vcf.write_phylip(str(tmp_path / "parts.phy"), names, [b[:, ::1] for b in blocks])
+    assert open(tmp_path / "parts.fa", "rb").read() == open(tmp_path / "want.fa", "rb").read()
+    assert open(tmp_path / "parts.phy", "rb").read() == open(tmp_path / "want.phy", "rb").read()
 
 
 def test_bootstrap_block_plan_depends_on_the_whole_matrix_only():
@@ -163,3 +168,144 @@ def test_planes_shift_restatement():
     want = oracle.pack_planes(padded)
     got = oracle.shift_planes(oracle.pack_planes(codes), n, m, shift)
     assert np.array_equal(got, want)
+
+
+# ---------------------------------------------------------------- worker threads (gpu_workers = threads)
+def _threads(world, body):
+    """Run body(rank) on `world` worker threads of a ThreadGroup; returns (status, per-rank results)."""
+    results = [None] * world
+
+    def work():
+        rank, w = multigpu.worker_env()
+        assert w == world
+        results[rank] = body(rank)
+        return 0
+
+    return multigpu.run_threads(work, world), results
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_worker_threads_exchange_helpers(world):
+    def body(rank):
+        assert multigpu.comm_rank_world() == (rank, world)
+        table = multigpu.gather_ints([10 + rank, 7])
+        assert table == [[10 + r, 7] for r in range(world)]
+        assert multigpu.agree_ok(True) is True
+        assert multigpu.agree_ok(rank != world - 1) is False
+        multigpu.barrier()
+        return "ok"
+
+    status, results = _threads(world, body)
+    assert status == 0 and results == ["ok"] * world
+    assert multigpu.worker_env() == (0, 1) and multigpu.comm_rank_world() == (0, 1)     # the caller is no worker
+
+
+@pytest.mark.parametrize("world,shape", [(2, (3, 5, 5)), (3, (3, 7, 7)), (8, (3, 2, 2)), (4, (5,)), (5, (2, 3))])
+def test_worker_threads_sum_counts_through_slices(world, shape):
+    """thread_allreduce_sum without NCCL (host tensors here; device tensors of workers that share a GPU in the -m gpu
+    tests): every worker ends with the integer sum, also when there are more workers than elements per slice."""
+    import torch
+    rng = np.random.default_rng(world)
+    parts = [rng.integers(-1000, 1000, size=shape).astype(np.int32) for _ in range(world)]
+    want = sum(p.astype(np.int64) for p in parts).astype(np.int32)
+
+    def body(rank):
+        t = torch.from_numpy(parts[rank].copy())
+        out = sharding.allreduce_counts(t)
+        assert out is t
+        again = torch.from_numpy(parts[rank].copy())           # a second call in the same group
+        sharding.allreduce_counts(again)
+        return t.numpy(), again.numpy()
+
+    status, results = _threads(world, body)
+    assert status == 0
+    for got, again in results:
+        assert np.array_equal(got, want) and np.array_equal(again, want)
+
+
+def test_worker_threads_sum_rows_with_padding():
+    """Block matrices with a padded row stride (engine.bootstrap_tree) are cut along the first axis."""
+    import torch
+    world = 3
+    base = [torch.arange(4 * 10, dtype=torch.int32).reshape(4, 10) * (r + 1) for r in range(world)]
+
+    def body(rank):
+        view = base[rank].as_strided((4, 7), (10, 1))
+        assert not view.is_contiguous()
+        sharding.allreduce_counts(view)
+        return base[rank].clone()
+
+    status, results = _threads(world, body)
+    assert status == 0
+    want = torch.arange(40, dtype=torch.int32).reshape(4, 10) * 6
+    for r, got in enumerate(results):
+        assert torch.equal(got[:, :7], want[:, :7])
+        assert torch.equal(got[:, 7:], (torch.arange(40, dtype=torch.int32).reshape(4, 10) * (r + 1))[:, 7:])   # padding untouched
+
+
+def test_a_failing_worker_thread_fails_the_run_and_releases_the_others():
+    def work():
+        rank, _ = multigpu.worker_env()
+        if rank == 1:
+            sys.exit(3)                       # the workflow's own exit (a record the reference cannot convert, ...)
+        multigpu.barrier()                    # the others would wait here forever
+        return 0
+
+    assert multigpu.run_threads(work, 3) == 3
+
+    def work2():
+        if multigpu.worker_env()[0] == 0:
+            raise RuntimeError("boom")
+        multigpu.gather_ints([1])
+        return 0
+
+    assert multigpu.run_threads(work2, 2) == 1
+    assert multigpu.run_threads(lambda: None, 2) == 0      # a workflow that returns nothing succeeded
+
+
+def test_gpu_workers_config_key(tmp_path, capsys):
+    from phyloforge_b200.script import RunCmd
+    src = tmp_path / "x.vcf"
+    src.write_text("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\tA\tB\n")
+    cfg = tmp_path / "run.cfg"
+    base = f"[snp_opt]\nvcf_file = {src}\nout_path = {tmp_path / 'out'}\ntree_software = treebest\nthread = 4\n"
+    cfg.write_text(base)
+    assert RunCmd(str(cfg), "snp").gpu_workers == "threads"            # default: worker threads of one process
+    cfg.write_text(base + "gpus = 2\ngpu_workers = Processes\n")
+    rc = RunCmd(str(cfg), "snp")
+    assert (rc.gpus, rc.gpu_workers) == (2, "processes")
+    cfg.write_text(base + "gpu_workers = fibers\n")
+    with pytest.raises(SystemExit):
+        RunCmd(str(cfg), "snp")
+    assert "gpu_workers" in capsys.readouterr().out
+
+
+@pytest.mark.parametrize("threads", [1, 3, 8])
+def test_chunk_reader_with_several_positional_reads_per_buffer(golden_dir, monkeypatch, threads):
+    """A buffer of a plain-text file is filled by several reads in flight at once (pieces of READ_PIECE bytes): the
+    chunks handed out are the same whole lines, for the whole file and for a worker's byte range."""
+    monkeypatch.setattr(vcf._ChunkReader, "READ_PIECE", 1000)
+    path = os.path.join(golden_dir, "snp_rand_b.vcf")
+    data, body = _body_lines(path)
+    longest = max(len(ln) for ln in data.split(b"\n")) + 2
+
+    def read(rng, buf):
+        reader = vcf._ChunkReader(path, len(data) if rng is None else rng[1] - rng[0], buf, byte_range=rng,
+                                  read_threads=threads)
+        out = []
+        try:
+            for bi, nb in reader.chunks():
+                chunk = bytes(reader.bufs[bi].numpy()[:nb])
+                assert chunk.endswith(b"\n") or len(b"".join(out)) + len(chunk) == len(data) - (0 if rng is None else rng[0])
+                out.append(chunk)
+                reader.release(bi)
+        finally:
+            reader.close()
+        return b"".join(out)
+
+    for buf in (2 * longest, 7919, 1 << 20):
+        buf = max(buf, 2 * longest)
+        assert read(None, buf) == data
+        for world in (2, 3):
+            got = b"".join(read(vcf.byte_range_of_rank(path, body, r, world), buf) for r in range(world))
+            assert got == data[body:]
