@@ -12,6 +12,10 @@
  *    Python side); h_* are host pointers. No entry point allocates memory that outlives
  *    the call unless documented. `stream` is a cudaStream_t passed as void* (NULL = the
  *    default stream). Calls are asynchronous on `stream` unless documented.
+ *  - devices and threads: every call acts on the calling thread's CURRENT device (cudaSetDevice); a host that
+ *    drives several GPUs calls from one thread per device (phyloforge_b200/multigpu.py: gpu_workers = threads).
+ *    Calls from different threads on different devices do not wait for each other; the A/B and profiling switches
+ *    (pf_*_set_impl, pf_*_profile, pf_*_timing) are process-wide and meant for single-threaded diagnostic runs.
  *  - genotype codes: 0 hom-REF, 1 HET, 2 hom-ALT, 3 missing.
  *  - packed layout ("planes"): uint32 words; sample tile T = i / PF_TILE (64), site word
  *    w = s / 32, plane p (0 = low code bit L, 1 = high code bit H):
@@ -273,6 +277,13 @@ PF_API int pf_nj_batch(double* d_dist, int64_t n, int64_t ld, int n_mat, int64_t
 PF_API int64_t pf_newick_from_merges(const int32_t* h_merge, const double* h_len, int64_t n,
                                      const char* const* names, const double* h_support, char* h_out,
                                      int64_t capacity);
+
+/* Host-side: the PHYLIP square distance matrix file that stands beside the tree (`{out}/SNP.dist`, SURVEY.md 8(f).2;
+ * the reference's tree step is `treebest nj`, treetool/script.py:359-360): the line "n", then per sample its label,
+ * two blanks and its n distances as "%.<decimals>f" separated by single blanks (correctly rounded, the digits Python's
+ * and glibc's formatting give). h_dist: n rows of ld doubles in host memory. n_threads <= 0: all host threads. */
+PF_API int pf_write_distance_matrix(const char* path, const char* const* names, int64_t n, const double* h_dist,
+                                    int64_t ld, int decimals, int n_threads);
 
 /* Block bootstrap (csrc/bootstrap.cu; the reproducible counterpart of the `-b 1000` the reference passes to
  * `treebest nj`, treetool/script.py:359-360). The caller keeps the count matrices of n_blocks contiguous

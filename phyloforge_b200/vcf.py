@@ -398,6 +398,101 @@ class _ChunkReader:
         self.free.put(None)
 
 
+class _CharSink:
+    """Where the character matrix of the alignment file (all_snp.fa / SV.matrix) goes as the chunks are converted:
+    every chunk's [n, columns] block is copied device -> one of two page-locked staging buffers (asynchronously,
+    behind the kernels that made it) and from there, by a host thread, into its columns of the result - one pageable
+    [n, bound] array when the text size bounds the columns (its untouched tail costs nothing), else a list of
+    blocks joined at the end. Page-locking a fresh buffer per chunk cost more than the copy it served."""
+
+    COPY_THREADS = 4
+
+    def __init__(self, n: int, cols_bound):
+        self.n, self.off, self.error = n, 0, None
+        self.final = None
+        if cols_bound is not None:
+            try:
+                self.final = np.empty((n, max(1, int(cols_bound))), dtype=np.uint8)
+            except MemoryError:
+                self.final = None
+        self.blocks = []
+        self.staging = [None, None]
+        self.free = [threading.Event(), threading.Event()]
+        for e in self.free:
+            e.set()
+        self.k = 0
+        self.q = queue.Queue()
+        self.pool = ThreadPoolExecutor(self.COPY_THREADS, thread_name_prefix="phyloforge-chars") if n >= 64 else None
+        self.thread = threading.Thread(target=self._run, name="phyloforge-chars", daemon=True)
+        self.thread.start()
+
+    def push(self, block: torch.Tensor):
+        """block: device uint8 [n, c], complete on the current stream once the work queued so far has run."""
+        c = int(block.shape[1])
+        k = self.k
+        self.k ^= 1
+        self.free[k].wait()
+        if self.error is not None:
+            raise self.error
+        self.free[k].clear()
+        need = self.n * c
+        if self.staging[k] is None or self.staging[k].numel() < need:
+            self.staging[k] = None
+            self.staging[k] = torch.empty(need + need // 8, dtype=torch.uint8).pin_memory()
+        stage = self.staging[k][:need].view(self.n, c)
+        stage.copy_(block, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record()
+        self.q.put((k, done, stage, block))        # (the device block stays alive until its copy has run)
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                if self.pool is not None:
+                    self.pool.shutdown(wait=False)
+                return
+            k, done, stage, _block = item
+            try:
+                if self.error is None:
+                    done.synchronize()
+                    c = stage.shape[1]
+                    if self.final is not None and self.off + c <= self.final.shape[1]:
+                        src, dst = stage.numpy(), self.final[:, self.off:self.off + c]
+                        if self.pool is None or self.n * c < (8 << 20):
+                            dst[:] = src
+                        else:                            # row ranges on a few threads (numpy copies outside the lock)
+                            cuts = [self.n * j // self.COPY_THREADS for j in range(self.COPY_THREADS + 1)]
+                            jobs = [self.pool.submit(np.copyto, dst[a:b], src[a:b]) for a, b in zip(cuts, cuts[1:]) if b > a]
+                            for job in jobs:
+                                job.result()
+                    else:
+                        if self.final is not None:       # more columns than the bound (cannot happen for text that
+                            self.blocks.append(self.final[:, :self.off].copy())   # parses): keep going in blocks
+                            self.final = None
+                        self.blocks.append(stage.numpy().copy())
+                    self.off += c
+            except BaseException as e:  # noqa: BLE001 - handed to the loader
+                self.error = e
+            finally:
+                self.free[k].set()
+
+    def finish(self) -> np.ndarray:
+        self.q.put(None)
+        self.thread.join()
+        if self.error is not None:
+            raise self.error
+        if self.final is not None:
+            return self.final[:, :self.off]
+        if not self.blocks:
+            return np.zeros((self.n, 0), dtype=np.uint8)
+        return self.blocks[0] if len(self.blocks) == 1 else np.concatenate(self.blocks, axis=1)
+
+    def abandon(self):
+        if self.thread.is_alive():
+            self.q.put(None)
+
+
 def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, chunk_bytes: int,
           rank: int = 0, world: int = 1):
     lib, dev = engine.lib, engine.device
@@ -465,7 +560,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     n_lines_total = _HEADER_LINES.get(path, 0) if (world > 1 and rank == 0) else 0
     n_unfit_total = 0
     h2d = 0
-    char_blocks = []
+    sink = _CharSink(n, (size // min_line + 2) * rpl if known else None) if keep_chars else None
     extra_blocks = []
     summary = (C.c_int64 * 5)()
     parse = lib.pf_vcf_snp_parse if kind == "snp" else lib.pf_vcf_sv_parse
@@ -523,10 +618,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 extra_blocks.append(d_chars.index_select(0, is_unfit.nonzero().flatten()))
             if keep_chars:
                 if n_all:
-                    block = engine.transpose_u8(d_chars, n, rows=rows_all, n_rows=n_all)
-                    host_block = torch.empty(block.shape, dtype=torch.uint8).pin_memory()
-                    host_block.copy_(block, non_blocking=True)
-                    char_blocks.append(host_block)
+                    sink.push(engine.transpose_u8(d_chars, n, rows=rows_all, n_rows=n_all))
             # pack: full words now, remainder carried to the next chunk
             d_rows[carry_rows:carry_rows + n_cols] += carry_rows        # rows index into d_codes
             first = carry_rows - n_carry
@@ -553,14 +645,17 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
             engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done, rows=rows, n_sites=n_carry)
         n_sites = words_done * 32 + n_carry
         torch.cuda.current_stream().synchronize()
+    except BaseException:
+        if sink is not None:
+            sink.abandon()             # the copier thread ends behind what was queued
+        raise
     finally:
         reader.close()
 
     chars = None
     n_columns = n_sites
     if keep_chars:
-        chars = (np.concatenate([b.numpy() for b in char_blocks], axis=1) if len(char_blocks) != 1
-                 else char_blocks[0].numpy()) if char_blocks else np.zeros((n, 0), dtype=np.uint8)
+        chars = sink.finish()
         n_columns = chars.shape[1]
     return PackedGenotypes(names=names, n_samples=n, n_sites=n_sites, n_words=n_words_cap, planes=planes,
                            chars=chars, n_columns=n_columns, n_lines=n_lines_total,
@@ -581,38 +676,82 @@ def load_sv_vcf(engine, path: str, keep_chars: bool = True,
     return _load(engine, path, "sv", keep_chars, "error", chunk_bytes, rank, world)
 
 
-def _row_writer(chars):
-    """chars: one [n, m] character matrix, or a list of them (column blocks of the same samples, in order: the
-    workers' shards). Returns (total columns, write(f, i)) where write puts row i of every block into f."""
-    parts = list(chars) if isinstance(chars, (list, tuple)) else [chars]
-    parts = [np.ascontiguousarray(p) for p in parts]
+PARALLEL_WRITE_MIN_BYTES = 32 << 20
+WRITE_THREADS = 8
+
+
+def _pwritev_all(fd: int, bufs, offset: int):
+    """All of `bufs` at `offset` (a positional write may stop short: very long rows, signals)."""
+    bufs = [memoryview(b).cast("B") for b in bufs if len(b)]
+    while bufs:
+        done = os.pwritev(fd, bufs[:512], offset)
+        offset += done
+        while bufs and done >= len(bufs[0]):
+            done -= len(bufs[0])
+            bufs.pop(0)
+        if bufs and done:
+            bufs[0] = bufs[0][done:]
+
+
+def _write_rows(path: str, first_line: bytes, heads, chars, threads=None):
+    """first_line, then per sample i: heads[i], row i of every block of `chars`, a newline. chars: one [n, m]
+    character matrix or a list of them (column blocks of the same samples in order: the workers' shards, concatenated
+    per sample as merge_seq does with the chunk files, vcftree.py:145-157); rows must be contiguous. Large files are
+    written by several threads with positional writes at the rows' offsets (one thread copies into the page cache
+    at ~3 GB/s, which made the alignment file the longest step of a converted VCF)."""
+    parts = [p for p in (list(chars) if isinstance(chars, (list, tuple)) else [chars])]
+    parts = [p if p.ndim == 2 and (p.shape[1] == 0 or p.strides[1] == 1) else np.ascontiguousarray(p) for p in parts]
+    parts = [p for p in parts if p.shape[1]]
     total = sum(int(p.shape[1]) for p in parts)
+    n = len(heads)
+    if threads is None:
+        try:
+            threads = int(os.environ.get("PHYLOFORGE_B200_WRITE_THREADS", WRITE_THREADS))
+        except ValueError:
+            threads = WRITE_THREADS
+        threads = max(1, min(threads, os.cpu_count() or 1))
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    offsets[0] = len(first_line)
+    if n:
+        offsets[1:] = len(first_line) + np.cumsum([len(h) + total + 1 for h in heads])
+    size = int(offsets[n])
+    if threads <= 1 or size < PARALLEL_WRITE_MIN_BYTES or n < 2 or not hasattr(os, "pwritev"):
+        with open(path, "wb", buffering=1 << 20) as f:
+            f.write(first_line)
+            for i in range(n):
+                f.write(heads[i])
+                for p in parts:
+                    f.write(memoryview(p[i]))
+                f.write(b"\n")
+        return total
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o666)
+    try:
+        os.ftruncate(fd, size)
+        if first_line:
+            _pwritev_all(fd, [first_line], 0)
 
-    def write(f, i):
-        for p in parts:
-            if p.shape[1]:
-                f.write(memoryview(p[i]))
+        def job(lo, hi):
+            for i in range(lo, hi):
+                _pwritev_all(fd, [heads[i], *[p[i] for p in parts], b"\n"], int(offsets[i]))
 
-    return total, write
+        n_jobs = min(n, 4 * threads)
+        cuts = [n * j // n_jobs for j in range(n_jobs + 1)]
+        with ThreadPoolExecutor(threads, thread_name_prefix="phyloforge-write") as pool:
+            for fut in [pool.submit(job, a, b) for a, b in zip(cuts, cuts[1:]) if b > a]:
+                fut.result()
+    finally:
+        os.close(fd)
+    return total
 
 
-def write_fasta(path: str, names, chars):
+def write_fasta(path: str, names, chars, threads=None):
     """``>id\\nseq\\n`` per sample (vcftree.py:168-171, svtree.py:122-125). chars: a matrix or a list of column
-    blocks (concatenated per sample, what merge_seq does with the chunk files, vcftree.py:145-157)."""
-    _, write = _row_writer(chars)
-    with open(path, "wb", buffering=1 << 20) as f:
-        for i, name in enumerate(names):
-            f.write(b">" + name.encode() + b"\n")
-            write(f, i)
-            f.write(b"\n")
+    blocks (see _write_rows)."""
+    _write_rows(path, b"", [b">" + name.encode() + b"\n" for name in names], chars, threads)
 
 
-def write_phylip(path: str, names, chars):
+def write_phylip(path: str, names, chars, threads=None):
     """``N L`` then ``id  seq`` per sample (vcftree.py:159-166)."""
-    total, write = _row_writer(chars)
-    with open(path, "wb", buffering=1 << 20) as f:
-        f.write(f"{len(names)} {total}\n".encode())
-        for i, name in enumerate(names):
-            f.write(name.encode() + b"  ")
-            write(f, i)
-            f.write(b"\n")
+    parts = list(chars) if isinstance(chars, (list, tuple)) else [chars]
+    total = sum(int(p.shape[1]) for p in parts)
+    _write_rows(path, f"{len(names)} {total}\n".encode(), [name.encode() + b"  " for name in names], chars, threads)

@@ -303,3 +303,40 @@ def test_bgzf_reader_inflates_blocks_in_order(tmp_path):
             buf = bytearray(1 << 20)
             while r.readinto(buf):
                 pass
+
+
+@pytest.mark.parametrize("decimals", [10, 6, 0])
+def test_native_distance_writer_matches_python_formatting(tmp_path, decimals):
+    """pf_write_distance_matrix (host threads, exact 128-bit fixed-point formatting) against Python's "%.<d>f": ties at
+    the last digit, rationals k / V as the path produces them, zeros, tiny and large values, NaN, padded rows."""
+    rng = np.random.default_rng(decimals)
+    n = 211
+    vals = [0.0, 1.0, 0.5, 0.25, 0.125, 2.0 ** -33, 2.0 ** -34, 2.0 ** -35, 3 * 2.0 ** -35, 5e-11, 1.5e-10, 2.5e-10,
+            0.99999999995, 0.999999999949999, 1023.99999999995, 1e-300, 5e-324, 1024.0, 123456.789, 1e22, -0.25,
+            float("nan"), 0.30000000000000004, 1 / 3, 2 / 3, 0.1, 0.7]
+    vals += [k / (1 << 11) + 2.0 ** -12 for k in range(40)]                       # exact ties for few decimals
+    vals += [(2 * k + 1) / 2 ** (decimals + 1) / 5.0 ** decimals for k in range(40)]   # close to ...5 at the last digit
+    v = rng.integers(1, 10_000_000, size=n * n)
+    k = (rng.random(n * n) * v).astype(np.int64)
+    d = (k / v).reshape(n, n)
+    flat = d.reshape(-1)
+    flat[:len(vals)] = vals
+    ld = n + 5
+    padded = np.full((n, ld), 7.0)
+    padded[:, :n] = d
+    names = [f"s{i}" for i in range(n)]
+    names[3] = "with blank"
+    want = tmp_path / "want.dist"
+    phylip.write_distance_matrix_py(str(want), names, d, fmt=f"%.{decimals}f")
+    for threads in (1, 3, 0):
+        got = tmp_path / f"got{threads}.dist"
+        phylip.write_distance_matrix(str(got), names, padded[:, :n] if threads else d, decimals=decimals, threads=threads)
+        assert got.read_bytes() == want.read_bytes(), threads
+    # empty and one-sample matrices; an unwritable path fails loudly
+    phylip.write_distance_matrix(str(tmp_path / "e.dist"), [], np.zeros((0, 0)))
+    assert (tmp_path / "e.dist").read_bytes() == b"0\n"
+    phylip.write_distance_matrix(str(tmp_path / "o.dist"), ["x"], np.zeros((1, 1)), decimals=2)
+    assert (tmp_path / "o.dist").read_bytes() == b"1\nx  0.00\n"
+    from phyloforge_b200._lib import PhyloForgeError
+    with pytest.raises(PhyloForgeError):
+        phylip.write_distance_matrix(str(tmp_path / "no" / "such" / "dir.dist"), ["x"], np.zeros((1, 1)))
