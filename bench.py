@@ -68,6 +68,11 @@ DTYPE = ("e2m1 x e2m1 -> f32 tensor-core indicator products (exact: integers < 2
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
 NCU_TRAFFIC_BYTES_TC = 54_051_894_000  # r01: 52.15 GB read + 1.90 GB written per launch of pair_counts_tc2_kernel (profiles/r01_ncu_pair_counts_tc2_raw_subset.csv), N=1
+# r02 (profiles/r02_ncu_counts_stage_raw_subset.csv, launches over 2,000,000 sites x 3,000 samples): pack_kernel 6.720 GB read + 1.489 GB written against 6.0 + 1.5 GB algorithmic;
+# planes_to_e2m1_kernel 2.179 GB read + 3.208 GB written against 1.5 + 3.1 GB
+NCU_TRAFFIC_BYTES_PACK = 8_209_060_000
+NCU_TRAFFIC_SITES_PACK = 2_000_000
+NCU_TRAFFIC_BYTES_CONV = 5_386_406_000
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
@@ -598,7 +603,13 @@ def run_ours(args):
     pack_bytes = my_sites * ld + my_words * ((n + 63) // 64) * 64 * 8
     roofline_pack = {"bound": "hbm", "achieved": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9 / hbm_peak,
-                     "traffic": None, "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"], "peak_source": hbm_src}
+                     "traffic": int(NCU_TRAFFIC_BYTES_PACK * my_sites / NCU_TRAFFIC_SITES_PACK) if n == 3000 else None,
+                     "traffic_note": "ncu dram bytes (read + write) of a pack_kernel launch over %d sites x 3,000 samples "
+                                     "(8.21 GB against 7.5 GB algorithmic, x 1.09; profiles/r02_ncu_counts_stage_raw_"
+                                     "subset.csv), scaled linearly to the %d sites this launch packs; the operand-stream "
+                                     "conversion of the captured sites moved %.2f GB against 4.6 algorithmic"
+                                     % (NCU_TRAFFIC_SITES_PACK, my_sites, NCU_TRAFFIC_BYTES_CONV / 1e9),
+                     "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"], "peak_source": hbm_src}
     roofline_nj = _roofline_nj(n, stages_ms["nj"], hbm_peak, hbm_src, main.get("nj_counters"), main.get("nj_calls", 1))
     if "c5" in extra:
         extra["c5"]["roofline_nj"] = _roofline_nj(WORKLOADS["c5"][0], extra["c5"]["stages_ms"]["nj"], hbm_peak, hbm_src,

@@ -834,12 +834,14 @@ nj_lazy_kernel(const NjLazyParams P) {
     const float snu = static_cast<float>(su - Mn);
     const double sue = static_cast<double>(snu);
     M = fmax(Mn, su - sue);
-    if (tid == 0) {
-      // (read again only after the next CTA barrier: list evaluations, rescans, the next update)
+    if (lane == 0) {
+      // Lane 0 of EVERY warp writes the same values: the list evaluations of phase A (by the warp of a row's owner,
+      // before the next CTA barrier) read s_snap of the merged node's column, and a warp is ordered only against its
+      // own writes there (__syncwarp below). The maps are read after the next cluster barrier.
       C.s_snap[wa] = snu;
       C.s_s2p[wa] = static_cast<unsigned short>(spare);
       if (move) C.s_s2p[wb] = static_cast<unsigned short>(plast);
-      s_cnt = 0;
+      if (tid == 0) s_cnt = 0;   // (queue of phase B, behind the barrier that ends phase A)
     }
 
     // ---- F: the rows of this CTA (a thread per row): slot relabelling, list maintenance

@@ -447,7 +447,7 @@ class Engine:
             # returned is a view of that buffer: valid until the next call that fetches distances.
             pinned = getattr(self, "_dist_pinned", None)
             if pinned is None or pinned.shape[0] != n:
-                pinned = self._dist_pinned = torch.empty((n, n), dtype=torch.float64).pin_memory()
+                pinned = self._dist_pinned = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream())
             copy = self._copy_stream()
@@ -553,7 +553,7 @@ class Engine:
             except (OSError, AttributeError):
                 libc = None
         try:
-            buf = torch.empty(shape, dtype=dtype).pin_memory()
+            buf = torch.empty(shape, dtype=dtype, pin_memory=True)       # (page-locked directly: no pageable copy first)
         finally:
             if libc is not None:
                 libc.syscall(C.c_long(238), C.c_long(0), None, C.c_ulong(0))                                            # MPOL_DEFAULT

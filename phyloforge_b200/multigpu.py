@@ -64,12 +64,43 @@ class WorkerAborted(RuntimeError):
     """Another worker thread of the group failed: this one leaves at its next meeting point."""
 
 
+class _Meeting:
+    """Barrier of the worker threads. Unlike threading.Barrier, a meeting that everybody reached stays reached: a
+    worker that fails right behind it (and aborts the group) does not take that meeting away from peers that have not
+    woken up yet - they go on, say what they have to say, and fail at the NEXT meeting."""
+
+    def __init__(self, parties: int):
+        self.parties, self.count, self.generation, self.broken = parties, 0, 0, False
+        self.cv = threading.Condition()
+
+    def wait(self):
+        with self.cv:
+            if self.broken:
+                raise WorkerAborted()
+            generation = self.generation
+            self.count += 1
+            if self.count == self.parties:
+                self.count = 0
+                self.generation += 1
+                self.cv.notify_all()
+                return
+            while generation == self.generation and not self.broken:
+                self.cv.wait()
+            if generation == self.generation:
+                raise WorkerAborted()
+
+    def abort(self):
+        with self.cv:
+            self.broken = True
+            self.cv.notify_all()
+
+
 class ThreadGroup:
     """Meeting points of the worker threads of one `gpus = N` run (gpu_workers = threads)."""
 
     def __init__(self, world: int):
         self.world = world
-        self._barrier = threading.Barrier(world)
+        self._barrier = _Meeting(world)
         self.slots = [None] * world
         self.status = [None] * world
         self.reduce_mode = None           # "nccl" | "p2p", decided by rank 0 at the first allreduce
@@ -78,10 +109,7 @@ class ThreadGroup:
         self._warm_error = None
 
     def barrier(self):
-        try:
-            self._barrier.wait()
-        except threading.BrokenBarrierError:
-            raise WorkerAborted() from None
+        self._barrier.wait()
 
     def abort(self):
         self._barrier.abort()
@@ -238,10 +266,18 @@ def run_threads(work, world: int) -> int:
     group.start_nccl_warmup()
     threads = [threading.Thread(target=_thread_main, args=(group, r, work), name=f"phyloforge-worker-{r}")
                for r in range(world)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    # the workers spend their time inside the library, torch and file reads (no interpreter lock held); what is
+    # left are short hand-overs between many threads, and a waiting thread asks for the lock only every switch
+    # interval (5 ms by default: longer than a chunk's kernels take)
+    interval = sys.getswitchinterval()
+    sys.setswitchinterval(min(interval, 2e-4))
+    try:
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    finally:
+        sys.setswitchinterval(interval)
     for st in group.status:                       # the first worker (in rank order) that failed by itself
         if st not in (0, None):
             return st

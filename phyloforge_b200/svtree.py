@@ -55,8 +55,9 @@ class SvTree(RunCmd):
             wd = os.path.join(self.out_path, "working_dir")
             os.makedirs(wd, exist_ok=True)
             chunk = [os.path.join(wd, f"SV{r}.matrix") for r in range(self.world)]
-            vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
             shards = multigpu.gather_local(packed.chars)   # worker threads: the shards themselves; processes: None
+            if shards is None:
+                vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
             multigpu.barrier()
             if chief:
                 if shards is None:

@@ -293,7 +293,7 @@ class _ChunkReader:
         # page-locked staging buffers (plain ones only where no CUDA driver exists: the reader's line cutting is
         # exercised by the CPU tests; the loader itself needs the GPU)
         pin = torch.cuda.is_available()
-        self.bufs = [torch.empty(buf_bytes, dtype=torch.uint8).pin_memory() if pin else
+        self.bufs = [torch.empty(buf_bytes, dtype=torch.uint8, pin_memory=True) if pin else
                      torch.empty(buf_bytes, dtype=torch.uint8) for _ in range(n_bufs)]
         self.free = queue.Queue()
         self.full = queue.Queue()
@@ -335,7 +335,8 @@ class _ChunkReader:
                     if pool is not None and not eof:
                         # cut [pos, pos + want) into pieces, one positional read each, all in flight together
                         want = min(left, self.buf_bytes - filled)
-                        cuts = list(range(0, want, self.READ_PIECE)) + [want]
+                        piece = max(self.READ_PIECE, -(-want // self.read_threads))      # one read per thread
+                        cuts = list(range(0, want, piece)) + [want]
                         jobs = [pool.submit(_pread_full, f.fileno(), mv[filled + a:filled + b], pos + a)
                                 for a, b in zip(cuts, cuts[1:])]
                         got = 0
@@ -438,7 +439,7 @@ class _CharSink:
         need = self.n * c
         if self.staging[k] is None or self.staging[k].numel() < need:
             self.staging[k] = None
-            self.staging[k] = torch.empty(need + need // 8, dtype=torch.uint8).pin_memory()
+            self.staging[k] = torch.empty(need + need // 8, dtype=torch.uint8, pin_memory=True)
         stage = self.staging[k][:need].view(self.n, c)
         stage.copy_(block, non_blocking=True)
         done = torch.cuda.Event()
@@ -565,7 +566,9 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     summary = (C.c_int64 * 5)()
     parse = lib.pf_vcf_snp_parse if kind == "snp" else lib.pf_vcf_sv_parse
     try:
+        from .multigpu import trace
         for (bi, nb) in reader.chunks():
+            trace(f"chunk of {nb} bytes read")
             h_buf = reader.bufs[bi]
             d_text[:nb].copy_(h_buf[:nb], non_blocking=True)
             h2d += nb
@@ -581,6 +584,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                                        d_work.data_ptr(), stream)
             check(rc)
             reader.release(bi)          # pf_line_index synchronised the stream: the H2D copy is done
+            trace("chunk on the device, lines indexed")
             nl = n_lines.value
             codes_body = d_codes[carry_rows:]
             check(parse(d_text.data_ptr(), nb, d_lines.data_ptr(), nl, n, d_chars.data_ptr(),
@@ -640,11 +644,13 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
                 d_codes[:rem] = d_codes.index_select(0, idx)
             n_carry = rem
             n_lines_total += nl
+            trace("chunk parsed, packed (queued)")
         if n_carry:
             rows = torch.arange(0, n_carry, dtype=torch.int64, device=dev)
             engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done, rows=rows, n_sites=n_carry)
         n_sites = words_done * 32 + n_carry
         torch.cuda.current_stream().synchronize()
+        trace("device work of the conversion done")
     except BaseException:
         if sink is not None:
             sink.abandon()             # the copier thread ends behind what was queued
@@ -657,6 +663,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     if keep_chars:
         chars = sink.finish()
         n_columns = chars.shape[1]
+        trace("character matrix on the host")
     return PackedGenotypes(names=names, n_samples=n, n_sites=n_sites, n_words=n_words_cap, planes=planes,
                            chars=chars, n_columns=n_columns, n_lines=n_lines_total,
                            n_not_2bit=n_unfit_total, h2d_bytes=h2d,

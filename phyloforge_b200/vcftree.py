@@ -151,13 +151,15 @@ class VcfTree(RunCmd):
                 vcf.write_phylip(infile, packed.names, packed.chars)
                 print(infile)
         else:
-            # the reference's own layout: one chunk FASTA per worker in working_dir, concatenated in chunk order
-            # (convert_vcf_to_seq -> merge_seq, vcftree.py:139-171)
+            # worker processes, the reference's own layout: one chunk FASTA per worker in working_dir, concatenated
+            # in chunk order (convert_vcf_to_seq -> merge_seq, vcftree.py:139-171); worker threads hand their shards
+            # to rank 0 in memory and working_dir stays empty, as with one GPU
             stem = os.path.splitext(os.path.basename(self.vcf_file))[0]
             chunk = [os.path.join(self.working_dir, f"{stem}{r}.fa") for r in range(self.world)]
-            vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
-            multigpu.trace("chunk FASTA written")
             shards = multigpu.gather_local(packed.chars)   # worker threads: the shards themselves; processes: None
+            if shards is None:
+                vcf.write_fasta(chunk[self.rank], packed.names, packed.chars)
+                multigpu.trace("chunk FASTA written")
             multigpu.barrier()
             infile = f"{self.out_path}/all_snp" + (".fa" if use_fasta else ".phy")
             if chief:

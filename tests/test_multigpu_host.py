@@ -309,3 +309,20 @@ def test_chunk_reader_with_several_positional_reads_per_buffer(golden_dir, monke
         for world in (2, 3):
             got = b"".join(read(vcf.byte_range_of_rank(path, body, r, world), buf) for r in range(world))
             assert got == data[body:]
+
+
+def test_a_meeting_everybody_reached_stays_reached():
+    """The worker that holds the failure message learns from agree_ok that the run failed, prints, and exits; a
+    faster peer that exits first (and aborts the group) must not take that answer away from it."""
+    for _ in range(200):
+        said = []
+
+        def work():
+            rank, _ = multigpu.worker_env()
+            ok = multigpu.agree_ok(rank != 1)
+            if rank == 1:
+                said.append(ok)               # (the failure text of the real workflow)
+            sys.exit(1)
+
+        assert multigpu.run_threads(work, 4) == 1
+        assert said == [False]
