@@ -281,7 +281,8 @@ class Engine:
                        extra0: int = 0, total_extra: int | None = None):
         """NJ tree of all sites with block-bootstrap support on its internal edges.
         Returns (TreeResult of the main tree with support labels in .newick, support [n-3] in percent,
-        replicate join lists [replicates, n-2, 3] int32).
+        replicate join lists [replicates, n-2, 3] int32); workers other than rank 0 return the main tree without
+        labels, an empty support array and None.
 
         Blocks: contiguous ranges of the global 32-site word axis, plus (extra_chars: the columns that do not fit
         the 2-bit code, site-major characters) contiguous ranges of those columns, in proportion to their number.
@@ -333,6 +334,10 @@ class Engine:
             rep_merges[r0:r0 + k] = merge
         if multi:
             allreduce_counts(rep_merges)             # every replicate was written by exactly one worker
+        if rank != 0:
+            # the host side (which splits of the main tree each replicate has) is rank 0's, who writes the tree: worker
+            # threads of one process would only queue for the interpreter lock to compute the same numbers eight times
+            return main, np.zeros((0,)), None
         rep_merges = rep_merges.cpu().numpy()
         support = split_support(main.merge, rep_merges, n_samples)
         main.newick = merges_to_newick_native(self.lib, main.merge, main.length, list(names), support=support)

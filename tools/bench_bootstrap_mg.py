@@ -50,7 +50,7 @@ for spec in [a for a in sys.argv[1:] if not a.startswith("--")] or ["3000,100000
         dist.barrier()
     t1 = time.perf_counter()
     rec = {"samples": n, "sites": m, "replicates": reps, "blocks": blocks, "gpus": world,
-           "tree_with_bootstrap_s": t1 - t0, "mean_support": float(support.mean())}
+           "tree_with_bootstrap_s": t1 - t0, "mean_support": float(support.mean()) if support.size else None}
     if check and rank == 0 and world > 1:
         pass
     if rank == 0:

@@ -5,7 +5,8 @@ for threads, both ways of summing the counts (in-process NCCL; peer copies): wal
 first run of every variant also pays the CUDA contexts of the devices it is the first to touch), the conversion and
 tree seconds the run itself reports, and whether every output file equals the one-GPU run's.
 
-usage: r02_vcf_mg.py WORLD [RECORDS] [variants, comma separated: threads-nccl,threads-p2p,processes] [reps]"""
+usage: r02_vcf_mg.py WORLD [RECORDS] [variants, comma separated: threads-nccl,threads-p2p,processes] [reps] [BOOTSTRAP]
+BOOTSTRAP > 0 adds `bootstrap = BOOTSTRAP` (seeded block-bootstrap support, the replicates dealt out over the workers)."""
 import json, os, sys, time, tempfile, shutil
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phyloforge_b200 import multigpu, run, synth
@@ -15,19 +16,21 @@ world = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 n, m = 1000, int(sys.argv[2]) if len(sys.argv) > 2 else 200_000
 variants = (sys.argv[3] if len(sys.argv) > 3 else "threads-nccl,threads-p2p,processes").split(",")
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+boot = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 eng = Engine(0)
 names = [f"S{i:04d}" for i in range(n)]
 codes = eng.synth_codes(n, 0, m, seed=42)[:, :n].cpu().numpy()
 text = synth.snp_vcf_bytes(codes, names)[0]
 del codes
 d = tempfile.mkdtemp(dir="/dev/shm")
-out = {"samples": n, "records": m, "vcf_bytes": len(text), "world": world, "reps": reps}
+out = {"samples": n, "records": m, "vcf_bytes": len(text), "world": world, "reps": reps, "bootstrap": boot}
 FILES = ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX")
 
 
 def one(tag, extra, env=None):
     cfg = os.path.join(d, f"run_{tag}.cfg")
-    open(cfg, "w").write(f"[snp_opt]\nvcf_file = {src}\nout_path = {d}/out_{tag}\ntree_software = treebest\nthread = 8\n{extra}")
+    open(cfg, "w").write(f"[snp_opt]\nvcf_file = {src}\nout_path = {d}/out_{tag}\ntree_software = treebest\nthread = 8\n{extra}"
+                         + (f"bootstrap = {boot}\nbootstrap_seed = 7\n" if boot else ""))
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
     try:
