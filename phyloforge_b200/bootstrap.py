@@ -59,7 +59,12 @@ def split_support(main_merge: np.ndarray, rep_merges: np.ndarray, n: int) -> np.
         return np.zeros((0,), dtype=np.float64)
     main = split_keys(main_merge, n)[0]
     reps = split_keys(rep_merges, n)
-    hits = np.zeros(main.shape[0], dtype=np.int64)
-    for r in range(reps.shape[0]):
-        hits += np.isin(main, reps[r])
+    # every replicate key looked up in the sorted distinct keys of the main tree at once; a replicate counts once per
+    # main edge however often it holds the key (hit is a boolean table)
+    uniq, inverse = np.unique(main, return_inverse=True)
+    pos = np.minimum(np.searchsorted(uniq, reps), uniq.shape[0] - 1)
+    rows, cols = np.nonzero(uniq[pos] == reps)
+    hit = np.zeros((reps.shape[0], uniq.shape[0]), dtype=bool)
+    hit[rows, pos[rows, cols]] = True
+    hits = hit.sum(axis=0, dtype=np.int64)[inverse]
     return 100.0 * hits / max(1, reps.shape[0])
