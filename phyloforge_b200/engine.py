@@ -323,15 +323,26 @@ class Engine:
         if n_samples < 4 or replicates <= 0:
             return main, np.zeros((0,)), np.zeros((0, max(0, n_samples - 2), 3), dtype=np.int32)
         rep_merges = torch.zeros((replicates, n_samples - 2, 3), dtype=torch.int32, device=self.device)
-        for i, r0 in enumerate(range(0, replicates, 8)):
-            if i % world != rank:
-                continue
-            k = min(8, replicates - r0)
-            w = self.bootstrap_weights(seed, r0, k, n_all)
-            rep = self.bootstrap_counts(blocks, w)
-            dists = torch.stack([self.normalise(rep[j], metric)[0] for j in range(k)])
-            merge, _ = self.nj_batch(dists)          # the replicates of a batch are joined concurrently
-            rep_merges[r0:r0 + k] = merge
+        # replicates are dealt out in eights (what one pf_bootstrap_counts call sums); several eights are joined by
+        # one pf_nj_batch call, as many as fill the device: below 1,536 samples the full-scan kernel shares the SMs
+        # among up to 18 matrices per launch (16 here), above it every matrix takes one 16-CTA cluster and nine
+        # clusters run at a time (72 = 8 full rounds of 9; eights alone leave one slot of nine idle)
+        mine = [r0 for i, r0 in enumerate(range(0, replicates, 8)) if i % world == rank]
+        eights = 2 if n_samples < 1536 else (9 if 72 * 20 * n_samples * n_samples <= (16 << 30) else 1)
+        for g0 in range(0, len(mine), eights):
+            group = mine[g0:g0 + eights]
+            dists = []
+            for r0 in group:
+                k = min(8, replicates - r0)
+                w = self.bootstrap_weights(seed, r0, k, n_all)
+                rep = self.bootstrap_counts(blocks, w)
+                dists.extend(self.normalise(rep[j], metric)[0] for j in range(k))
+            merge, _ = self.nj_batch(torch.stack(dists))       # the replicates of a group are joined concurrently
+            at = 0
+            for r0 in group:
+                k = min(8, replicates - r0)
+                rep_merges[r0:r0 + k] = merge[at:at + k]
+                at += k
         if multi:
             allreduce_counts(rep_merges)             # every replicate was written by exactly one worker
         if rank != 0:
