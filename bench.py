@@ -67,11 +67,12 @@ DTYPE = ("e2m1 x e2m1 -> f32 tensor-core indicator products (exact: integers < 2
          "f64 distances + NJ; u32 bit planes")
 # dram__bytes_read.sum + dram__bytes_write.sum per pair-count launch, from the committed
 # ncu --set full capture of this command (profiles/); None until measured
-NCU_TRAFFIC_BYTES_TC = 54_051_894_000  # r01: 52.15 GB read + 1.90 GB written per launch of pair_counts_tc2_kernel (profiles/r01_ncu_pair_counts_tc2_raw_subset.csv), N=1
-# r02 (profiles/r02_ncu_counts_stage_raw_subset.csv, launches over 2,000,000 sites x 3,000 samples): pack_kernel 6.720 GB read + 1.489 GB written against 6.0 + 1.5 GB algorithmic;
-# planes_to_e2m1_kernel 2.179 GB read + 3.208 GB written against 1.5 + 3.1 GB
-NCU_TRAFFIC_BYTES_PACK = 8_209_060_000
-NCU_TRAFFIC_SITES_PACK = 2_000_000
+NCU_TRAFFIC_BYTES_TC = 70_360_000_000  # r02, this build, the bench's own launch (3,000 x 10M, N=1): 66.3 / 72.4 / 71.5 GB read + 0.29 GB written in three captured launches of pair_counts_tc2_kernel (profiles/r02_ncu_step_kernels_raw_subset.csv; r01: 54.05 GB)
+# pack_kernel over 10,000,000 sites x 3,000 samples (the bench's launch): 33.60 GB read + 7.50 GB written against 30.0 + 7.5 GB
+# algorithmic (same capture); planes_to_e2m1 conversion over 2,000,000 sites: 2.18 GB read + 3.21 GB written against 1.5 + 3.1 GB
+# (profiles/r02_ncu_counts_stage_raw_subset.csv)
+NCU_TRAFFIC_BYTES_PACK = 41_105_000_000
+NCU_TRAFFIC_SITES_PACK = 10_000_000
 NCU_TRAFFIC_BYTES_CONV = 5_386_406_000
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
@@ -604,10 +605,11 @@ def run_ours(args):
     roofline_pack = {"bound": "hbm", "achieved": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9, "peak": hbm_peak,
                      "unit": "GB/s", "frac": pack_bytes / (stages_ms["pack"] * 1e-3) / 1e9 / hbm_peak,
                      "traffic": int(NCU_TRAFFIC_BYTES_PACK * my_sites / NCU_TRAFFIC_SITES_PACK) if n == 3000 else None,
-                     "traffic_note": "ncu dram bytes (read + write) of a pack_kernel launch over %d sites x 3,000 samples "
-                                     "(8.21 GB against 7.5 GB algorithmic, x 1.09; profiles/r02_ncu_counts_stage_raw_"
-                                     "subset.csv), scaled linearly to the %d sites this launch packs; the operand-stream "
-                                     "conversion of the captured sites moved %.2f GB against 4.6 algorithmic"
+                     "traffic_note": "ncu dram bytes (read + write) of the pack_kernel launch over %d sites x 3,000 samples "
+                                     "(41.1 GB against 37.5 GB algorithmic, x 1.10; profiles/r02_ncu_step_kernels_raw_"
+                                     "subset.csv), scaled linearly to the %d sites this rank packs; the operand-stream "
+                                     "conversion moved %.2f GB per 2,000,000 sites against 4.6 algorithmic "
+                                     "(profiles/r02_ncu_counts_stage_raw_subset.csv)"
                                      % (NCU_TRAFFIC_SITES_PACK, my_sites, NCU_TRAFFIC_BYTES_CONV / 1e9),
                      "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"], "peak_source": hbm_src}
     roofline_nj = _roofline_nj(n, stages_ms["nj"], hbm_peak, hbm_src, main.get("nj_counters"), main.get("nj_calls", 1))
