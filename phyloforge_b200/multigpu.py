@@ -3,10 +3,11 @@
 The reference shards the site axis of ONE VCF over worker processes inside ``snp_tree`` itself: ``cutFile`` cuts
 the body into ``thread`` contiguous line ranges, a ``multiprocessing.Pool`` converts them, ``merge_seq``
 concatenates the per-chunk sequences in chunk order (treetool/vcftree.py:67-94, 216-233). This module is the same
-axis on GPUs: the entry point starts one worker process per GPU; worker r converts the lines of byte range r of
+axis on GPUs: the entry point starts one worker per GPU; worker r converts the lines of byte range r of
 the file (cut at line starts, ``vcf.byte_range_of_rank``) on its GPU, packs and counts its own columns, the int32
-count matrices are summed with one allreduce (NCCL over NVLink), and rank 0 writes the artefacts. The chunk
-FASTAs land in ``{out}/working_dir`` as the reference's do and are concatenated in rank order.
+count matrices are summed with one allreduce (NCCL over NVLink), and rank 0 writes the artefacts: the workers'
+character shards concatenated per sample in rank order, as ``merge_seq`` does with the chunk files (worker processes
+exchange them through chunk FASTAs in ``{out}/working_dir`` like the reference's, worker threads in memory).
 
 So that word ranges of the packed matrix (bootstrap blocks) mean the same sites for any number of GPUs, every
 worker moves its packed columns onto the global 32-site word grid once the column counts of the ranks before it
