@@ -151,3 +151,36 @@ def test_gpu_bootstrap_tree_matches_oracle_replicate_by_replicate(engine, n, m, 
     assert np.array_equal(support, want)
     assert treecmp.compare(main.newick, merges_to_newick(main_m, main_l, names)) == (0, 0.0)
     assert 0.0 <= support.min() and support.max() <= 100.0
+
+
+@pytest.mark.gpu
+def test_gpu_bootstrap_replicates_in_groups_of_nine_eights_match_oracle(engine):
+    """From 1,536 samples on the replicates are joined by the bounded-scan kernel, one cluster per matrix, in groups of
+    up to 72 (nine eights): every replicate's join list equals the oracle's for the same draw, whatever group and
+    position it was joined in (80 replicates = a group of 72 and a group of 8)."""
+    import torch
+    n, m, B, R = 1600, 6400, 8, 80
+    names = [f"s{i:04d}" for i in range(n)]
+    codes = engine.synth_codes(n, 0, m, seed=23)
+    nw = engine.n_words(m)
+    planes = engine.alloc_planes(n, nw)
+    engine.pack_codes(codes, n, planes, nw)
+    main, support, rep_merges = engine.bootstrap_tree(planes, n, nw, names, replicates=R, seed=9, n_blocks=B, metric="p")
+    torch.cuda.synchronize()
+    sm = np.ascontiguousarray(oracle.synth_codes(n, 0, m, seed=23).T)
+    blocks = []
+    for b in range(B):
+        wb, we = shard_words(nw, B, b)
+        blocks.append(oracle.pair_counts(np.ascontiguousarray(sm[:, wb * 32:min(m, we * 32)]), method="bits"))
+    blocks = np.stack(blocks)
+    dist, _ = oracle.normalise(blocks.sum(0), "p")
+    main_m, main_l = oracle.nj(dist)
+    assert np.array_equal(main.merge, main_m) and np.array_equal(main.length, main_l)
+    w = oracle.bootstrap_weights(9, 0, R, B)
+    for r in (0, 7, 8, 35, 63, 71, 72, 79):                       # first / last of an eight, of the group of 72, of the rest
+        rep = oracle.bootstrap_counts(blocks, w[r:r + 1])[0]
+        d, _ = oracle.normalise(rep, "p")
+        mm, _ = oracle.nj(d)
+        assert np.array_equal(rep_merges[r], mm), f"replicate {r}"
+    assert len({rep_merges[r].tobytes() for r in range(R)}) > R // 2   # the replicates are different trees
+    assert support.shape == (n - 3,) and 0.0 <= support.min() and support.max() <= 100.0
