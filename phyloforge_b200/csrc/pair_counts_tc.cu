@@ -781,10 +781,24 @@ template <> struct Tc2Cfg<1> { static constexpr int J = 240, GROUP = 6, RAW = 3,
 template <> struct Tc2Cfg<2> { static constexpr int J = 240, GROUP = 5, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = false, SPLIT = true, A_TMA = true, TMAP = false; };
 template <> struct Tc2Cfg<3> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = false, TMAP = false; };
 template <> struct Tc2Cfg<4> { static constexpr int J = 208, GROUP = 5, RAW = 4, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true, TMAP = false; };
-constexpr int TC2_CFGS = 5;
-constexpr int tc2_cols(int cfg) { return cfg == 1 ? Tc2Cfg<1>::J : cfg == 2 ? Tc2Cfg<2>::J : cfg == 3 ? Tc2Cfg<3>::J : cfg == 4 ? Tc2Cfg<4>::J : Tc2Cfg<0>::J; }
-constexpr int tc2_group(int cfg) { return cfg == 1 ? Tc2Cfg<1>::GROUP : cfg == 2 ? Tc2Cfg<2>::GROUP : cfg == 3 ? Tc2Cfg<3>::GROUP : cfg == 4 ? Tc2Cfg<4>::GROUP : Tc2Cfg<0>::GROUP; }
-constexpr bool tc2_tmap(int cfg) { return cfg == 0 ? Tc2Cfg<0>::TMAP : false; }
+// Narrower tiles leave tensor-memory columns for more steps of the A plane. Measured on 3,000 x 10M (tools/ab_tc.py,
+// profiles/r02_ab_tc_ring.txt, where the variants are numbered 5..9): a DEEPER ring of expanded stages does not help -
+// J = 176 with 3 x 5 or 3 x 6 steps 247 clocks per step, J = 192 with 3 x 4 294, J = 160 with 4 x 5 248, whatever the
+// 176 / 192 / 160 clocks of their two instructions: the step is bound by the expansion warps' shared-memory traffic
+// and hand-over, not by the depth - but LONGER stages do: J = 192 with 2 x 7 steps 236 clocks per step = 1.23 per B
+// column against 1.28 for J = 208 with 2 x 5. That one is kept as cfg 5 for A/B runs; it is not the default: the
+// narrower tiles are more tiles (104 against 98 at 3,000 samples) with other split counts, and whole calls measure
+// 35.5 against 34.7 ms at 3,000 x 10M, 18.4 against 17.7 at 5,000 x 2M, 194 against 179-194 at 10,000 x 5M, and win
+// only on short site ranges (4.42 against 4.63 ms at 3,000 x 1.25M, one GPU's share of eight);
+// profiles/r02_ab_tc_auto.txt. A per-call choice from the kernel's cost model was tried and predicted none of this.
+template <> struct Tc2Cfg<5> { static constexpr int J = 192, GROUP = 7, RAW = 3, EXP = 2; static constexpr bool AH_TMEM = true, SPLIT = true, A_TMA = true, TMAP = true; };
+constexpr int TC2_CFGS = 6;
+#define TC2_CFG_FIELD(cfg, F)                                                                                        \
+  ((cfg) == 1 ? Tc2Cfg<1>::F : (cfg) == 2 ? Tc2Cfg<2>::F : (cfg) == 3 ? Tc2Cfg<3>::F : (cfg) == 4 ? Tc2Cfg<4>::F     \
+   : (cfg) == 5 ? Tc2Cfg<5>::F : Tc2Cfg<0>::F)
+constexpr int tc2_cols(int cfg) { return TC2_CFG_FIELD(cfg, J); }
+constexpr int tc2_group(int cfg) { return TC2_CFG_FIELD(cfg, GROUP); }
+constexpr bool tc2_tmap(int cfg) { return TC2_CFG_FIELD(cfg, TMAP); }
 template <int CFG> struct Tc2Geo {
   using C = Tc2Cfg<CFG>;
   static constexpr int J = C::J, JH = C::J / 2;
@@ -1327,6 +1341,7 @@ struct TcModePlan {
 struct TcPlan {
   int64_t n_local, n_tiles, n_tiles_padded, hsum_ld;
   int n_itiles;
+  int cfg;        // tile / pipeline geometry of the CTA-pair kernel this call uses (Tc2Cfg)
   TcModePlan m[2];
   int64_t n_steps, nib_bytes, stream1_off, refv_off, flags_off, hsum_off, total;
 };
@@ -1380,6 +1395,23 @@ int tc2_cluster_slots() {
 // the GEMM kernel that will run: the CTA-pair kernel unless it was switched off or the device cannot run clusters of two
 int tc_effective_impl() { return (g_tc_impl == 2 && tc2_cluster_slots() != 0) ? 2 : 1; }
 
+// The pair kernel's cost model (see tc_plan): waves x (steps per item + per-item overhead), in pipeline steps
+double tc2_model_steps(int64_t pairs, int64_t n_local, int slots, int64_t* best_splits) {
+  const double overhead_steps = 1400.0;
+  const double steps = static_cast<double>((n_local + 1) / 2);
+  double best = 1e300;
+  int64_t splits = 1;
+  for (int64_t c = 1; c <= 64; ++c) {
+    const double waves = static_cast<double>(pf_ceil_div(c * pairs, static_cast<int64_t>(slots)));
+    const double cost = waves * (steps / static_cast<double>(c) + overhead_steps);
+    if (cost < best * 0.999) {
+      best = cost;
+      splits = c;
+    }
+  }
+  if (best_splits) *best_splits = splits;
+  return best;
+}
 TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   TcPlan L;
   L.n_local = n_local;
@@ -1388,21 +1420,22 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
   L.n_itiles = static_cast<int>(pf_ceil_div(n_samples, pair_kernel ? TC2_I : TC_I));
   const int widths[2] = {TcCfg<0>::J, TcCfg<1>::J};
   L.n_tiles_padded = 2 * static_cast<int64_t>(L.n_itiles);
+  L.cfg = g_tc_cfg;
   if (pair_kernel) {
-    // A blocks of 256 rows; the B tiles of block ti start at its first row, so the last one ends before n + J
-    const int64_t rows = static_cast<int64_t>(TC2_I) * L.n_itiles;
-    const int J2 = tc2_cols(g_tc_cfg);
-    L.n_tiles_padded = pf_ceil_div(rows > n_samples + J2 ? rows : n_samples + J2, PF_TILE);
     const int slots = tc2_cluster_slots();
     sms = slots > 0 ? slots : sms / 2;           // work items run on CTA pairs
     if (sms < 1) sms = 1;
+    // A blocks of 256 rows; the B tiles of block ti start at its first row, so the last one ends before n + J
+    const int64_t rows = static_cast<int64_t>(TC2_I) * L.n_itiles;
+    const int J2 = tc2_cols(L.cfg);
+    L.n_tiles_padded = pf_ceil_div(rows > n_samples + J2 ? rows : n_samples + J2, PF_TILE);
   }
   for (int mode = 0; mode < 2; ++mode) {
     TcModePlan& M = L.m[mode];
     const int J = widths[mode];
     M.pairs = 0;
     if (pair_kernel) {
-      const int J2 = tc2_cols(g_tc_cfg);
+      const int J2 = tc2_cols(L.cfg);
       M.n_jtiles = static_cast<int>(pf_ceil_div(n_samples, J2));
       for (int ti = 0; ti < L.n_itiles; ++ti)
         M.pairs += static_cast<int>(pf_ceil_div(n_samples - static_cast<int64_t>(TC2_I) * ti, J2));
@@ -1434,17 +1467,7 @@ TcPlan tc_plan(int64_t n_samples, int64_t n_local, int sms) {
       // drain of the last stage and 160 K scattered int32 atomics per CTA), as much as ~1,400 pipeline steps, and
       // 18 splits of 3,000 x 10M spent 14 % of the launch there. Time = waves x (steps per item + that overhead):
       // take the split count that minimises it (3,000 x 10M: 3 splits = 3.97 waves instead of 18 = 23.8).
-      const double overhead_steps = 1400.0;
-      const double steps = static_cast<double>((n_local + 1) / 2);
-      double best = 1e300;
-      for (int64_t c = 1; c <= 64; ++c) {
-        const double waves = static_cast<double>(pf_ceil_div(c * M.pairs, static_cast<int64_t>(sms)));
-        const double cost = waves * (steps / static_cast<double>(c) + overhead_steps);
-        if (cost < best * 0.999) {
-          best = cost;
-          splits = c;
-        }
-      }
+      tc2_model_steps(M.pairs, n_local, sms, &splits);
     }
     const int64_t max_splits = pf_ceil_div(n_local, 64);
     if (splits > max_splits) splits = max_splits;
@@ -1515,12 +1538,13 @@ cudaError_t tc2_launch_cfg(const TcParams& P, int64_t items, cudaStream_t s) {
   return cudaGetLastError();
 }
 template <int MODE>
-cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s) {
-  switch (g_tc_cfg) {
+cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s, int cfg) {
+  switch (cfg) {
     case 1: return tc2_launch_cfg<MODE, 1>(P, items, s);
     case 2: return tc2_launch_cfg<MODE, 2>(P, items, s);
     case 3: return tc2_launch_cfg<MODE, 3>(P, items, s);
     case 4: return tc2_launch_cfg<MODE, 4>(P, items, s);
+    case 5: return tc2_launch_cfg<MODE, 5>(P, items, s);
     default: return tc2_launch_cfg<MODE, 0>(P, items, s);
   }
 }
@@ -1528,7 +1552,7 @@ cudaError_t tc2_launch(const TcParams& P, int64_t items, cudaStream_t s) {
 }  // namespace
 
 // Diagnostic / A-B switch: impl 1 = single-CTA GEMM kernel (128 x 192 tiles), 2 = CTA-pair kernel (256 x 240
-// tiles, default); cfg = pipeline geometry of the pair kernel (0..3). Affects later pf_pair_counts_tc* calls
+// tiles, default); cfg = tile / pipeline geometry of the pair kernel (Tc2Cfg 0..5). Affects later pf_pair_counts_tc* calls
 // (the workspace layout depends on it: query pf_pair_counts_tc_work_bytes again).
 PF_API int pf_pair_counts_tc_set_impl(int impl, int cfg) {
   if ((impl != 1 && impl != 2) || cfg < 0 || cfg >= TC2_CFGS) return pf_fail("pf_pair_counts_tc_set_impl: bad arguments");
@@ -1625,13 +1649,13 @@ PF_API int pf_pair_counts_tc(const uint32_t* d_planes, int64_t n_samples, int64_
     P.words_per_split = static_cast<int>(M.words_per_split);
     const int64_t grid = M.splits * M.pairs;
     if (grid > 0x3fffffffLL) return pf_fail("pf_pair_counts_tc: grid too large");
-    if (tc_effective_impl() == 2 && tc2_tmap(g_tc_cfg)) {
-      const int J2 = tc2_cols(g_tc_cfg), G2 = tc2_group(g_tc_cfg);
+    if (tc_effective_impl() == 2 && tc2_tmap(L.cfg)) {
+      const int J2 = tc2_cols(L.cfg), G2 = tc2_group(L.cfg);
       if (!tc_make_tensor_map(&P.tm_a, P.stream, L.n_tiles_padded, L.n_steps, TC2_IH / 8, G2) ||
           !tc_make_tensor_map(&P.tm_b, P.stream, L.n_tiles_padded, L.n_steps, J2 / 16, G2))
         return pf_fail_code(PF_ERR_CUDA, "pf_pair_counts_tc: cuTensorMapEncodeTiled failed or is unavailable");
     }
-    if (tc_effective_impl() == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s) : tc2_launch<1>(P, grid, s));
+    if (tc_effective_impl() == 2) PF_CUDA(mode == 0 ? tc2_launch<0>(P, grid, s, L.cfg) : tc2_launch<1>(P, grid, s, L.cfg));
     else PF_CUDA(mode == 0 ? tc_launch<0>(P, grid, s) : tc_launch<1>(P, grid, s));
   }
   if (g_tc_timing) PF_CUDA(cudaEventRecord(g_tc_ev[2], s));

@@ -335,8 +335,10 @@ def test_host_buffer_path_matches_resident_path(engine):
         assert np.array_equal(got.dist_host, want.dist.cpu().numpy()) and got.d2h_bytes > 0
 
 
-@pytest.fixture(params=[(2, 0, False), (2, 1, False), (2, 2, False), (2, 3, False), (2, 4, False), (2, 0, True), (1, 0, False)],
-                ids=["pair", "pair-j240-regs", "pair-j240-tma", "pair-j208-regs", "pair-bulk-copies", "pair-strict", "single-cta"])
+@pytest.fixture(params=[(2, 0, False), (2, 1, False), (2, 2, False), (2, 3, False), (2, 4, False), (2, 5, False),
+                        (2, 0, True), (1, 0, False)],
+                ids=["pair", "pair-j240-regs", "pair-j240-tma", "pair-j208-regs", "pair-bulk-copies", "pair-j192-7steps",
+                     "pair-strict", "single-cta"])
 def tc_impl(engine, request):
     """Every GEMM kernel behind pf_pair_counts_tc: the CTA-pair kernel (default geometry, the alternatives, and
     with cluster-scope release on the hand-over) and the single-CTA kernel."""

@@ -13,7 +13,7 @@ from phyloforge_b200._lib import check
 from phyloforge_b200.engine import Engine
 
 eng = Engine(0)
-cfgs = [(1, 0, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (2, 3, 0)]     # (impl, cfg, debug bits)
+cfgs = [(1, 0, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (2, 3, 0), (2, 5, 0)]     # (impl, cfg, debug bits)
 if len(sys.argv) > 3:
     cfgs = [tuple(int(x) for x in a.split(":")) for a in sys.argv[3].split(",")]
 skip_parity = len(sys.argv) > 4 and sys.argv[4] == "noparity"
