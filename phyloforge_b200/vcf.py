@@ -302,6 +302,23 @@ class _ChunkReader:
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
+    def _read_pieces(self, pool, fd: int, out, pos: int):
+        """Fill `out` from file offset `pos`: cut into one piece per reader thread (>= READ_PIECE bytes each), one
+        positional read per piece, all in flight together. Returns (bytes read in file order, whether the file
+        ended inside `out` - it shrank under us)."""
+        want = len(out)
+        piece = max(self.READ_PIECE, -(-want // self.read_threads))
+        cuts = list(range(0, want, piece)) + [want]
+        spans = list(zip(cuts, cuts[1:]))
+        jobs = [pool.submit(_pread_full, fd, out[a:b], pos + a) for a, b in spans]
+        got, short = 0, False
+        for (a, b), job in zip(spans, jobs):
+            k_got = job.result()
+            if not short:
+                got += k_got
+            short = short or k_got < b - a
+        return got, short
+
     def _run(self):
         pool = None
         try:
@@ -333,19 +350,7 @@ class _ChunkReader:
                     filled = k
                     mv = memoryview(arr)
                     if pool is not None and not eof:
-                        # cut [pos, pos + want) into pieces, one positional read each, all in flight together
-                        want = min(left, self.buf_bytes - filled)
-                        piece = max(self.READ_PIECE, -(-want // self.read_threads))      # one read per thread
-                        cuts = list(range(0, want, piece)) + [want]
-                        jobs = [pool.submit(_pread_full, f.fileno(), mv[filled + a:filled + b], pos + a)
-                                for a, b in zip(cuts, cuts[1:])]
-                        got = 0
-                        short = False
-                        for (a, b), job in zip(zip(cuts, cuts[1:]), jobs):
-                            k_got = job.result()
-                            if not short:
-                                got += k_got
-                            short = short or k_got < b - a          # the file ended inside this piece (it shrank)
+                        got, short = self._read_pieces(pool, f.fileno(), mv[filled:filled + min(left, self.buf_bytes - filled)], pos)
                         filled += got
                         done += got
                         pos += got
