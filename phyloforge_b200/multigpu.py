@@ -260,11 +260,14 @@ def _thread_main(group: ThreadGroup, rank: int, work):
         _TLS.ctx = None
 
 
-def run_threads(work, world: int) -> int:
+def run_threads(work, world: int, will_reduce: bool = True) -> int:
     """Run `work()` as `world` worker threads of this process, one per GPU (rank and world reach the workflow
-    through worker_env); returns the exit status: 0 only if every worker returned 0, else the first failure's."""
+    through worker_env); returns the exit status: 0 only if every worker returned 0, else the first failure's.
+    will_reduce: the workflow sums count matrices over the workers (the GPU tree); without it (an external tree tool
+    on the merged alignment file) no NCCL communicator is created."""
     group = ThreadGroup(world)
-    group.start_nccl_warmup()
+    if will_reduce:
+        group.start_nccl_warmup()
     threads = [threading.Thread(target=_thread_main, args=(group, r, work), name=f"phyloforge-worker-{r}")
                for r in range(world)]
     # the workers spend their time inside the library, torch and file reads (no interpreter lock held); what is
@@ -279,6 +282,8 @@ def run_threads(work, world: int) -> int:
             t.join()
     finally:
         sys.setswitchinterval(interval)
+        if group._warm is not None:
+            group._warm.join()            # (a run that failed before its first allreduce: never leave while NCCL initialises)
     for st in group.status:                       # the first worker (in rank order) that failed by itself
         if st not in (0, None):
             return st

@@ -152,7 +152,8 @@ class RunCmd:
         if self.gpu_workers == "threads":
             cls, cfg, kind = type(self), self.cfg_path, self.tree_kind
             method = {"-s": "snp_tree", "-S": "sv_tree"}[flag]
-            status = multigpu.run_threads(lambda: getattr(cls(cfg, kind), method)(), self.gpus)
+            status = multigpu.run_threads(lambda: getattr(cls(cfg, kind), method)(), self.gpus,
+                                          will_reduce=self.tree_software in ("treebest", "nj"))
         else:
             status = multigpu.spawn_workers([flag, self.cfg_path], self.gpus)
         if status != 0:
