@@ -326,3 +326,38 @@ def test_a_meeting_everybody_reached_stays_reached():
 
         assert multigpu.run_threads(work, 4) == 1
         assert said == [False]
+
+
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_alignment_files_written_by_positional_writes(tmp_path, monkeypatch, threads):
+    """Large alignment files are written by several threads at the rows' offsets (vcf._write_rows): the same bytes as
+    the sequential writer, for one matrix, for column blocks (the workers' shards), for rows that are views of a wider
+    array (the loader's result), for empty blocks and for a single sample."""
+    monkeypatch.setattr(vcf, "PARALLEL_WRITE_MIN_BYTES", 1)
+    rng = np.random.default_rng(threads)
+    n = 37
+    names = [f"sample_{i}" + "x" * (i % 5) for i in range(n)]           # headers of different lengths
+    wide = rng.choice(np.frombuffer(b"ACGTMRWSYK-N", dtype=np.uint8), size=(n, 5000))
+    blocks = [wide[:, :1234], wide[:, 1234:1234], np.ascontiguousarray(wide[:, 1234:4000]), wide[:, 4000:]]
+    whole = np.ascontiguousarray(wide)
+
+    def sequential(path, first, heads):
+        with open(path, "wb") as f:
+            f.write(first)
+            for h, row in zip(heads, whole):
+                f.write(h + row.tobytes() + b"\n")
+
+    sequential(tmp_path / "want.fa", b"", [b">" + x.encode() + b"\n" for x in names])
+    sequential(tmp_path / "want.phy", f"{n} {whole.shape[1]}\n".encode(), [x.encode() + b"  " for x in names])
+    for tag, chars in (("one", whole), ("blocks", blocks), ("view", wide[:, :5000])):
+        vcf.write_fasta(str(tmp_path / f"{tag}.fa"), names, chars, threads=threads)
+        vcf.write_phylip(str(tmp_path / f"{tag}.phy"), names, chars, threads=threads)
+        assert (tmp_path / f"{tag}.fa").read_bytes() == (tmp_path / "want.fa").read_bytes(), tag
+        assert (tmp_path / f"{tag}.phy").read_bytes() == (tmp_path / "want.phy").read_bytes(), tag
+    vcf.write_fasta(str(tmp_path / "single.fa"), names[:1], whole[:1], threads=threads)
+    assert (tmp_path / "single.fa").read_bytes() == b">" + names[0].encode() + b"\n" + whole[0].tobytes() + b"\n"
+    vcf.write_fasta(str(tmp_path / "none.fa"), names, np.zeros((n, 0), dtype=np.uint8), threads=threads)
+    assert (tmp_path / "none.fa").read_bytes() == b"".join(b">" + x.encode() + b"\n\n" for x in names)
+    # rewriting a longer file in place leaves no tail of the old one
+    vcf.write_fasta(str(tmp_path / "one.fa"), names[:3], whole[:3, :10], threads=threads)
+    assert (tmp_path / "one.fa").read_bytes() == b"".join(b">" + x.encode() + b"\n" + r.tobytes() + b"\n" for x, r in zip(names[:3], whole[:3, :10]))
