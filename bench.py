@@ -69,11 +69,11 @@ DTYPE = ("e2m1 x e2m1 -> f32 tensor-core indicator products (exact: integers < 2
 # ncu --set full capture of this command (profiles/); None until measured
 NCU_TRAFFIC_BYTES_TC = 70_360_000_000  # r02, this build, the bench's own launch (3,000 x 10M, N=1): 66.3 / 72.4 / 71.5 GB read + 0.29 GB written in three captured launches of pair_counts_tc2_kernel (profiles/r02_ncu_step_kernels_raw_subset.csv; r01: 54.05 GB)
 # pack_kernel over 10,000,000 sites x 3,000 samples (the bench's launch): 33.60 GB read + 7.50 GB written against 30.0 + 7.5 GB
-# algorithmic (same capture); planes_to_e2m1 conversion over 2,000,000 sites: 2.18 GB read + 3.21 GB written against 1.5 + 3.1 GB
-# (profiles/r02_ncu_counts_stage_raw_subset.csv)
+# algorithmic (same capture); planes_to_e2m1_x4_kernel over the same sites: 7.52 GB read + 16.27 GB written against 7.5 + 15.4 GB
+# (4.00 ms: 5.95 TB/s, 0.91 of the measured HBM peak)
 NCU_TRAFFIC_BYTES_PACK = 41_105_000_000
 NCU_TRAFFIC_SITES_PACK = 10_000_000
-NCU_TRAFFIC_BYTES_CONV = 5_386_406_000
+NCU_TRAFFIC_BYTES_CONV = 23_787_000_000
 NCU_TRAFFIC_BYTES = 47_233_049_744  # r01: 46.45 GB read + 0.78 GB written (profiles/r01_ncu_pair_counts_csa_raw_subset.csv), N=1
 
 
@@ -608,8 +608,8 @@ def run_ours(args):
                      "traffic_note": "ncu dram bytes (read + write) of the pack_kernel launch over %d sites x 3,000 samples "
                                      "(41.1 GB against 37.5 GB algorithmic, x 1.10; profiles/r02_ncu_step_kernels_raw_"
                                      "subset.csv), scaled linearly to the %d sites this rank packs; the operand-stream "
-                                     "conversion moved %.2f GB per 2,000,000 sites against 4.6 algorithmic "
-                                     "(profiles/r02_ncu_counts_stage_raw_subset.csv)"
+                                     "conversion of the same sites moved %.2f GB against 22.9 algorithmic in 4.00 ms "
+                                     "(0.91 of the HBM peak; same capture)"
                                      % (NCU_TRAFFIC_SITES_PACK, my_sites, NCU_TRAFFIC_BYTES_CONV / 1e9),
                      "kernel": "pack_kernel", "kernel_ms": stages_ms["pack"], "peak_source": hbm_src}
     roofline_nj = _roofline_nj(n, stages_ms["nj"], hbm_peak, hbm_src, main.get("nj_counters"), main.get("nj_calls", 1))
