@@ -99,11 +99,16 @@ class _BgzfReader:
     GROUP_BYTES = 2 << 20        # compressed bytes per task
     READ_BYTES = 8 << 20
 
-    def __init__(self, path: str, threads: int | None = None):
+    def __init__(self, path: str, threads: int | None = None, c_begin: int = 0, c_end: int | None = None):
+        """c_begin / c_end: offsets of block starts in the compressed file; the blocks in [c_begin, c_end) are handed
+        out by readinto, `read_through_newline` then goes on behind c_end (a worker's share of a file cut over
+        several workers, _BgzfLines)."""
         from collections import deque
-        from concurrent.futures import ThreadPoolExecutor
         self.path = path
         self.f = open(path, "rb", buffering=0)
+        self.f.seek(c_begin)
+        self.c_pos = c_begin         # offset in the file of self.raw[0]
+        self.c_end = c_end
         self.threads = threads or max(2, min(16, (os.cpu_count() or 4)))
         self.pool = ThreadPoolExecutor(self.threads)
         self.ahead = 2 * self.threads
@@ -129,7 +134,11 @@ class _BgzfReader:
         """Cut one group of whole blocks off the front of the compressed bytes and hand it to the pool."""
         while True:
             blocks, off = [], 0
+            ended = False                # the next block starts at or behind c_end: not this reader's
             while off + 18 <= len(self.raw) and off < self.GROUP_BYTES:
+                if self.c_end is not None and self.c_pos + off >= self.c_end:
+                    ended = True
+                    break
                 size = _bgzf_block_size(self.raw[off:off + 18 + 64])
                 if size < 26:
                     raise VcfFormatError(f"{self.path}: not a BGZF block where one is expected (mixed or damaged gzip file)")
@@ -137,10 +146,13 @@ class _BgzfReader:
                     break
                 blocks.append((off, size, int.from_bytes(self.raw[off + 10:off + 12], "little")))
                 off += size
-            if blocks and (off >= self.GROUP_BYTES or self.raw_eof):
+            if blocks and (off >= self.GROUP_BYTES or self.raw_eof or ended):
                 chunk, self.raw = self.raw[:off], self.raw[off:]
+                self.c_pos += off
                 self.pending.append(self.pool.submit(self._inflate_group, self.path, chunk, blocks))
                 return True
+            if ended:
+                return False
             if self.raw_eof:
                 if self.raw:
                     raise VcfFormatError(f"{self.path}: truncated BGZF block")
@@ -173,9 +185,154 @@ class _BgzfReader:
             filled += k
         return filled
 
+    def read_through_newline(self) -> bytes:
+        """After readinto has handed out everything up to c_end: the text from there through the first newline (or
+        to the end of the file), block by block."""
+        out = []
+        while True:
+            while len(self.raw) < 18 and not self.raw_eof:
+                more = self.f.read(1 << 16)
+                if not more:
+                    self.raw_eof = True
+                else:
+                    self.raw += more
+            if len(self.raw) == 0:
+                break
+            size = _bgzf_block_size(self.raw[:18 + 64])
+            if size < 26:
+                raise VcfFormatError(f"{self.path}: not a BGZF block where one is expected (mixed or damaged gzip file)")
+            while len(self.raw) < size and not self.raw_eof:
+                more = self.f.read(1 << 16)
+                if not more:
+                    self.raw_eof = True
+                else:
+                    self.raw += more
+            if len(self.raw) < size:
+                raise VcfFormatError(f"{self.path}: truncated BGZF block")
+            try:
+                text = self._inflate_group(self.path, self.raw[:size], [(0, size, int.from_bytes(self.raw[10:12], "little"))])
+            except VcfFormatError:
+                raise
+            except Exception as e:  # zlib.error
+                raise VcfFormatError(f"{self.path}: corrupt BGZF block ({e})") from None
+            self.raw = self.raw[size:]
+            self.c_pos += size
+            k = text.find(b"\n")
+            if k >= 0:
+                out.append(text[:k + 1])
+                break
+            out.append(text)
+        return b"".join(out)
+
     def close(self):
         self.pool.shutdown(wait=False, cancel_futures=True)
         self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def _bgzf_block_start_at_or_after(f, pos: int, size: int) -> int:
+    """Offset of the first BGZF block that starts at `pos` or later (`size` when there is none). A candidate - the
+    gzip magic with FEXTRA and a 'BC' subfield - counts when the two blocks behind it chain up as well (or the file
+    ends there): deflate data can hold the magic bytes, three consistent headers in a row it does not."""
+    if pos <= 0:
+        return 0
+    at = pos
+    while at < size:
+        f.seek(at)
+        window = f.read((1 << 18) + 128)              # more than three blocks of at most 64 KB
+        if len(window) < 18:
+            return size
+        k = window.find(b"\x1f\x8b\x08\x04")
+        while k >= 0:
+            ok, q = True, k
+            for _ in range(3):
+                if at + q == size:
+                    break
+                bs = _bgzf_block_size(window[q:q + 18 + 64])
+                if bs < 26 or at + q + bs > size:
+                    ok = False
+                    break
+                q += bs
+                if q + 18 > len(window):
+                    break                              # (a chain that leaves the window was long enough)
+            if ok:
+                return at + k
+            k = window.find(b"\x1f\x8b\x08\x04", k + 1)
+        at += max(1, len(window) - 17)
+    return size
+
+
+def bgzf_range_of_rank(path: str, rank: int, world: int):
+    """(begin, end) offsets in a bgzip file of the blocks worker `rank` of `world` starts from: the compressed bytes are
+    cut evenly and every cut is moved forward to the next block start. The lines of the text are dealt out along these
+    cuts by _BgzfLines. Raises for gzip files that are not BGZF (one deflate stream cannot be entered in the middle)."""
+    size = os.path.getsize(path)
+    with open(path, "rb", buffering=0) as f:
+        if not _bgzf_block_size(f.read(18 + 256)):
+            raise VcfFormatError(f"{path}: a gzip file that was not written by bgzip cannot be cut over several workers; "
+                                 "use gpus = 1 (or bgzip / unpack it)")
+        cut = [_bgzf_block_start_at_or_after(f, size * r // world, size) if r else 0 for r in (rank, rank + 1)]
+    if rank + 1 == world:
+        cut[1] = size
+    return cut[0], max(cut[1], cut[0])
+
+
+class _BgzfLines:
+    """`readinto` over worker `rank`'s lines of a bgzip file cut at block starts (bgzf_range_of_rank). The blocks'
+    text is one stream of lines; a line belongs to the worker in whose blocks its first newline-terminated
+    predecessor ends - in practice: every worker but the first drops the text through the first newline of its
+    blocks, every worker but the last goes on behind its blocks through the next newline. Every line of the file is
+    handed out by exactly one worker (tests/test_multigpu_host.py), whatever the block and line lengths."""
+
+    def __init__(self, path: str, rank: int, world: int, threads: int | None = None):
+        c_begin, c_end = bgzf_range_of_rank(path, rank, world)
+        self.inner = _BgzfReader(path, threads=threads, c_begin=c_begin, c_end=c_end)
+        self.skipping = rank > 0          # still looking for the newline behind which this worker's lines start
+        self.owns_tail = rank + 1 < world
+        self.started = rank == 0          # a line of this worker is open or may follow
+        self.tail = None                  # the text behind the blocks, once it has been read
+        self.tail_at = 0
+
+    def readinto(self, out) -> int:
+        mv = memoryview(out).cast("B")
+        filled = 0
+        while filled < len(mv):
+            if self.tail is not None:
+                k = min(len(self.tail) - self.tail_at, len(mv) - filled)
+                if k <= 0:
+                    break
+                mv[filled:filled + k] = self.tail[self.tail_at:self.tail_at + k]
+                self.tail_at += k
+                filled += k
+                continue
+            got = self.inner.readinto(mv[filled:])
+            if got == 0:
+                # the blocks are exhausted: a worker that never found its first newline owns nothing (the line
+                # it sat in belongs to a worker before it, who reads through that line's end)
+                self.tail = self.inner.read_through_newline() if (self.owns_tail and self.started) else b""
+                continue
+            if self.skipping:
+                piece = bytes(mv[filled:filled + got])
+                k = piece.find(b"\n")
+                if k < 0:
+                    continue                       # all of it belongs to the worker before
+                self.skipping = False
+                self.started = True
+                rest = piece[k + 1:]
+                mv[filled:filled + len(rest)] = rest
+                filled += len(rest)
+                continue
+            filled += got
+        return filled
+
+    def close(self):
+        self.inner.close()
 
     def __enter__(self):
         return self
@@ -282,9 +439,11 @@ class _ChunkReader:
     READ_PIECE = 8 << 20
     READ_THREADS = 8
 
-    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2, byte_range=None, read_threads=None):
+    def __init__(self, path: str, size: int, buf_bytes: int, n_bufs: int = 2, byte_range=None, read_threads=None,
+                 bgzf_share=None):
         self.path, self.size, self.buf_bytes = path, size, buf_bytes
         self.byte_range = byte_range          # (begin, end) of a plain-text file, cut at line starts
+        self.bgzf_share = bgzf_share          # (rank, world): this worker's lines of a bgzip file (_BgzfLines)
         if read_threads is None:
             from . import multigpu
             world = max(1, multigpu.worker_env()[1])      # worker threads / processes of one box share its cores
@@ -325,7 +484,7 @@ class _ChunkReader:
             carry = b""
             done = 0
             eof = False
-            with _open_stream(self.path) as f:
+            with (_BgzfLines(self.path, *self.bgzf_share) if self.bgzf_share else _open_stream(self.path)) as f:
                 left = None
                 if self.byte_range is not None:
                     f.seek(self.byte_range[0])
@@ -509,12 +668,14 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     stream = torch.cuda.current_stream().cuda_stream
     if size == 0:
         raise VcfFormatError(f"{path}: empty file")
-    byte_range = None
+    byte_range = bgzf_share = None
     if world > 1:
         if size is None:
-            raise VcfFormatError(f"{path}: a compressed VCF cannot be cut into byte ranges; use gpus = 1 (or unpack it)")
-        byte_range = byte_range_of_rank(path, body, rank, world)
-        size = byte_range[1] - byte_range[0]
+            bgzf_range_of_rank(path, rank, world)     # (raises for gzip files that bgzip did not write)
+            bgzf_share = (rank, world)                # cut at block starts; the header lines are some worker's lines too
+        else:
+            byte_range = byte_range_of_rank(path, body, rank, world)
+            size = byte_range[1] - byte_range[0]
 
     # A record that yields a matrix column has 9 fixed fields and n sample fields of >= 1 byte, each
     # followed by a separator: at least 2n + 18 bytes. That bounds the columns of a plain-text file and
@@ -545,7 +706,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
         return PackedGenotypes(names=names, n_samples=n, n_sites=0, n_words=n_words_cap, planes=planes,
                                chars=np.zeros((n, 0), dtype=np.uint8) if keep_chars else None, n_columns=0, n_lines=0)
 
-    reader = _ChunkReader(path, size, buf_bytes, byte_range=byte_range)
+    reader = _ChunkReader(path, size, buf_bytes, byte_range=byte_range, bgzf_share=bgzf_share)
     d_text = torch.empty(buf_bytes, dtype=torch.uint8, device=dev)
     d_work = torch.empty(int(lib.pf_line_index_work_bytes(buf_bytes)), dtype=torch.uint8, device=dev)
     carry_rows = 32     # rows [0, 32) of the code buffer carry the sites left over from the previous chunk
@@ -563,7 +724,7 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
     words_done = 0
     # lines before this worker's first line: the header for the first of several workers (so that its line
     # numbers are the file's and the workers' line counts add up to the file's), nothing otherwise
-    n_lines_total = _HEADER_LINES.get(path, 0) if (world > 1 and rank == 0) else 0
+    n_lines_total = _HEADER_LINES.get(path, 0) if (world > 1 and rank == 0 and bgzf_share is None) else 0
     n_unfit_total = 0
     h2d = 0
     sink = _CharSink(n, (size // min_line + 2) * rpl if known else None) if keep_chars else None
@@ -654,6 +815,8 @@ def _load(engine, path: str, kind: str, keep_chars: bool, non_biallelic: str, ch
             rows = torch.arange(0, n_carry, dtype=torch.int64, device=dev)
             engine.pack_codes(d_codes, n, planes, n_words_cap, word0=words_done, rows=rows, n_sites=n_carry)
         n_sites = words_done * 32 + n_carry
+        if n_sites == 0:
+            planes.fill_(-1)           # a worker whose share holds no site: an empty shard (every word is code 3)
         torch.cuda.current_stream().synchronize()
         trace("device work of the conversion done")
     except BaseException:

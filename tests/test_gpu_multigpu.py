@@ -133,3 +133,34 @@ def test_worker_threads_leave_the_caller_single(engine, tmp_path):
     for name in ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX"):
         assert (a / name).read_bytes() == (b / name).read_bytes(), name
     assert torch.cuda.current_device() == engine.device.index
+
+
+@pytest.mark.parametrize("workers", ["threads", "processes"])
+def test_bgzip_input_cut_over_workers_equals_one_gpu(engine, tmp_path, workers, capsys):
+    """A bgzip file is cut at block starts and its lines dealt out along the cuts (vcf._BgzfLines): same artefacts as one
+    GPU on the plain text; a gzip file bgzip did not write cannot be cut and says so."""
+    import gzip
+    text, _ = vcfgen.random_snp_vcf(29, 33, 1800, miss=0.03, multi_p=0.1, star_p=0.03)
+    plain = tmp_path / "in.vcf"
+    plain.write_text(text)
+    bz = tmp_path / "in.vcf.gz"
+    vcfgen.write_bgzf(bz, text.encode(), block=2500, seed=4)
+    extra = "distance = ibs\nbootstrap = 8\n"
+    one = _run(tmp_path, "1", "snp_opt", "-s", plain, "treebest", extra)
+    many = _run(tmp_path, "3", "snp_opt", "-s", bz, "treebest", extra + f"gpus = 3\ngpu_workers = {workers}\n")
+    for name in ("all_snp.fa", "SNP.dist", "SNP_treebest.NHX"):
+        assert (one / name).read_bytes() == (many / name).read_bytes(), name
+    rep1 = json.loads((one / "SNP.phyloforge_b200.json").read_text())
+    repn = json.loads((many / "SNP.phyloforge_b200.json").read_text())
+    for key in ("samples", "sites", "lines", "alignment_columns", "sites_not_2bit"):
+        assert rep1[key] == repn[key], key
+    if workers == "threads":
+        gz = tmp_path / "plain.vcf.gz"
+        with gzip.open(gz, "wb") as f:
+            f.write(text.encode())
+        cfg = tmp_path / "run_gz.cfg"
+        _cfg(cfg, "snp_opt", gz, tmp_path / "out_gz", "treebest", "gpus = 2\n")
+        capsys.readouterr()
+        with pytest.raises(SystemExit) as ei:
+            run.main(["-s", str(cfg)])
+        assert ei.value.code == 1 and "bgzip" in capsys.readouterr().out

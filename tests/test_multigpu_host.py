@@ -361,3 +361,71 @@ def test_alignment_files_written_by_positional_writes(tmp_path, monkeypatch, thr
     # rewriting a longer file in place leaves no tail of the old one
     vcf.write_fasta(str(tmp_path / "one.fa"), names[:3], whole[:3, :10], threads=threads)
     assert (tmp_path / "one.fa").read_bytes() == b"".join(b">" + x.encode() + b"\n" + r.tobytes() + b"\n" for x, r in zip(names[:3], whole[:3, :10]))
+
+
+def _bgzf_lines(path, rank, world, threads=2):
+    with vcf._BgzfLines(str(path), rank, world, threads=threads) as r:
+        out = bytearray()
+        buf = bytearray(1237)                          # an awkward read size
+        while True:
+            k = r.readinto(buf)
+            if k == 0:
+                return bytes(out)
+            out += buf[:k]
+
+
+@pytest.mark.parametrize("block", [40, 700, 5000, 0xff00])
+@pytest.mark.parametrize("world", [2, 3, 8, 33])
+def test_bgzf_file_cut_over_workers_hands_out_every_line_once(golden_dir, tmp_path, block, world):
+    """A bgzip file is cut at block starts; every worker but the first drops the text through its first newline, every
+    worker but the last reads on through the next one: the workers' texts, in rank order, are the file's text, each
+    made of whole lines - for blocks much shorter and much longer than a line, and for more workers than blocks."""
+    text = open(os.path.join(golden_dir, "snp_rand_b.vcf"), "rb").read()
+    path = tmp_path / "x.vcf.gz"
+    vcfgen.write_bgzf(path, text, block=block, seed=block + world)
+    size = os.path.getsize(path)
+    cuts = [vcf.bgzf_range_of_rank(str(path), r, world) for r in range(world)]
+    assert cuts[0][0] == 0 and cuts[-1][1] == size
+    for (b0, e0), (b1, e1) in zip(cuts, cuts[1:]):
+        assert e0 == b1 and b0 <= e0
+    raw = open(path, "rb").read()
+    for b, _ in cuts:
+        assert b == size or vcf._bgzf_block_size(raw[b:b + 18 + 64]) >= 26          # every cut is a block start
+    parts = [_bgzf_lines(path, r, world) for r in range(world)]
+    assert b"".join(parts) == text
+    for part in parts[:-1]:
+        assert part == b"" or part.endswith(b"\n")
+    # and through the chunk reader, as the loader reads it
+    got = b""
+    for r in range(world):
+        reader = vcf._ChunkReader(str(path), None, 1 << 16, bgzf_share=(r, world))
+        try:
+            for bi, nb in reader.chunks():
+                got += bytes(reader.bufs[bi].numpy()[:nb])
+                reader.release(bi)
+        finally:
+            reader.close()
+    assert got == text
+
+
+def test_bgzf_cut_corner_cases(tmp_path):
+    # no newline at the end; one very long line over many blocks; deflate payloads that contain the gzip magic
+    rng = np.random.default_rng(5)
+    magic = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00"
+    long_line = bytes(rng.integers(65, 91, size=30_000, dtype=np.uint8))
+    noise = [bytes(rng.integers(0, 256, size=int(k), dtype=np.uint8)).replace(b"\n", b"x") + magic for k in rng.integers(1, 300, size=400)]
+    text = b"#h1\n#h2\n" + long_line + b"\n" + b"\n".join(noise) + b"\nlast line without newline"
+    for block, world in ((64, 5), (3000, 4), (50_000, 3), (50_000, 16)):
+        path = tmp_path / f"c{block}_{world}.gz"
+        vcfgen.write_bgzf(path, text, block=block, seed=block)
+        parts = [_bgzf_lines(path, r, world) for r in range(world)]
+        assert b"".join(parts) == text, (block, world)
+        for r, p_r in enumerate(parts[:-1]):          # whole lines; the unterminated last line has one owner
+            assert p_r == b"" or p_r.endswith(b"\n") or all(q == b"" for q in parts[r + 1:])
+    # a gzip file that bgzip did not write cannot be entered in the middle
+    import gzip
+    plain = tmp_path / "plain.vcf.gz"
+    with gzip.open(plain, "wb") as f:
+        f.write(text)
+    with pytest.raises(vcf.VcfFormatError, match="bgzip"):
+        vcf.bgzf_range_of_rank(str(plain), 1, 2)
