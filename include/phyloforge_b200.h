@@ -285,6 +285,13 @@ PF_API int64_t pf_newick_from_merges(const int32_t* h_merge, const double* h_len
 PF_API int pf_write_distance_matrix(const char* path, const char* const* names, int64_t n, const double* h_dist,
                                     int64_t ld, int decimals, int n_threads);
 
+/* Host-side: bootstrap support of the main tree's internal edges - h_support[t], t < n - 3, = percentage of the n_reps
+ * replicate join lists (pf_nj / pf_nj_batch outputs copied to the host, [n_reps][n - 2][3]) whose tree has the split
+ * above node n + t of the main join list; the numbers the reference asks `treebest nj -b 1000` for
+ * (treetool/script.py:359-360). n >= 4. n_threads <= 0: all host threads. */
+PF_API int pf_bootstrap_support(const int32_t* h_main_merge, const int32_t* h_rep_merges, int64_t n, int64_t n_reps,
+                                double* h_support, int n_threads);
+
 /* Block bootstrap (csrc/bootstrap.cu; the reproducible counterpart of the `-b 1000` the reference passes to
  * `treebest nj`, treetool/script.py:359-360). The caller keeps the count matrices of n_blocks contiguous
  * site blocks (pf_pair_counts / pf_pair_counts_tc on word ranges into separate [3][n][ld] buffers,

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "pf_normalise": (_i32, [_vp, _i64, _i64, _i32, _vp, _i64, _vp, _vp]),
     "pf_newick_from_merges": (_i64, [_vp, _vp, _i64, _vp, _vp, _vp, _i64]),
     "pf_write_distance_matrix": (_i32, [C.c_char_p, _vp, _i64, _vp, _i64, _i32, _i32]),
+    "pf_bootstrap_support": (_i32, [_vp, _vp, _i64, _i64, _vp, _i32]),
     "pf_bootstrap_weights": (_i32, [_u64, _i64, _i32, _i32, _vp, _vp]),
     "pf_bootstrap_counts": (_i32, [_vp, _i32, _i64, _vp, _i32, _vp, _vp]),
     "pf_nj_work_bytes": (_i64, [_i64]),

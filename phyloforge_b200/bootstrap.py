@@ -52,9 +52,27 @@ def split_keys(merges: np.ndarray, n: int) -> np.ndarray:
         return a1 ^ (a2 * np.uint64(0x9E3779B97F4A7C15))
 
 
-def split_support(main_merge: np.ndarray, rep_merges: np.ndarray, n: int) -> np.ndarray:
+def split_support(main_merge: np.ndarray, rep_merges: np.ndarray, n: int, threads: int = 0) -> np.ndarray:
     """Percentage of replicate trees that contain each internal edge of the main tree: [n-3] float64,
-    entry t belongs to node n+t of the main join list."""
+    entry t belongs to node n+t of the main join list. Computed by the library's host threads
+    (csrc/artefacts.cu: pf_bootstrap_support, the same split keys as split_keys below)."""
+    if n < 4:
+        return np.zeros((0,), dtype=np.float64)
+    from . import _lib
+    main = np.ascontiguousarray(main_merge, dtype=np.int32)
+    reps = np.ascontiguousarray(rep_merges, dtype=np.int32)
+    if reps.ndim == 2:
+        reps = reps[None]
+    if main.shape != (n - 2, 3) or reps.shape[1:] != (n - 2, 3):
+        raise ValueError(f"join lists of shape {main.shape} / {reps.shape} for {n} leaves")
+    out = np.zeros(n - 3, dtype=np.float64)
+    _lib.check(_lib.load().pf_bootstrap_support(main.ctypes.data, reps.ctypes.data, n, reps.shape[0], out.ctypes.data,
+                                                threads))
+    return out
+
+
+def split_support_py(main_merge: np.ndarray, rep_merges: np.ndarray, n: int) -> np.ndarray:
+    """The same numbers with numpy: the statement the tests hold the library to."""
     if n < 4:
         return np.zeros((0,), dtype=np.float64)
     main = split_keys(main_merge, n)[0]

@@ -184,3 +184,52 @@ def test_gpu_bootstrap_replicates_in_groups_of_nine_eights_match_oracle(engine):
         assert np.array_equal(rep_merges[r], mm), f"replicate {r}"
     assert len({rep_merges[r].tobytes() for r in range(R)}) > R // 2   # the replicates are different trees
     assert support.shape == (n - 3,) and 0.0 <= support.min() and support.max() <= 100.0
+
+
+def _random_join_list(n, rng):
+    live = list(range(n))
+    m = np.zeros((n - 2, 3), dtype=np.int32)
+    for t in range(n - 3):
+        i = int(rng.integers(len(live)))
+        a = live[i]
+        live[i] = live[-1]
+        live.pop()
+        j = int(rng.integers(len(live)))
+        b = live[j]
+        live[j] = n + t
+        m[t] = (a, b, 0)
+    m[n - 3] = live
+    return m
+
+
+@pytest.mark.parametrize("n,R", [(4, 3), (5, 40), (12, 50), (97, 130), (1000, 37)])
+def test_native_split_support_equals_numpy(n, R):
+    """pf_bootstrap_support (host threads of the library) against bootstrap.split_support_py: replicates that are the
+    main tree, relabelled main trees (some splits survive), random trees; any number of threads."""
+    from phyloforge_b200.bootstrap import split_support, split_support_py
+    rng = np.random.default_rng(n + R)
+    main = _random_join_list(n, rng)
+    reps = []
+    for r in range(R):
+        kind = r % 3
+        if kind == 0:
+            reps.append(main.copy())
+        elif kind == 1:                                   # swap two leaves of the main tree
+            m = main.copy()
+            a, b = (int(x) for x in rng.choice(n, 2, replace=False))
+            m[main == a], m[main == b] = b, a
+            reps.append(m)
+        else:
+            reps.append(_random_join_list(n, rng))
+    reps = np.stack(reps)
+    want = split_support_py(main, reps, n)
+    for threads in (1, 3, 0):
+        got = split_support(main, reps, n, threads=threads)
+        assert np.array_equal(got, want), threads
+    assert want.max() <= 100.0 and want.min() >= 100.0 * ((R + 2) // 3) / R - 1e-9   # every third replicate is the main tree
+    assert np.array_equal(split_support(main, reps[:0], n), np.zeros(n - 3))       # no replicates: zeros
+    bad = reps.copy()
+    bad[R // 2, 0, 0] = n + 5                                                       # a node that does not exist yet
+    from phyloforge_b200._lib import PhyloForgeError
+    with pytest.raises(PhyloForgeError):
+        split_support(main, bad, n)
