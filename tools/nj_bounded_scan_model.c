@@ -97,7 +97,9 @@ int main(int argc, char** argv) {
     Best dummy = {INFINITY, INT64_MAX, INT64_MAX};
     for (int64_t i = 0; i < n; ++i) rescan(i, (double)(na - 2), &dummy);
     n_rescan = 0; n_reeval = 0; }
-  int64_t t = 0, bad = 0, iters_resc = 0, max_resc = 0;
+  int64_t t = 0, bad = 0, iters_resc = 0, max_resc = 0, path_resc = 0;   /* path_resc: sum over iterations of the most
+                                                                          rescans any one CTA does (what the others wait for) */
+  int64_t* cta_resc = malloc(NC * 8);
   double* du = malloc(n * 8);
   Best* cb = malloc(NC * sizeof(Best)); Best* cb2 = malloc(NC * sizeof(Best));
   double T0 = INFINITY;   /* exact q of the previous exchange's runner-up in the current frame: a threshold for every CTA */
@@ -112,16 +114,18 @@ int main(int argc, char** argv) {
     }
     const int64_t resc0 = n_rescan;
     memcpy(cb2, cb, NC * sizeof(Best));
+    memset(cta_resc, 0, NC * 8);
     /* bounds that do not clear the threshold: rescan the row, or evaluate its list */
     for (int64_t i = 0; i < na; ++i) {
       Row* R = &rows[i]; const double T = fmin(cb[owner[i]].q, T0), si = r[i] * inv;
-      if (!(R->R2 == INFINITY) && !bound_clears(R->R2, si, n2, T)) rescan(i, n2, &cb2[owner[i]]);
+      if (!(R->R2 == INFINITY) && !bound_clears(R->R2, si, n2, T)) { rescan(i, n2, &cb2[owner[i]]); ++cta_resc[owner[i]]; }
       else if (!(R->R1 == INFINITY) && !bound_clears(R->R1, si, n2, T)) list_evaluate(i, n2, &cb2[owner[i]]);
     }
     Best W = {INFINITY, INT64_MAX, INT64_MAX};
     for (int c = 0; c < NC; ++c)
       if (cb2[c].q < W.q || (cb2[c].q == W.q && (cb2[c].a < W.a || (cb2[c].a == W.a && cb2[c].b < W.b)))) W = cb2[c];
     if (n_rescan > resc0) { ++iters_resc; if (n_rescan - resc0 > max_resc) max_resc = n_rescan - resc0; }
+    { int64_t m = 0; for (int c = 0; c < NC; ++c) if (cta_resc[c] > m) m = cta_resc[c]; path_resc += m; }
     int64_t ba = W.a, bb = W.b;
     if (ba == INT64_MAX) { ba = 0; bb = 1; }
     /* the runner-up: the best published record whose nodes are not joined now */
@@ -231,7 +235,7 @@ int main(int argc, char** argv) {
     }
   }
   printf("n=%lld G=%d ctas=%d epoch=%d perm=%d: mismatches %lld; rescans %.3f / iteration (iterations with one: %lld of %lld, max %lld); "
-         "list evaluations %.2f / iteration\n", (long long)n, G, NC, E, perm, (long long)bad, (double)n_rescan / t,
-         (long long)iters_resc, (long long)t, (long long)max_resc, (double)n_reeval / t);
+         "on the busiest CTA %.3f / iteration; list evaluations %.2f / iteration\n", (long long)n, G, NC, E, perm, (long long)bad,
+         (double)n_rescan / t, (long long)iters_resc, (long long)t, (long long)max_resc, (double)path_resc / t, (double)n_reeval / t);
   return bad != 0;
 }
