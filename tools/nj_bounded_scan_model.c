@@ -74,6 +74,10 @@ int main(int argc, char** argv) {
   n = atoll(argv[1]); const char* path = argv[2];
   G = argc > 3 ? atoi(argv[3]) : 32; NC = argc > 4 ? atoi(argv[4]) : 16; E = argc > 5 ? atoi(argv[5]) : 8;
   const int perm = argc > 6 ? atoi(argv[6]) : 0;
+  /* what-if switch (design tool only; the kernel does not do this): 1 = in an iteration in which some CTA has to rescan,
+   * every CTA that does not refreshes its row with the least slack (in the shadow of the wait); 2 = in every iteration */
+  const int proactive = argc > 7 ? atoi(argv[7]) : 0;
+  int64_t n_proactive = 0;
   if (G > GMAX || G < 1 || n < 4) return 2;
   ld = n;
   D = malloc(n * n * 8); double* D0 = malloc(n * n * 8);
@@ -125,7 +129,21 @@ int main(int argc, char** argv) {
     for (int c = 0; c < NC; ++c)
       if (cb2[c].q < W.q || (cb2[c].q == W.q && (cb2[c].a < W.a || (cb2[c].a == W.a && cb2[c].b < W.b)))) W = cb2[c];
     if (n_rescan > resc0) { ++iters_resc; if (n_rescan - resc0 > max_resc) max_resc = n_rescan - resc0; }
-    { int64_t m = 0; for (int c = 0; c < NC; ++c) if (cta_resc[c] > m) m = cta_resc[c]; path_resc += m; }
+    { int64_t m = 0; for (int c = 0; c < NC; ++c) if (cta_resc[c] > m) m = cta_resc[c]; path_resc += m;
+      if (getenv("NJ_MODEL_TRACE") && m > 0) fprintf(stderr, "t=%lld na=%lld phase=%lld total=%lld busiest=%lld M=%.3e\n", (long long)t,
+                                                     (long long)na, (long long)(t % E), (long long)(n_rescan - resc0), (long long)m, M); }
+    if (proactive == 2 || (proactive == 1 && n_rescan > resc0)) {
+      for (int c = 0; c < NC; ++c) {
+        if (cta_resc[c]) continue;
+        int64_t pick = -1; double least = INFINITY;
+        for (int64_t i = 0; i < na; ++i) {
+          if (owner[i] != c || rows[i].R2 == INFINITY) continue;
+          const double slack = n2 * ((rows[i].R2 - M) - r[i] * inv);
+          if (slack < least) { least = slack; pick = i; }
+        }
+        if (pick >= 0) { Best dummy = {INFINITY, INT64_MAX, INT64_MAX}; rescan(pick, n2, &dummy); --n_rescan; ++n_proactive; }
+      }
+    }
     int64_t ba = W.a, bb = W.b;
     if (ba == INT64_MAX) { ba = 0; bb = 1; }
     /* the runner-up: the best published record whose nodes are not joined now */
@@ -234,6 +252,7 @@ int main(int argc, char** argv) {
       if (x.q < INFINITY) T0 = x.q;
     }
   }
+  if (proactive) printf("proactive refreshes (mode %d): %.3f / iteration\n", proactive, (double)n_proactive / t);
   printf("n=%lld G=%d ctas=%d epoch=%d perm=%d: mismatches %lld; rescans %.3f / iteration (iterations with one: %lld of %lld, max %lld); "
          "on the busiest CTA %.3f / iteration; list evaluations %.2f / iteration\n", (long long)n, G, NC, E, perm, (long long)bad,
          (double)n_rescan / t, (long long)iters_resc, (long long)t, (long long)max_resc, (double)path_resc / t, (double)n_reeval / t);
